@@ -1,0 +1,210 @@
+"""Thin object wrapper over the C ABI: one Engine = one vbnmf_handle = one GPU holding the CSC
+count matrix (or one shard of its cells).  Host code only; all arithmetic runs in libvbnmf.so."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+EPS = float(np.finfo(np.float64).eps)  # .Machine$double.eps (R/bayesian.R:238)
+HKEYS = ("aw", "bw", "ah", "bh")
+
+
+def _dp(a):
+    return None if a is None else a.ctypes.data_as(_lib.c_dp)
+
+
+def hyper_vec(hyper):
+    if isinstance(hyper, dict):
+        return np.array([float(hyper[k]) for k in HKEYS], dtype=np.float64)
+    return np.array(hyper, dtype=np.float64)
+
+
+def hyper_dict(v):
+    return {k: float(x) for k, x in zip(HKEYS, v)}
+
+
+class Engine:
+    """Device-resident VB-NMF state for one count matrix.
+
+    counts: scipy.sparse matrix (genes x cells) or anything scipy can convert to CSC -- the
+    `counts(object)` of an scNMFSet (R/bayesian.R:239).
+    """
+
+    def __init__(self, counts=None, device=0, _device_csc=None):
+        self.lib = _lib.load()
+        self.handle = C.c_void_p()
+        self._keep = None
+        if _device_csc is not None:
+            n, m, nnz, d_colptr, d_rowidx, d_val, keep = _device_csc
+            self._keep = keep  # borrowed device arrays must outlive the handle
+            rc = self.lib.vbnmf_create_from_device(C.byref(self.handle), n, m, nnz,
+                                                   C.c_void_p(d_colptr), C.c_void_p(d_rowidx),
+                                                   C.c_void_p(d_val), int(device))
+        else:
+            import scipy.sparse as sp
+            csc = sp.csc_matrix(counts)
+            csc.sort_indices()
+            n, m = csc.shape
+            nnz = csc.nnz
+            rowidx = np.ascontiguousarray(csc.indices, dtype=np.int32)
+            values = np.ascontiguousarray(csc.data, dtype=np.float64)
+            p32 = p64 = None
+            if csc.indptr.dtype == np.int32:  # dgCMatrix @p is int32
+                ptr = np.ascontiguousarray(csc.indptr)
+                p32 = ptr.ctypes.data_as(_lib.c_i32p)
+            else:
+                ptr = np.ascontiguousarray(csc.indptr, dtype=np.int64)
+                p64 = ptr.ctypes.data_as(_lib.c_i64p)
+            rc = self.lib.vbnmf_create(C.byref(self.handle), n, m, nnz, p32, p64,
+                                       rowidx.ctypes.data_as(_lib.c_i32p), _dp(values), int(device))
+        if rc != 0:
+            msg = self.lib.vbnmf_last_error(None)
+            self.handle = C.c_void_p()
+            raise _lib.VbnmfError(rc, msg.decode() if msg else "unknown")
+        self.n, self.m, self.nnz = int(n), int(m), int(nnz)
+        self.r = 0
+
+    @classmethod
+    def from_device_csc(cls, n, m, nnz, colptr_i64, rowidx_i32, values_f32, device=0):
+        """colptr/rowidx/values: torch CUDA tensors (int64, int32, float32) already on `device`."""
+        keep = (colptr_i64, rowidx_i32, values_f32)
+        return cls(device=device, _device_csc=(int(n), int(m), int(nnz), colptr_i64.data_ptr(),
+                                               rowidx_i32.data_ptr(), values_f32.data_ptr(), keep))
+
+    # -- lifetime ------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "handle", None) and self.handle.value:
+            self.lib.vbnmf_destroy(self.handle)
+            self.handle = C.c_void_p()
+        self._keep = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _ck(self, rc):
+        _lib.check(rc, self.handle)
+
+    # -- configuration -------------------------------------------------------------------------
+    def set_stream(self, cuda_stream_ptr):
+        self._ck(self.lib.vbnmf_set_stream(self.handle, C.c_void_p(int(cuda_stream_ptr))))
+
+    def set_precision(self, precision):
+        self._ck(self.lib.vbnmf_set_precision(self.handle, int(precision)))
+
+    @staticmethod
+    def nccl_unique_id():
+        buf = (C.c_char * 128)()
+        rc = _lib.load().vbnmf_nccl_unique_id(buf)
+        if rc != 0:
+            _lib.check(rc, None)
+        return bytes(buf)
+
+    def comm_init(self, nranks, rank, uid):
+        buf = (C.c_char * 128).from_buffer_copy(uid) if uid is not None else None
+        self._ck(self.lib.vbnmf_comm_init(self.handle, int(nranks), int(rank), buf))
+
+    def info(self):
+        v = (C.c_int64 * 8)()
+        self._ck(self.lib.vbnmf_info(self.handle, v))
+        return dict(zip(("n", "m", "nnz", "r", "rs", "precision", "nranks", "m_global"), v))
+
+    # -- state ---------------------------------------------------------------------------------
+    def set_state(self, lw, lh, ew=None, eh=None):
+        """wh list of vbnmf_update (src/vbnmf_update.cpp:22-25): lw, ew n x r; lh, eh r x m."""
+        lw = np.asfortranarray(lw, dtype=np.float64)
+        lh = np.asfortranarray(lh, dtype=np.float64)
+        r = lw.shape[1]
+        if lw.shape != (self.n, r) or lh.shape != (r, self.m):
+            raise ValueError("lw must be n x r and lh r x m")
+        ew = None if ew is None else np.asfortranarray(ew, dtype=np.float64)
+        eh = None if eh is None else np.asfortranarray(eh, dtype=np.float64)
+        self._ck(self.lib.vbnmf_set_state(self.handle, r, _dp(lw), _dp(lh), _dp(ew), _dp(eh)))
+        self.r = r
+
+    def get_state(self, which=("lw", "lh", "ew", "eh", "dw", "dh")):
+        r = self.r
+        out = {}
+        for k in which:
+            out[k] = np.zeros((self.n, r) if k[1] == "w" else (r, self.m), order="F")
+        args = [_dp(out.get(k)) for k in ("lw", "lh", "ew", "eh", "dw", "dh")]
+        self._ck(self.lib.vbnmf_get_state(self.handle, *args))
+        return out
+
+    def step(self, hyper, fudge=EPS):
+        """One vbnmf_update (src/vbnmf_update.cpp:16-102).  Returns lkh."""
+        hy = hyper_vec(hyper)
+        lkh = C.c_double(0.0)
+        self._ck(self.lib.vbnmf_step(self.handle, _dp(hy), float(fudge), C.byref(lkh)))
+        return lkh.value
+
+    def means(self):
+        v = np.zeros(4)
+        self._ck(self.lib.vbnmf_get_means(self.handle, _dp(v)))
+        return v
+
+    def run(self, hyper, Itmax=10000, Tol=1e-5, hyper_update=(True,) * 4, n0=10, dn=1, fudge=EPS):
+        """The it-loop of vb_iterate (R/bayesian.R:336-352).  Returns a dict with the final hyper,
+        lml (= lk0 of :379), niter, stop_reason and the per-iteration traces."""
+        cfg = _lib.VbnmfCfg()
+        cfg.itmax = int(Itmax)
+        cfg.tol = float(Tol)
+        for i in range(4):
+            cfg.hyper_update[i] = int(bool(hyper_update[i]))
+        cfg.n0, cfg.dn, cfg.fudge = int(n0), int(dn), float(fudge)
+        hy = hyper_vec(hyper)
+        trace = np.full(cfg.itmax, np.nan)
+        htrace = np.full((cfg.itmax, 4), np.nan)
+        niter, reason, lml = C.c_int(0), C.c_int(0), C.c_double(0.0)
+        self._ck(self.lib.vbnmf_run(self.handle, C.byref(cfg), _dp(hy), _dp(trace), _dp(htrace),
+                                    C.byref(niter), C.byref(lml), C.byref(reason)))
+        it = niter.value
+        return dict(hyper=hyper_dict(hy), lml=lml.value, niter=it, stop_reason=reason.value,
+                    lkh_trace=trace[:it].copy(), hyper_trace=htrace[:it].copy())
+
+    def cluster_id(self):
+        cid = np.zeros(self.m, dtype=np.int32)
+        self._ck(self.lib.vbnmf_cluster_id(self.handle, cid.ctypes.data_as(_lib.c_i32p)))
+        return cid
+
+    def uniform_columns(self, tol):
+        fl = np.zeros(self.r, dtype=np.int32)
+        self._ck(self.lib.vbnmf_uniform_columns(self.handle, float(tol),
+                                                fl.ctypes.data_as(_lib.c_i32p)))
+        return fl.astype(bool)
+
+    # -- ML path -------------------------------------------------------------------------------
+    def ml_run(self, w0, h0, Itmax=10000, Tol=1e-5):
+        """it-loop of factorize(), criterion='likelihood' (R/factorize.R:189-212)."""
+        w0 = np.asfortranarray(w0, dtype=np.float64)
+        h0 = np.asfortranarray(h0, dtype=np.float64)
+        r = w0.shape[1]
+        w = np.zeros((self.n, r), order="F")
+        h = np.zeros((r, self.m), order="F")
+        trace = np.full(int(Itmax), np.nan)
+        niter = C.c_int(0)
+        self._ck(self.lib.mlnmf_run(self.handle, r, _dp(w0), _dp(h0), int(Itmax), float(Tol),
+                                    _dp(w), _dp(h), _dp(trace), C.byref(niter)))
+        self.r = r
+        it = niter.value
+        return dict(w=w, h=h, niter=it, lik_trace=trace[:it].copy(), lik=float(trace[it - 1]))
+
+    # -- measurement ---------------------------------------------------------------------------
+    def bench_iterations(self, hyper, iters, fudge=EPS):
+        hy = hyper_vec(hyper)
+        ms = np.zeros(4)
+        launches = C.c_int64(0)
+        lkh = C.c_double(0.0)
+        self._ck(self.lib.vbnmf_bench_iterations(self.handle, _dp(hy), float(fudge), int(iters),
+                                                 _dp(ms), C.byref(launches), C.byref(lkh)))
+        return dict(ms_total=ms[0], ms_cols=ms[1], ms_rows=ms[2], ms_other=ms[3],
+                    launches=launches.value, lkh=lkh.value)

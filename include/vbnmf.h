@@ -1,0 +1,144 @@
+/* libvbnmf — C ABI of the B200-native variational-Bayes Poisson-NMF engine.
+ *
+ * This is the drop-in boundary for ONE path of the R package ccfindR: the per-iteration VB update
+ * and the loop that drives it.  Citations are file:line in the reference tree.
+ *
+ *   reference interface replaced                                     entry point here
+ *   ---------------------------------------------------------------  -------------------------
+ *   .Call(`_ccfindR_vbnmf_update`, X, wh, hyper, fudge)               vbnmf_create + vbnmf_set_state
+ *     R/RcppExports.R:4-6, src/RcppExports.cpp:11-22                  + vbnmf_step + vbnmf_get_state
+ *   vbnmf_update(): one VB iteration, src/vbnmf_update.cpp:16-102     vbnmf_step
+ *   return list w,h,lw,lh,ew,eh,lkh,dw,dh, src/vbnmf_update.cpp:92-100 vbnmf_get_state (+ *lkh)
+ *   for(it in seq_len(Itmax)) loop of vb_iterate, R/bayesian.R:336-352 vbnmf_run
+ *   hyper_update(), R/bayesian.R:2-53                                  (inside vbnmf_run)
+ *   uniform-column test, R/bayesian.R:368-369                          vbnmf_uniform_columns
+ *   cluster_id(): apply(h,2,which.max), R/utils.R:903-909              vbnmf_cluster_id
+ *   nmf_updateR() + likelihood() loop, R/factorize.R:189-212           mlnmf_run
+ *   Rmpi task farm over restarts, R/bayesian.R:263                     one handle per process/GPU;
+ *                                                                      cells sharded with vbnmf_comm_init
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; vbnmf_last_error() gives the text.
+ *     No C++ exception crosses this boundary.
+ *   - all matrices are column-major doubles exactly as R stores them: lw/ew/dw are n x r,
+ *     lh/eh/dh are r x m.  hyper = {aw, bw, ah, bh}.
+ *   - the count matrix is CSC as in Matrix::dgCMatrix: colptr = @p (length m+1), rowidx = @i
+ *     (0-based), values = @x.  Column pointers may be 32- or 64-bit; on the device they are 64-bit.
+ *   - a handle owns one CUDA device and is not thread-safe.  There is no CPU fallback: creating a
+ *     handle without a usable CUDA device fails.
+ *   - when cells are sharded over several GPUs (one process and one handle per GPU), m is the
+ *     LOCAL number of cells, lh/eh/dh are the local columns, lw/ew/dw are replicated, and every
+ *     rank must make the same sequence of calls (set_state/step/run are collective).
+ */
+#ifndef VBNMF_H
+#define VBNMF_H
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define VBNMF_API __attribute__((visibility("default")))
+#else
+#define VBNMF_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vbnmf_handle vbnmf_handle;
+
+/* mirrors the `bundle` of vb_factorize (R/bayesian.R:252-259) for the fields the loop reads */
+typedef struct {
+    int itmax;            /* Itmax */
+    double tol;           /* Tol */
+    int hyper_update[4];  /* hyper.update: aw, bw, ah, bh */
+    int n0;               /* hyper.update.n0 */
+    int dn;               /* hyper.update.dn */
+    double fudge;         /* fudge (R passes .Machine$double.eps when NULL, R/bayesian.R:238) */
+} vbnmf_cfg;
+
+enum { VBNMF_FP64 = 0, VBNMF_FP32_STORAGE = 1 };
+enum { VBNMF_STOP_ITMAX = 0, VBNMF_STOP_CONVERGED = 1, VBNMF_STOP_NAN = 2 };
+enum {
+    VBNMF_OK = 0,
+    VBNMF_ERR_ARG = 1,
+    VBNMF_ERR_HYPER = 2, /* 'Hyper-parameter update failed to converge', R/bayesian.R:43 */
+    VBNMF_ERR_CUDA = 3,
+    VBNMF_ERR_STATE = 4,
+    VBNMF_ERR_NCCL = 5,
+    VBNMF_ERR_EMPTY = 6  /* 'Input matrix contains empty rows/columns', R/bayesian.R:244-247 */
+};
+
+/* Upload a CSC count matrix from HOST memory and build the device-side layouts.
+ * Exactly one of colptr32 / colptr64 is non-NULL.  device = CUDA ordinal. */
+VBNMF_API int vbnmf_create(vbnmf_handle **out, int64_t n, int64_t m, int64_t nnz, const int32_t *colptr32,
+                 const int64_t *colptr64, const int32_t *rowidx, const double *values, int device);
+
+/* Same, from arrays already resident on `device` (int64 colptr, int32 rowidx, fp32 counts).
+ * The arrays are borrowed: they must outlive the handle. */
+VBNMF_API int vbnmf_create_from_device(vbnmf_handle **out, int64_t n, int64_t m, int64_t nnz,
+                             const int64_t *d_colptr, const int32_t *d_rowidx, const float *d_values,
+                             int device);
+
+VBNMF_API void vbnmf_destroy(vbnmf_handle *h);
+VBNMF_API const char *vbnmf_last_error(const vbnmf_handle *h); /* h may be NULL: error of the last create */
+
+/* VBNMF_FP64 (default): all arithmetic IEEE double, as the reference.
+ * VBNMF_FP32_STORAGE: lw/lh panels held in fp32, per-nonzero arithmetic fp32, all sums fp64. */
+VBNMF_API int vbnmf_set_precision(vbnmf_handle *h, int precision);
+
+/* Run the engine's kernels on a caller-provided CUDA stream (cudaStream_t cast to void*). */
+VBNMF_API int vbnmf_set_stream(vbnmf_handle *h, void *cuda_stream);
+
+/* Multi-GPU: join an NCCL communicator of `nranks` handles that hold disjoint cell ranges.
+ * uid = 128-byte ncclUniqueId from vbnmf_nccl_unique_id() on rank 0, distributed by the host. */
+VBNMF_API int vbnmf_nccl_unique_id(void *uid128);
+VBNMF_API int vbnmf_comm_init(vbnmf_handle *h, int nranks, int rank, const void *uid128);
+
+/* Load the state list `wh` (R/bayesian.R:170: lw, lh, ew, eh).  ew may be NULL (it is overwritten
+ * before use, src/vbnmf_update.cpp:44); eh NULL means eh = lh (vb_init). */
+VBNMF_API int vbnmf_set_state(vbnmf_handle *h, int r, const double *lw, const double *lh, const double *ew,
+                    const double *eh);
+
+/* One call of vbnmf_update (src/vbnmf_update.cpp:16-102): state <- update(state); *lkh = bound. */
+VBNMF_API int vbnmf_step(vbnmf_handle *h, const double hyper[4], double fudge, double *lkh);
+
+/* The loop of vb_iterate for one rank (R/bayesian.R:336-352) on the loaded state.
+ * hyper: in = initial {aw,bw,ah,bh}, out = final.  lkh_trace (itmax doubles, may be NULL):
+ * lkh of every executed iteration.  hyper_trace (4*itmax, may be NULL): hyper after each iteration.
+ * *lml = lk0 as stored at R/bayesian.R:379 (NOT updated by the iteration that breaks). */
+VBNMF_API int vbnmf_run(vbnmf_handle *h, const vbnmf_cfg *cfg, double hyper[4], double *lkh_trace,
+              double *hyper_trace, int *niter, double *lml, int *stop_reason);
+
+/* Copy the state out; any pointer may be NULL.  dw, dh are variances (the R driver stores their
+ * square roots, R/bayesian.R:382-383). */
+VBNMF_API int vbnmf_get_state(vbnmf_handle *h, double *lw, double *lh, double *ew, double *eh, double *dw,
+                    double *dh);
+
+/* inputs of hyper_update for the current state: mean(log lw), mean(log lh), mean(ew), mean(eh) */
+VBNMF_API int vbnmf_get_means(vbnmf_handle *h, double means[4]);
+
+/* cid[j] = 1-based index of the first maximum of column j of eh (local cells) */
+VBNMF_API int vbnmf_cluster_id(vbnmf_handle *h, int32_t *cid);
+
+/* flags[k] = 1 when column k of ew has |max - min| < tol (R/bayesian.R:368-369) */
+VBNMF_API int vbnmf_uniform_columns(vbnmf_handle *h, double tol, int32_t *flags);
+
+/* Maximum-likelihood path: the it-loop of factorize() with criterion='likelihood'
+ * (R/factorize.R:189-212) from initial w0 (n x r), h0 (r x m).  lik_trace may be NULL. */
+VBNMF_API int mlnmf_run(vbnmf_handle *h, int r, const double *w0, const double *h0, int itmax, double tol,
+              double *w, double *h_out, double *lik_trace, int *niter);
+
+/* Measurement hooks (bench.py).  Runs `iters` steady-state VB iterations (posterior update +
+ * nonzero sweep [+ all-reduce]) with fixed hypers and reports CUDA-event times in ms:
+ * ms[0] = whole timed region, ms[1] = sum over the column-sweep kernel, ms[2] = row-sweep kernel,
+ * ms[3] = everything else.  launches = kernels launched inside the timed region. */
+VBNMF_API int vbnmf_bench_iterations(vbnmf_handle *h, const double hyper[4], double fudge, int iters,
+                           double ms[4], int64_t *launches, double *lkh_last);
+
+/* shape / layout facts for the host side */
+VBNMF_API int vbnmf_info(const vbnmf_handle *h, int64_t info[8]); /* n, m, nnz, r, rs, precision, nranks, m_global */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

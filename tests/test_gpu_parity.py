@@ -1,0 +1,180 @@
+"""GPU parity tests (run on the B200 box): the CUDA engine, called through the C ABI, against
+(1) the golden vectors produced by the reference's own src/vbnmf_update.cpp and (2) the CPU oracle on
+fresh seeded inputs.  fp64 mode tolerance: 1e-9 relative on the bound and on every factor entry
+(BASELINE.json north_star); cluster assignments bit-exact."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from conftest import (RUN_CASES, STEP_CASES, hyper_dict, load_counts, load_golden, relerr,
+                      run_kwargs)
+
+pytestmark = pytest.mark.gpu
+FACT = ("lw", "lh", "ew", "eh", "dw", "dh")
+TOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def Engine():
+    import torch
+    assert torch.cuda.is_available(), "these tests need a CUDA device"
+    from ccfindr_b200.engine import Engine as E
+    return E
+
+
+@pytest.mark.parametrize("case", sorted(STEP_CASES))
+def test_step_matches_reference_golden(Engine, case):
+    g = load_golden(case)
+    with Engine(load_counts(STEP_CASES[case])) as eng:
+        eng.set_state(g["in_lw"], g["in_lh"], g["in_ew"], g["in_eh"])
+        lkh = eng.step(hyper_dict(g["hyper"]), float(g["fudge"]))
+        st = eng.get_state()
+    assert relerr(lkh, g["lkh"]) < TOL
+    for k in FACT:
+        assert relerr(st[k], g["out_" + k]) < TOL, k
+
+
+@pytest.mark.parametrize("case", sorted(RUN_CASES))
+def test_run_matches_reference_golden(Engine, case):
+    g = load_golden(case)
+    kw = run_kwargs(g)
+    flags = kw.pop("hyper_update_flags", (True,) * 4)
+    with Engine(load_counts(RUN_CASES[case])) as eng:
+        eng.set_state(g["w0"], g["h0"])
+        res = eng.run(hyper_dict(g["hyper0"]), hyper_update=flags, **kw)
+        st = eng.get_state()
+        cid = eng.cluster_id()
+    assert res["niter"] == int(g["niter"])
+    assert res["stop_reason"] == int(g["stop_reason"])
+    assert relerr(res["lkh_trace"], g["lkh_trace"]) < TOL
+    assert relerr(res["hyper_trace"], g["hyper_trace"]) < TOL
+    assert relerr(res["lml"], g["lml"]) < TOL
+    for k in FACT:
+        assert relerr(st[k], g[k]) < TOL, k
+    assert np.array_equal(cid, g["cid"])  # bit-exact cluster assignments
+
+
+def _random_problem(n, m, r, density, seed, integer=True):
+    rng = np.random.default_rng(seed)
+    X = sp.random(n, m, density=density, random_state=rng, format="csc",
+                  data_rvs=lambda k: rng.integers(1, 30, size=k).astype(float) if integer
+                  else rng.gamma(2.0, 1.5, size=k))
+    from ccfindr_b200 import synth
+    X = synth.fix_empty(X, seed)
+    w0 = rng.gamma(1.0, 1.0, size=(n, r)) + 1e-3
+    h0 = rng.gamma(1.0, 1.0, size=(r, m)) + 1e-3
+    return X, w0, h0
+
+
+@pytest.mark.parametrize("n,m,r,density,integer", [
+    (300, 200, 1, 0.1, True),      # rank 1 (padded to 2)
+    (257, 513, 7, 0.05, True),     # odd rank, ragged sizes
+    (64, 2000, 13, 0.3, False),    # non-integer counts -> fp64 value storage
+    (3000, 40, 20, 0.02, True),    # few cells, very short rows
+    (500, 300, 33, 0.1, True),     # rank > 32 (padded to 40)
+])
+def test_steps_match_oracle(Engine, n, m, r, density, integer):
+    from oracle import bindings as ob
+    from oracle import oracle_dense as od
+    X, w0, h0 = _random_problem(n, m, r, density, seed=n + m + r, integer=integer)
+    hyper = dict(aw=0.7, bw=1.3, ah=1.1, bh=0.9)
+    ref = od.vb_init_from(w0, h0)
+    with Engine(X) as eng:
+        eng.set_state(w0, h0)
+        for it in range(4):
+            ref = ob.sparse_vb_step(X, ref, hyper, od.EPS)
+            lkh = eng.step(hyper, od.EPS)
+            assert relerr(lkh, ref["lkh"]) < TOL, it
+            assert relerr(eng.means(), ref["means"]) < TOL
+        st = eng.get_state()
+        cid = eng.cluster_id()
+    for k in FACT:
+        assert relerr(st[k], ref[k]) < TOL, k
+    assert np.array_equal(cid, od.cluster_id(ref["eh"]))
+
+
+def test_int64_colptr_and_single_nonzero_columns(Engine):
+    from oracle import bindings as ob
+    from oracle import oracle_dense as od
+    n, m, r = 50, 30, 3
+    rows = np.arange(m) % n
+    X = sp.csc_matrix((np.ones(m) * 3.0, (rows, np.arange(m))), shape=(n, m))
+    X = (X + sp.csc_matrix((np.ones(n), (np.arange(n), np.arange(n) % m)), shape=(n, m))).tocsc()
+    X.indptr = X.indptr.astype(np.int64)
+    rng = np.random.default_rng(0)
+    w0, h0 = rng.random((n, r)) + 0.1, rng.random((r, m)) + 0.1
+    hyper = dict(aw=1.0, bw=1.0, ah=1.0, bh=1.0)
+    ref = ob.sparse_vb_step(X, od.vb_init_from(w0, h0), hyper, od.EPS)
+    with Engine(X) as eng:
+        eng.set_state(w0, h0)
+        lkh = eng.step(hyper)
+        st = eng.get_state()
+    assert relerr(lkh, ref["lkh"]) < TOL
+    for k in FACT:
+        assert relerr(st[k], ref[k]) < TOL, k
+
+
+def test_state_before_any_step_is_what_was_loaded(Engine):
+    X, w0, h0 = _random_problem(40, 30, 4, 0.3, seed=3)
+    with Engine(X) as eng:
+        eng.set_state(w0, h0)
+        st = eng.get_state()
+    assert np.array_equal(st["lw"], w0) and np.array_equal(st["lh"], h0)
+    assert np.array_equal(st["ew"], w0) and np.array_equal(st["eh"], h0)
+    assert not st["dw"].any() and not st["dh"].any()  # vb_init: dw = dh = 0 (R/bayesian.R:161-162)
+
+
+def test_sufficient_statistics_sum_rule_large(Engine):
+    """Size-independent property: sum_k sw_ik = rowsum_i(X) and sum_k sh_kj = colsum_j(X), because
+    sum_k lw_ik lh_kj / p_ij = 1.  With alpha = a + s and alpha = e^2/d from the returned moments."""
+    n, m, r = 4000, 30000, 10
+    X, w0, h0 = _random_problem(n, m, r, 0.02, seed=11)
+    aw, ah = 0.9, 1.2
+    with Engine(X) as eng:
+        eng.set_state(w0, h0)
+        eng.step(dict(aw=aw, bw=1.0, ah=ah, bh=1.0))
+        st = eng.get_state(("ew", "eh", "dw", "dh"))
+    alw = st["ew"] ** 2 / st["dw"]
+    alh = st["eh"] ** 2 / st["dh"]
+    rs = np.asarray(X.sum(axis=1)).ravel()
+    cs = np.asarray(X.sum(axis=0)).ravel()
+    assert relerr((alw - aw).sum(axis=1), rs) < 1e-9
+    assert relerr((alh - ah).sum(axis=0), cs) < 1e-9
+
+
+def test_runs_are_bitwise_reproducible(Engine):
+    X, w0, h0 = _random_problem(800, 1200, 6, 0.05, seed=5)
+    out = []
+    for _ in range(2):
+        with Engine(X) as eng:
+            eng.set_state(w0, h0)
+            res = eng.run(dict(aw=1.0, bw=1.0, ah=1.0, bh=1.0), Itmax=15)
+            out.append((res["lkh_trace"], eng.get_state()))
+    assert np.array_equal(out[0][0], out[1][0])
+    for k in FACT:
+        assert np.array_equal(out[0][1][k], out[1][1][k])
+
+
+@pytest.mark.parametrize("counts,r", [("tiny", 3), ("pbmc", 4)])
+def test_ml_path_matches_oracle(Engine, counts, r):
+    from ccfindr_b200 import synth
+    from oracle import bindings as ob
+    X = load_counts(counts)
+    n, m = X.shape
+    w0, h0 = synth.uniform_init(n, m, r, 4)
+    ref = ob.sparse_ml_run(X, w0, h0, Itmax=40, Tol=1e-7)
+    with Engine(X) as eng:
+        res = eng.ml_run(w0, h0, Itmax=40, Tol=1e-7)
+    assert res["niter"] == ref["niter"]
+    assert relerr(res["lik_trace"], ref["lik_trace"]) < TOL
+    assert relerr(res["w"], ref["w"]) < TOL and relerr(res["h"], ref["h"]) < TOL
+
+
+def test_errors_are_reported_not_thrown(Engine):
+    from ccfindr_b200 import _lib
+    X, w0, h0 = _random_problem(40, 30, 4, 0.3, seed=3)
+    with Engine(X) as eng:
+        with pytest.raises(_lib.VbnmfError):
+            eng.step(dict(aw=1.0, bw=1.0, ah=1.0, bh=1.0))  # no state loaded
+        with pytest.raises(ValueError):
+            eng.set_state(w0[:-1], h0)
