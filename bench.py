@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""Benchmark of the VB-NMF hot path (BASELINE.json metric: nnz*rank updates/s per VB iteration).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA engine
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU code (rank 0)
+
+A "step" is one VB iteration (posterior update of W and H, nonzero sweep, lower bound, the
+per-iteration host readback of the loop) over the whole synthetic matrix.  Workload at N GPUs
+(weak scaling): BASELINE config 2 per GPU -- 20,000 genes x 100,000 cells per GPU, ~8 % nonzero
+10x-shaped Poisson counts (SURVEY.md 8d generator), rank 10, fp64; cells sharded over the ranks,
+one NCCL all-reduce of the W-side statistics per iteration.  One JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: genes, cells per GPU, true rank, density, seed, fit rank
+    "c2": dict(n=20000, m_per_gpu=100000, r_true=10, density=0.08, seed=2, rank=10,
+               label="C2: vb_factorize rank=10, 20k genes x 100k cells per GPU, ~8% nonzero"),
+    "c3": dict(n=20000, m_per_gpu=None, m_total=1300000, r_true=20, density=0.08, seed=3, rank=20,
+               label="C3: vb_factorize rank=20, 20k genes x 1.3M cells sharded over the GPUs"),
+    "small": dict(n=2000, m_per_gpu=8000, r_true=5, density=0.08, seed=4, rank=6,
+                  label="small: plumbing check, 2k genes x 8k cells per GPU"),
+}
+HYPER = dict(aw=1.0, bw=1.0, ah=1.0, bh=1.0)  # gamma.a = gamma.b = 1 (R/bayesian.R:231)
+METRIC = "VB-NMF nnz*rank updates/s per iteration"
+UNIT = "nnz*rank updates/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def algorithmic_bytes(nnz, n, m, r):
+    """B_alg = nnz*(4+4) + 8*(m+1) + 2*r*m*8 + 2*n*r*8 bytes per VB iteration."""
+    return nnz * 8 + 8 * (m + 1) + 2 * r * m * 8 + 2 * n * r * 8
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return None
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [ln.strip().split(",") for ln in open(self.f.name) if ln.strip()]
+        os.unlink(self.f.name)
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1])); smax.append(float(r[2]))
+            except Exception:
+                continue
+            for nm, v in zip(names, r[5:9]):
+                if v.strip().lower() == "active":
+                    reasons.add(nm)
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def env_rank():
+    return (int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)),
+            int(os.environ.get("WORLD_SIZE", 1)))
+
+
+def shard_bounds(m_total, nranks, chunk):
+    """Contiguous cell ranges in whole generator chunks, as even as possible."""
+    nch = -(-m_total // chunk)
+    base, extra = divmod(nch, nranks)
+    b = [0]
+    for r in range(nranks):
+        b.append(min(m_total, b[-1] + (base + (1 if r < extra else 0)) * chunk))
+    return b
+
+
+def init_factors(n, m_total, rank, seed):
+    from ccfindr_b200 import synth
+    return synth.random_init(n, m_total, rank, HYPER, seed)  # vb_init 'random'
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from ccfindr_b200 import synth
+    from ccfindr_b200.engine import Comm, Engine
+
+    rank, local_rank, world = env_rank()
+    if args.gpus != world and world > 1:
+        raise SystemExit("--gpus must equal WORLD_SIZE under torchrun")
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    comm = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            uid = torch.tensor(list(Engine.nccl_unique_id()), dtype=torch.uint8, device=dev)
+        dist.broadcast(uid, 0)
+        comm = Comm(world, rank, bytes(uid.cpu().tolist()), device=local_rank)
+
+    wl = WORKLOADS[args.workload]
+    n, r = wl["n"], wl["rank"]
+    m_total = wl["m_per_gpu"] * world if wl.get("m_per_gpu") else wl["m_total"]
+    bounds = shard_bounds(m_total, world, synth.TENX_CHUNK)
+    c0, c1 = bounds[rank], bounds[rank + 1]
+    t_gen = time.time()
+    colptr, rowidx, values, scale = synth.tenx_like_device(n, m_total, wl["r_true"], wl["density"],
+                                                           wl["seed"], dev, c0, c1)
+    torch.cuda.synchronize()
+    t_gen = time.time() - t_gen
+    m_loc, nnz_loc = c1 - c0, int(rowidx.numel())
+    w0, h0 = init_factors(n, m_total, r, seed=1000 * r + 1)
+    h0_loc = np.asfortranarray(h0[:, c0:c1])
+
+    # ---- device-resident arm: inputs already in HBM when the timed region starts --------------
+    eng = Engine.from_device_csc(n, m_loc, nnz_loc, colptr, rowidx, values, device=local_rank)
+    if comm is not None:
+        eng.attach_comm(comm)
+    eng.set_state(w0, h0_loc)
+    eng.bench_iterations(HYPER, max(args.warmup, 1))          # warm-up (untimed)
+    nnz_t = torch.tensor([float(nnz_loc)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(nnz_t)
+    nnz_total = int(nnz_t.item())
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    if sampler:
+        sampler.start()
+    t0 = time.time()
+    res = eng.bench_iterations(HYPER, args.steps)             # EXACTLY K iterations, CUDA events
+    torch.cuda.synchronize()
+    wall_ms = (time.time() - t0) * 1e3
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop() if sampler else None
+    tms = torch.tensor([res["ms_total"], res["ms_cols"], res["ms_rows"], wall_ms],
+                       dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_total, ms_cols, ms_rows, wall_ms = [float(v) for v in tms.tolist()]
+    ms_step = ms_total / args.steps
+    value = nnz_total * r / (ms_step * 1e-3)
+    lkh_dev = res["lkh"]
+
+    # ---- end-to-end arm: HOST buffers through the C ABI, copies inside the timed region ---------
+    h_colptr = colptr.cpu().numpy()
+    h_rowidx = rowidx.cpu().numpy()
+    h_values = values.cpu().numpy().astype(np.float64)        # dgCMatrix @x is double
+    eng.close()
+    del colptr, rowidx, values
+    torch.cuda.empty_cache()
+    import scipy.sparse as sp
+    csc = sp.csc_matrix((h_values, h_rowidx, h_colptr), shape=(n, m_loc))
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.time()
+    eng2 = Engine(csc, device=local_rank)                      # H2D of X + device layouts
+    if comm is not None:
+        eng2.attach_comm(comm)
+    eng2.set_state(w0, h0_loc)                                 # H2D of the initial factors
+    # Tol = 0 never satisfies |1 - lkh/lk0| < Tol: exactly K iterations with the reference's own
+    # loop (hyper updates from iteration 11 on, R/bayesian.R:342)
+    out = eng2.run(HYPER, Itmax=args.steps, Tol=0.0)
+    st = eng2.get_state(("ew", "eh"))                          # D2H of the result
+    torch.cuda.synchronize()
+    e2e_s = time.time() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+    assert out["niter"] == args.steps and np.isfinite(st["ew"]).all()
+    h2d = (h_values.nbytes + h_rowidx.nbytes + h_colptr.nbytes + w0.nbytes + h0_loc.nbytes)
+    d2h = st["ew"].nbytes + st["eh"].nbytes + 5 * 8 * args.steps
+    e2e_value = nnz_total * r * args.steps / e2e_s
+    eng2.close()
+
+    # ---- CPU baseline on rank 0 (bounded sample of the same workload) -------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_baseline_port(n, r, h_colptr, h_rowidx, h_values, w0, h0_loc)
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        b_alg_local = algorithmic_bytes(nnz_loc, n, m_loc, r)
+        t_sweep = (ms_cols + ms_rows) / args.steps * 1e-3
+        ach = b_alg_local / t_sweep / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get(args.workload)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak" if wl.get("m_per_gpu") else "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl["label"], "genes": n, "cells_total": m_total,
+                       "nnz_total": nnz_total, "rank": r, "precision": "fp64",
+                       "sharding": "cells over %d GPU(s), 1 all-reduce/iter" % world,
+                       "l2": "inputs larger than L2 (CSC+CSR %.2f GB per GPU vs 126 MB)"
+                             % (nnz_loc * 16 / 1e9),
+                       "generator_scale": scale, "gen_seconds": round(t_gen, 2)},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps,
+                    "d2h_bytes_per_step": d2h / args.steps, "seconds": e2e_s,
+                    "iterations": args.steps,
+                    "what": "vbnmf_create(host CSC) + set_state + vbnmf_run(K) + get_state(ew, eh)"},
+            "gpu_launches": int(res["launches"]),
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                         "frac": ach / peak, "traffic": traffic,
+                         "kernel": "sweep_cols_kernel + sweep_rows_kernel (the nonzero sweep)",
+                         "algorithmic_bytes_per_launch": b_alg_local,
+                         "ms_per_launch": {"sweep_cols": ms_cols / args.steps,
+                                           "sweep_rows": ms_rows / args.steps},
+                         "iteration_frac": b_alg_local / (ms_step * 1e-3) / 1e9 / peak,
+                         "peak_source": peak_src},
+            "cpu_baseline": cpu,
+            "wall_ms_per_step": wall_ms / args.steps,
+            "lkh_last": lkh_dev,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        if comm is not None:
+            comm.close()
+        dist.destroy_process_group()
+
+
+def cpu_baseline_port(n, r, colptr, rowidx, values, w0, h0, max_cols=24000, iters=2):
+    """oracle/oracle_sparse.c (OpenMP, all host threads) on the first max_cols cells."""
+    from oracle import bindings as ob
+    mc = min(max_cols, len(colptr) - 1)
+    end = int(colptr[mc])
+    arrays = (n, mc, np.ascontiguousarray(colptr[:mc + 1], dtype=np.int64),
+              np.ascontiguousarray(rowidx[:end], dtype=np.int32),
+              np.ascontiguousarray(values[:end], dtype=np.float64))
+    hy = np.array([HYPER[k] for k in ("aw", "bw", "ah", "bh")])
+    sec, lkh, threads = ob.sparse_time_iterations(arrays, w0, h0[:, :mc], hy,
+                                                  np.finfo(np.float64).eps, iters)
+    return {"value": end * r / sec, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "first %d cells (%d nnz) of the same matrix, %d iterations of "
+                      "oracle_sparse.c (CSC, OpenMP, fp64)" % (mc, end, iters),
+            "seconds_per_iteration": sec}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """The reference's own vbnmf_update (src/vbnmf_update.cpp:16-102, compiled in place into
+    oracle/_ref) on the host cores; each step = one call on a dense slab of the workload."""
+    rank, _, world = env_rank()
+    if rank != 0:
+        return
+    import torch
+    from ccfindr_b200 import synth
+    from oracle import bindings as ob
+    wl = WORKLOADS[args.workload]
+    n, r = wl["n"], wl["rank"]
+    m_total = wl["m_per_gpu"] * max(world, args.gpus) if wl.get("m_per_gpu") else wl["m_total"]
+    ms = min(args.ref_cells, synth.TENX_CHUNK, m_total)
+    # first generator chunk of the same matrix (sampled on the CPU here), first ms cells
+    colptr, rowidx, values, _ = synth.tenx_like_device(n, m_total, wl["r_true"], wl["density"],
+                                                       wl["seed"], torch.device("cpu"), 0,
+                                                       synth.TENX_CHUNK)
+    colptr, rowidx, values = colptr.numpy(), rowidx.numpy(), values.numpy().astype(np.float64)
+    end = int(colptr[ms])
+    import scipy.sparse as sp
+    csc = sp.csc_matrix((values[:end], rowidx[:end], colptr[:ms + 1]), shape=(n, ms))
+    w0, h0 = init_factors(n, m_total, r, seed=1000 * r + 1)
+    h0 = np.asfortranarray(h0[:, :ms])
+    have_ref = ob.ref_lib() is not None
+    if have_ref:
+        X = np.asfortranarray(csc.toarray())
+        kind, cores = "reference", ob.sparse_lib().osp_num_threads()
+        wh = dict(lw=w0, lh=h0, ew=w0, eh=h0)
+        step = lambda wh: ob.ref_vbnmf_update(X, wh, HYPER, np.finfo(np.float64).eps)
+        what = ("src/vbnmf_update.cpp compiled in place (oracle/_ref; stand-in Eigen/Rcpp/GSL "
+                "headers, GEMM loops OpenMP-parallel, the rest serial as in the reference)")
+    else:
+        kind, cores = "port", ob.sparse_lib().osp_num_threads()
+        wh = dict(lw=w0, lh=h0, ew=w0, eh=h0)
+        step = lambda wh: ob.sparse_vb_step(csc, wh, HYPER, np.finfo(np.float64).eps)
+        what = "oracle_sparse.c osp_vb_step (oracle/_ref not available)"
+    for _ in range(args.warmup):
+        wh = step(wh)
+    t0 = time.time()
+    for _ in range(args.steps):
+        wh = step(wh)
+    sec = (time.time() - t0) / args.steps
+    value = end * r / sec
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+        "n_gpus": max(world, args.gpus), "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak" if wl.get("m_per_gpu") else "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["label"], "genes": n, "cells_total": m_total, "rank": r,
+                   "precision": "fp64"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": "dense slab: first %d cells (%d nnz) of the same matrix per "
+                                   "step; %s" % (ms, end, what)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "lkh_last": float(wh["lkh"]),
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--ref-cells", type=int, default=400,
+                    help="cells in the dense slab one reference step processes")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

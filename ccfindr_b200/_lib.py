@@ -39,7 +39,9 @@ SIGNATURES = {
     "vbnmf_set_precision": (C.c_int, [C.c_void_p, C.c_int]),
     "vbnmf_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "vbnmf_nccl_unique_id": (C.c_int, [C.c_void_p]),
-    "vbnmf_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "vbnmf_comm_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_void_p, C.c_int]),
+    "vbnmf_comm_destroy": (None, [C.c_void_p]),
+    "vbnmf_attach_comm": (C.c_int, [C.c_void_p, C.c_void_p]),
     "vbnmf_set_state": (C.c_int, [C.c_void_p, C.c_int, c_dp, c_dp, c_dp, c_dp]),
     "vbnmf_step": (C.c_int, [C.c_void_p, c_dp, C.c_double, c_dp]),
     "vbnmf_run": (C.c_int, [C.c_void_p, C.POINTER(VbnmfCfg), c_dp, c_dp, c_dp, c_ip, c_dp, c_ip]),

@@ -74,6 +74,11 @@ NcclApi g_nccl;
 
 }  // namespace
 
+struct vbnmf_comm {
+    int nranks = 1, rank = 0, device = 0;
+    ncclComm_t comm = nullptr;
+};
+
 struct vbnmf_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -488,7 +493,6 @@ void vbnmf_destroy(vbnmf_handle *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     free_panels(h);
     if (!h->borrowed) {
         cudaFree(h->d_colptr); cudaFree(h->d_rowidx); cudaFree(h->d_val);
@@ -604,18 +608,46 @@ int vbnmf_nccl_unique_id(void *uid128) {
     return 0;
 }
 
-int vbnmf_comm_init(vbnmf_handle *h, int nranks, int rank, const void *uid128) {
-    if (!h || nranks < 1 || rank < 0 || rank >= nranks) return VBNMF_ERR_ARG;
-    if (nranks == 1) return 0;
-    if (!uid128) return fail(h, VBNMF_ERR_ARG, "uid required");
-    if (!g_nccl.load(h->err)) return VBNMF_ERR_NCCL;
-    CK(cudaSetDevice(h->device));
+int vbnmf_comm_create(vbnmf_comm **out, int nranks, int rank, const void *uid128, int device) {
+    if (!out || nranks < 1 || rank < 0 || rank >= nranks || !uid128) return VBNMF_ERR_ARG;
+    *out = nullptr;
+    if (!g_nccl.load(g_create_error)) return VBNMF_ERR_NCCL;
+    if (cudaSetDevice(device) != cudaSuccess) {
+        g_create_error = "vbnmf_comm_create: bad device";
+        return VBNMF_ERR_CUDA;
+    }
+    vbnmf_comm *c = new vbnmf_comm();
+    c->nranks = nranks; c->rank = rank; c->device = device;
     ncclUniqueId id;
     memcpy(&id, uid128, 128);
-    CKN(g_nccl.CommInitRank(&h->comm, nranks, id, rank));
-    h->nranks = nranks;
-    h->rank = rank;
-    // global constants: total cells and the nonzero sums
+    ncclResult_t e = g_nccl.CommInitRank(&c->comm, nranks, id, rank);
+    if (e != ncclSuccess) {
+        g_create_error = std::string("ncclCommInitRank: ") +
+                         (g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "error");
+        delete c;
+        return VBNMF_ERR_NCCL;
+    }
+    *out = c;
+    return 0;
+}
+
+void vbnmf_comm_destroy(vbnmf_comm *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    delete c;
+}
+
+int vbnmf_attach_comm(vbnmf_handle *h, vbnmf_comm *c) {
+    if (!h || !c) return VBNMF_ERR_ARG;
+    if (c->device != h->device) return fail(h, VBNMF_ERR_ARG, "communicator is on another device");
+    if (h->nranks > 1) return fail(h, VBNMF_ERR_STATE, "a communicator is already attached");
+    if (c->nranks == 1) return 0;
+    CK(cudaSetDevice(h->device));
+    h->comm = c->comm;
+    h->nranks = c->nranks;
+    h->rank = c->rank;
+    // global constants: total cells and the sums over nonzeros
     double *d3 = nullptr, h3[3] = {(double)h->m, h->lgx, h->mlconst};
     CK(cudaMalloc(&d3, 24));
     CK(cudaMemcpyAsync(d3, h3, 24, cudaMemcpyHostToDevice, h->stream));
@@ -627,6 +659,7 @@ int vbnmf_comm_init(vbnmf_handle *h, int nranks, int rank, const void *uid128) {
     h->m_global = (int64_t)llround(h3[0]);
     h->lgx = h3[1];
     h->mlconst = h3[2];
+    h->stats_valid = false;
     return 0;
 }
 

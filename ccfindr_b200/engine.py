@@ -109,9 +109,10 @@ class Engine:
             _lib.check(rc, None)
         return bytes(buf)
 
-    def comm_init(self, nranks, rank, uid):
-        buf = (C.c_char * 128).from_buffer_copy(uid) if uid is not None else None
-        self._ck(self.lib.vbnmf_comm_init(self.handle, int(nranks), int(rank), buf))
+    def attach_comm(self, comm):
+        """comm: a Comm (one NCCL communicator per process); cells are sharded over its ranks."""
+        self._ck(self.lib.vbnmf_attach_comm(self.handle, comm.ptr))
+        self._comm = comm
 
     def info(self):
         v = (C.c_int64 * 8)()
@@ -208,3 +209,22 @@ class Engine:
                                                  _dp(ms), C.byref(launches), C.byref(lkh)))
         return dict(ms_total=ms[0], ms_cols=ms[1], ms_rows=ms[2], ms_other=ms[3],
                     launches=launches.value, lkh=lkh.value)
+
+
+class Comm:
+    """Process-level NCCL communicator for cell-sharded factorizations (vbnmf_comm)."""
+
+    def __init__(self, nranks, rank, uid, device=0):
+        self.lib = _lib.load()
+        self.ptr = C.c_void_p()
+        buf = (C.c_char * 128).from_buffer_copy(uid)
+        rc = self.lib.vbnmf_comm_create(C.byref(self.ptr), int(nranks), int(rank), buf, int(device))
+        if rc != 0:
+            msg = self.lib.vbnmf_last_error(None)
+            raise _lib.VbnmfError(rc, msg.decode() if msg else "unknown")
+        self.nranks, self.rank = int(nranks), int(rank)
+
+    def close(self):
+        if self.ptr and self.ptr.value:
+            self.lib.vbnmf_comm_destroy(self.ptr)
+            self.ptr = C.c_void_p()

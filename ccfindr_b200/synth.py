@@ -62,3 +62,73 @@ def fix_empty(csc, seed=0):
     out = (csc + add).tocsc()
     out.sort_indices()
     return out
+
+
+# ---- 10x-shaped generator, sampled on the GPU ------------------------
+TENX_CHUNK = 4000  # cells per Philox stream; shard boundaries must be multiples of this
+
+
+def tenx_factors(n, m, r_true, seed):
+    """Host-side latent factors of the generator: W, H ~ Gamma(shape 0.3, mean 1) and per-cell
+    depth ~ LogNormal(0, 0.5), all m cells (so that any shard slices the same draw)."""
+    g = _rng(seed, stream=10)
+    W = g.gamma(shape=0.3, scale=1.0 / 0.3, size=(n, r_true)).astype(np.float32)
+    H = g.gamma(shape=0.3, scale=1.0 / 0.3, size=(m, r_true)).astype(np.float32)  # cell-major
+    d = g.lognormal(mean=0.0, sigma=0.5, size=m).astype(np.float32)
+    return W, H, d
+
+
+def tenx_scale(W, H, d, density, seed, device):
+    """Scalar s such that the nonzero fraction of Poisson(s d_j (W H)_ij) is `density`:
+    bisection on mean(1 - exp(-s d_j (WH)_ij)) over a fixed sample of 2048 cells."""
+    import torch
+    g = _rng(seed, stream=11)
+    m = H.shape[0]
+    cols = np.sort(g.choice(m, size=min(2048, m), replace=False))
+    Wt = torch.from_numpy(W).to(device=device, dtype=torch.float64)
+    Ht = torch.from_numpy(H[cols]).to(device=device, dtype=torch.float64)
+    dt = torch.from_numpy(d[cols]).to(device=device, dtype=torch.float64)
+    lam = (Ht @ Wt.T) * dt[:, None]
+    lo, hi = 0.0, 1.0
+    while float((1.0 - torch.exp(-hi * lam)).mean()) < density:
+        hi *= 2.0
+    for _ in range(60):
+        mid = 0.5 * (lo + hi)
+        if float((1.0 - torch.exp(-mid * lam)).mean()) < density:
+            lo = mid
+        else:
+            hi = mid
+    return 0.5 * (lo + hi)
+
+
+def tenx_like_device(n, m, r_true, density, seed, device, col_start=0, col_end=None):
+    """CSC arrays (torch CUDA tensors: colptr int64, rowidx int32, values float32) of columns
+    [col_start, col_end) of the synthetic n x m matrix G(n, m, r_true, density, seed).
+    col_start must be a multiple of TENX_CHUNK (one Philox stream per chunk of cells)."""
+    import torch
+    col_end = m if col_end is None else col_end
+    assert col_start % TENX_CHUNK == 0
+    W, H, d = tenx_factors(n, m, r_true, seed)
+    s = tenx_scale(W, H, d, density, seed, device)
+    Wt = torch.from_numpy(W).to(device)
+    rows, vals, counts = [], [], []
+    for c0 in range(col_start, col_end, TENX_CHUNK):
+        c1 = min(c0 + TENX_CHUNK, col_end, m)
+        Hc = torch.from_numpy(H[c0:c1]).to(device)
+        dc = torch.from_numpy(d[c0:c1]).to(device) * float(s)
+        lam = (Hc @ Wt.T) * dc[:, None]                      # cells x genes
+        gen = torch.Generator(device=device)
+        gen.manual_seed((int(seed) << 32) + c0 // TENX_CHUNK)
+        x = torch.poisson(lam, generator=gen)
+        nz = torch.nonzero(x)                                # sorted by (cell, gene) = CSC order
+        rows.append(nz[:, 1].to(torch.int32))
+        vals.append(x[nz[:, 0], nz[:, 1]].to(torch.float32))
+        counts.append(torch.bincount(nz[:, 0], minlength=c1 - c0))
+        del lam, x, nz
+    rowidx = torch.cat(rows)
+    values = torch.cat(vals)
+    del rows, vals
+    cnt = torch.cat(counts)
+    colptr = torch.zeros(cnt.numel() + 1, dtype=torch.int64, device=device)
+    colptr[1:] = torch.cumsum(cnt, 0)
+    return colptr, rowidx, values, s

@@ -15,7 +15,7 @@
  *   cluster_id(): apply(h,2,which.max), R/utils.R:903-909              vbnmf_cluster_id
  *   nmf_updateR() + likelihood() loop, R/factorize.R:189-212           mlnmf_run
  *   Rmpi task farm over restarts, R/bayesian.R:263                     one handle per process/GPU;
- *                                                                      cells sharded with vbnmf_comm_init
+ *                                                                      cells sharded: vbnmf_attach_comm
  *
  * Conventions
  *   - every function returns 0 on success, non-zero on failure; vbnmf_last_error() gives the text.
@@ -89,10 +89,15 @@ VBNMF_API int vbnmf_set_precision(vbnmf_handle *h, int precision);
 /* Run the engine's kernels on a caller-provided CUDA stream (cudaStream_t cast to void*). */
 VBNMF_API int vbnmf_set_stream(vbnmf_handle *h, void *cuda_stream);
 
-/* Multi-GPU: join an NCCL communicator of `nranks` handles that hold disjoint cell ranges.
- * uid = 128-byte ncclUniqueId from vbnmf_nccl_unique_id() on rank 0, distributed by the host. */
+/* Multi-GPU: an NCCL communicator of `nranks` processes (one per GPU) that hold disjoint cell
+ * ranges of one matrix.  The communicator belongs to the process, not to a handle: create it once
+ * (uid = 128-byte ncclUniqueId from vbnmf_nccl_unique_id() on rank 0, distributed by the host, e.g.
+ * over MPI where the reference uses Rmpi, R/bayesian.R:263) and attach it to each handle. */
+typedef struct vbnmf_comm vbnmf_comm;
 VBNMF_API int vbnmf_nccl_unique_id(void *uid128);
-VBNMF_API int vbnmf_comm_init(vbnmf_handle *h, int nranks, int rank, const void *uid128);
+VBNMF_API int vbnmf_comm_create(vbnmf_comm **out, int nranks, int rank, const void *uid128, int device);
+VBNMF_API void vbnmf_comm_destroy(vbnmf_comm *c);
+VBNMF_API int vbnmf_attach_comm(vbnmf_handle *h, vbnmf_comm *c);
 
 /* Load the state list `wh` (R/bayesian.R:170: lw, lh, ew, eh).  ew may be NULL (it is overwritten
  * before use, src/vbnmf_update.cpp:44); eh NULL means eh = lh (vb_init). */

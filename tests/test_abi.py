@@ -18,7 +18,7 @@ def test_header_declares_expected_entry_points():
     syms = declared_symbols()
     for must in ("vbnmf_create", "vbnmf_set_state", "vbnmf_step", "vbnmf_run", "vbnmf_get_state",
                  "vbnmf_cluster_id", "mlnmf_run", "vbnmf_last_error", "vbnmf_destroy",
-                 "vbnmf_comm_init"):
+                 "vbnmf_attach_comm"):
         assert must in syms
 
 
