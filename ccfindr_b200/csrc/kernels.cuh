@@ -1,5 +1,6 @@
-// CUDA kernels of the VB-NMF engine (sm_100a).  See DESIGN.md for the data layout and the
-// roofline of each kernel.  Reference maths: src/vbnmf_update.cpp:33-90 (file:line cited per kernel).
+// CUDA kernels of the VB-NMF engine that depend on the padded rank (sm_100a).  See DESIGN.md for
+// the data layout and the roofline of each kernel.  Reference maths: src/vbnmf_update.cpp:33-90
+// (file:line cited per kernel).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -8,9 +9,16 @@
 
 namespace vb {
 
-constexpr int kBlock = 256;          // threads per CTA for all kernels here
+constexpr int kBlock = 256;  // threads per CTA of the elementwise / reduction kernels
 constexpr int kWarpsPerBlock = kBlock / 32;
 constexpr unsigned kFull = 0xffffffffu;
+constexpr int kGroup = 8;    // lanes that share one sweep segment (= one LDS.128 bank phase)
+
+// Panel row stride (doubles) for compute width RP (even): RP when RP/2 is odd, else RP + 2, so that
+// a row is an ODD number of 16-byte units.  Rows whose indices differ mod 8 then start in
+// different 16-byte bank groups of shared memory, which is what the build-time ordering of the
+// nonzeros relies on to make the 8 gathers of a quarter-warp conflict-free.
+__host__ __device__ constexpr int row_stride(int rp) { return ((rp / 2) & 1) ? rp : rp + 2; }
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -18,18 +26,16 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// deterministic block sum; result valid in thread 0
-__device__ __forceinline__ double block_sum(double v, double *sm /*kWarpsPerBlock*/) {
+// deterministic block sum for any blockDim that is a multiple of 32 (<= 1024); valid in thread 0
+__device__ __forceinline__ double block_sum(double v, double *sm /* >= blockDim/32 */) {
     v = warp_sum(v);
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
     __syncthreads();
     if (lane == 0) sm[w] = v;
     __syncthreads();
     double t = 0.0;
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int i = 0; i < kWarpsPerBlock; i++) t += sm[i];
-    }
+    if (threadIdx.x == 0)
+        for (int i = 0; i < nw; i++) t += sm[i];
     return t;
 }
 
@@ -51,22 +57,17 @@ __device__ __forceinline__ void last_block_reduce(const double *part, int W, dou
     const int nb = gridDim.x;
     for (int c = 0; c < W; c++) {
         double a = 0.0;
-        for (int b = threadIdx.x; b < nb; b += kBlock) a += __ldcg(part + (size_t)b * W + c);
+        for (int b = threadIdx.x; b < nb; b += blockDim.x) a += __ldcg(part + (size_t)b * W + c);
         const double s = block_sum(a, sm);
         if (threadIdx.x == 0) out[c] = s;
     }
 }
 
-template <typename T>
-__device__ __forceinline__ T ld_stream(const T *p) {
-    return __ldcs(p);
-}
-
-// load one panel row (RP entries, 16-byte aligned) into registers
+// load one panel row (RP of RS entries, 16-byte aligned) into registers through the read-only path
 template <int RP>
 __device__ __forceinline__ void load_row_d(const double *__restrict__ base, int64_t row,
                                            double (&out)[RP]) {
-    const double2 *p = reinterpret_cast<const double2 *>(base + row * RP);
+    const double2 *p = reinterpret_cast<const double2 *>(base + row * row_stride(RP));
 #pragma unroll
     for (int k = 0; k < RP / 2; k++) {
         const double2 v = __ldg(p + k);
@@ -75,122 +76,274 @@ __device__ __forceinline__ void load_row_d(const double *__restrict__ base, int6
     }
 }
 
+// 1/p to ~1 ulp: hardware seed (>= 20 bits) + two Newton steps.  p is a positive normal double
+// here (p >= r * fudge^2 > 0), so no special-case handling is needed.
+__device__ __forceinline__ double fast_rcp(double p) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(p));
+    r = fma(fma(-p, r, 1.0), r, r);
+    r = fma(fma(-p, r, 1.0), r, r);
+    return r;
+}
+
+// ---- mbarrier / bulk-copy (TMA) primitives ---------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+    // bounded spin: a bulk copy that never lands (bad address) traps instead of hanging the GPU
+    for (unsigned spin = 0; !mbar_try_wait(bar, parity); spin++)
+        if (spin > (1u << 26)) __trap();
+}
+// one bulk asynchronous copy global -> shared (the TMA engine, SASS UBLKCP); bytes % 16 == 0
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes,
+                                         uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
 // ------------------------------------------------------------------------------------------
-// Column sweep (cell-owner pass).  One warp per cell column j, lanes over its nonzeros.
-//   p_ij = sum_k lw_ik lh_kj, q_ij = x_ij / p_ij               src/vbnmf_update.cpp:33-34
-//   ShRaw[j][k] = sum_i lw_ik q_ij   (sh = lh o ShRaw)          src/vbnmf_update.cpp:36
-//   col_xlogp[j] = sum_i x_ij log p_ij                          data term of :73-77
-//   col_enth[j]  = sum_k log(lh_kj) lh_kj ShRaw[j][k]           B-term of :71-77 (entropy collapse)
-// lh_j and the Sh accumulators stay in registers; lw rows are gathered; no atomics on outputs.
-template <int RP, typename VT>
-__global__ void __launch_bounds__(kBlock)
-sweep_cols_kernel(int64_t m, int r, const int64_t *__restrict__ colptr,
-                  const int32_t *__restrict__ rowidx, const VT *__restrict__ val,
-                  const double *__restrict__ lw, const double *__restrict__ lh,
-                  double *__restrict__ ShRaw, double *__restrict__ col_xlogp,
-                  double *__restrict__ col_enth, unsigned long long *work_counter) {
-    const int lane = threadIdx.x & 31;
-    for (;;) {
-        unsigned long long jj = 0;
-        if (lane == 0) jj = atomicAdd(work_counter, 1ull);
-        jj = __shfl_sync(kFull, jj, 0);
-        if (jj >= (unsigned long long)m) break;
-        const int64_t j = (int64_t)jj;
-        double lhj[RP], acc[RP];
-        load_row_d<RP>(lh, j, lhj);
+// Tiled nonzero sweep.  Both passes of the sweep are this kernel:
+//   COLS = true  (cell-owner pass, src/vbnmf_update.cpp:33-34,36 and the data term of :73-77)
+//       owner = cell j (lh_j in registers), tile = a slab of T gene rows of lw in shared memory,
+//       Part[slab][j][k] = sum_{i in slab} lw_ik q_ij ; plus sum x_ij log p_ij
+//   COLS = false (gene-owner pass, src/vbnmf_update.cpp:33-35)
+//       owner = gene i (lw_i in registers), tile = a slab of T cell rows of lh in shared memory,
+//       Part[slab][i][k] = sum_{j in slab} q_ij lh_kj
+// with p_ij = sum_k lw_ik lh_kj and q_ij = x_ij / p_ij recomputed in each pass.
+//
+// Work decomposition: the nonzeros are stored slab-major in "segments" e = slab * NO + owner
+// (ptr[e] .. ptr[e+1]).  CTA b owns the contiguous segment range split[b] .. split[b+1], chosen at
+// build time so that every CTA gets the same number of nonzeros; it stages each slab it touches
+// with ONE bulk asynchronous copy (TMA) into shared memory, then its 8-lane groups walk their
+// segments gathering tile rows with 128-bit shared loads.  Outputs are plain stores: no atomics.
+//
+// The build step orders the nonzeros of a segment so that 8 consecutive ones hit tile rows that
+// differ mod 8 -> with an odd row stride the 8 gathers of a group are bank-conflict free.
+template <int RP>
+struct SweepCfg {
+    // register budget: own + acc + tile row = 6*RP, plus the log-product accumulators
+    static constexpr int kThreads = (RP <= 12) ? 512 : 256;
+    static constexpr int kGroups = kThreads / kGroup;
+};
+
+constexpr int kLogBits = 6;  // counts < 64 go through the bit-sliced log-product
+
+struct SweepTiledArgs {
+    int64_t NO;              // owners per slab (device-ordered rows of the owner panel)
+    int T;                   // tile rows
+    const int64_t *split;    // gridDim.x + 1 segment indices
+    const int64_t *ptr;      // segment pointers, nslabs*NO + 1
+    const int32_t *idx;      // local tile row of each nonzero
+    const void *val;         // counts (float or double)
+    const double *owner;     // owner panel, NO x RS
+    const double *tiles;     // tile panel, nslabs*T x RS
+    double *Part;            // nslabs x NO x RS
+    double *xl_part;         // COLS: gridDim.x partial sums of x log p
+    int int_counts;          // all counts are integers in [0, 2^31): log-product path allowed
+};
+
+template <int RP, typename VT, bool COLS>
+__global__ void __launch_bounds__(SweepCfg<RP>::kThreads, 1)
+sweep_tiled_kernel(const SweepTiledArgs a) {
+    constexpr int RS = row_stride(RP);
+    constexpr int NT = SweepCfg<RP>::kThreads;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *tile = reinterpret_cast<double *>(smem_raw);
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ double red[NT / 32];
+    const int gid = threadIdx.x / kGroup, gl = threadIdx.x % kGroup;
+    // the 4 groups of a warp run different trip counts: shuffles name only their own 8 lanes
+    const unsigned gmask = 0xffu << ((threadIdx.x & 31) & ~(kGroup - 1));
+    const int64_t e0 = a.split[blockIdx.x], e1 = a.split[blockIdx.x + 1];
+    const unsigned tile_bytes = (unsigned)a.T * RS * 8u;
+    if (threadIdx.x == 0) mbar_init(&mbar, 1);
+    __syncthreads();
+    unsigned parity = 0;
+
+    // x log p through products: P[b] = prod of p over nonzeros whose count has bit b set
+    double P[kLogBits];
+    int PE[kLogBits];
+    double xl_slow = 0.0;
 #pragma unroll
-        for (int k = 0; k < RP; k++) acc[k] = 0.0;
-        double xl = 0.0;
-        const int64_t beg = __ldg(colptr + j), end = __ldg(colptr + j + 1);
-        for (int64_t t = beg + lane; t < end; t += 32) {
-            const int32_t i = ld_stream(rowidx + t);
-            const double x = (double)ld_stream(val + t);
-            double lwi[RP];
-            load_row_d<RP>(lw, i, lwi);
-            double p = 0.0;
-#pragma unroll
-            for (int k = 0; k < RP; k++) p = fma(lwi[k], lhj[k], p);
-            const double q = x / p;
-            xl = fma(x, log(p), xl);
-#pragma unroll
-            for (int k = 0; k < RP; k++) acc[k] = fma(lwi[k], q, acc[k]);
+    for (int b = 0; b < kLogBits; b++) { P[b] = 1.0; PE[b] = 0; }
+    int since_norm = 0;
+
+    for (int64_t ebase = e0; ebase < e1;) {
+        const int64_t slab = ebase / a.NO;
+        const int64_t eend = min(e1, (slab + 1) * a.NO);
+        __syncthreads();  // every group is done with the previous tile
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(&mbar, tile_bytes);
+            bulk_g2s(tile, a.tiles + slab * (int64_t)a.T * RS, tile_bytes, &mbar);
         }
-        constexpr int NH = (RP + 31) / 32;
-        double mine[NH], mylh[NH];
+        mbar_wait(&mbar, parity);
+        parity ^= 1;
+        for (int64_t e = ebase + gid; e < eend; e += SweepCfg<RP>::kGroups) {
+            const int64_t o = e - slab * a.NO;
+            const int64_t beg = __ldg(a.ptr + e), end = __ldg(a.ptr + e + 1);
+            double acc[RP];
 #pragma unroll
-        for (int q = 0; q < NH; q++) { mine[q] = 0.0; mylh[q] = 1.0; }
+            for (int k = 0; k < RP; k++) acc[k] = 0.0;
+            if (beg < end) {
+                double own[RP];
+                load_row_d<RP>(a.owner, o, own);
+                for (int64_t t = beg + gl; t < end; t += kGroup) {
+                    const int32_t ti = __ldcs(a.idx + t);
+                    const VT xv = __ldcs(reinterpret_cast<const VT *>(a.val) + t);
+                    const double x = (double)xv;
+                    const double2 *rowp = reinterpret_cast<const double2 *>(tile + (int64_t)ti * RS);
+                    double tr[RP];
 #pragma unroll
-        for (int k = 0; k < RP; k++) {
-            const double s = warp_sum(acc[k]);
-            if ((k & 31) == lane) { mine[k >> 5] = s; mylh[k >> 5] = lhj[k]; }
-        }
-        xl = warp_sum(xl);
-        double e = 0.0;
+                    for (int k = 0; k < RP / 2; k++) {
+                        const double2 v = rowp[k];
+                        tr[2 * k] = v.x;
+                        tr[2 * k + 1] = v.y;
+                    }
+                    double p0 = 0.0, p1 = 0.0;
 #pragma unroll
-        for (int q = 0; q < NH; q++) {
-            const int kk = lane + 32 * q;
-            if (kk < RP) ShRaw[j * RP + kk] = mine[q];
-            if (kk < r) e += log(mylh[q]) * mylh[q] * mine[q];
+                    for (int k = 0; k < RP; k += 2) {
+                        p0 = fma(own[k], tr[k], p0);
+                        p1 = fma(own[k + 1], tr[k + 1], p1);
+                    }
+                    const double p = p0 + p1;
+                    const double q = x * fast_rcp(p);
+#pragma unroll
+                    for (int k = 0; k < RP; k++) acc[k] = fma(tr[k], q, acc[k]);
+                    if (COLS) {
+                        if (a.int_counts) {
+                            const int xi = (int)xv;
+                            if (xi < (1 << kLogBits)) {
+#pragma unroll
+                                for (int b = 0; b < kLogBits; b++)
+                                    if ((xi >> b) & 1) P[b] *= p;
+                            } else {
+                                xl_slow = fma(x, log(p), xl_slow);
+                            }
+                            if (++since_norm == 8) {
+                                since_norm = 0;
+#pragma unroll
+                                for (int b = 0; b < kLogBits; b++) {
+                                    const int hi = __double2hiint(P[b]);
+                                    PE[b] += ((hi >> 20) & 0x7ff) - 1023;
+                                    P[b] = __hiloint2double((hi & 0x800fffff) | 0x3ff00000,
+                                                            __double2loint(P[b]));
+                                }
+                            }
+                        } else {
+                            xl_slow = fma(x, log(p), xl_slow);
+                        }
+                    }
+                }
+            }
+            // sum over the 8 lanes of the group; lane gl keeps k = gl, gl+8, ...
+            constexpr int NH = (RP + kGroup - 1) / kGroup;
+            double mine[NH];
+#pragma unroll
+            for (int h = 0; h < NH; h++) mine[h] = 0.0;
+#pragma unroll
+            for (int k = 0; k < RP; k++) {
+                double s = acc[k];
+                s += __shfl_xor_sync(gmask, s, 4);
+                s += __shfl_xor_sync(gmask, s, 2);
+                s += __shfl_xor_sync(gmask, s, 1);
+                if ((k % kGroup) == gl) mine[k / kGroup] = s;
+            }
+            double *out = a.Part + e * RS;
+#pragma unroll
+            for (int h = 0; h < NH; h++) {
+                const int kk = gl + kGroup * h;
+                if (kk < RP) out[kk] = mine[h];
+            }
         }
-        e = warp_sum(e);
-        if (lane == 0) {
-            col_xlogp[j] = xl;
-            col_enth[j] = e;
+        ebase = eend;
+    }
+    if (COLS) {
+        // sum x log p = sum_b 2^b (log(mantissa_b) + exponent_b ln 2) + slow-path terms
+        double xl = xl_slow;
+        if (a.int_counts) {
+#pragma unroll
+            for (int b = 0; b < kLogBits; b++) {
+                const int hi = __double2hiint(P[b]);
+                const int ex = PE[b] + ((hi >> 20) & 0x7ff) - 1023;
+                const double mant = __hiloint2double((hi & 0x800fffff) | 0x3ff00000,
+                                                     __double2loint(P[b]));
+                xl += (double)(1 << b) * (log(mant) + (double)ex * 0.6931471805599453094);
+            }
         }
+        xl = block_sum(xl, red);
+        if (threadIdx.x == 0) a.xl_part[blockIdx.x] = xl;
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// Row sweep (gene-owner pass) over the CSR mirror.  One warp per work item = (gene row, chunk of
-// its nonzeros); recomputes p, q at the same lw, lh and accumulates
-//   SwPart[item][k] = sum_{j in chunk} q_ij lh_kj   (sw = lw o SwRaw) src/vbnmf_update.cpp:35
-// Partials of one row are summed in item order by combine_rows_kernel: no atomics.
-template <int RP, typename VT>
+// Combine the per-slab partial statistics of a sweep pass in slab order and take the entropy-
+// collapse term of the bound in the same pass (src/vbnmf_update.cpp:69-77):
+//   SRaw[o][k] = sum_slab Part[slab][o][k];   out[0] = sum_{o,k<r} log(l_ok) l_ok SRaw[o][k]
+// rows beyond the valid owners (layout padding) hold zeros in l and are skipped.
+template <int RP>
 __global__ void __launch_bounds__(kBlock)
-sweep_rows_kernel(int64_t n_items, const int32_t *__restrict__ item_row,
-                  const int64_t *__restrict__ item_beg, const int32_t *__restrict__ item_len,
-                  const int32_t *__restrict__ colidx, const VT *__restrict__ val,
-                  const double *__restrict__ lw, const double *__restrict__ lh,
-                  double *__restrict__ SwPart, unsigned long long *work_counter) {
-    const int lane = threadIdx.x & 31;
-    for (;;) {
-        unsigned long long it = 0;
-        if (lane == 0) it = atomicAdd(work_counter, 1ull);
-        it = __shfl_sync(kFull, it, 0);
-        if (it >= (unsigned long long)n_items) break;
-        const int64_t i = __ldg(item_row + it);
-        const int64_t beg = __ldg(item_beg + it), end = beg + __ldg(item_len + it);
-        double lwi[RP], acc[RP];
-        load_row_d<RP>(lw, i, lwi);
-#pragma unroll
-        for (int k = 0; k < RP; k++) acc[k] = 0.0;
-        for (int64_t t = beg + lane; t < end; t += 32) {
-            const int32_t j = ld_stream(colidx + t);
-            const double x = (double)ld_stream(val + t);
-            double lhj[RP];
-            load_row_d<RP>(lh, j, lhj);
-            double p = 0.0;
-#pragma unroll
-            for (int k = 0; k < RP; k++) p = fma(lwi[k], lhj[k], p);
-            const double q = x / p;
-#pragma unroll
-            for (int k = 0; k < RP; k++) acc[k] = fma(lhj[k], q, acc[k]);
+combine_kernel(int64_t NO, int nslabs, int r, const double *__restrict__ Part,
+               const double *__restrict__ l, double *__restrict__ SRaw, double *__restrict__ part,
+               double *__restrict__ out, unsigned *counter, const double *__restrict__ xl_part,
+               int nxl) {
+    constexpr int RS = row_stride(RP);
+    __shared__ double sm[kWarpsPerBlock];
+    double ent = 0.0;
+    const int64_t tot = NO * (RS / 2);
+    for (int64_t u = (int64_t)blockIdx.x * kBlock + threadIdx.x; u < tot;
+         u += (int64_t)gridDim.x * kBlock) {
+        const int64_t o = u / (RS / 2);
+        const int k2 = (int)(u - o * (RS / 2)) * 2;
+        double2 s = make_double2(0.0, 0.0);
+        for (int sl = 0; sl < nslabs; sl++) {
+            const double2 v =
+                __ldcs(reinterpret_cast<const double2 *>(Part + ((int64_t)sl * NO + o) * RS + k2));
+            s.x += v.x;
+            s.y += v.y;
         }
-        constexpr int NH = (RP + 31) / 32;
-        double mine[NH];
-#pragma unroll
-        for (int q = 0; q < NH; q++) mine[q] = 0.0;
-#pragma unroll
-        for (int k = 0; k < RP; k++) {
-            const double s = warp_sum(acc[k]);
-            if ((k & 31) == lane) mine[k >> 5] = s;
-        }
-#pragma unroll
-        for (int q = 0; q < NH; q++) {
-            const int kk = lane + 32 * q;
-            if (kk < RP) SwPart[(int64_t)it * RP + kk] = mine[q];
-        }
+        if (k2 >= RP) s = make_double2(0.0, 0.0);
+        *reinterpret_cast<double2 *>(SRaw + o * RS + k2) = s;
+        const double2 lv = *reinterpret_cast<const double2 *>(l + o * RS + k2);
+        if (k2 < r && lv.x > 0.0) ent += log(lv.x) * lv.x * s.x;
+        if (k2 + 1 < r && lv.y > 0.0) ent += log(lv.y) * lv.y * s.y;
     }
+    // per-CTA partial sums of x log p from the sweep ride along (out[1])
+    double xl = 0.0;
+    for (int i = blockIdx.x * kBlock + threadIdx.x; i < nxl; i += gridDim.x * kBlock)
+        xl += xl_part[i];
+    ent = block_sum(ent, sm);
+    xl = block_sum(xl, sm);
+    if (threadIdx.x == 0) {
+        part[blockIdx.x * 2 + 0] = ent;
+        part[blockIdx.x * 2 + 1] = xl;
+    }
+    last_block_reduce(part, 2, out, counter, sm);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -200,18 +353,20 @@ sweep_rows_kernel(int64_t n_items, const int32_t *__restrict__ item_row,
 //   e = al / be_k                                                                :44 / 54
 //   l_new = max(exp(psi(al)) / be_k, fud)                                        :58-65
 // and the reductions the bound and hyper_update need:
-//   out[0..RP)   : sum over rows of e  (colSums(ew) / rowSums(eh))
-//   out[RP+0]    : sum [ -(a/b) e + al (1 - log be_k) + lgamma(al) ]   (:84-86 / :88-89; the
+//   out[0..RS)   : sum over rows of e  (colSums(ew) / rowSums(eh))
+//   out[RS+0]    : sum [ -(a/b) e + al (1 - log be_k) + lgamma(al) ]   (:84-86 / :88-89; the
 //                  constant lga term is added on the host)
-//   out[RP+1]    : sum log l_new                                       (R/bayesian.R:8-9)
-//   out[RP+2]    : sum e                                               (R/bayesian.R:10-11)
-// One thread per row.  al is kept for ew/dw (eh/dh) export.
+//   out[RS+1]    : sum log l_new                                       (R/bayesian.R:8-9)
+//   out[RS+2]    : sum e                                               (R/bayesian.R:10-11)
+// One thread per panel row.  Rows are in device order: row d = slab*T + local holds the item at
+// sorted position local*S + slab, valid when that is < nvalid.  al is kept for ew/dw (eh/dh).
 template <int RP>
 __global__ void __launch_bounds__(kBlock)
-posterior_kernel(int64_t rows, int r, double a, double b, double fud,
+posterior_kernel(int64_t rows, int T, int S, int64_t nvalid, int r, double a, double b, double fud,
                  const double *__restrict__ osum, const double *__restrict__ SRaw,
                  double *__restrict__ l, double *__restrict__ al_out, double *__restrict__ part,
                  double *__restrict__ out, unsigned *counter) {
+    constexpr int RS = row_stride(RP);
     __shared__ double sm[kWarpsPerBlock];
     __shared__ double be[RP], lbe[RP];
     if (threadIdx.x < RP) {
@@ -225,7 +380,12 @@ posterior_kernel(int64_t rows, int r, double a, double b, double fud,
     double prior = 0.0, sll = 0.0, se = 0.0;
 #pragma unroll
     for (int k = 0; k < RP; k++) es[k] = 0.0;
-    if (row < rows) {
+    bool valid = row < rows;
+    if (valid) {
+        const int64_t slab = row / T, local = row - slab * T;
+        valid = local * S + slab < nvalid;
+    }
+    if (valid) {
         double lv[RP], sv[RP];
         load_row_d<RP>(l, row, lv);
         load_row_d<RP>(SRaw, row, sv);
@@ -248,45 +408,54 @@ posterior_kernel(int64_t rows, int r, double a, double b, double fud,
                 sv[k] = 0.0;
             }
         }
-        double2 *lp = reinterpret_cast<double2 *>(l + row * RP);
-        double2 *ap = reinterpret_cast<double2 *>(al_out + row * RP);
+        double2 *lp = reinterpret_cast<double2 *>(l + row * RS);
+        double2 *ap = reinterpret_cast<double2 *>(al_out + row * RS);
 #pragma unroll
         for (int k = 0; k < RP / 2; k++) {
             lp[k] = make_double2(lv[2 * k], lv[2 * k + 1]);
             ap[k] = make_double2(sv[2 * k], sv[2 * k + 1]);
         }
     }
-    constexpr int W = RP + 3;
+    constexpr int W = RS + 3;
     double *mypart = part + (size_t)blockIdx.x * W;
 #pragma unroll
     for (int k = 0; k < RP; k++) {
         const double s = block_sum(es[k], sm);
         if (threadIdx.x == 0) mypart[k] = s;
     }
+    if (threadIdx.x == 0)
+        for (int k = RP; k < RS; k++) mypart[k] = 0.0;
     prior = block_sum(prior, sm);
     sll = block_sum(sll, sm);
     se = block_sum(se, sm);
     if (threadIdx.x == 0) {
-        mypart[RP + 0] = prior;
-        mypart[RP + 1] = sll;
-        mypart[RP + 2] = se;
+        mypart[RS + 0] = prior;
+        mypart[RS + 1] = sll;
+        mypart[RS + 2] = se;
     }
     last_block_reduce(part, W, out, counter, sm);
 }
 
 // ---- maximum-likelihood multiplicative updates (R/factorize.R:8-15 for h, :17-24 for w) ----
-//   v_new = max(v o SRaw / osum_k, eps);  out[0..RP) = sum over rows of v_new
+//   v_new = max(v o SRaw / osum_k, eps);  out[0..RS) = sum over rows of v_new
 template <int RP>
 __global__ void __launch_bounds__(kBlock)
-ml_update_kernel(int64_t rows, int r, double eps, const double *__restrict__ osum,
-                 const double *__restrict__ SRaw, double *__restrict__ v,
-                 double *__restrict__ part, double *__restrict__ out, unsigned *counter) {
+ml_update_kernel(int64_t rows, int T, int S, int64_t nvalid, int r, double eps,
+                 const double *__restrict__ osum, const double *__restrict__ SRaw,
+                 double *__restrict__ v, double *__restrict__ part, double *__restrict__ out,
+                 unsigned *counter) {
+    constexpr int RS = row_stride(RP);
     __shared__ double sm[kWarpsPerBlock];
     const int64_t row = (int64_t)blockIdx.x * kBlock + threadIdx.x;
     double es[RP];
 #pragma unroll
     for (int k = 0; k < RP; k++) es[k] = 0.0;
-    if (row < rows) {
+    bool valid = row < rows;
+    if (valid) {
+        const int64_t slab = row / T, local = row - slab * T;
+        valid = local * S + slab < nvalid;
+    }
+    if (valid) {
         double lv[RP], sv[RP];
         load_row_d<RP>(v, row, lv);
         load_row_d<RP>(SRaw, row, sv);
@@ -301,37 +470,42 @@ ml_update_kernel(int64_t rows, int r, double eps, const double *__restrict__ osu
                 lv[k] = 0.0;
             }
         }
-        double2 *lp = reinterpret_cast<double2 *>(v + row * RP);
+        double2 *lp = reinterpret_cast<double2 *>(v + row * RS);
 #pragma unroll
         for (int k = 0; k < RP / 2; k++) lp[k] = make_double2(lv[2 * k], lv[2 * k + 1]);
     }
-    double *mypart = part + (size_t)blockIdx.x * RP;
+    double *mypart = part + (size_t)blockIdx.x * RS;
 #pragma unroll
     for (int k = 0; k < RP; k++) {
         const double s = block_sum(es[k], sm);
         if (threadIdx.x == 0) mypart[k] = s;
     }
-    last_block_reduce(part, RP, out, counter, sm);
+    if (threadIdx.x == 0)
+        for (int k = RP; k < RS; k++) mypart[k] = 0.0;
+    last_block_reduce(part, RS, out, counter, sm);
 }
 
-// column sums of a rows x RP panel: out[k] = sum_row v[row][k]
+// column sums of a rows x RS panel (padding rows hold zeros): out[k] = sum_row v[row][k]
 template <int RP>
 __global__ void __launch_bounds__(kBlock)
 panel_colsum_kernel(int64_t rows, const double *__restrict__ v, double *__restrict__ part,
                     double *__restrict__ out, unsigned *counter) {
+    constexpr int RS = row_stride(RP);
     __shared__ double sm[kWarpsPerBlock];
     const int64_t row = (int64_t)blockIdx.x * kBlock + threadIdx.x;
     double lv[RP];
 #pragma unroll
     for (int k = 0; k < RP; k++) lv[k] = 0.0;
     if (row < rows) load_row_d<RP>(v, row, lv);
-    double *mypart = part + (size_t)blockIdx.x * RP;
+    double *mypart = part + (size_t)blockIdx.x * RS;
 #pragma unroll
     for (int k = 0; k < RP; k++) {
         const double s = block_sum(lv[k], sm);
         if (threadIdx.x == 0) mypart[k] = s;
     }
-    last_block_reduce(part, RP, out, counter, sm);
+    if (threadIdx.x == 0)
+        for (int k = RP; k < RS; k++) mypart[k] = 0.0;
+    last_block_reduce(part, RS, out, counter, sm);
 }
 
 }  // namespace vb

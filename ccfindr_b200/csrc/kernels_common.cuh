@@ -4,95 +4,46 @@
 
 namespace vb {
 
-// SwRaw[i][k] = sum over the items of row i, in item order
-__global__ void __launch_bounds__(kBlock)
-combine_rows_kernel(int64_t n, int RP, const int64_t *__restrict__ row_item_ptr,
-                    const double *__restrict__ SwPart, double *__restrict__ SwRaw) {
-    const int64_t e = (int64_t)blockIdx.x * kBlock + threadIdx.x;
-    if (e >= n * RP) return;
-    const int64_t i = e / RP;
-    const int k = (int)(e - i * RP);
-    double a = 0.0;
-    for (int64_t it = row_item_ptr[i]; it < row_item_ptr[i + 1]; it++) a += SwPart[it * RP + k];
-    SwRaw[e] = a;
-}
-
-// sum the per-column scalars of the column sweep: out[0] = sum xlogp, out[1] = sum enth
-__global__ void __launch_bounds__(kBlock)
-reduce_cols_kernel(int64_t m, const double *__restrict__ col_xlogp,
-                   const double *__restrict__ col_enth, double *__restrict__ part,
-                   double *__restrict__ out, unsigned *counter) {
-    __shared__ double sm[kWarpsPerBlock];
-    double a = 0.0, b = 0.0;
-    for (int64_t j = (int64_t)blockIdx.x * kBlock + threadIdx.x; j < m;
-         j += (int64_t)gridDim.x * kBlock) {
-        a += col_xlogp[j];
-        b += col_enth[j];
-    }
-    a = block_sum(a, sm);
-    b = block_sum(b, sm);
-    if (threadIdx.x == 0) {
-        part[blockIdx.x * 2 + 0] = a;
-        part[blockIdx.x * 2 + 1] = b;
-    }
-    last_block_reduce(part, 2, out, counter, sm);
-}
-
-// out[0] = sum_ik log(lw_ik) lw_ik SwRaw_ik   (A-term of src/vbnmf_update.cpp:69-77)
-__global__ void __launch_bounds__(kBlock)
-entropy_w_kernel(int64_t n, int RP, int r, const double *__restrict__ lw,
-                 const double *__restrict__ SwRaw, double *__restrict__ part,
-                 double *__restrict__ out, unsigned *counter) {
-    __shared__ double sm[kWarpsPerBlock];
-    double a = 0.0;
-    const int64_t tot = n * RP;
-    for (int64_t e = (int64_t)blockIdx.x * kBlock + threadIdx.x; e < tot;
-         e += (int64_t)gridDim.x * kBlock) {
-        const int k = (int)(e % RP);
-        if (k < r) {
-            const double v = lw[e];
-            a += log(v) * v * SwRaw[e];
-        }
-    }
-    a = block_sum(a, sm);
-    if (threadIdx.x == 0) part[blockIdx.x] = a;
-    last_block_reduce(part, 1, out, counter, sm);
-}
-
 // ---- one-time helpers ----------------------------------------------------------------------
 // sum over nonzeros of lgamma(x+1) (src/vbnmf_update.cpp:80-81; zeros contribute 0) and of
-// -x log x + x (R/factorize.R:45-46); out[0], out[1]
+// -x log x + x (R/factorize.R:45-46); out[0], out[1].  out[2] = number of values that are not
+// integers in [0, 2^31) (those force the general x*log(p) path of the sweep).
 template <typename VT>
 __global__ void __launch_bounds__(kBlock)
 count_constants_kernel(int64_t nnz, const VT *__restrict__ val, double *__restrict__ part,
                        double *__restrict__ out, unsigned *counter) {
     __shared__ double sm[kWarpsPerBlock];
-    double a = 0.0, b = 0.0;
+    double a = 0.0, b = 0.0, c = 0.0;
     for (int64_t t = (int64_t)blockIdx.x * kBlock + threadIdx.x; t < nnz;
          t += (int64_t)gridDim.x * kBlock) {
         const double x = (double)val[t];
         a += lgamma(x + 1.0);
         if (x > 0) b += -x * log(x) + x;
+        if (!(x >= 0.0 && x < 2147483648.0 && x == floor(x))) c += 1.0;
     }
     a = block_sum(a, sm);
     b = block_sum(b, sm);
+    c = block_sum(c, sm);
     if (threadIdx.x == 0) {
-        part[blockIdx.x * 2 + 0] = a;
-        part[blockIdx.x * 2 + 1] = b;
+        part[blockIdx.x * 3 + 0] = a;
+        part[blockIdx.x * 3 + 1] = b;
+        part[blockIdx.x * 3 + 2] = c;
     }
-    last_block_reduce(part, 2, out, counter, sm);
+    last_block_reduce(part, 3, out, counter, sm);
 }
 
-// expand CSC column pointers into a per-nonzero column index; count nonzeros per row
+// expand CSC column pointers into a per-nonzero column index; count nonzeros per row and column
 __global__ void __launch_bounds__(kBlock)
 expand_cols_kernel(int64_t m, const int64_t *__restrict__ colptr,
                    const int32_t *__restrict__ rowidx, int32_t *__restrict__ colof,
-                   unsigned long long *__restrict__ row_count) {
+                   unsigned long long *__restrict__ row_count,
+                   unsigned long long *__restrict__ col_count) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * kBlock + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * kBlock) >> 5;
     for (int64_t j = warp; j < m; j += nwarps) {
         const int64_t beg = colptr[j], end = colptr[j + 1];
+        if (lane == 0) col_count[j] = (unsigned long long)(end - beg);
         for (int64_t t = beg + lane; t < end; t += 32) {
             colof[t] = (int32_t)j;
             atomicAdd(row_count + rowidx[t], 1ull);
@@ -100,37 +51,107 @@ expand_cols_kernel(int64_t m, const int64_t *__restrict__ colptr,
     }
 }
 
-// gather the CSR mirror through the stable row sort permutation
-template <typename VT>
+// sort key of every nonzero for one pass of the tiled layout:
+//   key = slab(tile side) * NO + owner(device row of the owner side),  payload = nonzero index
 __global__ void __launch_bounds__(kBlock)
-gather_csr_kernel(int64_t nnz, const uint32_t *__restrict__ perm, const int32_t *__restrict__ colof,
-                  const VT *__restrict__ val, int32_t *__restrict__ colidx_out,
-                  VT *__restrict__ val_out) {
+make_keys_kernel(int64_t nnz, const int32_t *__restrict__ rowidx, const int32_t *__restrict__ colof,
+                 const int32_t *__restrict__ gene_dev, const int32_t *__restrict__ cell_dev, int T,
+                 int64_t NO, bool cols_pass, uint32_t *__restrict__ key,
+                 uint32_t *__restrict__ payload) {
     for (int64_t t = (int64_t)blockIdx.x * kBlock + threadIdx.x; t < nnz;
          t += (int64_t)gridDim.x * kBlock) {
-        const uint32_t s = perm[t];
-        colidx_out[t] = colof[s];
-        val_out[t] = val[s];
+        const int64_t gd = gene_dev[rowidx[t]], cd = cell_dev[colof[t]];
+        const int64_t k = cols_pass ? (gd / T) * NO + cd : (cd / T) * NO + gd;
+        key[t] = (uint32_t)k;
+        payload[t] = (uint32_t)t;
     }
 }
 
+// ptr[e] = first sorted position whose key is >= e, e in [0, E]
 __global__ void __launch_bounds__(kBlock)
-iota_kernel(int64_t nnz, uint32_t *__restrict__ out) {
-    for (int64_t t = (int64_t)blockIdx.x * kBlock + threadIdx.x; t < nnz;
-         t += (int64_t)gridDim.x * kBlock)
-        out[t] = (uint32_t)t;
+segment_ptr_kernel(int64_t E, int64_t nnz, const uint32_t *__restrict__ sorted_key,
+                   int64_t *__restrict__ ptr) {
+    for (int64_t e = (int64_t)blockIdx.x * kBlock + threadIdx.x; e <= E;
+         e += (int64_t)gridDim.x * kBlock) {
+        int64_t lo = 0, hi = nnz;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if ((int64_t)sorted_key[mid] < e) lo = mid + 1; else hi = mid;
+        }
+        ptr[e] = lo;
+    }
 }
 
-// cid[j] = 1 + index of the first maximum over k of alh[j][k] / beh[k]   (R/utils.R:906)
+// Gather one pass of the tiled layout through the sort permutation and order each segment for
+// conflict-free shared-memory gathers: the nonzeros of a segment are bucketed by (tile row mod 8)
+// and emitted round-robin, one from every non-empty bucket per round, so that 8 consecutive
+// nonzeros touch tile rows that differ mod 8 (until the smaller buckets run dry).
+// One thread per segment; the order inside a bucket is the sorted (stable) order.
+template <typename VT>
 __global__ void __launch_bounds__(kBlock)
-cluster_id_kernel(int64_t m, int RP, int r, const double *__restrict__ alh,
+build_segments_kernel(int64_t E, const int64_t *__restrict__ ptr,
+                      const uint32_t *__restrict__ perm, const int32_t *__restrict__ rowidx,
+                      const int32_t *__restrict__ colof, const int32_t *__restrict__ gene_dev,
+                      const int32_t *__restrict__ cell_dev, const VT *__restrict__ val, int T,
+                      bool cols_pass, int32_t *__restrict__ idx_out, VT *__restrict__ val_out) {
+    for (int64_t e = (int64_t)blockIdx.x * kBlock + threadIdx.x; e < E;
+         e += (int64_t)gridDim.x * kBlock) {
+        const int64_t beg = ptr[e], end = ptr[e + 1];
+        if (beg == end) continue;
+        int cnt[8];
+#pragma unroll
+        for (int b = 0; b < 8; b++) cnt[b] = 0;
+        for (int64_t t = beg; t < end; t++) {
+            const uint32_t s = perm[t];
+            const int32_t d = cols_pass ? gene_dev[rowidx[s]] : cell_dev[colof[s]];
+            cnt[(d % T) & 7]++;
+        }
+        int seen[8];
+#pragma unroll
+        for (int b = 0; b < 8; b++) seen[b] = 0;
+        for (int64_t t = beg; t < end; t++) {
+            const uint32_t s = perm[t];
+            const int32_t d = cols_pass ? gene_dev[rowidx[s]] : cell_dev[colof[s]];
+            const int local = d % T, b = local & 7;
+            const int round = seen[b]++;
+            // position = elements of all buckets in earlier rounds + earlier buckets in this round
+            int64_t pos = 0;
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                pos += min(cnt[c], round);
+                if (c < b && cnt[c] > round) pos++;
+            }
+            idx_out[beg + pos] = local;
+            val_out[beg + pos] = val[s];
+        }
+    }
+}
+
+// split[b] = first segment whose start offset is >= b * nnz / nparts; split[nparts] = E
+__global__ void split_kernel(int nparts, int64_t E, int64_t nnz, const int64_t *__restrict__ ptr,
+                             int64_t *__restrict__ split) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > nparts) return;
+    if (b == nparts) { split[b] = E; return; }
+    const int64_t target = (int64_t)((double)nnz * b / nparts);
+    int64_t lo = 0, hi = E;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (ptr[mid] < target) lo = mid + 1; else hi = mid;
+    }
+    split[b] = lo;
+}
+
+// cid[d] = 1 + index of the first maximum over k of alh[d][k] / beh[k]   (R/utils.R:906)
+__global__ void __launch_bounds__(kBlock)
+cluster_id_kernel(int64_t rows, int RS, int r, const double *__restrict__ alh,
                   const double *__restrict__ beh, int32_t *__restrict__ cid) {
     const int64_t j = (int64_t)blockIdx.x * kBlock + threadIdx.x;
-    if (j >= m) return;
+    if (j >= rows) return;
     int best = 0;
-    double bv = alh[j * RP] / beh[0];
+    double bv = alh[j * RS] / beh[0];
     for (int k = 1; k < r; k++) {
-        const double v = alh[j * RP + k] / beh[k];
+        const double v = alh[j * RS + k] / beh[k];
         if (v > bv) { bv = v; best = k; }
     }
     cid[j] = best + 1;

@@ -12,52 +12,46 @@ namespace vb {
 namespace {
 
 constexpr int RP = VB_RP;
+constexpr int RS = row_stride(RP);
 
-void sweep_cols(const SweepColsArgs &a, bool vf, int grid, cudaStream_t s) {
-    if (vf)
-        sweep_cols_kernel<RP, float><<<grid, kBlock, 0, s>>>(
-            a.m, a.r, a.colptr, a.rowidx, (const float *)a.val, a.lw, a.lh, a.ShRaw, a.col_xlogp,
-            a.col_enth, a.work_counter);
-    else
-        sweep_cols_kernel<RP, double><<<grid, kBlock, 0, s>>>(
-            a.m, a.r, a.colptr, a.rowidx, (const double *)a.val, a.lw, a.lh, a.ShRaw, a.col_xlogp,
-            a.col_enth, a.work_counter);
-}
-
-void sweep_rows(const SweepRowsArgs &a, bool vf, int grid, cudaStream_t s) {
-    if (vf)
-        sweep_rows_kernel<RP, float><<<grid, kBlock, 0, s>>>(
-            a.n_items, a.item_row, a.item_beg, a.item_len, a.colidx, (const float *)a.val, a.lw,
-            a.lh, a.SwPart, a.work_counter);
-    else
-        sweep_rows_kernel<RP, double><<<grid, kBlock, 0, s>>>(
-            a.n_items, a.item_row, a.item_beg, a.item_len, a.colidx, (const double *)a.val, a.lw,
-            a.lh, a.SwPart, a.work_counter);
+int sweep_prepare(int smem_bytes) {
+    cudaError_t e = cudaSuccess;
+#define VB_OPT(K)                                                                               \
+    if (e == cudaSuccess)                                                                       \
+        e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    VB_OPT((sweep_tiled_kernel<RP, float, true>))
+    VB_OPT((sweep_tiled_kernel<RP, float, false>))
+    VB_OPT((sweep_tiled_kernel<RP, double, true>))
+    VB_OPT((sweep_tiled_kernel<RP, double, false>))
+#undef VB_OPT
+    return e == cudaSuccess ? 0 : 1;
 }
 
-template <typename K>
-int ctas_per_sm(K k) {
-    int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, kBlock, 0) != cudaSuccess || nb < 1)
-        nb = 1;
-    return nb;
-}
-int occ_cols(bool vf) {
-    return vf ? ctas_per_sm(sweep_cols_kernel<RP, float>) : ctas_per_sm(sweep_cols_kernel<RP, double>);
-}
-int occ_rows(bool vf) {
-    return vf ? ctas_per_sm(sweep_rows_kernel<RP, float>) : ctas_per_sm(sweep_rows_kernel<RP, double>);
+void sweep(const SweepTiledArgs &a, bool cols, bool vf, int grid, int smem, cudaStream_t s) {
+    constexpr int NT = SweepCfg<RP>::kThreads;
+    if (cols) {
+        if (vf) sweep_tiled_kernel<RP, float, true><<<grid, NT, smem, s>>>(a);
+        else sweep_tiled_kernel<RP, double, true><<<grid, NT, smem, s>>>(a);
+    } else {
+        if (vf) sweep_tiled_kernel<RP, float, false><<<grid, NT, smem, s>>>(a);
+        else sweep_tiled_kernel<RP, double, false><<<grid, NT, smem, s>>>(a);
+    }
 }
 
 inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+void combine(const CombineArgs &a, cudaStream_t s) {
+    combine_kernel<RP><<<a.grid, kBlock, 0, s>>>(a.NO, a.nslabs, a.r, a.Part, a.l, a.SRaw, a.part,
+                                                 a.out, a.counter, a.xl_part, a.nxl);
+}
 void posterior(const PosteriorArgs &a, cudaStream_t s) {
     posterior_kernel<RP><<<cdiv(a.rows, kBlock), kBlock, 0, s>>>(
-        a.rows, a.r, a.a, a.b, a.fud, a.osum, a.SRaw, a.l, a.al_out, a.part, a.out, a.counter);
+        a.rows, a.T, a.S, a.nvalid, a.r, a.a, a.b, a.fud, a.osum, a.SRaw, a.l, a.al_out, a.part,
+        a.out, a.counter);
 }
 void ml_update(const MlUpdateArgs &a, cudaStream_t s) {
-    ml_update_kernel<RP><<<cdiv(a.rows, kBlock), kBlock, 0, s>>>(a.rows, a.r, a.eps, a.osum, a.SRaw,
-                                                                 a.v, a.part, a.out, a.counter);
+    ml_update_kernel<RP><<<cdiv(a.rows, kBlock), kBlock, 0, s>>>(
+        a.rows, a.T, a.S, a.nvalid, a.r, a.eps, a.osum, a.SRaw, a.v, a.part, a.out, a.counter);
 }
 void colsum(const ColsumArgs &a, cudaStream_t s) {
     panel_colsum_kernel<RP><<<cdiv(a.rows, kBlock), kBlock, 0, s>>>(a.rows, a.v, a.part, a.out,
@@ -67,7 +61,8 @@ void colsum(const ColsumArgs &a, cudaStream_t s) {
 }  // namespace
 
 extern const RpTable VB_CAT(rp_table_, VB_RP);
-const RpTable VB_CAT(rp_table_, VB_RP) = {RP,       sweep_cols, sweep_rows, occ_cols,
-                                          occ_rows, posterior,  ml_update,  colsum};
+const RpTable VB_CAT(rp_table_, VB_RP) = {RP,      RS,        SweepCfg<RP>::kThreads, sweep_prepare,
+                                          sweep,   combine,   posterior,              ml_update,
+                                          colsum};
 
 }  // namespace vb

@@ -4,33 +4,25 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "kernels.cuh"
+
 namespace vb {
 
-struct SweepColsArgs {
-    int64_t m;
-    int r;
-    const int64_t *colptr;
-    const int32_t *rowidx;
-    const void *val;
-    const double *lw, *lh;
-    double *ShRaw, *col_xlogp, *col_enth;
-    unsigned long long *work_counter;
-};
-
-struct SweepRowsArgs {
-    int64_t n_items;
-    const int32_t *item_row;
-    const int64_t *item_beg;
-    const int32_t *item_len;
-    const int32_t *colidx;
-    const void *val;
-    const double *lw, *lh;
-    double *SwPart;
-    unsigned long long *work_counter;
+struct CombineArgs {
+    int64_t NO;
+    int nslabs, r;
+    const double *Part, *l;
+    double *SRaw, *part, *out;
+    unsigned *counter;
+    const double *xl_part;  // optional per-CTA partial sums folded into out[1]
+    int nxl;
+    int grid;
 };
 
 struct PosteriorArgs {
     int64_t rows;
+    int T, S;
+    int64_t nvalid;
     int r;
     double a, b, fud;
     const double *osum, *SRaw;
@@ -40,6 +32,8 @@ struct PosteriorArgs {
 
 struct MlUpdateArgs {
     int64_t rows;
+    int T, S;
+    int64_t nvalid;
     int r;
     double eps;
     const double *osum, *SRaw;
@@ -55,12 +49,14 @@ struct ColsumArgs {
 };
 
 struct RpTable {
-    int rp;
-    // val_is_float selects the count storage type; grid = CTAs to launch (persistent kernels)
-    void (*sweep_cols)(const SweepColsArgs &, bool val_is_float, int grid, cudaStream_t);
-    void (*sweep_rows)(const SweepRowsArgs &, bool val_is_float, int grid, cudaStream_t);
-    int (*sweep_cols_ctas_per_sm)(bool val_is_float);
-    int (*sweep_rows_ctas_per_sm)(bool val_is_float);
+    int rp, rs;
+    int sweep_threads;
+    // cols: cell-owner pass; val_is_float selects the count storage type; int_counts = all counts
+    // are integers (enables the log-product path); grid = CTAs (one per SM, persistent)
+    int (*sweep_prepare)(int smem_bytes);  // opt in to the dynamic shared memory size; 0 = ok
+    void (*sweep)(const SweepTiledArgs &, bool cols, bool val_is_float, int grid, int smem_bytes,
+                  cudaStream_t);
+    void (*combine)(const CombineArgs &, cudaStream_t);
     void (*posterior)(const PosteriorArgs &, cudaStream_t);
     void (*ml_update)(const MlUpdateArgs &, cudaStream_t);
     void (*colsum)(const ColsumArgs &, cudaStream_t);

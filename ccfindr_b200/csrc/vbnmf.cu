@@ -4,6 +4,15 @@
 // iteration loop R/bayesian.R:336-352 that calls it (plus hyper_update, R/bayesian.R:2-53), and
 // for factorize() the loop R/factorize.R:189-212.  No CPU fallback: every entry point needs the
 // CUDA device the handle was created on.
+//
+// Device data layout (DESIGN.md has the picture):
+//   * genes and cells are renumbered: sorted by nonzero count (descending) and dealt round-robin
+//     over S = ceil(count / T) slabs of T rows, device row = slab * T + local.  Slabs therefore
+//     hold the same mix of dense and sparse rows, and neighbouring rows have similar lengths.
+//   * panels lw, alw, SwRaw are (Sg*T) x RS, lh, alh, ShRaw are (Sc*T) x RS, row-major with the
+//     rank index fastest; RS = row_stride(RP) doubles, padding rows/columns are zero.
+//   * the count matrix is stored twice, once per sweep pass, slab-major in segments
+//     (tile slab, owner row); see kernels.cuh sweep_tiled_kernel.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <nccl.h>
@@ -14,6 +23,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cub/cub.cuh>
+#include <numeric>
 #include <string>
 #include <vector>
 
@@ -41,7 +51,8 @@ const RpTable *rp_table(int rp) {
 namespace {
 
 constexpr int kMaxRank = 64;
-constexpr int64_t kRowChunk = 4096;  // nonzeros per row-sweep work item
+constexpr int kTileBytes = 204800;  // shared-memory budget of one staged slab
+const int kTileRows[] = {4096, 2560, 2048, 1536, 1152, 1024, 768, 512, 384, 256, 128};
 
 std::string g_create_error;
 
@@ -72,6 +83,34 @@ struct NcclApi {
 };
 NcclApi g_nccl;
 
+// one pass of the tiled count-matrix layout
+struct PassLayout {
+    int64_t E = 0;              // segments = tile slabs * owners
+    int64_t *d_ptr = nullptr;   // E + 1
+    int32_t *d_idx = nullptr;   // nnz
+    void *d_val = nullptr;      // nnz
+    int64_t *d_split = nullptr; // grid + 1
+    void release() {
+        cudaFree(d_ptr); cudaFree(d_idx); cudaFree(d_val); cudaFree(d_split);
+        d_ptr = nullptr; d_idx = nullptr; d_val = nullptr; d_split = nullptr;
+    }
+};
+
+// tiled layout for tile height T (cached per T; the rank only enters through T)
+struct Layout {
+    int T = 0, Sg = 0, Sc = 0;
+    int64_t NG = 0, NC = 0;
+    std::vector<int32_t> gene_dev, cell_dev;  // original index -> device row
+    int32_t *d_gene_dev = nullptr, *d_cell_dev = nullptr;
+    PassLayout cols, rows;
+    int grid = 0;
+    void release() {
+        cols.release(); rows.release();
+        cudaFree(d_gene_dev); cudaFree(d_cell_dev);
+        d_gene_dev = d_cell_dev = nullptr;
+    }
+};
+
 }  // namespace
 
 struct vbnmf_comm {
@@ -85,32 +124,29 @@ struct vbnmf_handle {
     bool own_stream = false;
     int num_sms = 148;
     int64_t n = 0, m = 0, nnz = 0, m_global = 0;
-    int r = 0, rs = 0;
+    int r = 0, rp = 0, rs = 0;
     int precision = VBNMF_FP64;
-    bool val_float = true;
+    bool val_float = true, int_counts = true;
     bool borrowed = false;
-    // CSC (cell columns) and CSR mirror (gene rows)
+    // the count matrix as given (CSC); the tiled layouts are derived from it
     int64_t *d_colptr = nullptr;
     int32_t *d_rowidx = nullptr;
     void *d_val = nullptr;
-    int32_t *d_colidx = nullptr;
-    void *d_valr = nullptr;
-    // row-sweep work items
-    int64_t n_items = 0;
-    int32_t *d_item_row = nullptr, *d_item_len = nullptr;
-    int64_t *d_item_beg = nullptr, *d_row_item_ptr = nullptr;
-    // panels, n x rs and m x rs row-major (rank index fastest)
-    double *d_lw = nullptr, *d_lh = nullptr, *d_alw = nullptr, *d_alh = nullptr;
-    double *d_red = nullptr;  // [SwRaw n*rs | ehsum rs | hprior, sumloglh, sumeh | xlogp, enth | pad]
-    double *d_ShRaw = nullptr, *d_SwPart = nullptr, *d_colx = nullptr, *d_cole = nullptr;
-    double *d_scal = nullptr;  // [ewsum rs | wprior, sumloglw, sumew | entw | pad]
-    double *h_scal = nullptr;  // pinned mirror: [d_scal (rs+8) | tail of d_red (rs+8)]
-    double *d_partW = nullptr, *d_partH = nullptr, *d_partC = nullptr, *d_partE = nullptr;
-    unsigned *d_counters = nullptr;
-    unsigned long long *d_work = nullptr;
-    int gridC = 0, gridE = 0;
+    std::vector<unsigned long long> row_count, col_count;  // row counts are global once sharded
+    std::vector<Layout *> layouts;
+    Layout *L = nullptr;
     const vb::RpTable *tab = nullptr;
-    int grid_cols = 0, grid_rows = 0;  // persistent sweep grids for the current rank
+    int smem_bytes = 0;
+    // panels in device order
+    double *d_lw = nullptr, *d_lh = nullptr, *d_alw = nullptr, *d_alh = nullptr;
+    // d_red = [SwRaw NG*rs | ehsum rs | hprior, sumloglh, sumeh | enth, xlogp | entw, - | pad]
+    double *d_red = nullptr;
+    double *d_ShRaw = nullptr, *d_Part1 = nullptr, *d_Part2 = nullptr, *d_xl = nullptr;
+    double *d_scal = nullptr;  // [ewsum rs | wprior, sumloglw, sumew | pad]
+    double *h_scal = nullptr;  // pinned mirror: [d_scal (rs+8) | tail of d_red (rs+8)]
+    double *d_partW = nullptr, *d_partH = nullptr, *d_partC = nullptr;
+    unsigned *d_counters = nullptr;
+    int gridC = 0;
     double lgx = 0.0, mlconst = 0.0;  // global sums over nonzeros
     // host copies of the small vectors
     double ehsum[kMaxRank], ewsum[kMaxRank], bew[kMaxRank], beh[kMaxRank];
@@ -153,40 +189,260 @@ int fail(H *h, int code, const std::string &msg) {
 
 inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 inline int pad_rank(int r) {
-    int rs = (r + 1) & ~1;
-    if (rs < 2) rs = 2;
-    if (rs > 32) rs = (rs + 7) & ~7;
-    return rs;
+    int rp = (r + 1) & ~1;
+    if (rp < 2) rp = 2;
+    if (rp > 32) rp = (rp + 7) & ~7;
+    return rp;
 }
-inline int64_t tail_off(const H *h) { return h->n * h->rs; }
-inline int64_t red_len(const H *h) { return h->n * h->rs + h->rs + 8; }
+inline int64_t tail_off(const H *h) { return h->L->NG * h->rs; }
+inline int64_t red_len(const H *h) { return h->L->NG * h->rs + h->rs + 8; }
 
-int launch_sweep_cols(H *h) {
-    CK(cudaMemsetAsync(h->d_work, 0, 2 * sizeof(unsigned long long), h->stream));
-    double *tail = h->d_red + tail_off(h);
-    vb::SweepColsArgs a{h->m, h->r, h->d_colptr, h->d_rowidx, h->d_val, h->d_lw, h->d_lh,
-                        h->d_ShRaw, h->d_colx, h->d_cole, h->d_work};
-    h->tab->sweep_cols(a, h->val_float, h->grid_cols, h->stream);
-    vb::reduce_cols_kernel<<<h->gridC, vb::kBlock, 0, h->stream>>>(
-        h->m, h->d_colx, h->d_cole, h->d_partC, tail + h->rs + 3, h->d_counters + 2);
-    h->launches += 2;
+int choose_tile_rows(const H *h, int rs) {
+    int T = 128;
+    for (int t : kTileRows)
+        if ((int64_t)t * rs * 8 <= kTileBytes) { T = t; break; }
+    const int64_t big = std::max(h->n, h->m);
+    const int64_t cap = std::max<int64_t>(128, ((big + 127) / 128) * 128);
+    return (int)std::min<int64_t>(T, cap);
+}
+
+int allreduce(H *h, double *buf, int64_t count) {
+    if (h->nranks <= 1) return 0;
+    CKN(g_nccl.AllReduce(buf, buf, (size_t)count, ncclFloat64, ncclSum, h->comm, h->stream));
+    h->launches += 1;
     return 0;
 }
 
-int launch_sweep_rows(H *h) {
-    vb::SweepRowsArgs a{h->n_items, h->d_item_row, h->d_item_beg, h->d_item_len, h->d_colidx,
-                        h->d_valr, h->d_lw, h->d_lh, h->d_SwPart, h->d_work + 1};
-    h->tab->sweep_rows(a, h->val_float, h->grid_rows, h->stream);
-    vb::combine_rows_kernel<<<cdiv(h->n * h->rs, vb::kBlock), vb::kBlock, 0, h->stream>>>(
-        h->n, h->rs, h->d_row_item_ptr, h->d_SwPart, h->d_red);
-    h->launches += 2;
+// ---- building the tiled layouts ---------------------------------------------------------------
+// sorted position -> device row for `count` items dealt over S slabs of T rows
+void deal(const std::vector<unsigned long long> &cnt, int T, int S, std::vector<int32_t> &dev) {
+    const int64_t n = (int64_t)cnt.size();
+    std::vector<int64_t> order((size_t)n);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(),
+                     [&](int64_t a, int64_t b) { return cnt[a] > cnt[b]; });
+    dev.resize((size_t)n);
+    for (int64_t pos = 0; pos < n; pos++) {
+        const int64_t slab = pos % S, local = pos / S;
+        dev[(size_t)order[pos]] = (int32_t)(slab * T + local);
+    }
+}
+
+template <typename VT>
+int build_pass(H *h, Layout *L, bool cols_pass, const int32_t *d_colof) {
+    PassLayout &P = cols_pass ? L->cols : L->rows;
+    const int64_t nnz = h->nnz;
+    const int64_t NO = cols_pass ? L->NC : L->NG;
+    const int nslabs = cols_pass ? L->Sg : L->Sc;
+    P.E = (int64_t)nslabs * NO;
+    if (P.E >= (int64_t)UINT32_MAX)
+        return fail(h, VBNMF_ERR_ARG, "matrix too large for 32-bit segment keys on one GPU");
+    const int g = h->num_sms * 8;
+    uint32_t *k_in = nullptr, *k_out = nullptr, *p_in = nullptr, *p_out = nullptr;
+    CK(cudaMalloc(&k_in, (size_t)nnz * 4));
+    CK(cudaMalloc(&k_out, (size_t)nnz * 4));
+    CK(cudaMalloc(&p_in, (size_t)nnz * 4));
+    CK(cudaMalloc(&p_out, (size_t)nnz * 4));
+    vb::make_keys_kernel<<<g, vb::kBlock, 0, h->stream>>>(nnz, h->d_rowidx, d_colof, L->d_gene_dev,
+                                                          L->d_cell_dev, L->T, NO, cols_pass, k_in,
+                                                          p_in);
+    int bits = 1;
+    while (((int64_t)1 << bits) < P.E) bits++;
+    size_t tmp_bytes = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in, k_out, p_in, p_out, nnz, 0, bits,
+                                       h->stream));
+    void *d_tmp = nullptr;
+    CK(cudaMalloc(&d_tmp, tmp_bytes));
+    CK(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, k_in, k_out, p_in, p_out, nnz, 0, bits,
+                                       h->stream));
+    CK(cudaMalloc(&P.d_ptr, (size_t)(P.E + 1) * 8));
+    vb::segment_ptr_kernel<<<g, vb::kBlock, 0, h->stream>>>(P.E, nnz, k_out, P.d_ptr);
+    CK(cudaStreamSynchronize(h->stream));
+    cudaFree(d_tmp); cudaFree(k_in); cudaFree(k_out); cudaFree(p_in);
+    CK(cudaMalloc(&P.d_idx, (size_t)nnz * 4));
+    CK(cudaMalloc(&P.d_val, (size_t)nnz * sizeof(VT)));
+    vb::build_segments_kernel<VT><<<g, vb::kBlock, 0, h->stream>>>(
+        P.E, P.d_ptr, p_out, h->d_rowidx, d_colof, L->d_gene_dev, L->d_cell_dev,
+        (const VT *)h->d_val, L->T, cols_pass, P.d_idx, (VT *)P.d_val);
+    CK(cudaMalloc(&P.d_split, (size_t)(L->grid + 1) * 8));
+    vb::split_kernel<<<cdiv(L->grid + 1, 128), 128, 0, h->stream>>>(L->grid, P.E, nnz, P.d_ptr,
+                                                                   P.d_split);
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+    cudaFree(p_out);
     return 0;
 }
 
+int get_layout(H *h, int T, Layout **out) {
+    for (Layout *l : h->layouts)
+        if (l->T == T) { *out = l; return 0; }
+    Layout *L = new Layout();
+    L->T = T;
+    L->Sg = cdiv(h->n, T);
+    L->Sc = cdiv(h->m, T);
+    L->NG = (int64_t)L->Sg * T;
+    L->NC = (int64_t)L->Sc * T;
+    L->grid = h->num_sms;
+    deal(h->row_count, T, L->Sg, L->gene_dev);
+    deal(h->col_count, T, L->Sc, L->cell_dev);
+    auto bail = [&](int rc) { L->release(); delete L; return rc; };
+    auto body = [&]() -> int {
+        CK(cudaMalloc(&L->d_gene_dev, (size_t)h->n * 4));
+        CK(cudaMalloc(&L->d_cell_dev, (size_t)h->m * 4));
+        CK(cudaMemcpy(L->d_gene_dev, L->gene_dev.data(), (size_t)h->n * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(L->d_cell_dev, L->cell_dev.data(), (size_t)h->m * 4, cudaMemcpyHostToDevice));
+        int32_t *d_colof = nullptr;
+        unsigned long long *d_cnt = nullptr;
+        CK(cudaMalloc(&d_colof, (size_t)h->nnz * 4));
+        CK(cudaMalloc(&d_cnt, (size_t)(h->n + h->m) * 8));
+        CK(cudaMemsetAsync(d_cnt, 0, (size_t)(h->n + h->m) * 8, h->stream));
+        vb::expand_cols_kernel<<<h->num_sms * 8, vb::kBlock, 0, h->stream>>>(
+            h->m, h->d_colptr, h->d_rowidx, d_colof, d_cnt, d_cnt + h->n);
+        int rc = h->val_float ? build_pass<float>(h, L, true, d_colof)
+                              : build_pass<double>(h, L, true, d_colof);
+        if (!rc)
+            rc = h->val_float ? build_pass<float>(h, L, false, d_colof)
+                              : build_pass<double>(h, L, false, d_colof);
+        cudaFree(d_colof);
+        cudaFree(d_cnt);
+        return rc;
+    };
+    int rc = body();
+    if (rc) return bail(rc);
+    h->layouts.push_back(L);
+    *out = L;
+    return 0;
+}
+
+void drop_layouts(H *h) {
+    for (Layout *l : h->layouts) { l->release(); delete l; }
+    h->layouts.clear();
+    h->L = nullptr;
+}
+
+// nonzero counts per gene / cell and the constants over the nonzeros
+template <typename VT>
+int scan_matrix_t(H *h) {
+    const int64_t n = h->n, m = h->m, nnz = h->nnz;
+    const int gridK = h->num_sms * 8;
+    double *d_part = nullptr, *d_out = nullptr;
+    CK(cudaMalloc(&d_part, (size_t)gridK * 3 * 8));
+    CK(cudaMalloc(&d_out, 3 * 8));
+    vb::count_constants_kernel<VT><<<gridK, vb::kBlock, 0, h->stream>>>(
+        nnz, (const VT *)h->d_val, d_part, d_out, h->d_counters + 4);
+    double consts[3];
+    CK(cudaMemcpyAsync(consts, d_out, 24, cudaMemcpyDeviceToHost, h->stream));
+    int32_t *d_colof = nullptr;
+    unsigned long long *d_cnt = nullptr;
+    CK(cudaMalloc(&d_colof, (size_t)nnz * 4));
+    CK(cudaMalloc(&d_cnt, (size_t)(n + m) * 8));
+    CK(cudaMemsetAsync(d_cnt, 0, (size_t)(n + m) * 8, h->stream));
+    vb::expand_cols_kernel<<<h->num_sms * 8, vb::kBlock, 0, h->stream>>>(
+        m, h->d_colptr, h->d_rowidx, d_colof, d_cnt, d_cnt + n);
+    h->row_count.resize((size_t)n);
+    h->col_count.resize((size_t)m);
+    CK(cudaMemcpyAsync(h->row_count.data(), d_cnt, (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->col_count.data(), d_cnt + n, (size_t)m * 8, cudaMemcpyDeviceToHost,
+                       h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+    cudaFree(d_part); cudaFree(d_out); cudaFree(d_colof); cudaFree(d_cnt);
+    h->lgx = consts[0];
+    h->mlconst = consts[1];
+    h->int_counts = h->val_float && consts[2] == 0.0;
+    return 0;
+}
+
+// ---- panels -------------------------------------------------------------------------------------
+void free_panels(H *h) {
+    double **ps[] = {&h->d_lw, &h->d_lh, &h->d_alw, &h->d_alh, &h->d_red, &h->d_ShRaw,
+                     &h->d_Part1, &h->d_Part2, &h->d_xl, &h->d_scal, &h->d_partW, &h->d_partH,
+                     &h->d_partC};
+    for (auto p : ps) {
+        if (*p) cudaFree(*p);
+        *p = nullptr;
+    }
+    if (h->h_scal) cudaFreeHost(h->h_scal);
+    h->h_scal = nullptr;
+}
+
+int alloc_panels(H *h, int r) {
+    const int rp = pad_rank(r);
+    const vb::RpTable *tab = vb::rp_table(rp);
+    if (!tab) return fail(h, VBNMF_ERR_ARG, "no kernels compiled for this rank");
+    const int rs = tab->rs;
+    const int T = choose_tile_rows(h, rs);
+    Layout *L = nullptr;
+    int rc = get_layout(h, T, &L);
+    if (rc) return rc;
+    if (rp == h->rp && L == h->L && h->d_lw) { h->r = r; return 0; }
+    free_panels(h);
+    h->tab = tab;
+    h->L = L;
+    h->r = r; h->rp = rp; h->rs = rs;
+    h->smem_bytes = T * rs * 8;
+    if (tab->sweep_prepare(h->smem_bytes))
+        return fail(h, VBNMF_ERR_CUDA, "cannot opt in to the shared-memory tile size");
+    const size_t gr = (size_t)L->NG * rs * 8, cr = (size_t)L->NC * rs * 8;
+    CK(cudaMalloc(&h->d_lw, gr));
+    CK(cudaMalloc(&h->d_alw, gr));
+    CK(cudaMalloc(&h->d_lh, cr));
+    CK(cudaMalloc(&h->d_alh, cr));
+    CK(cudaMalloc(&h->d_ShRaw, cr));
+    CK(cudaMalloc(&h->d_red, (size_t)red_len(h) * 8));
+    CK(cudaMalloc(&h->d_Part1, (size_t)L->Sg * cr));
+    CK(cudaMalloc(&h->d_Part2, (size_t)L->Sc * gr));
+    CK(cudaMalloc(&h->d_xl, (size_t)L->grid * 8));
+    CK(cudaMalloc(&h->d_scal, (size_t)(rs + 8) * 8));
+    h->gridC = h->num_sms * 4;
+    CK(cudaMalloc(&h->d_partW, (size_t)cdiv(L->NG, vb::kBlock) * (rs + 3) * 8));
+    CK(cudaMalloc(&h->d_partH, (size_t)cdiv(L->NC, vb::kBlock) * (rs + 3) * 8));
+    CK(cudaMalloc(&h->d_partC, (size_t)h->gridC * 2 * 8));
+    CK(cudaMallocHost(&h->h_scal, (size_t)2 * (rs + 8) * 8));
+    CK(cudaMemsetAsync(h->d_red, 0, (size_t)red_len(h) * 8, h->stream));
+    CK(cudaMemsetAsync(h->d_scal, 0, (size_t)(rs + 8) * 8, h->stream));
+    CK(cudaMemsetAsync(h->d_ShRaw, 0, cr, h->stream));
+    return 0;
+}
+
+// host column-major (rows x r, `rows` genes) or r x cols (cells; contiguous r per cell) -> device
+// panel in device order, zero padded
+int upload_panel(H *h, double *dst, const double *src, bool wside, int r) {
+    const Layout *L = h->L;
+    const int rs = h->rs;
+    const int64_t cnt = wside ? h->n : h->m, N = wside ? L->NG : L->NC;
+    const std::vector<int32_t> &dev = wside ? L->gene_dev : L->cell_dev;
+    std::vector<double> tmp((size_t)N * rs, 0.0);
+    if (wside) {
+        for (int k = 0; k < r; k++)
+            for (int64_t i = 0; i < cnt; i++)
+                tmp[(size_t)dev[i] * rs + k] = src[(size_t)k * cnt + i];
+    } else {
+        for (int64_t j = 0; j < cnt; j++)
+            for (int k = 0; k < r; k++) tmp[(size_t)dev[j] * rs + k] = src[(size_t)j * r + k];
+    }
+    CK(cudaMemcpyAsync(dst, tmp.data(), tmp.size() * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int download_panel(H *h, const double *src, std::vector<double> &tmp, bool wside) {
+    const Layout *L = h->L;
+    const int64_t N = wside ? L->NG : L->NC;
+    tmp.resize((size_t)N * h->rs);
+    CK(cudaMemcpy(tmp.data(), src, tmp.size() * 8, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// ---- one iteration --------------------------------------------------------------------------------
 int launch_posterior(H *h, bool wside, double a, double b, double fud) {
+    const Layout *L = h->L;
     double *tail = h->d_red + tail_off(h);
     vb::PosteriorArgs p;
-    p.rows = wside ? h->n : h->m;
+    p.rows = wside ? L->NG : L->NC;
+    p.T = L->T;
+    p.S = wside ? L->Sg : L->Sc;
+    p.nvalid = wside ? h->n : h->m;
     p.r = h->r;
     p.a = a; p.b = b; p.fud = fud;
     p.osum = wside ? tail : h->d_scal;
@@ -201,23 +457,40 @@ int launch_posterior(H *h, bool wside, double a, double b, double fud) {
     return 0;
 }
 
-int allreduce(H *h, double *buf, int64_t count) {
-    if (h->nranks <= 1) return 0;
-    CKN(g_nccl.AllReduce(buf, buf, (size_t)count, ncclFloat64, ncclSum, h->comm, h->stream));
-    h->launches += 1;
+// cell-owner pass: ShRaw, enth -> tail[rs+3], xlogp -> tail[rs+4]
+int launch_sweep_cols(H *h) {
+    const Layout *L = h->L;
+    double *tail = h->d_red + tail_off(h);
+    vb::SweepTiledArgs a{L->NC, L->T, L->cols.d_split, L->cols.d_ptr, L->cols.d_idx, L->cols.d_val,
+                         h->d_lh, h->d_lw, h->d_Part1, h->d_xl, h->int_counts ? 1 : 0};
+    h->tab->sweep(a, true, h->val_float, L->grid, h->smem_bytes, h->stream);
+    vb::CombineArgs c{L->NC, L->Sg, h->r, h->d_Part1, h->d_lh, h->d_ShRaw, h->d_partC,
+                      tail + h->rs + 3, h->d_counters + 2, h->d_xl, L->grid, h->gridC};
+    h->tab->combine(c, h->stream);
+    h->launches += 2;
     return 0;
 }
 
-// statistics at the current lw, lh: ShRaw, SwRaw (global), xlogp, enth, and entw
+// gene-owner pass: SwRaw (local part) -> d_red, entw (local part) -> tail[rs+5]
+int launch_sweep_rows(H *h) {
+    const Layout *L = h->L;
+    double *tail = h->d_red + tail_off(h);
+    vb::SweepTiledArgs a{L->NG, L->T, L->rows.d_split, L->rows.d_ptr, L->rows.d_idx, L->rows.d_val,
+                         h->d_lw, h->d_lh, h->d_Part2, nullptr, 0};
+    h->tab->sweep(a, false, h->val_float, L->grid, h->smem_bytes, h->stream);
+    vb::CombineArgs c{L->NG, L->Sc, h->r, h->d_Part2, h->d_lw, h->d_red, h->d_partC,
+                      tail + h->rs + 5, h->d_counters + 3, nullptr, 0, h->gridC};
+    h->tab->combine(c, h->stream);
+    h->launches += 2;
+    return 0;
+}
+
+// statistics at the current lw, lh: ShRaw, SwRaw (global), xlogp, enth, entw
 int sweep(H *h) {
     int rc;
     if ((rc = launch_sweep_cols(h))) return rc;
     if ((rc = launch_sweep_rows(h))) return rc;
     if ((rc = allreduce(h, h->d_red, red_len(h)))) return rc;
-    vb::entropy_w_kernel<<<h->gridE, vb::kBlock, 0, h->stream>>>(
-        h->n, h->rs, h->r, h->d_lw, h->d_red, h->d_partE, h->d_scal + h->rs + 3,
-        h->d_counters + 3);
-    h->launches += 1;
     CK(cudaGetLastError());
     h->stats_valid = true;
     return 0;
@@ -245,9 +518,9 @@ double absorb_scalars(H *h, const double *hyper) {
     }
     for (int k = 0; k < r; k++) h->ehsum[k] = hs[k];
     for (int c = 0; c < 3; c++) { h->wacc[c] = ws[rs + c]; h->hacc[c] = hs[rs + c]; }
-    h->entw = ws[rs + 3];
-    h->xlogp = hs[rs + 3];
-    h->enth = hs[rs + 4];
+    h->enth = hs[rs + 3];
+    h->xlogp = hs[rs + 4];
+    h->entw = hs[rs + 5];
     const double nr = (double)h->n * r, mr = (double)h->m_global * r;
     double U = 0.0;
     for (int k = 0; k < r; k++) U -= h->ewsum[k] * h->ehsum[k];       // -sum(ew.eh), :78
@@ -316,146 +589,6 @@ int hyper_update(const int *flags, const double *mn, double *hyper, int niter, d
     return 0;
 }
 
-void free_panels(H *h) {
-    double **ps[] = {&h->d_lw, &h->d_lh, &h->d_alw, &h->d_alh, &h->d_red, &h->d_ShRaw,
-                     &h->d_SwPart, &h->d_scal, &h->d_partW, &h->d_partH};
-    for (auto p : ps) {
-        if (*p) cudaFree(*p);
-        *p = nullptr;
-    }
-    if (h->h_scal) cudaFreeHost(h->h_scal);
-    h->h_scal = nullptr;
-}
-
-int alloc_panels(H *h, int r) {
-    const int rs = pad_rank(r);
-    if (rs == h->rs && h->d_lw) { h->r = r; return 0; }
-    const vb::RpTable *tab = vb::rp_table(rs);
-    if (!tab) return fail(h, VBNMF_ERR_ARG, "no kernels compiled for this rank");
-    free_panels(h);
-    h->tab = tab;
-    h->grid_cols = tab->sweep_cols_ctas_per_sm(h->val_float) * h->num_sms;
-    h->grid_rows = tab->sweep_rows_ctas_per_sm(h->val_float) * h->num_sms;
-    h->r = r;
-    h->rs = rs;
-    const size_t nr = (size_t)h->n * rs * 8, mr = (size_t)h->m * rs * 8;
-    CK(cudaMalloc(&h->d_lw, nr));
-    CK(cudaMalloc(&h->d_alw, nr));
-    CK(cudaMalloc(&h->d_lh, mr));
-    CK(cudaMalloc(&h->d_alh, mr));
-    CK(cudaMalloc(&h->d_ShRaw, mr));
-    CK(cudaMalloc(&h->d_red, (size_t)red_len(h) * 8));
-    CK(cudaMalloc(&h->d_SwPart, (size_t)h->n_items * rs * 8));
-    CK(cudaMalloc(&h->d_scal, (size_t)(rs + 8) * 8));
-    CK(cudaMalloc(&h->d_partW, (size_t)cdiv(h->n, vb::kBlock) * (rs + 3) * 8));
-    CK(cudaMalloc(&h->d_partH, (size_t)cdiv(h->m, vb::kBlock) * (rs + 3) * 8));
-    CK(cudaMallocHost(&h->h_scal, (size_t)2 * (rs + 8) * 8));
-    CK(cudaMemsetAsync(h->d_red, 0, (size_t)red_len(h) * 8, h->stream));
-    CK(cudaMemsetAsync(h->d_scal, 0, (size_t)(rs + 8) * 8, h->stream));
-    return 0;
-}
-
-// host n x r column-major -> device n x rs row-major (zero padded)
-int upload_cm(H *h, double *dst, const double *src, int64_t rows, int r) {
-    const int rs = h->rs;
-    std::vector<double> tmp((size_t)rows * rs, 0.0);
-    for (int k = 0; k < r; k++)
-        for (int64_t i = 0; i < rows; i++) tmp[(size_t)i * rs + k] = src[(size_t)k * rows + i];
-    CK(cudaMemcpyAsync(dst, tmp.data(), tmp.size() * 8, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    return 0;
-}
-// host r x m column-major (= m rows of r) -> device m x rs
-int upload_rm(H *h, double *dst, const double *src, int64_t rows, int r) {
-    const int rs = h->rs;
-    if (rs != r) CK(cudaMemsetAsync(dst, 0, (size_t)rows * rs * 8, h->stream));
-    CK(cudaMemcpy2DAsync(dst, (size_t)rs * 8, src, (size_t)r * 8, (size_t)r * 8, (size_t)rows,
-                         cudaMemcpyHostToDevice, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    return 0;
-}
-
-template <typename VT>
-int build_layouts_t(H *h) {
-    const int64_t n = h->n, m = h->m, nnz = h->nnz;
-    if (nnz >= (int64_t)UINT32_MAX) return fail(h, VBNMF_ERR_ARG, "nnz per GPU must be < 2^32-1");
-    const VT *val = (const VT *)h->d_val;
-    // constants over the nonzeros
-    const int gridK = h->num_sms * 8;
-    double *d_part = nullptr, *d_out = nullptr;
-    CK(cudaMalloc(&d_part, (size_t)gridK * 2 * 8));
-    CK(cudaMalloc(&d_out, 2 * 8));
-    vb::count_constants_kernel<VT><<<gridK, vb::kBlock, 0, h->stream>>>(nnz, val, d_part, d_out,
-                                                                       h->d_counters + 4);
-    double consts[2];
-    CK(cudaMemcpyAsync(consts, d_out, 16, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    h->lgx = consts[0];
-    h->mlconst = consts[1];
-    cudaFree(d_part);
-    cudaFree(d_out);
-    // CSR mirror: stable sort of the nonzeros by gene row
-    int32_t *d_colof = nullptr, *d_keys_out = nullptr;
-    uint32_t *d_perm_in = nullptr, *d_perm_out = nullptr;
-    unsigned long long *d_rowcount = nullptr;
-    CK(cudaMalloc(&d_colof, (size_t)nnz * 4));
-    CK(cudaMalloc(&d_rowcount, (size_t)(n + 1) * 8));
-    CK(cudaMemsetAsync(d_rowcount, 0, (size_t)(n + 1) * 8, h->stream));
-    vb::expand_cols_kernel<<<h->num_sms * 8, vb::kBlock, 0, h->stream>>>(m, h->d_colptr, h->d_rowidx,
-                                                                        d_colof, d_rowcount);
-    CK(cudaMalloc(&d_keys_out, (size_t)nnz * 4));
-    CK(cudaMalloc(&d_perm_in, (size_t)nnz * 4));
-    CK(cudaMalloc(&d_perm_out, (size_t)nnz * 4));
-    vb::iota_kernel<<<h->num_sms * 8, vb::kBlock, 0, h->stream>>>(nnz, d_perm_in);
-    int bits = 1;
-    while (((int64_t)1 << bits) < n) bits++;
-    size_t tmp_bytes = 0;
-    CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, h->d_rowidx, d_keys_out, d_perm_in,
-                                       d_perm_out, nnz, 0, bits, h->stream));
-    void *d_tmp = nullptr;
-    CK(cudaMalloc(&d_tmp, tmp_bytes));
-    CK(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, h->d_rowidx, d_keys_out, d_perm_in,
-                                       d_perm_out, nnz, 0, bits, h->stream));
-    CK(cudaMalloc(&h->d_colidx, (size_t)nnz * 4));
-    CK(cudaMalloc(&h->d_valr, (size_t)nnz * sizeof(VT)));
-    vb::gather_csr_kernel<VT><<<h->num_sms * 8, vb::kBlock, 0, h->stream>>>(
-        nnz, d_perm_out, d_colof, val, h->d_colidx, (VT *)h->d_valr);
-    // row pointers on the host -> work items
-    std::vector<unsigned long long> rc((size_t)n + 1);
-    CK(cudaMemcpyAsync(rc.data(), d_rowcount, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost,
-                       h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    CK(cudaGetLastError());
-    cudaFree(d_tmp); cudaFree(d_colof); cudaFree(d_keys_out); cudaFree(d_perm_in);
-    cudaFree(d_perm_out); cudaFree(d_rowcount);
-    std::vector<int32_t> item_row, item_len;
-    std::vector<int64_t> item_beg, row_item_ptr((size_t)n + 1);
-    int64_t off = 0;
-    for (int64_t i = 0; i < n; i++) {
-        row_item_ptr[i] = (int64_t)item_row.size();
-        const int64_t cnt = (int64_t)rc[i];
-        for (int64_t b = 0; b < cnt; b += kRowChunk) {
-            item_row.push_back((int32_t)i);
-            item_beg.push_back(off + b);
-            item_len.push_back((int32_t)std::min(kRowChunk, cnt - b));
-        }
-        off += cnt;
-    }
-    row_item_ptr[n] = (int64_t)item_row.size();
-    h->n_items = (int64_t)item_row.size();
-    const size_t ni = std::max<size_t>(1, item_row.size());
-    CK(cudaMalloc(&h->d_item_row, ni * 4));
-    CK(cudaMalloc(&h->d_item_len, ni * 4));
-    CK(cudaMalloc(&h->d_item_beg, ni * 8));
-    CK(cudaMalloc(&h->d_row_item_ptr, (size_t)(n + 1) * 8));
-    CK(cudaMemcpy(h->d_item_row, item_row.data(), item_row.size() * 4, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(h->d_item_len, item_len.data(), item_len.size() * 4, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(h->d_item_beg, item_beg.data(), item_beg.size() * 8, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(h->d_row_item_ptr, row_item_ptr.data(), (size_t)(n + 1) * 8,
-                  cudaMemcpyHostToDevice));
-    return 0;
-}
-
 int init_common(H *h, int device) {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
@@ -470,13 +603,6 @@ int init_common(H *h, int device) {
     h->own_stream = true;
     CK(cudaMalloc(&h->d_counters, 16 * sizeof(unsigned)));
     CK(cudaMemset(h->d_counters, 0, 16 * sizeof(unsigned)));
-    CK(cudaMalloc(&h->d_work, 2 * sizeof(unsigned long long)));
-    h->gridC = std::min<int64_t>(h->num_sms * 4, std::max<int64_t>(1, cdiv(h->m, vb::kBlock)));
-    h->gridE = std::min<int64_t>(h->num_sms * 4, std::max<int64_t>(1, cdiv(h->n * 2, vb::kBlock)));
-    CK(cudaMalloc(&h->d_colx, (size_t)std::max<int64_t>(1, h->m) * 8));
-    CK(cudaMalloc(&h->d_cole, (size_t)std::max<int64_t>(1, h->m) * 8));
-    CK(cudaMalloc(&h->d_partC, (size_t)h->gridC * 2 * 8));
-    CK(cudaMalloc(&h->d_partE, (size_t)h->gridE * 8));
     h->m_global = h->m;
     return 0;
 }
@@ -494,14 +620,11 @@ void vbnmf_destroy(vbnmf_handle *h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     free_panels(h);
+    drop_layouts(h);
     if (!h->borrowed) {
         cudaFree(h->d_colptr); cudaFree(h->d_rowidx); cudaFree(h->d_val);
     }
-    cudaFree(h->d_colidx); cudaFree(h->d_valr);
-    cudaFree(h->d_item_row); cudaFree(h->d_item_len); cudaFree(h->d_item_beg);
-    cudaFree(h->d_row_item_ptr);
-    cudaFree(h->d_colx); cudaFree(h->d_cole); cudaFree(h->d_partC); cudaFree(h->d_partE);
-    cudaFree(h->d_counters); cudaFree(h->d_work);
+    cudaFree(h->d_counters);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -518,6 +641,8 @@ int vbnmf_create(vbnmf_handle **out, int64_t n, int64_t m, int64_t nnz, const in
     };
     if (n <= 0 || m <= 0 || nnz <= 0 || (!colptr32 == !colptr64) || !rowidx || !values)
         return bail(fail(h, VBNMF_ERR_ARG, "vbnmf_create: bad arguments"));
+    if (nnz >= (int64_t)UINT32_MAX)
+        return bail(fail(h, VBNMF_ERR_ARG, "nnz per GPU must be < 2^32-1"));
     h->n = n; h->m = m; h->nnz = nnz;
     int rc = init_common(h, device);
     if (rc) return bail(rc);
@@ -548,7 +673,7 @@ int vbnmf_create(vbnmf_handle **out, int64_t n, int64_t m, int64_t nnz, const in
         return 0;
     };
     if ((rc = up())) return bail(rc);
-    rc = as_float ? build_layouts_t<float>(h) : build_layouts_t<double>(h);
+    rc = as_float ? scan_matrix_t<float>(h) : scan_matrix_t<double>(h);
     if (rc) return bail(rc);
     *out = h;
     return 0;
@@ -567,6 +692,8 @@ int vbnmf_create_from_device(vbnmf_handle **out, int64_t n, int64_t m, int64_t n
     };
     if (n <= 0 || m <= 0 || nnz <= 0 || !d_colptr || !d_rowidx || !d_values)
         return bail(fail(h, VBNMF_ERR_ARG, "vbnmf_create_from_device: bad arguments"));
+    if (nnz >= (int64_t)UINT32_MAX)
+        return bail(fail(h, VBNMF_ERR_ARG, "nnz per GPU must be < 2^32-1"));
     h->n = n; h->m = m; h->nnz = nnz;
     int rc = init_common(h, device);
     if (rc) return bail(rc);
@@ -575,7 +702,7 @@ int vbnmf_create_from_device(vbnmf_handle **out, int64_t n, int64_t m, int64_t n
     h->d_colptr = const_cast<int64_t *>(d_colptr);
     h->d_rowidx = const_cast<int32_t *>(d_rowidx);
     h->d_val = const_cast<float *>(d_values);
-    if ((rc = build_layouts_t<float>(h))) return bail(rc);
+    if ((rc = scan_matrix_t<float>(h))) return bail(rc);
     *out = h;
     return 0;
 }
@@ -647,18 +774,26 @@ int vbnmf_attach_comm(vbnmf_handle *h, vbnmf_comm *c) {
     h->comm = c->comm;
     h->nranks = c->nranks;
     h->rank = c->rank;
-    // global constants: total cells and the sums over nonzeros
-    double *d3 = nullptr, h3[3] = {(double)h->m, h->lgx, h->mlconst};
-    CK(cudaMalloc(&d3, 24));
-    CK(cudaMemcpyAsync(d3, h3, 24, cudaMemcpyHostToDevice, h->stream));
-    int rc = allreduce(h, d3, 3);
+    // global quantities: total cells, the sums over nonzeros, and the per-gene nonzero counts
+    // (every rank must derive the same gene renumbering)
+    const int64_t len = 3 + h->n;
+    std::vector<double> hv((size_t)len);
+    hv[0] = (double)h->m; hv[1] = h->lgx; hv[2] = h->mlconst;
+    for (int64_t i = 0; i < h->n; i++) hv[3 + i] = (double)h->row_count[i];
+    double *dv = nullptr;
+    CK(cudaMalloc(&dv, (size_t)len * 8));
+    CK(cudaMemcpyAsync(dv, hv.data(), (size_t)len * 8, cudaMemcpyHostToDevice, h->stream));
+    int rc = allreduce(h, dv, len);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(h3, d3, 24, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(hv.data(), dv, (size_t)len * 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    cudaFree(d3);
-    h->m_global = (int64_t)llround(h3[0]);
-    h->lgx = h3[1];
-    h->mlconst = h3[2];
+    cudaFree(dv);
+    h->m_global = (int64_t)llround(hv[0]);
+    h->lgx = hv[1];
+    h->mlconst = hv[2];
+    for (int64_t i = 0; i < h->n; i++) h->row_count[i] = (unsigned long long)llround(hv[3 + i]);
+    free_panels(h);
+    drop_layouts(h);
     h->stats_valid = false;
     return 0;
 }
@@ -670,11 +805,11 @@ int vbnmf_set_state(vbnmf_handle *h, int r, const double *lw, const double *lh, 
     CK(cudaSetDevice(h->device));
     int rc;
     if ((rc = alloc_panels(h, r))) return rc;
-    if ((rc = upload_cm(h, h->d_lw, lw, h->n, r))) return rc;
-    if ((rc = upload_rm(h, h->d_lh, lh, h->m, r))) return rc;
+    if ((rc = upload_panel(h, h->d_lw, lw, true, r))) return rc;
+    if ((rc = upload_panel(h, h->d_lh, lh, false, r))) return rc;
     // before the first update ew/eh are whatever the caller holds (vb_init: ew = w, eh = h)
-    if ((rc = upload_cm(h, h->d_alw, ew ? ew : lw, h->n, r))) return rc;
-    if ((rc = upload_rm(h, h->d_alh, eh ? eh : lh, h->m, r))) return rc;
+    if ((rc = upload_panel(h, h->d_alw, ew ? ew : lw, true, r))) return rc;
+    if ((rc = upload_panel(h, h->d_alh, eh ? eh : lh, false, r))) return rc;
     const double *e = eh ? eh : lh;
     double *tail = h->d_red + tail_off(h);
     std::vector<double> s((size_t)h->rs + 8, 0.0);
@@ -757,34 +892,36 @@ int vbnmf_get_state(vbnmf_handle *h, double *lw, double *lh, double *ew, double 
     CK(cudaStreamSynchronize(h->stream));
     const int r = h->r, rs = h->rs;
     const int64_t n = h->n, m = h->m;
-    if (lw || ew || dw) {
-        std::vector<double> tmp((size_t)n * rs);
-        if (lw) {
-            CK(cudaMemcpy(tmp.data(), h->d_lw, tmp.size() * 8, cudaMemcpyDeviceToHost));
-            for (int k = 0; k < r; k++)
-                for (int64_t i = 0; i < n; i++) lw[(size_t)k * n + i] = tmp[(size_t)i * rs + k];
-        }
-        if (ew || dw) {
-            CK(cudaMemcpy(tmp.data(), h->d_alw, tmp.size() * 8, cudaMemcpyDeviceToHost));
-            for (int k = 0; k < r; k++)
-                for (int64_t i = 0; i < n; i++) {
-                    const double a = tmp[(size_t)i * rs + k], b = h->bew[k];
-                    if (ew) ew[(size_t)k * n + i] = a / b;                      // :44
-                    if (dw) dw[(size_t)k * n + i] = h->has_posterior ? a / b / b : 0.0;  // :46
-                }
-        }
+    const Layout *L = h->L;
+    std::vector<double> tmp;
+    int rc;
+    if (lw) {
+        if ((rc = download_panel(h, h->d_lw, tmp, true))) return rc;
+        for (int k = 0; k < r; k++)
+            for (int64_t i = 0; i < n; i++)
+                lw[(size_t)k * n + i] = tmp[(size_t)L->gene_dev[i] * rs + k];
     }
-    if (lh)
-        CK(cudaMemcpy2D(lh, (size_t)r * 8, h->d_lh, (size_t)rs * 8, (size_t)r * 8, (size_t)m,
-                        cudaMemcpyDeviceToHost));
+    if (ew || dw) {
+        if ((rc = download_panel(h, h->d_alw, tmp, true))) return rc;
+        for (int k = 0; k < r; k++)
+            for (int64_t i = 0; i < n; i++) {
+                const double a = tmp[(size_t)L->gene_dev[i] * rs + k], b = h->bew[k];
+                if (ew) ew[(size_t)k * n + i] = a / b;                               // :44
+                if (dw) dw[(size_t)k * n + i] = h->has_posterior ? a / b / b : 0.0;  // :46
+            }
+    }
+    if (lh) {
+        if ((rc = download_panel(h, h->d_lh, tmp, false))) return rc;
+        for (int64_t j = 0; j < m; j++)
+            for (int k = 0; k < r; k++)
+                lh[(size_t)j * r + k] = tmp[(size_t)L->cell_dev[j] * rs + k];
+    }
     if (eh || dh) {
-        std::vector<double> tmp((size_t)m * r);
-        CK(cudaMemcpy2D(tmp.data(), (size_t)r * 8, h->d_alh, (size_t)rs * 8, (size_t)r * 8,
-                        (size_t)m, cudaMemcpyDeviceToHost));
+        if ((rc = download_panel(h, h->d_alh, tmp, false))) return rc;
         for (int64_t j = 0; j < m; j++)
             for (int k = 0; k < r; k++) {
-                const double a = tmp[(size_t)j * r + k], b = h->beh[k];
-                if (eh) eh[(size_t)j * r + k] = a / b;                          // :54
+                const double a = tmp[(size_t)L->cell_dev[j] * rs + k], b = h->beh[k];
+                if (eh) eh[(size_t)j * r + k] = a / b;                               // :54
                 if (dh) dh[(size_t)j * r + k] = h->has_posterior ? a / b / b : 0.0;  // :56
             }
     }
@@ -795,17 +932,20 @@ int vbnmf_cluster_id(vbnmf_handle *h, int32_t *cid) {
     if (!h || !cid) return VBNMF_ERR_ARG;
     if (!h->d_lw) return fail(h, VBNMF_ERR_STATE, "vbnmf_set_state has not been called");
     CK(cudaSetDevice(h->device));
+    const Layout *L = h->L;
     double *d_beh = nullptr;
     int32_t *d_cid = nullptr;
+    std::vector<int32_t> tmp((size_t)L->NC);
     CK(cudaMalloc(&d_beh, kMaxRank * 8));
-    CK(cudaMalloc(&d_cid, (size_t)h->m * 4));
+    CK(cudaMalloc(&d_cid, (size_t)L->NC * 4));
     CK(cudaMemcpyAsync(d_beh, h->beh, kMaxRank * 8, cudaMemcpyHostToDevice, h->stream));
-    vb::cluster_id_kernel<<<cdiv(h->m, vb::kBlock), vb::kBlock, 0, h->stream>>>(
-        h->m, h->rs, h->r, h->d_alh, d_beh, d_cid);
-    CK(cudaMemcpyAsync(cid, d_cid, (size_t)h->m * 4, cudaMemcpyDeviceToHost, h->stream));
+    vb::cluster_id_kernel<<<cdiv(L->NC, vb::kBlock), vb::kBlock, 0, h->stream>>>(
+        L->NC, h->rs, h->r, h->d_alh, d_beh, d_cid);
+    CK(cudaMemcpyAsync(tmp.data(), d_cid, (size_t)L->NC * 4, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     cudaFree(d_beh);
     cudaFree(d_cid);
+    for (int64_t j = 0; j < h->m; j++) cid[j] = tmp[(size_t)L->cell_dev[j]];
     return 0;
 }
 
@@ -815,12 +955,14 @@ int vbnmf_uniform_columns(vbnmf_handle *h, double tol, int32_t *flags) {
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
     const int r = h->r, rs = h->rs;
-    std::vector<double> tmp((size_t)h->n * rs);
-    CK(cudaMemcpy(tmp.data(), h->d_alw, tmp.size() * 8, cudaMemcpyDeviceToHost));
+    const Layout *L = h->L;
+    std::vector<double> tmp;
+    int rc;
+    if ((rc = download_panel(h, h->d_alw, tmp, true))) return rc;
     for (int k = 0; k < r; k++) {
         double mx = -INFINITY, mn = INFINITY;
         for (int64_t i = 0; i < h->n; i++) {
-            const double v = tmp[(size_t)i * rs + k] / h->bew[k];
+            const double v = tmp[(size_t)L->gene_dev[i] * rs + k] / h->bew[k];
             mx = v > mx ? v : mx;
             mn = v < mn ? v : mn;
         }
@@ -842,11 +984,10 @@ int vbnmf_bench_iterations(vbnmf_handle *h, const double hyper[4], double fudge,
     const int64_t l0 = h->launches;
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaEventRecord(ev[0], h->stream));
-    const double aw = hyper[0], bw = hyper[1], ah = hyper[2], bh = hyper[3];
     for (int it = 0; it < iters; it++) {
-        // same sequence as iterate(), with events around the two sweep kernels
-        if ((rc = launch_posterior(h, true, aw, bw, fudge))) return rc;
-        if ((rc = launch_posterior(h, false, ah, bh, fudge))) return rc;
+        // same sequence as iterate(), with events around the two sweep passes
+        if ((rc = launch_posterior(h, true, hyper[0], hyper[1], fudge))) return rc;
+        if ((rc = launch_posterior(h, false, hyper[2], hyper[3], fudge))) return rc;
         CK(cudaEventRecord(ev[2 + it * 4 + 0], h->stream));
         if ((rc = launch_sweep_cols(h))) return rc;
         CK(cudaEventRecord(ev[2 + it * 4 + 1], h->stream));
@@ -854,10 +995,6 @@ int vbnmf_bench_iterations(vbnmf_handle *h, const double hyper[4], double fudge,
         if ((rc = launch_sweep_rows(h))) return rc;
         CK(cudaEventRecord(ev[2 + it * 4 + 3], h->stream));
         if ((rc = allreduce(h, h->d_red, red_len(h)))) return rc;
-        vb::entropy_w_kernel<<<h->gridE, vb::kBlock, 0, h->stream>>>(
-            h->n, h->rs, h->r, h->d_lw, h->d_red, h->d_partE, h->d_scal + h->rs + 3,
-            h->d_counters + 3);
-        h->launches += 1;
         if ((rc = fetch_scalars(h))) return rc;  // the per-iteration host readback of the loop
         lkh = absorb_scalars(h, hyper);
     }
@@ -894,15 +1031,16 @@ int mlnmf_run(vbnmf_handle *h, int r, const double *w0, const double *h0, int it
     CK(cudaSetDevice(h->device));
     int rc;
     if ((rc = alloc_panels(h, r))) return rc;
-    if ((rc = upload_cm(h, h->d_lw, w0, h->n, r))) return rc;
-    if ((rc = upload_rm(h, h->d_lh, h0, h->m, r))) return rc;
+    if ((rc = upload_panel(h, h->d_lw, w0, true, r))) return rc;
+    if ((rc = upload_panel(h, h->d_lh, h0, false, r))) return rc;
     h->stats_valid = false;
     h->has_posterior = false;
+    const Layout *L = h->L;
     const double eps = 2.220446049250313e-16;  // .Machine$double.eps, R/factorize.R:15,24
     const int rs = h->rs, wd = rs + 8;
     double *tail = h->d_red + tail_off(h);
     auto colsum = [&](bool wside) -> int {
-        vb::ColsumArgs a{wside ? h->n : h->m, wside ? h->d_lw : h->d_lh,
+        vb::ColsumArgs a{wside ? L->NG : L->NC, wside ? h->d_lw : h->d_lh,
                          wside ? h->d_partW : h->d_partH, wside ? h->d_scal : tail,
                          h->d_counters + (wside ? 0 : 1)};
         h->tab->colsum(a, h->stream);
@@ -910,7 +1048,8 @@ int mlnmf_run(vbnmf_handle *h, int r, const double *w0, const double *h0, int it
         return 0;
     };
     auto mlupd = [&](bool wside) -> int {
-        vb::MlUpdateArgs a{wside ? h->n : h->m, r, eps, wside ? tail : h->d_scal,
+        vb::MlUpdateArgs a{wside ? L->NG : L->NC, L->T, wside ? L->Sg : L->Sc,
+                           wside ? h->n : h->m, r, eps, wside ? tail : h->d_scal,
                            wside ? h->d_red : h->d_ShRaw, wside ? h->d_lw : h->d_lh,
                            wside ? h->d_partW : h->d_partH, wside ? h->d_scal : tail,
                            h->d_counters + (wside ? 0 : 1)};
@@ -924,7 +1063,7 @@ int mlnmf_run(vbnmf_handle *h, int r, const double *w0, const double *h0, int it
         if ((rc = fetch_scalars(h))) return rc;
         double swh = 0.0;
         for (int k = 0; k < r; k++) swh += h->h_scal[k] * h->h_scal[wd + k];
-        *lik = (h->h_scal[wd + rs + 3] - swh + h->mlconst) / (double)h->n / (double)h->m_global;
+        *lik = (h->h_scal[wd + rs + 4] - swh + h->mlconst) / (double)h->n / (double)h->m_global;
         return 0;
     };
     if ((rc = colsum(true))) return rc;   // colSums(w0)
@@ -955,7 +1094,6 @@ int mlnmf_run(vbnmf_handle *h, int r, const double *w0, const double *h0, int it
     }
     CK(cudaGetLastError());
     *niter = done;
-    // export w, h
     if (w || h_out) {
         if ((rc = vbnmf_get_state(h, w, h_out, nullptr, nullptr, nullptr, nullptr))) return rc;
     }
