@@ -147,32 +147,76 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
 // differ mod 8 -> with an odd row stride the 8 gathers of a group are bank-conflict free.
 template <int RP>
 struct SweepCfg {
-    // register budget: own + acc + tile row = 6*RP, plus the log-product accumulators
+    // register budget: own + acc + tile row = 6*RP doubles-halves, plus prefetched entries
     static constexpr int kThreads = (RP <= 12) ? 512 : 256;
     static constexpr int kGroups = kThreads / kGroup;
 };
 
-constexpr int kLogBits = 6;  // counts < 64 go through the bit-sliced log-product
+constexpr int kUnroll = 4;  // nonzeros per lane whose index/count loads are in flight together
+
+// log(p) for a positive normal double, ~1 ulp: p = 2^e m with m in [sqrt(1/2), sqrt(2)),
+// log m = 2 atanh(t), t = (m-1)/(m+1), |t| <= 0.1716, odd series through t^17 (next term < 3e-16).
+// No special cases (p > 0 finite is guaranteed by the fudge floor), ~20 FP64 + ~8 integer ops
+// against ~90 for the general log().
+__device__ __forceinline__ double fast_log_pos(double p) {
+    int hi = __double2hiint(p);
+    const int lo = __double2loint(p);
+    int e = (hi >> 20) - 1023;
+    hi = (hi & 0x000fffff) | 0x3ff00000;
+    if (hi >= 0x3ff6a09f) { hi -= 0x00100000; e += 1; }
+    const double m = __hiloint2double(hi, lo);
+    const double t = (m - 1.0) * fast_rcp(m + 1.0);
+    const double t2 = t * t;
+    double s = 2.0 / 17.0;
+    s = fma(s, t2, 2.0 / 15.0);
+    s = fma(s, t2, 2.0 / 13.0);
+    s = fma(s, t2, 2.0 / 11.0);
+    s = fma(s, t2, 2.0 / 9.0);
+    s = fma(s, t2, 2.0 / 7.0);
+    s = fma(s, t2, 2.0 / 5.0);
+    s = fma(s, t2, 2.0 / 3.0);
+    const double lm = fma(t * t2, s, 2.0 * t);
+    const double de = (double)e;
+    // ln 2 split so that e * ln2_hi is exact for |e| < 2^10
+    return fma(de, 6.93147180369123816490e-01, fma(de, 1.90821492927058770002e-10, lm));
+}
 
 struct SweepTiledArgs {
     int64_t NO;              // owners per slab (device-ordered rows of the owner panel)
     int T;                   // tile rows
     const int64_t *split;    // gridDim.x + 1 segment indices
     const int64_t *ptr;      // segment pointers, nslabs*NO + 1
-    const int32_t *idx;      // local tile row of each nonzero
-    const void *val;         // counts (float or double)
+    const void *ent;         // float counts: packed {int32 tile row, float count} per nonzero
+    const int32_t *idx;      // double counts: tile row of each nonzero ...
+    const double *val;       // ... and its count
     const double *owner;     // owner panel, NO x RS
     const double *tiles;     // tile panel, nslabs*T x RS
     double *Part;            // nslabs x NO x RS
     double *xl_part;         // COLS: gridDim.x partial sums of x log p
-    int int_counts;          // all counts are integers in [0, 2^31): log-product path allowed
 };
+
+template <typename VT>
+__device__ __forceinline__ void load_entry(const SweepTiledArgs &a, int64_t t, int32_t &ti, double &x);
+template <>
+__device__ __forceinline__ void load_entry<float>(const SweepTiledArgs &a, int64_t t, int32_t &ti,
+                                                  double &x) {
+    const int2 v = __ldcs(reinterpret_cast<const int2 *>(a.ent) + t);
+    ti = v.x;
+    x = (double)__int_as_float(v.y);
+}
+template <>
+__device__ __forceinline__ void load_entry<double>(const SweepTiledArgs &a, int64_t t, int32_t &ti,
+                                                   double &x) {
+    ti = __ldcs(a.idx + t);
+    x = __ldcs(a.val + t);
+}
 
 template <int RP, typename VT, bool COLS>
 __global__ void __launch_bounds__(SweepCfg<RP>::kThreads, 1)
 sweep_tiled_kernel(const SweepTiledArgs a) {
     constexpr int RS = row_stride(RP);
     constexpr int NT = SweepCfg<RP>::kThreads;
+    constexpr int U = kUnroll;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *tile = reinterpret_cast<double *>(smem_raw);
     __shared__ __align__(8) uint64_t mbar;
@@ -185,14 +229,7 @@ sweep_tiled_kernel(const SweepTiledArgs a) {
     if (threadIdx.x == 0) mbar_init(&mbar, 1);
     __syncthreads();
     unsigned parity = 0;
-
-    // x log p through products: P[b] = prod of p over nonzeros whose count has bit b set
-    double P[kLogBits];
-    int PE[kLogBits];
-    double xl_slow = 0.0;
-#pragma unroll
-    for (int b = 0; b < kLogBits; b++) { P[b] = 1.0; PE[b] = 0; }
-    int since_norm = 0;
+    double xl = 0.0;  // sum x log p of this thread's nonzeros (COLS)
 
     for (int64_t ebase = e0; ebase < e1;) {
         const int64_t slab = ebase / a.NO;
@@ -213,52 +250,51 @@ sweep_tiled_kernel(const SweepTiledArgs a) {
             if (beg < end) {
                 double own[RP];
                 load_row_d<RP>(a.owner, o, own);
-                for (int64_t t = beg + gl; t < end; t += kGroup) {
-                    const int32_t ti = __ldcs(a.idx + t);
-                    const VT xv = __ldcs(reinterpret_cast<const VT *>(a.val) + t);
-                    const double x = (double)xv;
-                    const double2 *rowp = reinterpret_cast<const double2 *>(tile + (int64_t)ti * RS);
-                    double tr[RP];
+                // software pipeline: the U index/count loads of the next chunk are issued before
+                // the current chunk is processed (a zero count makes a slot a no-op)
+                int32_t ti[U], tn[U];
+                double xv[U], xn[U];
 #pragma unroll
-                    for (int k = 0; k < RP / 2; k++) {
-                        const double2 v = rowp[k];
-                        tr[2 * k] = v.x;
-                        tr[2 * k + 1] = v.y;
+                for (int u = 0; u < U; u++) {
+                    const int64_t t = beg + gl + u * kGroup;
+                    ti[u] = 0; xv[u] = 0.0;
+                    if (t < end) load_entry<VT>(a, t, ti[u], xv[u]);
+                }
+                for (int64_t c = beg; c < end; c += U * kGroup) {
+#pragma unroll
+                    for (int u = 0; u < U; u++) {
+                        const int64_t t = c + U * kGroup + gl + u * kGroup;
+                        tn[u] = 0; xn[u] = 0.0;
+                        if (t < end) load_entry<VT>(a, t, tn[u], xn[u]);
                     }
-                    double p0 = 0.0, p1 = 0.0;
 #pragma unroll
-                    for (int k = 0; k < RP; k += 2) {
-                        p0 = fma(own[k], tr[k], p0);
-                        p1 = fma(own[k + 1], tr[k + 1], p1);
-                    }
-                    const double p = p0 + p1;
-                    const double q = x * fast_rcp(p);
+                    for (int u = 0; u < U; u++) {
+                        if (c + gl + u * kGroup < end) {
+                            const double x = xv[u];
+                            const double2 *rowp =
+                                reinterpret_cast<const double2 *>(tile + (int64_t)ti[u] * RS);
+                            double tr[RP];
 #pragma unroll
-                    for (int k = 0; k < RP; k++) acc[k] = fma(tr[k], q, acc[k]);
-                    if (COLS) {
-                        if (a.int_counts) {
-                            const int xi = (int)xv;
-                            if (xi < (1 << kLogBits)) {
-#pragma unroll
-                                for (int b = 0; b < kLogBits; b++)
-                                    if ((xi >> b) & 1) P[b] *= p;
-                            } else {
-                                xl_slow = fma(x, log(p), xl_slow);
+                            for (int k = 0; k < RP / 2; k++) {
+                                const double2 v = rowp[k];
+                                tr[2 * k] = v.x;
+                                tr[2 * k + 1] = v.y;
                             }
-                            if (++since_norm == 8) {
-                                since_norm = 0;
+                            double p0 = 0.0, p1 = 0.0;
 #pragma unroll
-                                for (int b = 0; b < kLogBits; b++) {
-                                    const int hi = __double2hiint(P[b]);
-                                    PE[b] += ((hi >> 20) & 0x7ff) - 1023;
-                                    P[b] = __hiloint2double((hi & 0x800fffff) | 0x3ff00000,
-                                                            __double2loint(P[b]));
-                                }
+                            for (int k = 0; k < RP; k += 2) {
+                                p0 = fma(own[k], tr[k], p0);
+                                p1 = fma(own[k + 1], tr[k + 1], p1);
                             }
-                        } else {
-                            xl_slow = fma(x, log(p), xl_slow);
+                            const double p = p0 + p1;
+                            const double q = x * fast_rcp(p);
+#pragma unroll
+                            for (int k = 0; k < RP; k++) acc[k] = fma(tr[k], q, acc[k]);
+                            if (COLS) xl = fma(x, fast_log_pos(p), xl);
                         }
                     }
+#pragma unroll
+                    for (int u = 0; u < U; u++) { ti[u] = tn[u]; xv[u] = xn[u]; }
                 }
             }
             // sum over the 8 lanes of the group; lane gl keeps k = gl, gl+8, ...
@@ -284,18 +320,6 @@ sweep_tiled_kernel(const SweepTiledArgs a) {
         ebase = eend;
     }
     if (COLS) {
-        // sum x log p = sum_b 2^b (log(mantissa_b) + exponent_b ln 2) + slow-path terms
-        double xl = xl_slow;
-        if (a.int_counts) {
-#pragma unroll
-            for (int b = 0; b < kLogBits; b++) {
-                const int hi = __double2hiint(P[b]);
-                const int ex = PE[b] + ((hi >> 20) & 0x7ff) - 1023;
-                const double mant = __hiloint2double((hi & 0x800fffff) | 0x3ff00000,
-                                                     __double2loint(P[b]));
-                xl += (double)(1 << b) * (log(mant) + (double)ex * 0.6931471805599453094);
-            }
-        }
         xl = block_sum(xl, red);
         if (threadIdx.x == 0) a.xl_part[blockIdx.x] = xl;
     }

@@ -93,7 +93,8 @@ build_segments_kernel(int64_t E, const int64_t *__restrict__ ptr,
                       const uint32_t *__restrict__ perm, const int32_t *__restrict__ rowidx,
                       const int32_t *__restrict__ colof, const int32_t *__restrict__ gene_dev,
                       const int32_t *__restrict__ cell_dev, const VT *__restrict__ val, int T,
-                      bool cols_pass, int32_t *__restrict__ idx_out, VT *__restrict__ val_out) {
+                      bool cols_pass, int32_t *__restrict__ idx_out, VT *__restrict__ val_out,
+                      int2 *__restrict__ ent_out) {
     for (int64_t e = (int64_t)blockIdx.x * kBlock + threadIdx.x; e < E;
          e += (int64_t)gridDim.x * kBlock) {
         const int64_t beg = ptr[e], end = ptr[e + 1];
@@ -121,8 +122,12 @@ build_segments_kernel(int64_t E, const int64_t *__restrict__ ptr,
                 pos += min(cnt[c], round);
                 if (c < b && cnt[c] > round) pos++;
             }
-            idx_out[beg + pos] = local;
-            val_out[beg + pos] = val[s];
+            if (ent_out) {  // float counts: packed {tile row, count bits}
+                ent_out[beg + pos] = make_int2(local, __float_as_int((float)val[s]));
+            } else {
+                idx_out[beg + pos] = local;
+                val_out[beg + pos] = val[s];
+            }
         }
     }
 }

@@ -87,12 +87,13 @@ NcclApi g_nccl;
 struct PassLayout {
     int64_t E = 0;              // segments = tile slabs * owners
     int64_t *d_ptr = nullptr;   // E + 1
-    int32_t *d_idx = nullptr;   // nnz
-    void *d_val = nullptr;      // nnz
+    int32_t *d_idx = nullptr;   // nnz (double counts only)
+    void *d_val = nullptr;      // nnz (double counts only)
+    void *d_ent = nullptr;      // nnz packed {int32 tile row, float count} (float counts)
     int64_t *d_split = nullptr; // grid + 1
     void release() {
-        cudaFree(d_ptr); cudaFree(d_idx); cudaFree(d_val); cudaFree(d_split);
-        d_ptr = nullptr; d_idx = nullptr; d_val = nullptr; d_split = nullptr;
+        cudaFree(d_ptr); cudaFree(d_idx); cudaFree(d_val); cudaFree(d_ent); cudaFree(d_split);
+        d_ptr = nullptr; d_idx = nullptr; d_val = nullptr; d_ent = nullptr; d_split = nullptr;
     }
 };
 
@@ -259,11 +260,15 @@ int build_pass(H *h, Layout *L, bool cols_pass, const int32_t *d_colof) {
     vb::segment_ptr_kernel<<<g, vb::kBlock, 0, h->stream>>>(P.E, nnz, k_out, P.d_ptr);
     CK(cudaStreamSynchronize(h->stream));
     cudaFree(d_tmp); cudaFree(k_in); cudaFree(k_out); cudaFree(p_in);
-    CK(cudaMalloc(&P.d_idx, (size_t)nnz * 4));
-    CK(cudaMalloc(&P.d_val, (size_t)nnz * sizeof(VT)));
+    if (sizeof(VT) == 4) {
+        CK(cudaMalloc(&P.d_ent, (size_t)nnz * 8));
+    } else {
+        CK(cudaMalloc(&P.d_idx, (size_t)nnz * 4));
+        CK(cudaMalloc(&P.d_val, (size_t)nnz * sizeof(VT)));
+    }
     vb::build_segments_kernel<VT><<<g, vb::kBlock, 0, h->stream>>>(
         P.E, P.d_ptr, p_out, h->d_rowidx, d_colof, L->d_gene_dev, L->d_cell_dev,
-        (const VT *)h->d_val, L->T, cols_pass, P.d_idx, (VT *)P.d_val);
+        (const VT *)h->d_val, L->T, cols_pass, P.d_idx, (VT *)P.d_val, (int2 *)P.d_ent);
     CK(cudaMalloc(&P.d_split, (size_t)(L->grid + 1) * 8));
     vb::split_kernel<<<cdiv(L->grid + 1, 128), 128, 0, h->stream>>>(L->grid, P.E, nnz, P.d_ptr,
                                                                    P.d_split);
@@ -461,8 +466,9 @@ int launch_posterior(H *h, bool wside, double a, double b, double fud) {
 int launch_sweep_cols(H *h) {
     const Layout *L = h->L;
     double *tail = h->d_red + tail_off(h);
-    vb::SweepTiledArgs a{L->NC, L->T, L->cols.d_split, L->cols.d_ptr, L->cols.d_idx, L->cols.d_val,
-                         h->d_lh, h->d_lw, h->d_Part1, h->d_xl, h->int_counts ? 1 : 0};
+    vb::SweepTiledArgs a{L->NC, L->T, L->cols.d_split, L->cols.d_ptr, L->cols.d_ent,
+                         L->cols.d_idx, (const double *)L->cols.d_val, h->d_lh, h->d_lw,
+                         h->d_Part1, h->d_xl};
     h->tab->sweep(a, true, h->val_float, L->grid, h->smem_bytes, h->stream);
     vb::CombineArgs c{L->NC, L->Sg, h->r, h->d_Part1, h->d_lh, h->d_ShRaw, h->d_partC,
                       tail + h->rs + 3, h->d_counters + 2, h->d_xl, L->grid, h->gridC};
@@ -475,8 +481,9 @@ int launch_sweep_cols(H *h) {
 int launch_sweep_rows(H *h) {
     const Layout *L = h->L;
     double *tail = h->d_red + tail_off(h);
-    vb::SweepTiledArgs a{L->NG, L->T, L->rows.d_split, L->rows.d_ptr, L->rows.d_idx, L->rows.d_val,
-                         h->d_lw, h->d_lh, h->d_Part2, nullptr, 0};
+    vb::SweepTiledArgs a{L->NG, L->T, L->rows.d_split, L->rows.d_ptr, L->rows.d_ent,
+                         L->rows.d_idx, (const double *)L->rows.d_val, h->d_lw, h->d_lh,
+                         h->d_Part2, nullptr};
     h->tab->sweep(a, false, h->val_float, L->grid, h->smem_bytes, h->stream);
     vb::CombineArgs c{L->NG, L->Sc, h->r, h->d_Part2, h->d_lw, h->d_red, h->d_partC,
                       tail + h->rs + 5, h->d_counters + 3, nullptr, 0, h->gridC};
