@@ -158,6 +158,10 @@ constexpr int kUnroll = 4;  // nonzeros per lane whose index/count loads are in 
 // log m = 2 atanh(t), t = (m-1)/(m+1), |t| <= 0.1716, odd series through t^17 (next term < 3e-16).
 // No special cases (p > 0 finite is guaranteed by the fudge floor), ~20 FP64 + ~8 integer ops
 // against ~90 for the general log().
+static __constant__ double kLogC[10] = {2.0 / 17.0, 2.0 / 15.0, 2.0 / 13.0, 2.0 / 11.0, 2.0 / 9.0,
+                                 2.0 / 7.0,  2.0 / 5.0,  2.0 / 3.0,
+                                 6.93147180369123816490e-01,   // ln2 hi (exact product with e)
+                                 1.90821492927058770002e-10};  // ln2 lo
 __device__ __forceinline__ double fast_log_pos(double p) {
     int hi = __double2hiint(p);
     const int lo = __double2loint(p);
@@ -167,18 +171,16 @@ __device__ __forceinline__ double fast_log_pos(double p) {
     const double m = __hiloint2double(hi, lo);
     const double t = (m - 1.0) * fast_rcp(m + 1.0);
     const double t2 = t * t;
-    double s = 2.0 / 17.0;
-    s = fma(s, t2, 2.0 / 15.0);
-    s = fma(s, t2, 2.0 / 13.0);
-    s = fma(s, t2, 2.0 / 11.0);
-    s = fma(s, t2, 2.0 / 9.0);
-    s = fma(s, t2, 2.0 / 7.0);
-    s = fma(s, t2, 2.0 / 5.0);
-    s = fma(s, t2, 2.0 / 3.0);
-    const double lm = fma(t * t2, s, 2.0 * t);
+    double s = kLogC[0];
+#pragma unroll
+    for (int i = 1; i < 8; i++) s = fma(s, t2, kLogC[i]);
+    const double lm = fma(t * t2, s, t + t);
     const double de = (double)e;
-    // ln 2 split so that e * ln2_hi is exact for |e| < 2^10
-    return fma(de, 6.93147180369123816490e-01, fma(de, 1.90821492927058770002e-10, lm));
+    return fma(de, kLogC[8], fma(de, kLogC[9], lm));
+}
+
+__device__ __forceinline__ void prefetch_l2(const void *p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
 struct SweepTiledArgs {
@@ -244,6 +246,13 @@ sweep_tiled_kernel(const SweepTiledArgs a) {
         for (int64_t e = ebase + gid; e < eend; e += SweepCfg<RP>::kGroups) {
             const int64_t o = e - slab * a.NO;
             const int64_t beg = __ldg(a.ptr + e), end = __ldg(a.ptr + e + 1);
+            // pull the entries of this group's NEXT segment from HBM into L2 while this one runs
+            if (sizeof(VT) == 4 && e + SweepCfg<RP>::kGroups < eend) {
+                const int64_t nb = __ldg(a.ptr + e + SweepCfg<RP>::kGroups);
+                const int64_t ne = __ldg(a.ptr + e + SweepCfg<RP>::kGroups + 1);
+                for (int64_t t = nb + gl * 16; t < ne; t += kGroup * 16)
+                    prefetch_l2(reinterpret_cast<const int2 *>(a.ent) + t);
+            }
             double acc[RP];
 #pragma unroll
             for (int k = 0; k < RP; k++) acc[k] = 0.0;
