@@ -23,6 +23,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+    del os.environ["NCCL_DEBUG"]  # keeps NCCL's banner off stdout (one JSON line is the contract)
 
 WORKLOADS = {
     # name: genes, cells per GPU, true rank, density, seed, fit rank
