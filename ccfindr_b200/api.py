@@ -1,0 +1,409 @@
+"""Host-side mirror of the ccfindR interface for the accelerated path.
+
+The reference's host code is R; R is not installed here, so this mirror is Python with the same
+function names, argument meaning and error behaviour (the R `.Call` shim that binds the same C ABI
+ships as source in r-shim/).  What runs where:
+
+    vb_factorize()   R/bayesian.R:229-301  validation, run/rank loops, best-run selection, slots:
+                                           here;  the it-loop of vb_iterate (:336-352), the update
+                                           (src/vbnmf_update.cpp) and hyper_update (:2-53): in
+                                           libvbnmf.so on the GPU (Engine.run)
+    factorize()      R/factorize.R:139-276 loops and measures here; the it-loop (:189-212) with
+                                           nmf_updateR + likelihood on the GPU (Engine.ml_run)
+    cluster_id()     R/utils.R:903-909     first-maximum argmax per cell (GPU: Engine.cluster_id)
+    optimal_rank()   R/utils2.R:59-95      host post-processing of measure (smoothing spline)
+
+There is no CPU fallback: every factorization needs libvbnmf.so and a CUDA device.
+"""
+import warnings
+
+import numpy as np
+import scipy.sparse as sp
+
+from . import synth
+from ._lib import ERR_HYPER, VbnmfError
+from .engine import EPS, Engine
+
+
+class scNMFSet:
+    """The slots of the reference's scNMFSet that this path reads and fills
+    (R/scNMF_class.R:66-71): counts (genes x cells), ranks, basis, dbasis, coeff, dcoeff, measure."""
+
+    def __init__(self, count=None, rowData=None, colData=None):
+        if count is None:
+            raise ValueError("count matrix required")
+        self.counts = sp.csc_matrix(count, dtype=np.float64)
+        self.counts.sort_indices()
+        self.rowData = list(rowData) if rowData is not None else list(range(1, self.counts.shape[0] + 1))
+        self.colData = list(colData) if colData is not None else list(range(1, self.counts.shape[1] + 1))
+        self.ranks = []
+        self.basis, self.dbasis, self.coeff, self.dcoeff = [], [], [], []
+        self.measure = None  # dict of columns, like the data.frame of R/bayesian.R:297-298
+        self.metadata = {}
+
+    def nrow(self):
+        return self.counts.shape[0]
+
+    def ncol(self):
+        return self.counts.shape[1]
+
+    def __repr__(self):
+        return "scNMFSet(%d genes x %d cells, ranks=%s)" % (self.nrow(), self.ncol(), self.ranks)
+
+
+def _check_no_empty(mat):
+    """R/bayesian.R:242-247, R/factorize.R:147-150."""
+    if int((np.asarray(mat.sum(axis=1)).ravel() == 0).sum()) > 0:
+        raise ValueError("Input matrix contains empty rows")
+    if int((np.asarray(mat.sum(axis=0)).ravel() == 0).sum()) > 0:
+        raise ValueError("Input matrix contains empty columns")
+
+
+def vb_init(nrow, ncol, mat, rank, hyper, initializer, seed):
+    """R/bayesian.R:109-171.  'random' draws from NumPy's Philox stream (R's RNG stream cannot be
+    reproduced without R); 'svd' and 'svd2' follow the reference formulas on a truncated SVD."""
+    if initializer == "random":
+        return synth.random_init(nrow, ncol, rank, hyper, seed)
+    if initializer not in ("svd", "svd2"):
+        raise ValueError("Unknown initializer")
+    from scipy.sparse.linalg import svds
+    if min(nrow, ncol) / 2 <= rank or min(nrow, ncol) - 1 <= rank:
+        u, d, vt = np.linalg.svd(np.asarray(mat.todense()), full_matrices=False)
+        u, d, vt = u[:, :rank], d[:rank], vt[:rank]
+    else:
+        u, d, vt = svds(mat.astype(np.float64), k=rank, random_state=np.random.default_rng(seed))
+        o = np.argsort(-d)
+        u, d, vt = u[:, o], d[o], vt[o]
+    v = vt.T
+    if initializer == "svd2":                                   # :150-159
+        w = np.abs(u)
+        h = np.abs(np.diag(d) @ v.T)
+        scale = hyper["bh"] / h.mean()
+        return w / scale, h * scale
+    w = np.zeros((nrow, rank))                                  # 'svd', :116-149
+    h = np.zeros((rank, ncol))
+    d1 = np.sqrt(d[0])
+    w[:, 0] = d1 * u[:, 0]
+    sgn = np.sign(w[0, 0])
+    if sgn < 0:
+        w = -w
+    h[0, :] = sgn * d1 * v[:, 0]
+    for k in range(1, rank):
+        x, y = u[:, k], v[:, k]
+        xp, yp = np.where(x > 0, x, 0.0), np.where(y > 0, y, 0.0)
+        xn, yn = np.where(x < 0, -x, 0.0), np.where(y < 0, -y, 0.0)
+        xpnrm, ypnrm = np.sqrt((xp ** 2).sum()), np.sqrt((yp ** 2).sum())
+        mp = xpnrm * ypnrm
+        xnnrm, ynnrm = np.sqrt((xp ** 2).sum()), np.sqrt((yp ** 2).sum())  # sic, :136-137 use xp, yp
+        mn = xnnrm * ynnrm
+        if mp >= mn:
+            uu, vv, sig = xp / xpnrm, yp / ypnrm, mp
+        else:
+            uu, vv, sig = xn / xnnrm, yn / ynnrm, mn
+        w[:, k] = np.sqrt(d[k] * sig) * uu
+        h[k, :] = np.sqrt(d[k] * sig) * vv
+    return w, h
+
+
+def dispersion_from_labels(label_runs):
+    """dispersion(conav/irun, ncol) of R/factorize.R:51-67 without the m(m-1)/2 connectivity vector:
+    cells are grouped by their tuple of cluster labels over the runs; two cells are co-clustered in
+    t runs iff their tuples agree in t positions."""
+    L = np.stack([np.asarray(v) for v in label_runs], axis=1)
+    nc, nrun = L.shape
+    tup, cnt = np.unique(L, axis=0, return_counts=True)
+    con = 0.0
+    for a in range(len(tup)):
+        con += cnt[a] * (cnt[a] - 1) / 2 * (1.0 - 0.5) ** 2
+        same = (tup[a + 1:] == tup[a]).sum(axis=1) / nrun
+        con += float((cnt[a] * cnt[a + 1:] * (same - 0.5) ** 2).sum())
+    return 1.0 / nc + 8.0 * con / nc ** 2
+
+
+def vb_factorize(object, ranks=2, nrun=1, verbose=2, progress_bar=True, initializer="random",
+                 Itmax=10000, hyper_update=(True,) * 4, gamma_a=1, gamma_b=1, Tol=1e-5,
+                 hyper_update_n0=10, hyper_update_dn=1, connectivity=True, fudge=None, ncores=1,
+                 useC=True, unif_stop=True, seed=1, device=0, inits=None):
+    """Bayesian NMF inference of a count matrix (R/bayesian.R:229-301).
+
+    Arguments as in the reference (dots replaced by underscores).  Extras: `seed` keys the NumPy
+    Philox streams of the 'random' initializer (run i, rank r uses seed*100003 + 1000*r + i);
+    `inits[(irun, rank)] = (w0, h0)` overrides the draw; `device` is the CUDA ordinal.
+    `ncores` and `useC` are accepted and ignored: the update always runs on the GPU.
+    """
+    if fudge is None:
+        fudge = EPS                                             # :238
+    mat = object.counts                                         # :239
+    if initializer in ("svd", "svd2") and nrun > 1:
+        raise ValueError("SVD initializer does not require nrun > 1")  # :241-242
+    _check_no_empty(mat)                                        # :244-247
+    nrow, ncol = mat.shape
+    ranks = [int(r) for r in np.atleast_1d(ranks) if r <= ncol]  # :249
+    nrank = len(ranks)
+    ga = np.atleast_1d(np.asarray(gamma_a, dtype=np.float64))
+    gb = np.atleast_1d(np.asarray(gamma_b, dtype=np.float64))
+
+    vb = []
+    with Engine(mat, device=device) as eng:
+        for irun in range(1, nrun + 1):                         # lapply over runs, :260-261
+            vb.append(_vb_iterate(eng, irun, mat, ranks, ga, gb, initializer, Itmax, hyper_update,
+                                  Tol, hyper_update_n0, hyper_update_dn, connectivity, fudge,
+                                  unif_stop, nrun, verbose, seed, inits, vb))
+
+    basis = [None] * nrank
+    coeff, dbasis, dcoeff = [None] * nrank, [None] * nrank, [None] * nrank
+    cols = {k: [] for k in ("rank", "lml", "aw", "bw", "ah", "bh", "nunif")}
+    for k in range(nrank):                                      # :268-292
+        rmax, imax = -np.inf, None
+        for i in range(nrun):
+            if vb[i]["rdat"][k] > rmax:                         # strict >: the first of equals wins
+                imax, rmax = i, vb[i]["rdat"][k]
+        if rmax == -np.inf:
+            continue
+        cols["rank"].append(ranks[k]); cols["lml"].append(rmax)
+        basis[k], coeff[k] = vb[imax]["wdat"][k], vb[imax]["hdat"][k]
+        dbasis[k], dcoeff[k] = vb[imax]["dwdat"][k], vb[imax]["dhdat"][k]
+        for key in ("aw", "bw", "ah", "bh"):
+            cols[key].append(vb[imax]["hyperp"][k][key])
+        cols["nunif"].append(vb[imax]["nunif"][k])
+    object.ranks = cols["rank"]                                 # :293-299
+    object.basis, object.dbasis = basis, dbasis
+    object.coeff, object.dcoeff = coeff, dcoeff
+    object.measure = {k: np.array(v) for k, v in cols.items()}
+    return object
+
+
+def _vb_iterate(eng, irun, mat, ranks, ga, gb, initializer, Itmax, hyper_update, Tol, n0, dn,
+                connectivity, fudge, unif_stop, nrun, verbose, seed, inits, previous):
+    """R/bayesian.R:303-390 for one run; the it-loop runs on the GPU."""
+    nrow, ncol = mat.shape
+    nrank = len(ranks)
+    out = dict(rdat=[-np.inf] * nrank, wdat=[None] * nrank, hdat=[None] * nrank,
+               dwdat=[None] * nrank, dhdat=[None] * nrank, hyperp=[None] * nrank,
+               nunif=[0] * nrank, labels=[None] * nrank, niter=[0] * nrank)
+    if verbose >= 2 and nrun > 1:
+        print("Run %d" % irun)
+    for irank, rank in enumerate(ranks):
+        if rank > min(nrow, ncol):
+            raise ValueError("Rank exceeded min(nrow,ncol)")    # :319-320
+        hyper = dict(aw=float(ga[0]), ah=float(ga[-1]), bw=float(gb[0]), bh=float(gb[-1]))  # :321-326
+        if inits is not None and (irun, rank) in inits:
+            w0, h0 = inits[(irun, rank)]
+        else:
+            w0, h0 = vb_init(nrow, ncol, mat, rank, hyper, initializer,
+                             seed * 100003 + 1000 * rank + irun)
+        eng.set_state(w0, h0)                                   # lw = ew = w, lh = eh = h (:170)
+        try:
+            res = eng.run(hyper, Itmax=Itmax, Tol=Tol, hyper_update=hyper_update, n0=n0, dn=dn,
+                          fudge=fudge)
+        except VbnmfError as e:
+            if e.code == ERR_HYPER:
+                raise RuntimeError("Hyper-parameter update failed to converge") from e  # :43
+            raise
+        hyper, lk0, it = res["hyper"], res["lml"], res["niter"]
+        if verbose >= 3:
+            for i in range(it):
+                hv = res["hyper_trace"][i]
+                print("%d, log(evidence) = %s, aw = %s, bw = %s, ah = %s, bh = %s"
+                      % (i + 1, res["lkh_trace"][i], hv[0], hv[1], hv[2], hv[3]))
+        disp = None
+        if connectivity:                                        # :353-357 (only printed)
+            out["labels"][irank] = eng.cluster_id()
+            runs = [p["labels"][irank] for p in previous if p["labels"][irank] is not None]
+            disp = dispersion_from_labels(runs + [out["labels"][irank]]) if ncol <= 200000 else np.nan
+        if verbose >= 2:
+            msg = "Rank = %d: Nsteps = %d, log(evidence) = %s, hyper = (%s,%s,%s,%s)" % (
+                rank, it, lk0, hyper["aw"], hyper["bw"], hyper["ah"], hyper["bh"])
+            print(msg + (", dispersion = %s" % disp if connectivity else ""))
+        unif = eng.uniform_columns(Tol)                         # :368-369
+        if unif.sum() > 0:
+            warnings.warn("Rank %d row/column %s constant." % (
+                rank, ",".join(str(i + 1) for i in np.flatnonzero(unif))))
+            if unif_stop:
+                warnings.warn("Rank scan stopped for rank >= %d" % rank)
+                if irank == 0:
+                    raise RuntimeError("Rerun with lower ranks")  # :375
+                break
+        st = eng.get_state(("ew", "eh", "dw", "dh"))
+        out["rdat"][irank] = lk0                                # :379-384
+        out["wdat"][irank], out["hdat"][irank] = st["ew"], st["eh"]
+        out["dwdat"][irank], out["dhdat"][irank] = np.sqrt(st["dw"]), np.sqrt(st["dh"])
+        out["hyperp"][irank] = hyper
+        out["niter"][irank] = it
+    return out
+
+
+def factorize(object, ranks=2, nrun=20, randomize=False, nsmpl=1, verbose=2, progress_bar=True,
+              Itmax=10000, ncnn_step=40, criterion="likelihood", linkage="average", Tol=1e-5,
+              store_connectivity=False, seed=1, device=0):
+    """Maximum likelihood factorization (R/factorize.R:139-276); the it-loop (:189-212) runs on the
+    GPU.  criterion='connectivity' (:194-206) needs the cluster labels of every iteration and is not
+    offered by the device loop."""
+    if criterion != "likelihood":
+        if criterion == "connectivity":
+            raise NotImplementedError("criterion='connectivity' is not available on the GPU path")
+        raise ValueError("Unknown stopping criterion.")
+    mat0 = object.counts
+    _check_no_empty(mat0)
+    nrow, ncol = mat0.shape
+    ranks = [int(r) for r in np.atleast_1d(ranks)]
+    nrank = len(ranks)
+    wdat, hdat = [None] * nrank, [None] * nrank
+    rave, dave, coav = np.zeros(nrank), np.zeros(nrank), np.zeros(nrank)
+    rste, dste, cste = np.full(nrank, np.nan), np.full(nrank, np.nan), np.full(nrank, np.nan)
+    g = np.random.Generator(np.random.Philox(key=[int(seed), 77]))
+    eng = Engine(mat0, device=device)
+    labels_last = None
+    try:
+        for irank, rank in enumerate(ranks):
+            if verbose > 0:
+                print("Rank %d" % rank)
+            rdat, ddat, cdat = [], [], []
+            for ismpl in range(1, nsmpl + 1):
+                mat = mat0
+                if randomize:                                    # :172-173 column-wise shuffle
+                    dense = np.asarray(mat0.todense())
+                    for j in range(ncol):
+                        dense[:, j] = g.permutation(dense[:, j])
+                    mat = sp.csc_matrix(dense)
+                    eng.close()
+                    eng = Engine(mat, device=device)
+                rmax, labels = -np.inf, []
+                for irun in range(1, nrun + 1):
+                    w0, h0 = synth.uniform_init(nrow, ncol, rank,
+                                                seed * 100003 + 1000 * rank + 37 * ismpl + irun)
+                    res = eng.ml_run(w0, h0, Itmax=Itmax, Tol=Tol)
+                    lk0 = res["lik"]
+                    labels.append(np.argmax(res["h"], axis=0) + 1)  # connectivity(), :51-60
+                    disp = dispersion_from_labels(labels)
+                    if verbose >= 2:
+                        print("Nsteps = %d , likelihood = %s , dispersion = %s\n" % (
+                            res["niter"], lk0, disp))
+                    if (irun == 1 or lk0 > rmax) and not np.isnan(lk0):  # :219-223
+                        rmax, wmax, hmax = lk0, res["w"], res["h"]
+                coph = _cophenet(labels, ncol, linkage)
+                labels_last = labels
+                if verbose >= 1:
+                    print("Sample# %d : Max(likelihood) = %s , dispersion = %s , cophenetic = %s"
+                          % (ismpl, rmax, disp, coph))
+                if ismpl == 1:
+                    wdat[irank], hdat[irank] = wmax.copy(), hmax.copy()
+                else:
+                    wdat[irank] += wmax
+                    hdat[irank] += hmax
+                rdat.append(rmax); ddat.append(disp); cdat.append(coph)
+            wdat[irank] /= nsmpl
+            hdat[irank] /= nsmpl
+            if nsmpl > 1:
+                den = np.sqrt(nsmpl - 1)
+                rste[irank] = np.std(rdat, ddof=1) / den
+                dste[irank] = np.std(ddat, ddof=1) / den
+                cste[irank] = np.std(cdat, ddof=1) / den
+            rave[irank], dave[irank], coav[irank] = np.mean(rdat), np.mean(ddat), np.mean(cdat)
+    finally:
+        eng.close()
+    object.ranks = ranks
+    object.basis, object.coeff = wdat, hdat
+    if randomize:
+        object.measure = dict(rank=np.array(ranks), likelihood=rave, r_se=rste, dispersion=dave,
+                              d_se=dste, cophenetic=coav, c_se=cste)
+    else:
+        object.measure = dict(rank=np.array(ranks), likelihood=rave, dispersion=dave,
+                              cophenetic=coav)
+    if store_connectivity:
+        object.metadata = dict(nrun=nrun, labels=labels_last)
+    return object
+
+
+def _cophenet(labels, nc, method="average"):
+    """cophenet(conav/nrun, ncol) of R/factorize.R:69-78.  Needs the nc x nc distance matrix, so it
+    is only evaluated for nc <= 5000 (the reference itself cannot go further)."""
+    if nc > 5000 or nc < 3:
+        return np.nan
+    from scipy.cluster.hierarchy import cophenet, linkage
+    from scipy.spatial.distance import squareform
+    L = np.stack(labels, axis=1)
+    con = np.zeros((nc, nc))
+    for t in range(L.shape[1]):
+        con += (L[:, t][:, None] == L[:, t][None, :])
+    d = squareform(1.0 - con / L.shape[1], checks=False)
+    if np.all(d == d[0]):
+        return np.nan
+    z = linkage(d, method=method)
+    return float(np.corrcoef(d, cophenet(z))[0, 1])
+
+
+def cluster_id(object, rank=2):
+    """R/utils.R:903-909: apply(h, 2, which.max) on coeff for `rank` (1-based, first maximum)."""
+    k = list(object.ranks).index(rank)
+    return np.argmax(np.asarray(object.coeff[k]), axis=0).astype(np.int32) + 1
+
+
+# ---- optimal_rank (R/utils2.R:59-111), host post-processing of ~30 numbers ----------------------
+def _smooth_spline(x, y, df):
+    """Natural cubic smoothing spline through (x, y) with `df` effective degrees of freedom
+    (what stats::smooth.spline(x, y, df=df) fits when every x is a knot).  Returns fitted y."""
+    x = np.asarray(x, float)
+    y = np.asarray(y, float)
+    n = len(x)
+    if df >= n - 1e-9 or n < 4:
+        return y.copy()
+    hk = np.diff(x)
+    Q = np.zeros((n, n - 2))
+    R = np.zeros((n - 2, n - 2))
+    for j in range(n - 2):
+        Q[j, j], Q[j + 1, j], Q[j + 2, j] = 1 / hk[j], -1 / hk[j] - 1 / hk[j + 1], 1 / hk[j + 1]
+        R[j, j] = (hk[j] + hk[j + 1]) / 3
+        if j + 1 < n - 2:
+            R[j, j + 1] = R[j + 1, j] = hk[j + 1] / 6
+    K = Q @ np.linalg.solve(R, Q.T)
+    ev, V = np.linalg.eigh(0.5 * (K + K.T))
+    ev = np.clip(ev, 0, None)
+    ev[:2] = 0.0  # the two zero eigenvalues: linear functions are not penalised
+    lo, hi = -40.0, 40.0
+    for _ in range(200):
+        mid = 0.5 * (lo + hi)
+        if (1.0 / (1.0 + np.exp(mid) * ev)).sum() > df:
+            lo = mid
+        else:
+            hi = mid
+    lam = np.exp(0.5 * (lo + hi))
+    return V @ ((V.T @ y) / (1.0 + lam * ev))
+
+
+def _slope(y, x):
+    """R/utils2.R:97-111."""
+    n = len(x)
+    s = np.zeros(n)
+    s[0] = (y[1] - y[0]) / (x[1] - x[0])
+    for i in range(1, n - 1):
+        s[i] = (y[i + 1] - y[i]) / (x[i + 1] - x[i])
+    s[n - 1] = s[n - 2]
+    return s
+
+
+def optimal_rank(object, df=10, BF_threshold=3, type=None, m=None):
+    """R/utils2.R:59-95.  object: scNMFSet after vb_factorize, or a dict with 'rank' and 'lml'."""
+    if isinstance(object, scNMFSet):
+        me_x, me_y = np.asarray(object.measure["rank"], float), np.asarray(object.measure["lml"])
+        m = object.nrow()
+    elif isinstance(object, dict):
+        me_x, me_y = np.asarray(object["rank"], float), np.asarray(object["lml"], float)
+        if m is None:
+            raise ValueError("No. of rows unknown")
+    else:
+        raise TypeError("Inappropriate class of object")
+    o = np.argsort(me_x)
+    fx, fy = me_x[o], _smooth_spline(me_x[o], me_y[o], min(df, len(me_x)))
+    rst = fx[int(np.argmax(fy))]
+    bf = np.log(BF_threshold) / m
+    if type is None:
+        rng = fx[np.abs(fy - fy.max()) <= bf]
+        type = 2 if me_x.max() in rng else 1
+    if type == 1:
+        ropt = rst
+    else:
+        sl = _slope(fy, fx)
+        idx = int(np.flatnonzero(sl < bf)[0]) if (sl < bf).sum() > 0 else len(fx) - 1
+        ropt = fx[idx]
+    return dict(type=int(type), ropt=float(ropt))

@@ -1,0 +1,169 @@
+/* R .Call shim over libvbnmf (include/vbnmf.h).  SOURCE ONLY: R is not installed in the build
+ * environment of this repository, so this file has not been compiled there; it uses nothing beyond
+ * the documented R C API (Rinternals.h, R_ext/Rdynload.h).
+ *
+ * It replaces, in ccfindR, the generated glue src/RcppExports.cpp:11-32 (one .Call per ITERATION,
+ * `_ccfindR_vbnmf_update`) by one .Call per RUN of iterations on a device-resident handle.
+ * Build inside an R package:  PKG_LIBS = -L<dir of libvbnmf.so> -lvbnmf ; PKG_CPPFLAGS = -I<repo>/include
+ */
+#include <R.h>
+#include <Rinternals.h>
+#include <R_ext/Rdynload.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "vbnmf.h"
+
+static void chk(int rc, vbnmf_handle *h) {
+    if (rc != 0) Rf_error("libvbnmf: %s", vbnmf_last_error(h)); /* like END_RCPP, RcppExports.cpp:21 */
+}
+
+static void handle_finalizer(SEXP ptr) {
+    vbnmf_handle *h = (vbnmf_handle *)R_ExternalPtrAddr(ptr);
+    if (h) vbnmf_destroy(h);
+    R_ClearExternalPtr(ptr);
+}
+
+static vbnmf_handle *get_handle(SEXP ptr) {
+    vbnmf_handle *h = (vbnmf_handle *)R_ExternalPtrAddr(ptr);
+    if (!h) Rf_error("libvbnmf: handle has been released");
+    return h;
+}
+
+/* dgCMatrix slots: p = @p (int, m+1), i = @i (int, 0-based), x = @x (double), dim = @Dim */
+SEXP C_vbnmf_create(SEXP p, SEXP i, SEXP x, SEXP dim, SEXP device) {
+    vbnmf_handle *h = NULL;
+    const int n = INTEGER(dim)[0], m = INTEGER(dim)[1];
+    const int64_t nnz = (int64_t)XLENGTH(x);
+    int rc = vbnmf_create(&h, n, m, nnz, INTEGER(p), NULL, INTEGER(i), REAL(x), Rf_asInteger(device));
+    if (rc != 0) Rf_error("libvbnmf: %s", vbnmf_last_error(NULL));
+    SEXP ptr = PROTECT(R_MakeExternalPtr(h, R_NilValue, R_NilValue));
+    R_RegisterCFinalizerEx(ptr, handle_finalizer, TRUE);
+    UNPROTECT(1);
+    return ptr;
+}
+
+SEXP C_vbnmf_destroy(SEXP ptr) {
+    handle_finalizer(ptr);
+    return R_NilValue;
+}
+
+/* wh list fields lw, lh, ew, eh as numeric matrices (column-major, as R stores them) */
+SEXP C_vbnmf_set_state(SEXP ptr, SEXP lw, SEXP lh, SEXP ew, SEXP eh) {
+    vbnmf_handle *h = get_handle(ptr);
+    const int r = Rf_ncols(lw);
+    chk(vbnmf_set_state(h, r, REAL(lw), REAL(lh), Rf_isNull(ew) ? NULL : REAL(ew),
+                        Rf_isNull(eh) ? NULL : REAL(eh)), h);
+    return R_NilValue;
+}
+
+/* one vbnmf_update (src/vbnmf_update.cpp:16-102); hyper = c(aw, bw, ah, bh) */
+SEXP C_vbnmf_step(SEXP ptr, SEXP hyper, SEXP fudge) {
+    vbnmf_handle *h = get_handle(ptr);
+    double lkh = NA_REAL;
+    chk(vbnmf_step(h, REAL(hyper), Rf_asReal(fudge), &lkh), h);
+    return Rf_ScalarReal(lkh);
+}
+
+/* the it-loop of vb_iterate (R/bayesian.R:336-352) */
+SEXP C_vbnmf_run(SEXP ptr, SEXP hyper, SEXP itmax, SEXP tol, SEXP hyper_update, SEXP n0, SEXP dn,
+                 SEXP fudge) {
+    vbnmf_handle *h = get_handle(ptr);
+    vbnmf_cfg cfg;
+    cfg.itmax = Rf_asInteger(itmax);
+    cfg.tol = Rf_asReal(tol);
+    for (int k = 0; k < 4; k++) cfg.hyper_update[k] = LOGICAL(hyper_update)[k] ? 1 : 0;
+    cfg.n0 = Rf_asInteger(n0);
+    cfg.dn = Rf_asInteger(dn);
+    cfg.fudge = Rf_asReal(fudge);
+    SEXP hy = PROTECT(Rf_duplicate(hyper));
+    SEXP trace = PROTECT(Rf_allocVector(REALSXP, cfg.itmax));
+    int niter = 0, reason = 0;
+    double lml = 0.0;
+    chk(vbnmf_run(h, &cfg, REAL(hy), REAL(trace), NULL, &niter, &lml, &reason), h);
+    const char *names[] = {"hyper", "lml", "niter", "stop_reason", "lkh_trace", ""};
+    SEXP out = PROTECT(Rf_mkNamed(VECSXP, names));
+    SET_VECTOR_ELT(out, 0, hy);
+    SET_VECTOR_ELT(out, 1, Rf_ScalarReal(lml));
+    SET_VECTOR_ELT(out, 2, Rf_ScalarInteger(niter));
+    SET_VECTOR_ELT(out, 3, Rf_ScalarInteger(reason));
+    SET_VECTOR_ELT(out, 4, Rf_lengthgets(trace, niter));
+    UNPROTECT(3);
+    return out;
+}
+
+/* list(lw, lh, ew, eh, dw, dh) with the shapes of src/vbnmf_update.cpp:92-100 */
+SEXP C_vbnmf_get_state(SEXP ptr, SEXP dims) {
+    vbnmf_handle *h = get_handle(ptr);
+    int64_t info[8];
+    chk(vbnmf_info(h, info), h);
+    const int n = (int)info[0], m = (int)info[1], r = (int)info[3];
+    (void)dims;
+    const char *names[] = {"lw", "lh", "ew", "eh", "dw", "dh", ""};
+    SEXP out = PROTECT(Rf_mkNamed(VECSXP, names));
+    for (int k = 0; k < 6; k++) {
+        const int wside = (k % 2 == 0);
+        SET_VECTOR_ELT(out, k, Rf_allocMatrix(REALSXP, wside ? n : r, wside ? r : m));
+    }
+    chk(vbnmf_get_state(h, REAL(VECTOR_ELT(out, 0)), REAL(VECTOR_ELT(out, 1)),
+                        REAL(VECTOR_ELT(out, 2)), REAL(VECTOR_ELT(out, 3)),
+                        REAL(VECTOR_ELT(out, 4)), REAL(VECTOR_ELT(out, 5))), h);
+    UNPROTECT(1);
+    return out;
+}
+
+SEXP C_vbnmf_uniform_columns(SEXP ptr, SEXP tol) {
+    vbnmf_handle *h = get_handle(ptr);
+    int64_t info[8];
+    chk(vbnmf_info(h, info), h);
+    SEXP out = PROTECT(Rf_allocVector(LGLSXP, (R_xlen_t)info[3]));
+    chk(vbnmf_uniform_columns(h, Rf_asReal(tol), (int32_t *)LOGICAL(out)), h);
+    UNPROTECT(1);
+    return out;
+}
+
+SEXP C_vbnmf_cluster_id(SEXP ptr) {
+    vbnmf_handle *h = get_handle(ptr);
+    int64_t info[8];
+    chk(vbnmf_info(h, info), h);
+    SEXP out = PROTECT(Rf_allocVector(INTSXP, (R_xlen_t)info[1]));
+    chk(vbnmf_cluster_id(h, (int32_t *)INTEGER(out)), h);
+    UNPROTECT(1);
+    return out;
+}
+
+/* it-loop of factorize(), criterion = 'likelihood' (R/factorize.R:189-212) */
+SEXP C_mlnmf_run(SEXP ptr, SEXP w0, SEXP h0, SEXP itmax, SEXP tol) {
+    vbnmf_handle *h = get_handle(ptr);
+    const int n = Rf_nrows(w0), r = Rf_ncols(w0), m = Rf_ncols(h0), it = Rf_asInteger(itmax);
+    const char *names[] = {"ew", "eh", "lik_trace", "niter", ""};
+    SEXP out = PROTECT(Rf_mkNamed(VECSXP, names));
+    SET_VECTOR_ELT(out, 0, Rf_allocMatrix(REALSXP, n, r));
+    SET_VECTOR_ELT(out, 1, Rf_allocMatrix(REALSXP, r, m));
+    SEXP trace = PROTECT(Rf_allocVector(REALSXP, it));
+    int niter = 0;
+    chk(mlnmf_run(h, r, REAL(w0), REAL(h0), it, Rf_asReal(tol), REAL(VECTOR_ELT(out, 0)),
+                  REAL(VECTOR_ELT(out, 1)), REAL(trace), &niter), h);
+    SET_VECTOR_ELT(out, 2, Rf_lengthgets(trace, niter));
+    SET_VECTOR_ELT(out, 3, Rf_ScalarInteger(niter));
+    UNPROTECT(2);
+    return out;
+}
+
+static const R_CallMethodDef CallEntries[] = {
+    {"C_vbnmf_create", (DL_FUNC)&C_vbnmf_create, 5},
+    {"C_vbnmf_destroy", (DL_FUNC)&C_vbnmf_destroy, 1},
+    {"C_vbnmf_set_state", (DL_FUNC)&C_vbnmf_set_state, 5},
+    {"C_vbnmf_step", (DL_FUNC)&C_vbnmf_step, 3},
+    {"C_vbnmf_run", (DL_FUNC)&C_vbnmf_run, 8},
+    {"C_vbnmf_get_state", (DL_FUNC)&C_vbnmf_get_state, 2},
+    {"C_vbnmf_uniform_columns", (DL_FUNC)&C_vbnmf_uniform_columns, 2},
+    {"C_vbnmf_cluster_id", (DL_FUNC)&C_vbnmf_cluster_id, 1},
+    {"C_mlnmf_run", (DL_FUNC)&C_mlnmf_run, 5},
+    {NULL, NULL, 0}};
+
+/* mirrors R_init_ccfindR, src/RcppExports.cpp:29-32 */
+void R_init_ccfindRgpu(DllInfo *dll) {
+    R_registerRoutines(dll, NULL, CallEntries, NULL, NULL);
+    R_useDynamicSymbols(dll, FALSE);
+}

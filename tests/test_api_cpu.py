@@ -1,0 +1,79 @@
+"""CPU tests of the host-side front end (no GPU): argument validation, the label-tuple form of the
+dispersion measure against the reference's pairwise definition (R/factorize.R:51-67), and
+optimal_rank (R/utils2.R:59-111)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from ccfindr_b200 import api
+
+
+def _dispersion_pairwise(label_runs):
+    """connectivity() + dispersion() exactly as R/factorize.R:51-67 (O(m^2))."""
+    nc = len(label_runs[0])
+    conav = np.zeros(nc * (nc - 1) // 2)
+    iu = np.triu_indices(nc, 1)
+    for cid in label_runs:
+        cid = np.asarray(cid)
+        conav += (cid[:, None] == cid[None, :])[iu]
+    cnn = conav / len(label_runs)
+    return 1.0 / nc + 8.0 * np.sum((cnn - 0.5) ** 2) / nc ** 2
+
+
+def test_dispersion_from_labels_equals_pairwise_definition():
+    rng = np.random.default_rng(0)
+    for nrun in (1, 2, 5):
+        runs = [rng.integers(1, 5, size=60) for _ in range(nrun)]
+        assert abs(api.dispersion_from_labels(runs) - _dispersion_pairwise(runs)) < 1e-12
+    same = [np.repeat([1, 2, 3], 20)] * 4
+    assert abs(api.dispersion_from_labels(same) - _dispersion_pairwise(same)) < 1e-12
+
+
+def test_empty_rows_and_columns_are_rejected():
+    x = np.ones((4, 5)); x[2] = 0
+    with pytest.raises(ValueError, match="empty rows"):
+        api._check_no_empty(sp.csc_matrix(x))
+    x = np.ones((4, 5)); x[:, 1] = 0
+    with pytest.raises(ValueError, match="empty columns"):
+        api._check_no_empty(sp.csc_matrix(x))
+
+
+def test_svd_initializer_with_several_runs_is_an_error():
+    s = api.scNMFSet(np.ones((6, 5)))
+    with pytest.raises(ValueError, match="SVD initializer"):
+        api.vb_factorize(s, ranks=2, nrun=2, initializer="svd2")
+
+
+def test_vb_init_shapes_and_positivity():
+    rng = np.random.default_rng(1)
+    mat = sp.csc_matrix(rng.poisson(2.0, size=(40, 30)).astype(float))
+    hyper = dict(aw=1.0, bw=1.0, ah=1.0, bh=1.0)
+    for init in ("random", "svd", "svd2"):
+        w, h = api.vb_init(40, 30, mat, 3, hyper, init, seed=3)
+        assert w.shape == (40, 3) and h.shape == (3, 30)
+        assert np.isfinite(w).all() and np.isfinite(h).all() and (w >= 0).all() and (h >= 0).all()
+    w, h = api.vb_init(40, 30, mat, 3, hyper, "svd2", seed=3)
+    assert abs(h.mean() - hyper["bh"]) < 1e-12   # scale <- bh/mean(h), R/bayesian.R:156-158
+
+
+def test_smooth_spline_limits():
+    x = np.arange(2, 12, dtype=float)
+    y = np.sin(x / 3.0) + 0.05 * np.cos(7 * x)
+    assert np.allclose(api._smooth_spline(x, y, len(x)), y)          # df = n interpolates
+    lin = api._smooth_spline(x, y, 2.0)                               # df = 2 is the LS line
+    a, b = np.polyfit(x, y, 1)
+    assert np.allclose(lin, a * x + b, atol=1e-6)
+    mid = api._smooth_spline(x, y, 5.0)
+    assert np.sum((mid - y) ** 2) < np.sum((lin - y) ** 2)
+
+
+def test_optimal_rank_types():
+    ranks = np.arange(2, 11)
+    peak = -0.7 - 0.01 * (ranks - 5.0) ** 2                          # clear maximum at 5 -> type 1
+    out = api.optimal_rank(dict(rank=ranks, lml=peak), m=1000)
+    assert out["type"] == 1 and out["ropt"] == 5.0
+    plateau = -0.7 - 0.05 * np.exp(-(ranks - 2.0))                   # saturating -> type 2
+    out = api.optimal_rank(dict(rank=ranks, lml=plateau), m=1000)
+    assert out["type"] == 2 and 3.0 <= out["ropt"] <= 10.0
+    with pytest.raises(ValueError):
+        api.optimal_rank(dict(rank=ranks, lml=peak))

@@ -1,0 +1,63 @@
+"""GPU tests of the ccfindR-style front end against the oracle's restatement of the R driver
+(vb_iterate + best-run selection, R/bayesian.R:265-390; factorize loop, R/factorize.R:187-223)."""
+import numpy as np
+import pytest
+
+from conftest import load_counts, relerr
+
+pytestmark = pytest.mark.gpu
+
+
+def test_vb_factorize_matches_reference_driver():
+    from ccfindr_b200 import api, synth
+    from oracle import bindings as ob
+    from oracle import oracle_dense as od
+    X = load_counts("c1s3")
+    n, m = X.shape
+    ranks, nrun = [2, 3, 4], 2
+    kw = dict(Itmax=60, Tol=1e-5)
+    hyper0 = dict(aw=1.0, bw=1.0, ah=1.0, bh=1.0)
+    inits = {(i, r): synth.random_init(n, m, r, hyper0, 100 * i + r)
+             for i in range(1, nrun + 1) for r in ranks}
+    s = api.vb_factorize(api.scNMFSet(X), ranks=ranks, nrun=nrun, verbose=0, inits=inits, **kw)
+    # reference driver: per run, per rank the loop of vb_iterate; then best run per rank
+    runs = []
+    for i in range(1, nrun + 1):
+        out = dict(rdat=[], wdat=[], hdat=[], dwdat=[], dhdat=[], hyperp=[], nunif=[])
+        for r in ranks:
+            res = ob.sparse_vb_run(X, *inits[(i, r)], hyper0, **kw)
+            out["rdat"].append(res["lml"]); out["wdat"].append(res["ew"]); out["hdat"].append(res["eh"])
+            out["dwdat"].append(np.sqrt(res["dw"])); out["dhdat"].append(np.sqrt(res["dh"]))
+            out["hyperp"].append(res["hyper"]); out["nunif"].append(0)
+        runs.append(out)
+    ref = od.vb_select(runs, ranks)
+    assert list(s.ranks) == ref["ranks"]
+    assert relerr(s.measure["lml"], ref["lml"]) < 1e-9
+    for key in ("aw", "bw", "ah", "bh"):
+        assert relerr(s.measure[key], ref[key]) < 1e-9
+    for k in range(len(ranks)):
+        assert relerr(s.basis[k], ref["basis"][k]) < 1e-9
+        assert relerr(s.coeff[k], ref["coeff"][k]) < 1e-9
+        assert relerr(s.dbasis[k], ref["dbasis"][k]) < 1e-9
+        assert relerr(s.dcoeff[k], ref["dcoeff"][k]) < 1e-9
+        assert np.array_equal(api.cluster_id(s, ranks[k]), od.cluster_id(ref["coeff"][k]))
+    out = api.optimal_rank(s)
+    assert out["type"] in (1, 2) and out["ropt"] in ranks
+
+
+def test_factorize_ml_matches_reference_loop():
+    from ccfindr_b200 import api, synth
+    from oracle import bindings as ob
+    X = load_counts("tiny")
+    n, m = X.shape
+    s = api.factorize(api.scNMFSet(X), ranks=[2, 3], nrun=3, verbose=0, Itmax=200, Tol=1e-6, seed=2)
+    for k, r in enumerate([2, 3]):
+        best = -np.inf
+        for irun in range(1, 4):
+            w0, h0 = synth.uniform_init(n, m, r, 2 * 100003 + 1000 * r + 37 + irun)
+            res = ob.sparse_ml_run(X, w0, h0, Itmax=200, Tol=1e-6)
+            if irun == 1 or res["lik"] > best:
+                best, wb, hb = res["lik"], res["w"], res["h"]
+        assert relerr(s.measure["likelihood"][k], best) < 1e-9
+        assert relerr(s.basis[k], wb) < 1e-8 and relerr(s.coeff[k], hb) < 1e-8
+    assert np.isfinite(s.measure["dispersion"]).all()
