@@ -179,6 +179,14 @@ __device__ __forceinline__ double fast_log_pos(double p) {
     return fma(de, kLogC[8], fma(de, kLogC[9], lm));
 }
 
+// 128-bit shared load from a 32-bit shared-window address (keeps the tile base in one register
+// instead of re-deriving it from the generic pointer at every gather)
+__device__ __forceinline__ double2 lds128(uint32_t addr) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+
 __device__ __forceinline__ void prefetch_l2(const void *p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
@@ -221,6 +229,7 @@ sweep_tiled_kernel(const SweepTiledArgs a) {
     constexpr int U = kUnroll;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *tile = reinterpret_cast<double *>(smem_raw);
+    const uint32_t tile_s = smem_u32(tile);
     __shared__ __align__(8) uint64_t mbar;
     __shared__ double red[NT / 32];
     const int gid = threadIdx.x / kGroup, gl = threadIdx.x % kGroup;
@@ -260,47 +269,47 @@ sweep_tiled_kernel(const SweepTiledArgs a) {
                 double own[RP];
                 load_row_d<RP>(a.owner, o, own);
                 // software pipeline: the U index/count loads of the next chunk are issued before
-                // the current chunk is processed (a zero count makes a slot a no-op)
+                // the current chunk is processed.  Slots past the end of the segment carry a zero
+                // count and tile row 0: they run through the same arithmetic and add nothing, so
+                // the U chains of a chunk are branch-free and can be interleaved by the scheduler.
+                const int len = (int)(end - beg);
                 int32_t ti[U], tn[U];
                 double xv[U], xn[U];
 #pragma unroll
                 for (int u = 0; u < U; u++) {
-                    const int64_t t = beg + gl + u * kGroup;
+                    const int t = gl + u * kGroup;
                     ti[u] = 0; xv[u] = 0.0;
-                    if (t < end) load_entry<VT>(a, t, ti[u], xv[u]);
+                    if (t < len) load_entry<VT>(a, beg + t, ti[u], xv[u]);
                 }
-                for (int64_t c = beg; c < end; c += U * kGroup) {
+                for (int c = 0; c < len; c += U * kGroup) {
 #pragma unroll
                     for (int u = 0; u < U; u++) {
-                        const int64_t t = c + U * kGroup + gl + u * kGroup;
+                        const int t = c + U * kGroup + gl + u * kGroup;
                         tn[u] = 0; xn[u] = 0.0;
-                        if (t < end) load_entry<VT>(a, t, tn[u], xn[u]);
+                        if (t < len) load_entry<VT>(a, beg + t, tn[u], xn[u]);
                     }
 #pragma unroll
                     for (int u = 0; u < U; u++) {
-                        if (c + gl + u * kGroup < end) {
-                            const double x = xv[u];
-                            const double2 *rowp =
-                                reinterpret_cast<const double2 *>(tile + (int64_t)ti[u] * RS);
-                            double tr[RP];
+                        const double x = xv[u];
+                        const uint32_t raddr = tile_s + (uint32_t)ti[u] * (RS * 8);
+                        double tr[RP];
 #pragma unroll
-                            for (int k = 0; k < RP / 2; k++) {
-                                const double2 v = rowp[k];
-                                tr[2 * k] = v.x;
-                                tr[2 * k + 1] = v.y;
-                            }
-                            double p0 = 0.0, p1 = 0.0;
-#pragma unroll
-                            for (int k = 0; k < RP; k += 2) {
-                                p0 = fma(own[k], tr[k], p0);
-                                p1 = fma(own[k + 1], tr[k + 1], p1);
-                            }
-                            const double p = p0 + p1;
-                            const double q = x * fast_rcp(p);
-#pragma unroll
-                            for (int k = 0; k < RP; k++) acc[k] = fma(tr[k], q, acc[k]);
-                            if (COLS) xl = fma(x, fast_log_pos(p), xl);
+                        for (int k = 0; k < RP / 2; k++) {
+                            const double2 v = lds128(raddr + k * 16);
+                            tr[2 * k] = v.x;
+                            tr[2 * k + 1] = v.y;
                         }
+                        double p0 = 0.0, p1 = 0.0;
+#pragma unroll
+                        for (int k = 0; k < RP; k += 2) {
+                            p0 = fma(own[k], tr[k], p0);
+                            p1 = fma(own[k + 1], tr[k + 1], p1);
+                        }
+                        const double p = p0 + p1;
+                        const double q = x * fast_rcp(p);
+#pragma unroll
+                        for (int k = 0; k < RP; k++) acc[k] = fma(tr[k], q, acc[k]);
+                        if (COLS) xl = fma(x, fast_log_pos(p), xl);
                     }
 #pragma unroll
                     for (int u = 0; u < U; u++) { ti[u] = tn[u]; xv[u] = xn[u]; }
