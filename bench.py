@@ -36,6 +36,7 @@ WORKLOADS = {
                   label="small: plumbing check, 2k genes x 8k cells per GPU"),
 }
 HYPER = dict(aw=1.0, bw=1.0, ah=1.0, bh=1.0)  # gamma.a = gamma.b = 1 (R/bayesian.R:231)
+MIXED = {}  # filled by run_ours: the fp32-storage mode measured beside the fp64 headline
 METRIC = "VB-NMF nnz*rank updates/s per iteration"
 UNIT = "nnz*rank updates/s"
 
@@ -47,9 +48,10 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def algorithmic_bytes(nnz, n, m, r):
-    """B_alg = nnz*(4+4) + 8*(m+1) + 2*r*m*8 + 2*n*r*8 bytes per VB iteration."""
-    return nnz * 8 + 8 * (m + 1) + 2 * r * m * 8 + 2 * n * r * 8
+def algorithmic_bytes(nnz, n, m, r, sp=8):
+    """B_alg = nnz*(4+4) + 8*(m+1) + 2*r*m*s_p + 2*n*r*s_p bytes per VB iteration,
+    s_p = 8 (fp64) or 4 (fp32-storage mode)."""
+    return nnz * 8 + 8 * (m + 1) + 2 * r * m * sp + 2 * n * r * sp
 
 
 class ClockSampler:
@@ -187,6 +189,39 @@ def run_ours(args):
     value = nnz_total * r / (ms_step * 1e-3)
     lkh_dev = res["lkh"]
 
+    # ---- same measurement in the fp32-storage / fp64-accumulate mode (reported beside fp64) -----
+    eng.set_precision(1)
+    eng.set_state(w0, h0_loc)
+    eng.bench_iterations(HYPER, max(args.warmup, 1))
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    r32 = eng.bench_iterations(HYPER, args.steps)
+    torch.cuda.synchronize()
+    t32 = torch.tensor([r32["ms_total"], r32["ms_cols"], r32["ms_rows"]], dtype=torch.float64,
+                       device=dev)
+    if world > 1:
+        dist.all_reduce(t32, op=dist.ReduceOp.MAX)
+    t32 = [float(v) / args.steps for v in t32.tolist()]
+    b32 = algorithmic_bytes(nnz_loc, n, m_loc, r, sp=4)
+    MIXED.update({"value": nnz_total * r / (t32[0] * 1e-3), "unit": UNIT, "ms_per_step": t32[0],
+                  "ms_per_launch": {"sweep_cols": t32[1], "sweep_rows": t32[2]},
+                  "roofline_frac": b32 / ((t32[1] + t32[2]) * 1e-3) / 1e9 / peaks()[0],
+                  "algorithmic_bytes_per_launch": b32, "lkh_last": r32["lkh"],
+                  "rel_diff_lkh_vs_fp64_same_iteration_count": None,
+                  "what": "panels lw/lh held in fp32, per-nonzero arithmetic fp32, every sum over "
+                          "lanes/slabs/ranks and the posterior update in fp64 (tolerance 1e-4)"})
+    eng.set_precision(0)
+
+    if args.no_e2e:
+        if rank == 0:
+            emit_line(args, wl, world, n, r, m_total, m_loc, nnz_loc, nnz_total, scale, t_gen,
+                      value, ms_step, ms_cols, ms_rows, wall_ms, clocks, res, None, None, lkh_dev)
+        if world > 1:
+            dist.barrier()
+            comm.close()
+            dist.destroy_process_group()
+        return
     # ---- end-to-end arm: HOST buffers through the C ABI, copies inside the timed region ---------
     h_colptr = colptr.cpu().numpy()
     h_rowidx = rowidx.cpu().numpy()
@@ -226,49 +261,59 @@ def run_ours(args):
         cpu = cpu_baseline_port(n, r, h_colptr, h_rowidx, h_values, w0, h0_loc)
 
     if rank == 0:
-        peak, peak_src = peaks()
-        b_alg_local = algorithmic_bytes(nnz_loc, n, m_loc, r)
-        t_sweep = (ms_cols + ms_rows) / args.steps * 1e-3
-        ach = b_alg_local / t_sweep / 1e9
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tp):
-            traffic = json.load(open(tp)).get(args.workload)
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak" if wl.get("m_per_gpu") else "strong", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wl["label"], "genes": n, "cells_total": m_total,
-                       "nnz_total": nnz_total, "rank": r, "precision": "fp64",
-                       "sharding": "cells over %d GPU(s), 1 all-reduce/iter" % world,
-                       "l2": "inputs larger than L2 (CSC+CSR %.2f GB per GPU vs 126 MB)"
-                             % (nnz_loc * 16 / 1e9),
-                       "generator_scale": scale, "gen_seconds": round(t_gen, 2)},
-            "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps,
-                    "d2h_bytes_per_step": d2h / args.steps, "seconds": e2e_s,
-                    "iterations": args.steps,
-                    "what": "vbnmf_create(host CSC) + set_state + vbnmf_run(K) + get_state(ew, eh)"},
-            "gpu_launches": int(res["launches"]),
-            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                         "frac": ach / peak, "traffic": traffic,
-                         "kernel": "sweep_cols_kernel + sweep_rows_kernel (the nonzero sweep)",
-                         "algorithmic_bytes_per_launch": b_alg_local,
-                         "ms_per_launch": {"sweep_cols": ms_cols / args.steps,
-                                           "sweep_rows": ms_rows / args.steps},
-                         "iteration_frac": b_alg_local / (ms_step * 1e-3) / 1e9 / peak,
-                         "peak_source": peak_src},
-            "cpu_baseline": cpu,
-            "wall_ms_per_step": wall_ms / args.steps,
-            "lkh_last": lkh_dev,
-        }
-        print(json.dumps(line), flush=True)
+        e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps,
+               "d2h_bytes_per_step": d2h / args.steps, "seconds": e2e_s, "iterations": args.steps,
+               "what": "vbnmf_create(host CSC) + set_state + vbnmf_run(K) + get_state(ew, eh)"}
+        emit_line(args, wl, world, n, r, m_total, m_loc, nnz_loc, nnz_total, scale, t_gen, value,
+                  ms_step, ms_cols, ms_rows, wall_ms, clocks, res, e2e, cpu, lkh_dev)
     if world > 1:
         dist.barrier()
         if comm is not None:
             comm.close()
         dist.destroy_process_group()
+
+
+def emit_line(args, wl, world, n, r, m_total, m_loc, nnz_loc, nnz_total, scale, t_gen, value,
+              ms_step, ms_cols, ms_rows, wall_ms, clocks, res, e2e, cpu, lkh_dev):
+    peak, peak_src = peaks()
+    b_alg_local = algorithmic_bytes(nnz_loc, n, m_loc, r)
+    t_sweep = (ms_cols + ms_rows) / args.steps * 1e-3
+    ach = b_alg_local / t_sweep / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(args.workload)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak" if wl.get("m_per_gpu") else "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["label"], "genes": n, "cells_total": m_total,
+                   "nnz_total": nnz_total, "rank": r, "precision": "fp64",
+                   "sharding": "cells over %d GPU(s), 1 all-reduce/iter" % world,
+                   "l2": "inputs larger than L2 (two tiled copies of X, %.2f GB per GPU vs 126 MB)"
+                         % (nnz_loc * 16 / 1e9),
+                   "generator_scale": scale, "gen_seconds": round(t_gen, 2)},
+        "clocks": clocks,
+        "e2e": e2e,
+        "gpu_launches": int(res["launches"]),
+        "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                     "frac": ach / peak, "traffic": traffic,
+                     "kernel": "sweep_tiled_kernel<COLS=1> + sweep_tiled_kernel<COLS=0> "
+                               "(the two passes of the nonzero sweep, incl. their combine kernels)",
+                     "algorithmic_bytes_per_launch": b_alg_local,
+                     "ms_per_launch": {"sweep_cols": ms_cols / args.steps,
+                                       "sweep_rows": ms_rows / args.steps},
+                     "iteration_frac": b_alg_local / (ms_step * 1e-3) / 1e9 / peak,
+                     "limiter": "shared-memory gather wavefronts + FP64 issue, not HBM "
+                                "(DESIGN.md section 5)",
+                     "peak_source": peak_src},
+        "cpu_baseline": cpu,
+        "fp32_storage_mode": MIXED or None,
+        "wall_ms_per_step": wall_ms / args.steps,
+        "lkh_last": lkh_dev,
+    }
+    print(json.dumps(line), flush=True)
 
 
 def cpu_baseline_port(n, r, colptr, rowidx, values, w0, h0, max_cols=24000, iters=2):
@@ -359,6 +404,7 @@ def main():
     ap.add_argument("--ref-cells", type=int, default=400,
                     help="cells in the dense slab one reference step processes")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

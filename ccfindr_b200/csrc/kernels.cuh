@@ -20,6 +20,16 @@ constexpr int kGroup = 8;    // lanes that share one sweep segment (= one LDS.12
 // nonzeros relies on to make the 8 gathers of a quarter-warp conflict-free.
 __host__ __device__ constexpr int row_stride(int rp) { return ((rp / 2) & 1) ? rp : rp + 2; }
 
+// fp32 mirror panels (VBNMF_FP32_STORAGE): stride in floats, a multiple of 4 (16 bytes) whose
+// number of 16-byte units is odd, for the same bank argument
+__host__ __device__ constexpr int row_stride_f32(int rp) {
+    return ((((rp + 3) / 4) & 1) ? ((rp + 3) / 4) : ((rp + 3) / 4) + 1) * 4;
+}
+template <typename PT>
+__host__ __device__ constexpr int panel_stride(int rp) {
+    return sizeof(PT) == 8 ? row_stride(rp) : row_stride_f32(rp);
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
@@ -73,6 +83,24 @@ __device__ __forceinline__ void load_row_d(const double *__restrict__ base, int6
         const double2 v = __ldg(p + k);
         out[2 * k] = v.x;
         out[2 * k + 1] = v.y;
+    }
+}
+
+template <int RP>
+__device__ __forceinline__ void load_row_t(const void *base, int64_t row, double (&out)[RP]) {
+    load_row_d<RP>(reinterpret_cast<const double *>(base), row, out);
+}
+template <int RP>
+__device__ __forceinline__ void load_row_t(const void *base, int64_t row, float (&out)[RP]) {
+    constexpr int RSF = row_stride_f32(RP);
+    const float4 *p = reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(base) + row * RSF);
+#pragma unroll
+    for (int c = 0; c < (RP + 3) / 4; c++) {
+        const float4 v = __ldg(p + c);
+        if (4 * c + 0 < RP) out[4 * c + 0] = v.x;
+        if (4 * c + 1 < RP) out[4 * c + 1] = v.y;
+        if (4 * c + 2 < RP) out[4 * c + 2] = v.z;
+        if (4 * c + 3 < RP) out[4 * c + 3] = v.w;
     }
 }
 
@@ -145,10 +173,10 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
 //
 // The build step orders the nonzeros of a segment so that 8 consecutive ones hit tile rows that
 // differ mod 8 -> with an odd row stride the 8 gathers of a group are bank-conflict free.
-template <int RP>
+template <int RP, typename PT>
 struct SweepCfg {
-    // register budget: own + acc + tile row = 6*RP doubles-halves, plus prefetched entries
-    static constexpr int kThreads = (RP <= 12) ? 512 : 256;
+    // register budget: own + acc + tile row = 3*RP values of PT, plus prefetched entries
+    static constexpr int kThreads = (RP * (int)sizeof(PT) <= 96) ? 512 : 256;
     static constexpr int kGroups = kThreads / kGroup;
 };
 
@@ -187,6 +215,38 @@ __device__ __forceinline__ double2 lds128(uint32_t addr) {
     return v;
 }
 
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "r"(addr));
+    return v;
+}
+template <int RP>
+__device__ __forceinline__ void gather_row(uint32_t raddr, double (&tr)[RP]) {
+#pragma unroll
+    for (int k = 0; k < RP / 2; k++) {
+        const double2 v = lds128(raddr + k * 16);
+        tr[2 * k] = v.x;
+        tr[2 * k + 1] = v.y;
+    }
+}
+template <int RP>
+__device__ __forceinline__ void gather_row(uint32_t raddr, float (&tr)[RP]) {
+#pragma unroll
+    for (int c = 0; c < (RP + 3) / 4; c++) {
+        const float4 v = lds128f(raddr + c * 16);
+        if (4 * c + 0 < RP) tr[4 * c + 0] = v.x;
+        if (4 * c + 1 < RP) tr[4 * c + 1] = v.y;
+        if (4 * c + 2 < RP) tr[4 * c + 2] = v.z;
+        if (4 * c + 3 < RP) tr[4 * c + 3] = v.w;
+    }
+}
+__device__ __forceinline__ double rcp_t(double p) { return fast_rcp(p); }
+__device__ __forceinline__ float rcp_t(float p) { return __frcp_rn(p); }
+__device__ __forceinline__ double log_t(double p) { return fast_log_pos(p); }
+__device__ __forceinline__ float log_t(float p) { return __logf(p); }
+
 __device__ __forceinline__ void prefetch_l2(const void *p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
@@ -199,8 +259,8 @@ struct SweepTiledArgs {
     const void *ent;         // float counts: packed {int32 tile row, float count} per nonzero
     const int32_t *idx;      // double counts: tile row of each nonzero ...
     const double *val;       // ... and its count
-    const double *owner;     // owner panel, NO x RS
-    const double *tiles;     // tile panel, nslabs*T x RS
+    const void *owner;       // owner panel, NO x stride (double, or float in fp32-storage mode)
+    const void *tiles;       // tile panel, nslabs*T x stride
     double *Part;            // nslabs x NO x RS
     double *xl_part;         // COLS: gridDim.x partial sums of x log p
 };
@@ -221,14 +281,15 @@ __device__ __forceinline__ void load_entry<double>(const SweepTiledArgs &a, int6
     x = __ldcs(a.val + t);
 }
 
-template <int RP, typename VT, bool COLS>
-__global__ void __launch_bounds__(SweepCfg<RP>::kThreads, 1)
+template <int RP, typename VT, bool COLS, typename PT>
+__global__ void __launch_bounds__(SweepCfg<RP, PT>::kThreads, 1)
 sweep_tiled_kernel(const SweepTiledArgs a) {
-    constexpr int RS = row_stride(RP);
-    constexpr int NT = SweepCfg<RP>::kThreads;
+    constexpr int RS = row_stride(RP);          // stride of the fp64 Part rows
+    constexpr int PS = panel_stride<PT>(RP);    // stride of the gathered / owner panels
+    constexpr int NT = SweepCfg<RP, PT>::kThreads;
     constexpr int U = kUnroll;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double *tile = reinterpret_cast<double *>(smem_raw);
+    PT *tile = reinterpret_cast<PT *>(smem_raw);
     const uint32_t tile_s = smem_u32(tile);
     __shared__ __align__(8) uint64_t mbar;
     __shared__ double red[NT / 32];
@@ -236,7 +297,7 @@ sweep_tiled_kernel(const SweepTiledArgs a) {
     // the 4 groups of a warp run different trip counts: shuffles name only their own 8 lanes
     const unsigned gmask = 0xffu << ((threadIdx.x & 31) & ~(kGroup - 1));
     const int64_t e0 = a.split[blockIdx.x], e1 = a.split[blockIdx.x + 1];
-    const unsigned tile_bytes = (unsigned)a.T * RS * 8u;
+    const unsigned tile_bytes = (unsigned)a.T * PS * (unsigned)sizeof(PT);
     if (threadIdx.x == 0) mbar_init(&mbar, 1);
     __syncthreads();
     unsigned parity = 0;
@@ -248,26 +309,28 @@ sweep_tiled_kernel(const SweepTiledArgs a) {
         __syncthreads();  // every group is done with the previous tile
         if (threadIdx.x == 0) {
             mbar_expect_tx(&mbar, tile_bytes);
-            bulk_g2s(tile, a.tiles + slab * (int64_t)a.T * RS, tile_bytes, &mbar);
+            bulk_g2s(tile, reinterpret_cast<const PT *>(a.tiles) + slab * (int64_t)a.T * PS,
+                     tile_bytes, &mbar);
         }
         mbar_wait(&mbar, parity);
         parity ^= 1;
-        for (int64_t e = ebase + gid; e < eend; e += SweepCfg<RP>::kGroups) {
+        for (int64_t e = ebase + gid; e < eend; e += SweepCfg<RP, PT>::kGroups) {
             const int64_t o = e - slab * a.NO;
             const int64_t beg = __ldg(a.ptr + e), end = __ldg(a.ptr + e + 1);
             // pull the entries of this group's NEXT segment from HBM into L2 while this one runs
-            if (sizeof(VT) == 4 && e + SweepCfg<RP>::kGroups < eend) {
-                const int64_t nb = __ldg(a.ptr + e + SweepCfg<RP>::kGroups);
-                const int64_t ne = __ldg(a.ptr + e + SweepCfg<RP>::kGroups + 1);
+            if (sizeof(VT) == 4 && e + SweepCfg<RP, PT>::kGroups < eend) {
+                const int64_t nb = __ldg(a.ptr + e + SweepCfg<RP, PT>::kGroups);
+                const int64_t ne = __ldg(a.ptr + e + SweepCfg<RP, PT>::kGroups + 1);
                 for (int64_t t = nb + gl * 16; t < ne; t += kGroup * 16)
                     prefetch_l2(reinterpret_cast<const int2 *>(a.ent) + t);
             }
-            double acc[RP];
+            PT acc[RP];
+            PT xls = 0;  // x log p of this segment in the arithmetic type
 #pragma unroll
-            for (int k = 0; k < RP; k++) acc[k] = 0.0;
+            for (int k = 0; k < RP; k++) acc[k] = 0;
             if (beg < end) {
-                double own[RP];
-                load_row_d<RP>(a.owner, o, own);
+                PT own[RP];
+                load_row_t<RP>(a.owner, o, own);
                 // software pipeline: the U index/count loads of the next chunk are issued before
                 // the current chunk is processed.  Slots past the end of the segment carry a zero
                 // count and tile row 0: they run through the same arithmetic and add nothing, so
@@ -290,30 +353,26 @@ sweep_tiled_kernel(const SweepTiledArgs a) {
                     }
 #pragma unroll
                     for (int u = 0; u < U; u++) {
-                        const double x = xv[u];
-                        const uint32_t raddr = tile_s + (uint32_t)ti[u] * (RS * 8);
-                        double tr[RP];
-#pragma unroll
-                        for (int k = 0; k < RP / 2; k++) {
-                            const double2 v = lds128(raddr + k * 16);
-                            tr[2 * k] = v.x;
-                            tr[2 * k + 1] = v.y;
-                        }
-                        double p0 = 0.0, p1 = 0.0;
+                        const PT x = (PT)xv[u];
+                        const uint32_t raddr = tile_s + (uint32_t)ti[u] * (PS * (int)sizeof(PT));
+                        PT tr[RP];
+                        gather_row<RP>(raddr, tr);
+                        PT p0 = 0, p1 = 0;
 #pragma unroll
                         for (int k = 0; k < RP; k += 2) {
                             p0 = fma(own[k], tr[k], p0);
                             p1 = fma(own[k + 1], tr[k + 1], p1);
                         }
-                        const double p = p0 + p1;
-                        const double q = x * fast_rcp(p);
+                        const PT p = p0 + p1;
+                        const PT q = x * rcp_t(p);
 #pragma unroll
                         for (int k = 0; k < RP; k++) acc[k] = fma(tr[k], q, acc[k]);
-                        if (COLS) xl = fma(x, fast_log_pos(p), xl);
+                        if (COLS) xls = fma(x, log_t(p), xls);
                     }
 #pragma unroll
                     for (int u = 0; u < U; u++) { ti[u] = tn[u]; xv[u] = xn[u]; }
                 }
+                if (COLS) xl += (double)xls;
             }
             // sum over the 8 lanes of the group; lane gl keeps k = gl, gl+8, ...
             constexpr int NH = (RP + kGroup - 1) / kGroup;
@@ -322,7 +381,7 @@ sweep_tiled_kernel(const SweepTiledArgs a) {
             for (int h = 0; h < NH; h++) mine[h] = 0.0;
 #pragma unroll
             for (int k = 0; k < RP; k++) {
-                double s = acc[k];
+                double s = (double)acc[k];  // fp64 from here on (sums over lanes, slabs, ranks)
                 s += __shfl_xor_sync(gmask, s, 4);
                 s += __shfl_xor_sync(gmask, s, 2);
                 s += __shfl_xor_sync(gmask, s, 1);
@@ -407,7 +466,7 @@ __global__ void __launch_bounds__(kBlock)
 posterior_kernel(int64_t rows, int T, int S, int64_t nvalid, int r, double a, double b, double fud,
                  const double *__restrict__ osum, const double *__restrict__ SRaw,
                  double *__restrict__ l, double *__restrict__ al_out, double *__restrict__ part,
-                 double *__restrict__ out, unsigned *counter) {
+                 double *__restrict__ out, unsigned *counter, float *__restrict__ l32) {
     constexpr int RS = row_stride(RP);
     __shared__ double sm[kWarpsPerBlock];
     __shared__ double be[RP], lbe[RP];
@@ -457,6 +516,10 @@ posterior_kernel(int64_t rows, int T, int S, int64_t nvalid, int r, double a, do
             lp[k] = make_double2(lv[2 * k], lv[2 * k + 1]);
             ap[k] = make_double2(sv[2 * k], sv[2 * k + 1]);
         }
+        if (l32) {  // fp32 mirror read by the sweep in VBNMF_FP32_STORAGE mode
+#pragma unroll
+            for (int k = 0; k < RP; k++) l32[row * row_stride_f32(RP) + k] = (float)lv[k];
+        }
     }
     constexpr int W = RS + 3;
     double *mypart = part + (size_t)blockIdx.x * W;
@@ -485,7 +548,7 @@ __global__ void __launch_bounds__(kBlock)
 ml_update_kernel(int64_t rows, int T, int S, int64_t nvalid, int r, double eps,
                  const double *__restrict__ osum, const double *__restrict__ SRaw,
                  double *__restrict__ v, double *__restrict__ part, double *__restrict__ out,
-                 unsigned *counter) {
+                 unsigned *counter, float *__restrict__ l32) {
     constexpr int RS = row_stride(RP);
     __shared__ double sm[kWarpsPerBlock];
     const int64_t row = (int64_t)blockIdx.x * kBlock + threadIdx.x;
@@ -515,6 +578,10 @@ ml_update_kernel(int64_t rows, int T, int S, int64_t nvalid, int r, double eps,
         double2 *lp = reinterpret_cast<double2 *>(v + row * RS);
 #pragma unroll
         for (int k = 0; k < RP / 2; k++) lp[k] = make_double2(lv[2 * k], lv[2 * k + 1]);
+        if (l32) {
+#pragma unroll
+            for (int k = 0; k < RP; k++) l32[row * row_stride_f32(RP) + k] = (float)lv[k];
+        }
     }
     double *mypart = part + (size_t)blockIdx.x * RS;
 #pragma unroll
@@ -525,6 +592,17 @@ ml_update_kernel(int64_t rows, int T, int S, int64_t nvalid, int r, double eps,
     if (threadIdx.x == 0)
         for (int k = RP; k < RS; k++) mypart[k] = 0.0;
     last_block_reduce(part, RS, out, counter, sm);
+}
+
+// fp32 mirror of a rows x RS panel (after set_state in VBNMF_FP32_STORAGE mode)
+template <int RP>
+__global__ void __launch_bounds__(kBlock)
+mirror_kernel(int64_t rows, const double *__restrict__ v, float *__restrict__ v32) {
+    const int64_t row = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (row >= rows) return;
+#pragma unroll
+    for (int k = 0; k < row_stride_f32(RP); k++)
+        v32[row * row_stride_f32(RP) + k] = k < RP ? (float)v[row * row_stride(RP) + k] : 0.f;
 }
 
 // column sums of a rows x RS panel (padding rows hold zeros): out[k] = sum_row v[row][k]

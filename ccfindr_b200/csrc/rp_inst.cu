@@ -19,23 +19,34 @@ int sweep_prepare(int smem_bytes) {
 #define VB_OPT(K)                                                                               \
     if (e == cudaSuccess)                                                                       \
         e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    VB_OPT((sweep_tiled_kernel<RP, float, true>))
-    VB_OPT((sweep_tiled_kernel<RP, float, false>))
-    VB_OPT((sweep_tiled_kernel<RP, double, true>))
-    VB_OPT((sweep_tiled_kernel<RP, double, false>))
+    VB_OPT((sweep_tiled_kernel<RP, float, true, double>))
+    VB_OPT((sweep_tiled_kernel<RP, float, false, double>))
+    VB_OPT((sweep_tiled_kernel<RP, double, true, double>))
+    VB_OPT((sweep_tiled_kernel<RP, double, false, double>))
+    VB_OPT((sweep_tiled_kernel<RP, float, true, float>))
+    VB_OPT((sweep_tiled_kernel<RP, float, false, float>))
+    VB_OPT((sweep_tiled_kernel<RP, double, true, float>))
+    VB_OPT((sweep_tiled_kernel<RP, double, false, float>))
 #undef VB_OPT
     return e == cudaSuccess ? 0 : 1;
 }
 
-void sweep(const SweepTiledArgs &a, bool cols, bool vf, int grid, int smem, cudaStream_t s) {
-    constexpr int NT = SweepCfg<RP>::kThreads;
+template <typename PT>
+void sweep_pt(const SweepTiledArgs &a, bool cols, bool vf, int grid, int smem, cudaStream_t s) {
+    constexpr int NT = SweepCfg<RP, PT>::kThreads;
     if (cols) {
-        if (vf) sweep_tiled_kernel<RP, float, true><<<grid, NT, smem, s>>>(a);
-        else sweep_tiled_kernel<RP, double, true><<<grid, NT, smem, s>>>(a);
+        if (vf) sweep_tiled_kernel<RP, float, true, PT><<<grid, NT, smem, s>>>(a);
+        else sweep_tiled_kernel<RP, double, true, PT><<<grid, NT, smem, s>>>(a);
     } else {
-        if (vf) sweep_tiled_kernel<RP, float, false><<<grid, NT, smem, s>>>(a);
-        else sweep_tiled_kernel<RP, double, false><<<grid, NT, smem, s>>>(a);
+        if (vf) sweep_tiled_kernel<RP, float, false, PT><<<grid, NT, smem, s>>>(a);
+        else sweep_tiled_kernel<RP, double, false, PT><<<grid, NT, smem, s>>>(a);
     }
+}
+
+void sweep(const SweepTiledArgs &a, bool cols, bool vf, bool pf32, int grid, int smem,
+           cudaStream_t s) {
+    if (pf32) sweep_pt<float>(a, cols, vf, grid, smem, s);
+    else sweep_pt<double>(a, cols, vf, grid, smem, s);
 }
 
 inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
@@ -47,11 +58,15 @@ void combine(const CombineArgs &a, cudaStream_t s) {
 void posterior(const PosteriorArgs &a, cudaStream_t s) {
     posterior_kernel<RP><<<cdiv(a.rows, kBlock), kBlock, 0, s>>>(
         a.rows, a.T, a.S, a.nvalid, a.r, a.a, a.b, a.fud, a.osum, a.SRaw, a.l, a.al_out, a.part,
-        a.out, a.counter);
+        a.out, a.counter, a.l32);
 }
 void ml_update(const MlUpdateArgs &a, cudaStream_t s) {
     ml_update_kernel<RP><<<cdiv(a.rows, kBlock), kBlock, 0, s>>>(
-        a.rows, a.T, a.S, a.nvalid, a.r, a.eps, a.osum, a.SRaw, a.v, a.part, a.out, a.counter);
+        a.rows, a.T, a.S, a.nvalid, a.r, a.eps, a.osum, a.SRaw, a.v, a.part, a.out, a.counter,
+        a.l32);
+}
+void mirror(int64_t rows, const double *v, float *v32, cudaStream_t s) {
+    mirror_kernel<RP><<<cdiv(rows, kBlock), kBlock, 0, s>>>(rows, v, v32);
 }
 void colsum(const ColsumArgs &a, cudaStream_t s) {
     panel_colsum_kernel<RP><<<cdiv(a.rows, kBlock), kBlock, 0, s>>>(a.rows, a.v, a.part, a.out,
@@ -61,8 +76,8 @@ void colsum(const ColsumArgs &a, cudaStream_t s) {
 }  // namespace
 
 extern const RpTable VB_CAT(rp_table_, VB_RP);
-const RpTable VB_CAT(rp_table_, VB_RP) = {RP,      RS,        SweepCfg<RP>::kThreads, sweep_prepare,
-                                          sweep,   combine,   posterior,              ml_update,
-                                          colsum};
+const RpTable VB_CAT(rp_table_, VB_RP) = {
+    RP,      RS,        row_stride_f32(RP), SweepCfg<RP, double>::kThreads, sweep_prepare, sweep, mirror,
+    combine, posterior, ml_update,          colsum};
 
 }  // namespace vb

@@ -28,6 +28,7 @@ struct PosteriorArgs {
     const double *osum, *SRaw;
     double *l, *al_out, *part, *out;
     unsigned *counter;
+    float *l32;  // fp32 mirror of l (fp32-storage mode) or nullptr
 };
 
 struct MlUpdateArgs {
@@ -39,6 +40,7 @@ struct MlUpdateArgs {
     const double *osum, *SRaw;
     double *v, *part, *out;
     unsigned *counter;
+    float *l32;
 };
 
 struct ColsumArgs {
@@ -49,13 +51,14 @@ struct ColsumArgs {
 };
 
 struct RpTable {
-    int rp, rs;
+    int rp, rs, rsf;  // padded rank, fp64 panel stride (doubles), fp32 mirror stride (floats)
     int sweep_threads;
     // cols: cell-owner pass; val_is_float selects the count storage type; int_counts = all counts
     // are integers (enables the log-product path); grid = CTAs (one per SM, persistent)
     int (*sweep_prepare)(int smem_bytes);  // opt in to the dynamic shared memory size; 0 = ok
-    void (*sweep)(const SweepTiledArgs &, bool cols, bool val_is_float, int grid, int smem_bytes,
-                  cudaStream_t);
+    void (*sweep)(const SweepTiledArgs &, bool cols, bool val_is_float, bool panels_f32, int grid,
+                  int smem_bytes, cudaStream_t);
+    void (*mirror)(int64_t rows, const double *v, float *v32, cudaStream_t);
     void (*combine)(const CombineArgs &, cudaStream_t);
     void (*posterior)(const PosteriorArgs &, cudaStream_t);
     void (*ml_update)(const MlUpdateArgs &, cudaStream_t);

@@ -140,6 +140,8 @@ struct vbnmf_handle {
     int smem_bytes = 0;
     // panels in device order
     double *d_lw = nullptr, *d_lh = nullptr, *d_alw = nullptr, *d_alh = nullptr;
+    float *d_lw32 = nullptr, *d_lh32 = nullptr;  // fp32 mirrors read by the sweep (fp32-storage mode)
+    int rsf = 0, panel_precision = -1;
     // d_red = [SwRaw NG*rs | ehsum rs | hprior, sumloglh, sumeh | enth, xlogp | entw, - | pad]
     double *d_red = nullptr;
     double *d_ShRaw = nullptr, *d_Part1 = nullptr, *d_Part2 = nullptr, *d_xl = nullptr;
@@ -198,10 +200,10 @@ inline int pad_rank(int r) {
 inline int64_t tail_off(const H *h) { return h->L->NG * h->rs; }
 inline int64_t red_len(const H *h) { return h->L->NG * h->rs + h->rs + 8; }
 
-int choose_tile_rows(const H *h, int rs) {
+int choose_tile_rows(const H *h, int row_bytes) {
     int T = 128;
     for (int t : kTileRows)
-        if ((int64_t)t * rs * 8 <= kTileBytes) { T = t; break; }
+        if ((int64_t)t * row_bytes <= kTileBytes) { T = t; break; }
     const int64_t big = std::max(h->n, h->m);
     const int64_t cap = std::max<int64_t>(128, ((big + 127) / 128) * 128);
     return (int)std::min<int64_t>(T, cap);
@@ -369,6 +371,8 @@ void free_panels(H *h) {
     }
     if (h->h_scal) cudaFreeHost(h->h_scal);
     h->h_scal = nullptr;
+    cudaFree(h->d_lw32); cudaFree(h->d_lh32);
+    h->d_lw32 = h->d_lh32 = nullptr;
 }
 
 int alloc_panels(H *h, int r) {
@@ -376,16 +380,22 @@ int alloc_panels(H *h, int r) {
     const vb::RpTable *tab = vb::rp_table(rp);
     if (!tab) return fail(h, VBNMF_ERR_ARG, "no kernels compiled for this rank");
     const int rs = tab->rs;
-    const int T = choose_tile_rows(h, rs);
+    const bool f32 = h->precision == VBNMF_FP32_STORAGE;
+    const int row_bytes = f32 ? tab->rsf * 4 : rs * 8;
+    const int T = choose_tile_rows(h, row_bytes);
     Layout *L = nullptr;
     int rc = get_layout(h, T, &L);
     if (rc) return rc;
-    if (rp == h->rp && L == h->L && h->d_lw) { h->r = r; return 0; }
+    if (rp == h->rp && L == h->L && h->d_lw && h->panel_precision == h->precision) {
+        h->r = r;
+        return 0;
+    }
     free_panels(h);
     h->tab = tab;
     h->L = L;
-    h->r = r; h->rp = rp; h->rs = rs;
-    h->smem_bytes = T * rs * 8;
+    h->r = r; h->rp = rp; h->rs = rs; h->rsf = tab->rsf;
+    h->panel_precision = h->precision;
+    h->smem_bytes = T * row_bytes;
     if (tab->sweep_prepare(h->smem_bytes))
         return fail(h, VBNMF_ERR_CUDA, "cannot opt in to the shared-memory tile size");
     const size_t gr = (size_t)L->NG * rs * 8, cr = (size_t)L->NC * rs * 8;
@@ -407,6 +417,20 @@ int alloc_panels(H *h, int r) {
     CK(cudaMemsetAsync(h->d_red, 0, (size_t)red_len(h) * 8, h->stream));
     CK(cudaMemsetAsync(h->d_scal, 0, (size_t)(rs + 8) * 8, h->stream));
     CK(cudaMemsetAsync(h->d_ShRaw, 0, cr, h->stream));
+    if (f32) {
+        CK(cudaMalloc(&h->d_lw32, (size_t)L->NG * h->rsf * 4));
+        CK(cudaMalloc(&h->d_lh32, (size_t)L->NC * h->rsf * 4));
+    }
+    return 0;
+}
+
+// fp32-storage mode: refresh the mirrors from the fp64 panels (after an upload)
+int refresh_mirrors(H *h) {
+    if (h->precision != VBNMF_FP32_STORAGE) return 0;
+    h->tab->mirror(h->L->NG, h->d_lw, h->d_lw32, h->stream);
+    h->tab->mirror(h->L->NC, h->d_lh, h->d_lh32, h->stream);
+    h->launches += 2;
+    CK(cudaGetLastError());
     return 0;
 }
 
@@ -457,6 +481,7 @@ int launch_posterior(H *h, bool wside, double a, double b, double fud) {
     p.part = wside ? h->d_partW : h->d_partH;
     p.out = wside ? h->d_scal : tail;
     p.counter = h->d_counters + (wside ? 0 : 1);
+    p.l32 = wside ? h->d_lw32 : h->d_lh32;  // nullptr in fp64 mode
     h->tab->posterior(p, h->stream);
     h->launches += 1;
     return 0;
@@ -466,10 +491,12 @@ int launch_posterior(H *h, bool wside, double a, double b, double fud) {
 int launch_sweep_cols(H *h) {
     const Layout *L = h->L;
     double *tail = h->d_red + tail_off(h);
+    const bool f32 = h->precision == VBNMF_FP32_STORAGE;
     vb::SweepTiledArgs a{L->NC, L->T, L->cols.d_split, L->cols.d_ptr, L->cols.d_ent,
-                         L->cols.d_idx, (const double *)L->cols.d_val, h->d_lh, h->d_lw,
-                         h->d_Part1, h->d_xl};
-    h->tab->sweep(a, true, h->val_float, L->grid, h->smem_bytes, h->stream);
+                         L->cols.d_idx, (const double *)L->cols.d_val,
+                         f32 ? (const void *)h->d_lh32 : (const void *)h->d_lh,
+                         f32 ? (const void *)h->d_lw32 : (const void *)h->d_lw, h->d_Part1, h->d_xl};
+    h->tab->sweep(a, true, h->val_float, f32, L->grid, h->smem_bytes, h->stream);
     vb::CombineArgs c{L->NC, L->Sg, h->r, h->d_Part1, h->d_lh, h->d_ShRaw, h->d_partC,
                       tail + h->rs + 3, h->d_counters + 2, h->d_xl, L->grid, h->gridC};
     h->tab->combine(c, h->stream);
@@ -481,10 +508,12 @@ int launch_sweep_cols(H *h) {
 int launch_sweep_rows(H *h) {
     const Layout *L = h->L;
     double *tail = h->d_red + tail_off(h);
+    const bool f32 = h->precision == VBNMF_FP32_STORAGE;
     vb::SweepTiledArgs a{L->NG, L->T, L->rows.d_split, L->rows.d_ptr, L->rows.d_ent,
-                         L->rows.d_idx, (const double *)L->rows.d_val, h->d_lw, h->d_lh,
-                         h->d_Part2, nullptr};
-    h->tab->sweep(a, false, h->val_float, L->grid, h->smem_bytes, h->stream);
+                         L->rows.d_idx, (const double *)L->rows.d_val,
+                         f32 ? (const void *)h->d_lw32 : (const void *)h->d_lw,
+                         f32 ? (const void *)h->d_lh32 : (const void *)h->d_lh, h->d_Part2, nullptr};
+    h->tab->sweep(a, false, h->val_float, f32, L->grid, h->smem_bytes, h->stream);
     vb::CombineArgs c{L->NG, L->Sc, h->r, h->d_Part2, h->d_lw, h->d_red, h->d_partC,
                       tail + h->rs + 5, h->d_counters + 3, nullptr, 0, h->gridC};
     h->tab->combine(c, h->stream);
@@ -716,9 +745,12 @@ int vbnmf_create_from_device(vbnmf_handle **out, int64_t n, int64_t m, int64_t n
 
 int vbnmf_set_precision(vbnmf_handle *h, int precision) {
     if (!h) return VBNMF_ERR_ARG;
-    if (precision != VBNMF_FP64)
-        return fail(h, VBNMF_ERR_ARG, "only VBNMF_FP64 is implemented in this build");
-    h->precision = precision;
+    if (precision != VBNMF_FP64 && precision != VBNMF_FP32_STORAGE)
+        return fail(h, VBNMF_ERR_ARG, "precision must be VBNMF_FP64 or VBNMF_FP32_STORAGE");
+    if (precision != h->precision) {
+        h->precision = precision;  // takes effect at the next vbnmf_set_state / mlnmf_run
+        h->stats_valid = false;
+    }
     return 0;
 }
 
@@ -817,6 +849,7 @@ int vbnmf_set_state(vbnmf_handle *h, int r, const double *lw, const double *lh, 
     // before the first update ew/eh are whatever the caller holds (vb_init: ew = w, eh = h)
     if ((rc = upload_panel(h, h->d_alw, ew ? ew : lw, true, r))) return rc;
     if ((rc = upload_panel(h, h->d_alh, eh ? eh : lh, false, r))) return rc;
+    if ((rc = refresh_mirrors(h))) return rc;
     const double *e = eh ? eh : lh;
     double *tail = h->d_red + tail_off(h);
     std::vector<double> s((size_t)h->rs + 8, 0.0);
@@ -1040,6 +1073,7 @@ int mlnmf_run(vbnmf_handle *h, int r, const double *w0, const double *h0, int it
     if ((rc = alloc_panels(h, r))) return rc;
     if ((rc = upload_panel(h, h->d_lw, w0, true, r))) return rc;
     if ((rc = upload_panel(h, h->d_lh, h0, false, r))) return rc;
+    if ((rc = refresh_mirrors(h))) return rc;
     h->stats_valid = false;
     h->has_posterior = false;
     const Layout *L = h->L;
@@ -1059,7 +1093,7 @@ int mlnmf_run(vbnmf_handle *h, int r, const double *w0, const double *h0, int it
                            wside ? h->n : h->m, r, eps, wside ? tail : h->d_scal,
                            wside ? h->d_red : h->d_ShRaw, wside ? h->d_lw : h->d_lh,
                            wside ? h->d_partW : h->d_partH, wside ? h->d_scal : tail,
-                           h->d_counters + (wside ? 0 : 1)};
+                           h->d_counters + (wside ? 0 : 1), wside ? h->d_lw32 : h->d_lh32};
         h->tab->ml_update(a, h->stream);
         h->launches += 1;
         return 0;

@@ -178,3 +178,57 @@ def test_errors_are_reported_not_thrown(Engine):
             eng.step(dict(aw=1.0, bw=1.0, ah=1.0, bh=1.0))  # no state loaded
         with pytest.raises(ValueError):
             eng.set_state(w0[:-1], h0)
+
+
+# ---- fp32-storage / fp64-accumulate mode (BASELINE.json north_star: within 1e-4) -------------------
+TOL32 = 1e-4
+
+
+def _relerr_floor(a, b, floor):
+    """relative error with an absolute floor: entries far below the scale of the matrix carry the
+    fp32 rounding of the panels relative to the dominant terms they were summed with"""
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor)))
+
+
+@pytest.mark.parametrize("case", ["run_c1s1_r3", "run_pbmc_r5", "run_c1s2_r3_conv", "run_c1s1_r2"])
+def test_fp32_storage_mode_within_1e4(Engine, case):
+    g = load_golden(case)
+    kw = run_kwargs(g)
+    flags = kw.pop("hyper_update_flags", (True,) * 4)
+    kw["Tol"] = 0.0               # fixed iteration count: compare like with like
+    kw["Itmax"] = int(g["niter"])
+    with Engine(load_counts(RUN_CASES[case])) as eng:
+        eng.set_precision(1)      # VBNMF_FP32_STORAGE
+        eng.set_state(g["w0"], g["h0"])
+        res = eng.run(hyper_dict(g["hyper0"]), hyper_update=flags, **kw)
+        st = eng.get_state()
+        cid = eng.cluster_id()
+    assert relerr(res["lkh_trace"], g["lkh_trace"]) < TOL32
+    assert relerr(res["hyper_trace"], g["hyper_trace"]) < TOL32
+    for k in ("ew", "eh", "lw", "lh"):
+        scale = float(np.abs(g[k]).max())
+        assert _relerr_floor(st[k], g[k], 1e-3 * scale) < TOL32, k
+    # cluster labels may only differ where the top two coefficients are within fp32 noise
+    diff = np.flatnonzero(cid != g["cid"])
+    for j in diff:
+        col = np.sort(g["eh"][:, j])[::-1]
+        assert (col[0] - col[1]) / col[0] < 1e-3
+
+
+def test_fp32_mode_step_matches_oracle_random(Engine):
+    from oracle import bindings as ob
+    from oracle import oracle_dense as od
+    X, w0, h0 = _random_problem(700, 900, 20, 0.05, seed=21)
+    hyper = dict(aw=0.7, bw=1.3, ah=1.1, bh=0.9)
+    ref = od.vb_init_from(w0, h0)
+    with Engine(X) as eng:
+        eng.set_precision(1)
+        eng.set_state(w0, h0)
+        for it in range(3):
+            ref = ob.sparse_vb_step(X, ref, hyper, od.EPS)
+            lkh = eng.step(hyper, od.EPS)
+            assert relerr(lkh, ref["lkh"]) < TOL32, it
+        st = eng.get_state()
+    for k in ("ew", "eh"):
+        assert _relerr_floor(st[k], ref[k], 1e-3 * float(np.abs(ref[k]).max())) < TOL32, k
