@@ -78,7 +78,7 @@ def build(force=False, verbose=False, jobs=None):
             futs.append(ex.submit(_run, [nvcc] + NVCC_FLAGS + args + ["-o", out], verbose))
         for f in futs:
             f.result()
-    _run([nvcc, "-shared", "-o", LIB] + objs + ["-lcudart", "-ldl"], verbose)
+    _run([nvcc, "-shared", "-o", LIB] + objs + ["-lcudart", "-ldl", "-lpthread"], verbose)
     with open(stamp, "w") as f:
         f.write(want)
     return LIB

@@ -19,12 +19,15 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
+#include <time.h>
 
 #include <algorithm>
 #include <cmath>
 #include <cub/cub.cuh>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/vbnmf.h"
@@ -55,6 +58,24 @@ constexpr int kTileBytes = 204800;  // shared-memory budget of one staged slab
 const int kTileRows[] = {4096, 2560, 2048, 1536, 1152, 1024, 768, 512, 384, 256, 128};
 
 std::string g_create_error;
+
+// VBNMF_TIMING=1 prints host-side stage times (setup paths only) to stderr
+struct StageTimer {
+    const char *name;
+    bool on;
+    timespec t0;
+    explicit StageTimer(const char *n) : name(n), on(getenv("VBNMF_TIMING") != nullptr) {
+        if (on) clock_gettime(CLOCK_MONOTONIC, &t0);
+    }
+    ~StageTimer() {
+        if (!on) return;
+        cudaDeviceSynchronize();
+        timespec t1;
+        clock_gettime(CLOCK_MONOTONIC, &t1);
+        fprintf(stderr, "[vbnmf] %-28s %8.2f ms\n", name,
+                (t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6);
+    }
+};
 
 struct NcclApi {
     void *lib = nullptr;
@@ -91,8 +112,10 @@ struct PassLayout {
     void *d_val = nullptr;      // nnz (double counts only)
     void *d_ent = nullptr;      // nnz packed {int32 tile row, float count} (float counts)
     int64_t *d_split = nullptr; // grid + 1
-    void release() {
-        cudaFree(d_ptr); cudaFree(d_idx); cudaFree(d_val); cudaFree(d_ent); cudaFree(d_split);
+    void release(cudaStream_t s) {
+        void *ps[] = {d_ptr, d_idx, d_val, d_ent, d_split};
+        for (void *q : ps)
+            if (q) cudaFreeAsync(q, s);
         d_ptr = nullptr; d_idx = nullptr; d_val = nullptr; d_ent = nullptr; d_split = nullptr;
     }
 };
@@ -105,9 +128,10 @@ struct Layout {
     int32_t *d_gene_dev = nullptr, *d_cell_dev = nullptr;
     PassLayout cols, rows;
     int grid = 0;
-    void release() {
-        cols.release(); rows.release();
-        cudaFree(d_gene_dev); cudaFree(d_cell_dev);
+    void release(cudaStream_t s) {
+        cols.release(s); rows.release(s);
+        if (d_gene_dev) cudaFreeAsync(d_gene_dev, s);
+        if (d_cell_dev) cudaFreeAsync(d_cell_dev, s);
         d_gene_dev = d_cell_dev = nullptr;
     }
 };
@@ -190,6 +214,21 @@ int fail(H *h, int code, const std::string &msg) {
     return code;
 }
 
+// Device memory comes from the stream-ordered pool (cudaMallocAsync) with a high release
+// threshold: the many GB-sized buffers of a handle are recycled instead of being mapped and
+// unmapped by the driver at every create/destroy (which cost more than the factorization itself).
+template <typename T>
+cudaError_t vmalloc(H *h, T **p, size_t bytes) {
+    return cudaMallocAsync((void **)p, bytes ? bytes : 16, h->stream);
+}
+inline void vfree(cudaStream_t s, void *p) {
+    if (p) cudaFreeAsync(p, s);
+}
+inline cudaError_t copy_sync(H *h, void *dst, const void *src, size_t bytes, cudaMemcpyKind kind) {
+    cudaError_t e = cudaMemcpyAsync(dst, src, bytes, kind, h->stream);
+    return e != cudaSuccess ? e : cudaStreamSynchronize(h->stream);
+}
+
 inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 inline int pad_rank(int r) {
     int rp = (r + 1) & ~1;
@@ -233,6 +272,7 @@ void deal(const std::vector<unsigned long long> &cnt, int T, int S, std::vector<
 
 template <typename VT>
 int build_pass(H *h, Layout *L, bool cols_pass, const int32_t *d_colof) {
+    StageTimer tm(cols_pass ? "build_pass(cols)" : "build_pass(rows)");
     PassLayout &P = cols_pass ? L->cols : L->rows;
     const int64_t nnz = h->nnz;
     const int64_t NO = cols_pass ? L->NC : L->NG;
@@ -242,47 +282,52 @@ int build_pass(H *h, Layout *L, bool cols_pass, const int32_t *d_colof) {
         return fail(h, VBNMF_ERR_ARG, "matrix too large for 32-bit segment keys on one GPU");
     const int g = h->num_sms * 8;
     uint32_t *k_in = nullptr, *k_out = nullptr, *p_in = nullptr, *p_out = nullptr;
-    CK(cudaMalloc(&k_in, (size_t)nnz * 4));
-    CK(cudaMalloc(&k_out, (size_t)nnz * 4));
-    CK(cudaMalloc(&p_in, (size_t)nnz * 4));
-    CK(cudaMalloc(&p_out, (size_t)nnz * 4));
+    CK(vmalloc(h, &k_in, (size_t)nnz * 4));
+    CK(vmalloc(h, &k_out, (size_t)nnz * 4));
+    CK(vmalloc(h, &p_in, (size_t)nnz * 4));
+    CK(vmalloc(h, &p_out, (size_t)nnz * 4));
+    { StageTimer t1("  make_keys");
     vb::make_keys_kernel<<<g, vb::kBlock, 0, h->stream>>>(nnz, h->d_rowidx, d_colof, L->d_gene_dev,
                                                           L->d_cell_dev, L->T, NO, cols_pass, k_in,
-                                                          p_in);
+                                                          p_in); }
     int bits = 1;
     while (((int64_t)1 << bits) < P.E) bits++;
     size_t tmp_bytes = 0;
     CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in, k_out, p_in, p_out, nnz, 0, bits,
                                        h->stream));
     void *d_tmp = nullptr;
-    CK(cudaMalloc(&d_tmp, tmp_bytes));
+    CK(vmalloc(h, &d_tmp, tmp_bytes));
+    { StageTimer t1("  radix_sort");
     CK(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, k_in, k_out, p_in, p_out, nnz, 0, bits,
-                                       h->stream));
-    CK(cudaMalloc(&P.d_ptr, (size_t)(P.E + 1) * 8));
-    vb::segment_ptr_kernel<<<g, vb::kBlock, 0, h->stream>>>(P.E, nnz, k_out, P.d_ptr);
+                                       h->stream)); }
+    CK(vmalloc(h, &P.d_ptr, (size_t)(P.E + 1) * 8));
+    { StageTimer t1("  segment_ptr");
+    vb::segment_ptr_kernel<<<g, vb::kBlock, 0, h->stream>>>(P.E, nnz, k_out, P.d_ptr); }
     CK(cudaStreamSynchronize(h->stream));
-    cudaFree(d_tmp); cudaFree(k_in); cudaFree(k_out); cudaFree(p_in);
+    vfree(h->stream, d_tmp); vfree(h->stream, k_in); vfree(h->stream, k_out); vfree(h->stream, p_in);
     if (sizeof(VT) == 4) {
-        CK(cudaMalloc(&P.d_ent, (size_t)nnz * 8));
+        CK(vmalloc(h, &P.d_ent, (size_t)nnz * 8));
     } else {
-        CK(cudaMalloc(&P.d_idx, (size_t)nnz * 4));
-        CK(cudaMalloc(&P.d_val, (size_t)nnz * sizeof(VT)));
+        CK(vmalloc(h, &P.d_idx, (size_t)nnz * 4));
+        CK(vmalloc(h, &P.d_val, (size_t)nnz * sizeof(VT)));
     }
+    { StageTimer t1("  build_segments");
     vb::build_segments_kernel<VT><<<g, vb::kBlock, 0, h->stream>>>(
         P.E, P.d_ptr, p_out, h->d_rowidx, d_colof, L->d_gene_dev, L->d_cell_dev,
-        (const VT *)h->d_val, L->T, cols_pass, P.d_idx, (VT *)P.d_val, (int2 *)P.d_ent);
-    CK(cudaMalloc(&P.d_split, (size_t)(L->grid + 1) * 8));
+        (const VT *)h->d_val, L->T, cols_pass, P.d_idx, (VT *)P.d_val, (int2 *)P.d_ent); }
+    CK(vmalloc(h, &P.d_split, (size_t)(L->grid + 1) * 8));
     vb::split_kernel<<<cdiv(L->grid + 1, 128), 128, 0, h->stream>>>(L->grid, P.E, nnz, P.d_ptr,
                                                                    P.d_split);
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaGetLastError());
-    cudaFree(p_out);
+    vfree(h->stream, p_out);
     return 0;
 }
 
 int get_layout(H *h, int T, Layout **out) {
     for (Layout *l : h->layouts)
         if (l->T == T) { *out = l; return 0; }
+    StageTimer tm("get_layout(total)");
     Layout *L = new Layout();
     L->T = T;
     L->Sg = cdiv(h->n, T);
@@ -292,26 +337,27 @@ int get_layout(H *h, int T, Layout **out) {
     L->grid = h->num_sms;
     deal(h->row_count, T, L->Sg, L->gene_dev);
     deal(h->col_count, T, L->Sc, L->cell_dev);
-    auto bail = [&](int rc) { L->release(); delete L; return rc; };
+    auto bail = [&](int rc) { L->release(h->stream); delete L; return rc; };
     auto body = [&]() -> int {
-        CK(cudaMalloc(&L->d_gene_dev, (size_t)h->n * 4));
-        CK(cudaMalloc(&L->d_cell_dev, (size_t)h->m * 4));
-        CK(cudaMemcpy(L->d_gene_dev, L->gene_dev.data(), (size_t)h->n * 4, cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(L->d_cell_dev, L->cell_dev.data(), (size_t)h->m * 4, cudaMemcpyHostToDevice));
+        CK(vmalloc(h, &L->d_gene_dev, (size_t)h->n * 4));
+        CK(vmalloc(h, &L->d_cell_dev, (size_t)h->m * 4));
+        CK(copy_sync(h, L->d_gene_dev, L->gene_dev.data(), (size_t)h->n * 4, cudaMemcpyHostToDevice));
+        CK(copy_sync(h, L->d_cell_dev, L->cell_dev.data(), (size_t)h->m * 4, cudaMemcpyHostToDevice));
         int32_t *d_colof = nullptr;
         unsigned long long *d_cnt = nullptr;
-        CK(cudaMalloc(&d_colof, (size_t)h->nnz * 4));
-        CK(cudaMalloc(&d_cnt, (size_t)(h->n + h->m) * 8));
+        CK(vmalloc(h, &d_colof, (size_t)h->nnz * 4));
+        CK(vmalloc(h, &d_cnt, (size_t)(h->n + h->m) * 8));
         CK(cudaMemsetAsync(d_cnt, 0, (size_t)(h->n + h->m) * 8, h->stream));
+        { StageTimer t1("  expand_cols");
         vb::expand_cols_kernel<<<h->num_sms * 8, vb::kBlock, 0, h->stream>>>(
-            h->m, h->d_colptr, h->d_rowidx, d_colof, d_cnt, d_cnt + h->n);
+            h->m, h->d_colptr, h->d_rowidx, d_colof, d_cnt, d_cnt + h->n); }
         int rc = h->val_float ? build_pass<float>(h, L, true, d_colof)
                               : build_pass<double>(h, L, true, d_colof);
         if (!rc)
             rc = h->val_float ? build_pass<float>(h, L, false, d_colof)
                               : build_pass<double>(h, L, false, d_colof);
-        cudaFree(d_colof);
-        cudaFree(d_cnt);
+        vfree(h->stream, d_colof);
+        vfree(h->stream, d_cnt);
         return rc;
     };
     int rc = body();
@@ -322,7 +368,7 @@ int get_layout(H *h, int T, Layout **out) {
 }
 
 void drop_layouts(H *h) {
-    for (Layout *l : h->layouts) { l->release(); delete l; }
+    for (Layout *l : h->layouts) { l->release(h->stream); delete l; }
     h->layouts.clear();
     h->L = nullptr;
 }
@@ -330,19 +376,20 @@ void drop_layouts(H *h) {
 // nonzero counts per gene / cell and the constants over the nonzeros
 template <typename VT>
 int scan_matrix_t(H *h) {
+    StageTimer tm("scan_matrix");
     const int64_t n = h->n, m = h->m, nnz = h->nnz;
     const int gridK = h->num_sms * 8;
     double *d_part = nullptr, *d_out = nullptr;
-    CK(cudaMalloc(&d_part, (size_t)gridK * 3 * 8));
-    CK(cudaMalloc(&d_out, 3 * 8));
+    CK(vmalloc(h, &d_part, (size_t)gridK * 3 * 8));
+    CK(vmalloc(h, &d_out, 3 * 8));
     vb::count_constants_kernel<VT><<<gridK, vb::kBlock, 0, h->stream>>>(
         nnz, (const VT *)h->d_val, d_part, d_out, h->d_counters + 4);
     double consts[3];
     CK(cudaMemcpyAsync(consts, d_out, 24, cudaMemcpyDeviceToHost, h->stream));
     int32_t *d_colof = nullptr;
     unsigned long long *d_cnt = nullptr;
-    CK(cudaMalloc(&d_colof, (size_t)nnz * 4));
-    CK(cudaMalloc(&d_cnt, (size_t)(n + m) * 8));
+    CK(vmalloc(h, &d_colof, (size_t)nnz * 4));
+    CK(vmalloc(h, &d_cnt, (size_t)(n + m) * 8));
     CK(cudaMemsetAsync(d_cnt, 0, (size_t)(n + m) * 8, h->stream));
     vb::expand_cols_kernel<<<h->num_sms * 8, vb::kBlock, 0, h->stream>>>(
         m, h->d_colptr, h->d_rowidx, d_colof, d_cnt, d_cnt + n);
@@ -353,7 +400,7 @@ int scan_matrix_t(H *h) {
                        h->stream));
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaGetLastError());
-    cudaFree(d_part); cudaFree(d_out); cudaFree(d_colof); cudaFree(d_cnt);
+    vfree(h->stream, d_part); vfree(h->stream, d_out); vfree(h->stream, d_colof); vfree(h->stream, d_cnt);
     h->lgx = consts[0];
     h->mlconst = consts[1];
     h->int_counts = h->val_float && consts[2] == 0.0;
@@ -366,12 +413,12 @@ void free_panels(H *h) {
                      &h->d_Part1, &h->d_Part2, &h->d_xl, &h->d_scal, &h->d_partW, &h->d_partH,
                      &h->d_partC};
     for (auto p : ps) {
-        if (*p) cudaFree(*p);
+        vfree(h->stream, *p);
         *p = nullptr;
     }
     if (h->h_scal) cudaFreeHost(h->h_scal);
     h->h_scal = nullptr;
-    cudaFree(h->d_lw32); cudaFree(h->d_lh32);
+    vfree(h->stream, h->d_lw32); vfree(h->stream, h->d_lh32);
     h->d_lw32 = h->d_lh32 = nullptr;
 }
 
@@ -399,27 +446,27 @@ int alloc_panels(H *h, int r) {
     if (tab->sweep_prepare(h->smem_bytes))
         return fail(h, VBNMF_ERR_CUDA, "cannot opt in to the shared-memory tile size");
     const size_t gr = (size_t)L->NG * rs * 8, cr = (size_t)L->NC * rs * 8;
-    CK(cudaMalloc(&h->d_lw, gr));
-    CK(cudaMalloc(&h->d_alw, gr));
-    CK(cudaMalloc(&h->d_lh, cr));
-    CK(cudaMalloc(&h->d_alh, cr));
-    CK(cudaMalloc(&h->d_ShRaw, cr));
-    CK(cudaMalloc(&h->d_red, (size_t)red_len(h) * 8));
-    CK(cudaMalloc(&h->d_Part1, (size_t)L->Sg * cr));
-    CK(cudaMalloc(&h->d_Part2, (size_t)L->Sc * gr));
-    CK(cudaMalloc(&h->d_xl, (size_t)L->grid * 8));
-    CK(cudaMalloc(&h->d_scal, (size_t)(rs + 8) * 8));
+    CK(vmalloc(h, &h->d_lw, gr));
+    CK(vmalloc(h, &h->d_alw, gr));
+    CK(vmalloc(h, &h->d_lh, cr));
+    CK(vmalloc(h, &h->d_alh, cr));
+    CK(vmalloc(h, &h->d_ShRaw, cr));
+    CK(vmalloc(h, &h->d_red, (size_t)red_len(h) * 8));
+    CK(vmalloc(h, &h->d_Part1, (size_t)L->Sg * cr));
+    CK(vmalloc(h, &h->d_Part2, (size_t)L->Sc * gr));
+    CK(vmalloc(h, &h->d_xl, (size_t)L->grid * 8));
+    CK(vmalloc(h, &h->d_scal, (size_t)(rs + 8) * 8));
     h->gridC = h->num_sms * 4;
-    CK(cudaMalloc(&h->d_partW, (size_t)cdiv(L->NG, vb::kBlock) * (rs + 3) * 8));
-    CK(cudaMalloc(&h->d_partH, (size_t)cdiv(L->NC, vb::kBlock) * (rs + 3) * 8));
-    CK(cudaMalloc(&h->d_partC, (size_t)h->gridC * 2 * 8));
+    CK(vmalloc(h, &h->d_partW, (size_t)cdiv(L->NG, vb::kBlock) * (rs + 3) * 8));
+    CK(vmalloc(h, &h->d_partH, (size_t)cdiv(L->NC, vb::kBlock) * (rs + 3) * 8));
+    CK(vmalloc(h, &h->d_partC, (size_t)h->gridC * 2 * 8));
     CK(cudaMallocHost(&h->h_scal, (size_t)2 * (rs + 8) * 8));
     CK(cudaMemsetAsync(h->d_red, 0, (size_t)red_len(h) * 8, h->stream));
     CK(cudaMemsetAsync(h->d_scal, 0, (size_t)(rs + 8) * 8, h->stream));
     CK(cudaMemsetAsync(h->d_ShRaw, 0, cr, h->stream));
     if (f32) {
-        CK(cudaMalloc(&h->d_lw32, (size_t)L->NG * h->rsf * 4));
-        CK(cudaMalloc(&h->d_lh32, (size_t)L->NC * h->rsf * 4));
+        CK(vmalloc(h, &h->d_lw32, (size_t)L->NG * h->rsf * 4));
+        CK(vmalloc(h, &h->d_lh32, (size_t)L->NC * h->rsf * 4));
     }
     return 0;
 }
@@ -459,7 +506,7 @@ int download_panel(H *h, const double *src, std::vector<double> &tmp, bool wside
     const Layout *L = h->L;
     const int64_t N = wside ? L->NG : L->NC;
     tmp.resize((size_t)N * h->rs);
-    CK(cudaMemcpy(tmp.data(), src, tmp.size() * 8, cudaMemcpyDeviceToHost));
+    CK(copy_sync(h, tmp.data(), src, tmp.size() * 8, cudaMemcpyDeviceToHost));
     return 0;
 }
 
@@ -625,6 +672,57 @@ int hyper_update(const int *flags, const double *mn, double *hyper, int niter, d
     return 0;
 }
 
+// Host -> device upload of a large array through two pinned staging buffers: worker threads
+// convert/validate a chunk into one buffer while the copy engine drains the other.  `conv` maps
+// src[i] -> dst element and returns false for an invalid element.
+struct Staging {
+    static constexpr size_t kBytes = (size_t)32 << 20;
+    void *buf[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2];
+    bool ok = false;
+    bool init() {
+        if (ok) return true;
+        for (int i = 0; i < 2; i++) {
+            if (cudaMallocHost(&buf[i], kBytes) != cudaSuccess) return false;
+            if (cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) return false;
+        }
+        ok = true;
+        return true;
+    }
+};
+Staging g_staging;
+
+template <typename Src, typename Dst, typename Conv>
+int staged_upload(H *h, Dst *d_dst, const Src *src, int64_t count, Conv conv, bool *all_ok) {
+    if (!g_staging.init()) return fail(h, VBNMF_ERR_CUDA, "cannot allocate pinned staging buffers");
+    const int64_t per = (int64_t)(Staging::kBytes / sizeof(Dst));
+    const int nthr = (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+    std::vector<char> good((size_t)nthr, 1);
+    int slot = 0;
+    for (int64_t lo = 0; lo < count; lo += per, slot ^= 1) {
+        const int64_t len = std::min(per, count - lo);
+        CK(cudaEventSynchronize(g_staging.ev[slot]));  // the copy that last used this buffer is done
+        Dst *out = (Dst *)g_staging.buf[slot];
+        auto work = [&](int t) {
+            const int64_t a = len * t / nthr, b = len * (t + 1) / nthr;
+            bool okk = true;
+            for (int64_t i = a; i < b; i++) okk &= conv(src[lo + i], out[i]);
+            if (!okk) good[(size_t)t] = 0;
+        };
+        std::vector<std::thread> th;
+        for (int t = 1; t < nthr; t++) th.emplace_back(work, t);
+        work(0);
+        for (auto &x : th) x.join();
+        CK(cudaMemcpyAsync(d_dst + lo, out, (size_t)len * sizeof(Dst), cudaMemcpyHostToDevice,
+                           h->stream));
+        CK(cudaEventRecord(g_staging.ev[slot], h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    *all_ok = true;
+    for (char c : good) *all_ok = *all_ok && c;
+    return 0;
+}
+
 int init_common(H *h, int device) {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
@@ -637,7 +735,15 @@ int init_common(H *h, int device) {
     h->num_sms = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     h->own_stream = true;
-    CK(cudaMalloc(&h->d_counters, 16 * sizeof(unsigned)));
+    {   // keep freed blocks in the device's default pool (VBNMF_POOL_KEEP_GB, default 32 GB)
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            const char *env = getenv("VBNMF_POOL_KEEP_GB");
+            uint64_t keep = (uint64_t)(env ? atof(env) : 32.0) << 30;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
+    CK(vmalloc(h, &h->d_counters, 16 * sizeof(unsigned)));
     CK(cudaMemset(h->d_counters, 0, 16 * sizeof(unsigned)));
     h->m_global = h->m;
     return 0;
@@ -658,9 +764,9 @@ void vbnmf_destroy(vbnmf_handle *h) {
     free_panels(h);
     drop_layouts(h);
     if (!h->borrowed) {
-        cudaFree(h->d_colptr); cudaFree(h->d_rowidx); cudaFree(h->d_val);
+        vfree(h->stream, h->d_colptr); vfree(h->stream, h->d_rowidx); vfree(h->stream, h->d_val);
     }
-    cudaFree(h->d_counters);
+    vfree(h->stream, h->d_counters);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -675,6 +781,7 @@ int vbnmf_create(vbnmf_handle **out, int64_t n, int64_t m, int64_t nnz, const in
         vbnmf_destroy(h);
         return rc;
     };
+    StageTimer tm("vbnmf_create(total)");
     if (n <= 0 || m <= 0 || nnz <= 0 || (!colptr32 == !colptr64) || !rowidx || !values)
         return bail(fail(h, VBNMF_ERR_ARG, "vbnmf_create: bad arguments"));
     if (nnz >= (int64_t)UINT32_MAX)
@@ -685,30 +792,42 @@ int vbnmf_create(vbnmf_handle **out, int64_t n, int64_t m, int64_t nnz, const in
     std::vector<int64_t> cp((size_t)m + 1);
     for (int64_t j = 0; j <= m; j++) cp[j] = colptr64 ? colptr64[j] : (int64_t)colptr32[j];
     if (cp[0] != 0 || cp[m] != nnz) return bail(fail(h, VBNMF_ERR_ARG, "colptr does not span nnz"));
+    for (int64_t j = 0; j < m; j++)
+        if (cp[j] > cp[j + 1]) return bail(fail(h, VBNMF_ERR_ARG, "colptr is not non-decreasing"));
     bool as_float = true;
-    for (int64_t t = 0; t < nnz; t++) {
-        if (rowidx[t] < 0 || rowidx[t] >= n)
-            return bail(fail(h, VBNMF_ERR_ARG, "row index out of range"));
-        if ((double)(float)values[t] != values[t]) as_float = false;
-    }
-    h->val_float = as_float;
     auto up = [&]() -> int {
-        CK(cudaMalloc(&h->d_colptr, (size_t)(m + 1) * 8));
-        CK(cudaMalloc(&h->d_rowidx, (size_t)nnz * 4));
-        CK(cudaMemcpy(h->d_colptr, cp.data(), (size_t)(m + 1) * 8, cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(h->d_rowidx, rowidx, (size_t)nnz * 4, cudaMemcpyHostToDevice));
-        if (as_float) {
-            std::vector<float> vf((size_t)nnz);
-            for (int64_t t = 0; t < nnz; t++) vf[t] = (float)values[t];
-            CK(cudaMalloc(&h->d_val, (size_t)nnz * 4));
-            CK(cudaMemcpy(h->d_val, vf.data(), (size_t)nnz * 4, cudaMemcpyHostToDevice));
+        StageTimer tu("  upload (staged, pinned)");
+        bool ok = true;
+        CK(vmalloc(h, &h->d_colptr, (size_t)(m + 1) * 8));
+        CK(vmalloc(h, &h->d_rowidx, (size_t)nnz * 4));
+        CK(copy_sync(h, h->d_colptr, cp.data(), (size_t)(m + 1) * 8, cudaMemcpyHostToDevice));
+        const int32_t nn = (int32_t)n;
+        int rc2 = staged_upload(h, h->d_rowidx, rowidx, nnz,
+                                [nn](int32_t v, int32_t &o) { o = v; return v >= 0 && v < nn; }, &ok);
+        if (rc2) return rc2;
+        if (!ok) return fail(h, VBNMF_ERR_ARG, "row index out of range");
+        // counts go to the device as fp32 when every one of them is exactly representable
+        float *dv = nullptr;
+        CK(vmalloc(h, &dv, (size_t)nnz * 4));
+        rc2 = staged_upload(h, dv, values, nnz,
+                            [](double v, float &o) { o = (float)v; return (double)o == v; }, &ok);
+        if (rc2) return rc2;
+        if (ok) {
+            h->d_val = dv;
         } else {
-            CK(cudaMalloc(&h->d_val, (size_t)nnz * 8));
-            CK(cudaMemcpy(h->d_val, values, (size_t)nnz * 8, cudaMemcpyHostToDevice));
+            as_float = false;
+            vfree(h->stream, dv);
+            double *dd = nullptr;
+            CK(vmalloc(h, &dd, (size_t)nnz * 8));
+            rc2 = staged_upload(h, dd, values, nnz, [](double v, double &o) { o = v; return true; },
+                                &ok);
+            if (rc2) return rc2;
+            h->d_val = dd;
         }
         return 0;
     };
     if ((rc = up())) return bail(rc);
+    h->val_float = as_float;
     rc = as_float ? scan_matrix_t<float>(h) : scan_matrix_t<double>(h);
     if (rc) return bail(rc);
     *out = h;
@@ -820,13 +939,13 @@ int vbnmf_attach_comm(vbnmf_handle *h, vbnmf_comm *c) {
     hv[0] = (double)h->m; hv[1] = h->lgx; hv[2] = h->mlconst;
     for (int64_t i = 0; i < h->n; i++) hv[3 + i] = (double)h->row_count[i];
     double *dv = nullptr;
-    CK(cudaMalloc(&dv, (size_t)len * 8));
+    CK(vmalloc(h, &dv, (size_t)len * 8));
     CK(cudaMemcpyAsync(dv, hv.data(), (size_t)len * 8, cudaMemcpyHostToDevice, h->stream));
     int rc = allreduce(h, dv, len);
     if (rc) return rc;
     CK(cudaMemcpyAsync(hv.data(), dv, (size_t)len * 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    cudaFree(dv);
+    vfree(h->stream, dv);
     h->m_global = (int64_t)llround(hv[0]);
     h->lgx = hv[1];
     h->mlconst = hv[2];
@@ -842,6 +961,7 @@ int vbnmf_set_state(vbnmf_handle *h, int r, const double *lw, const double *lh, 
     if (!h || !lw || !lh) return VBNMF_ERR_ARG;
     if (r < 1 || r > kMaxRank) return fail(h, VBNMF_ERR_ARG, "rank must be in 1..64");
     CK(cudaSetDevice(h->device));
+    StageTimer tm("vbnmf_set_state(total)");
     int rc;
     if ((rc = alloc_panels(h, r))) return rc;
     if ((rc = upload_panel(h, h->d_lw, lw, true, r))) return rc;
@@ -930,6 +1050,7 @@ int vbnmf_get_state(vbnmf_handle *h, double *lw, double *lh, double *ew, double 
     if (!h->d_lw) return fail(h, VBNMF_ERR_STATE, "vbnmf_set_state has not been called");
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
+    StageTimer tm("vbnmf_get_state(total)");
     const int r = h->r, rs = h->rs;
     const int64_t n = h->n, m = h->m;
     const Layout *L = h->L;
@@ -976,15 +1097,15 @@ int vbnmf_cluster_id(vbnmf_handle *h, int32_t *cid) {
     double *d_beh = nullptr;
     int32_t *d_cid = nullptr;
     std::vector<int32_t> tmp((size_t)L->NC);
-    CK(cudaMalloc(&d_beh, kMaxRank * 8));
-    CK(cudaMalloc(&d_cid, (size_t)L->NC * 4));
+    CK(vmalloc(h, &d_beh, kMaxRank * 8));
+    CK(vmalloc(h, &d_cid, (size_t)L->NC * 4));
     CK(cudaMemcpyAsync(d_beh, h->beh, kMaxRank * 8, cudaMemcpyHostToDevice, h->stream));
     vb::cluster_id_kernel<<<cdiv(L->NC, vb::kBlock), vb::kBlock, 0, h->stream>>>(
         L->NC, h->rs, h->r, h->d_alh, d_beh, d_cid);
     CK(cudaMemcpyAsync(tmp.data(), d_cid, (size_t)L->NC * 4, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    cudaFree(d_beh);
-    cudaFree(d_cid);
+    vfree(h->stream, d_beh);
+    vfree(h->stream, d_cid);
     for (int64_t j = 0; j < h->m; j++) cid[j] = tmp[(size_t)L->cell_dev[j]];
     return 0;
 }

@@ -43,8 +43,10 @@ class Engine:
                                                    C.c_void_p(d_val), int(device))
         else:
             import scipy.sparse as sp
-            csc = sp.csc_matrix(counts)
-            csc.sort_indices()
+            csc = counts if sp.isspmatrix_csc(counts) else sp.csc_matrix(counts)
+            if not csc.has_sorted_indices:
+                csc = csc.copy()
+                csc.sort_indices()
             n, m = csc.shape
             nnz = csc.nnz
             rowidx = np.ascontiguousarray(csc.indices, dtype=np.int32)
