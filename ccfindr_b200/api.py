@@ -120,16 +120,35 @@ def dispersion_from_labels(label_runs):
     return 1.0 / nc + 8.0 * con / nc ** 2
 
 
+def lpt_schedule(costs, nworkers):
+    """Longest-processing-time-first assignment of independent jobs to workers.
+    Returns a list (one per worker) of job indices, each in decreasing cost order."""
+    order = sorted(range(len(costs)), key=lambda i: (-costs[i], i))
+    load = [0.0] * nworkers
+    out = [[] for _ in range(nworkers)]
+    for i in order:
+        w = min(range(nworkers), key=lambda k: (load[k], k))
+        out[w].append(i)
+        load[w] += costs[i]
+    return out
+
+
 def vb_factorize(object, ranks=2, nrun=1, verbose=2, progress_bar=True, initializer="random",
                  Itmax=10000, hyper_update=(True,) * 4, gamma_a=1, gamma_b=1, Tol=1e-5,
                  hyper_update_n0=10, hyper_update_dn=1, connectivity=True, fudge=None, ncores=1,
-                 useC=True, unif_stop=True, seed=1, device=0, inits=None):
+                 useC=True, unif_stop=True, seed=1, device=0, inits=None, precision=0,
+                 parallel=False):
     """Bayesian NMF inference of a count matrix (R/bayesian.R:229-301).
 
     Arguments as in the reference (dots replaced by underscores).  Extras: `seed` keys the NumPy
     Philox streams of the 'random' initializer (run i, rank r uses seed*100003 + 1000*r + i);
     `inits[(irun, rank)] = (w0, h0)` overrides the draw; `device` is the CUDA ordinal.
     `ncores` and `useC` are accepted and ignored: the update always runs on the GPU.
+    `precision`: 0 = fp64 (reference arithmetic), 1 = fp32-storage / fp64-accumulate.
+    `parallel=True` (inside an initialised torch.distributed job, one process per GPU): the
+    nrun x len(ranks) independent factorizations are spread over the ranks (the role of
+    Rmpi::mpi.applyLB, R/bayesian.R:263), every rank holds a full copy of the matrix, results are
+    all-gathered and every rank returns the same object.
     """
     if fudge is None:
         fudge = EPS                                             # :238
@@ -143,12 +162,18 @@ def vb_factorize(object, ranks=2, nrun=1, verbose=2, progress_bar=True, initiali
     ga = np.atleast_1d(np.asarray(gamma_a, dtype=np.float64))
     gb = np.atleast_1d(np.asarray(gamma_b, dtype=np.float64))
 
+    common = (ga, gb, initializer, Itmax, hyper_update, Tol, hyper_update_n0, hyper_update_dn,
+              connectivity, fudge)
     vb = []
-    with Engine(mat, device=device) as eng:
-        for irun in range(1, nrun + 1):                         # lapply over runs, :260-261
-            vb.append(_vb_iterate(eng, irun, mat, ranks, ga, gb, initializer, Itmax, hyper_update,
-                                  Tol, hyper_update_n0, hyper_update_dn, connectivity, fudge,
-                                  unif_stop, nrun, verbose, seed, inits, vb))
+    if parallel:
+        vb = _vb_parallel(mat, ranks, nrun, common, unif_stop, verbose, seed, inits, device,
+                          precision)
+    else:
+        with Engine(mat, device=device) as eng:
+            eng.set_precision(precision)
+            for irun in range(1, nrun + 1):                     # lapply over runs, :260-261
+                vb.append(_vb_iterate(eng, irun, mat, ranks, *common, unif_stop, nrun, verbose,
+                                      seed, inits, vb))
 
     basis = [None] * nrank
     coeff, dbasis, dcoeff = [None] * nrank, [None] * nrank, [None] * nrank
@@ -173,6 +198,52 @@ def vb_factorize(object, ranks=2, nrun=1, verbose=2, progress_bar=True, initiali
     return object
 
 
+def _vb_parallel(mat, ranks, nrun, common, unif_stop, verbose, seed, inits, device, precision):
+    """Independent (run, rank) factorizations spread over the ranks of torch.distributed."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        raise RuntimeError("parallel=True needs an initialised torch.distributed process group")
+    world, me = dist.get_world_size(), dist.get_rank()
+    jobs = [(irun, k) for irun in range(1, nrun + 1) for k in range(len(ranks))]
+    mine = lpt_schedule([float(ranks[k]) for _, k in jobs], world)[me]
+    done = {}
+    with Engine(mat, device=device) as eng:
+        eng.set_precision(precision)
+        for j in mine:
+            irun, k = jobs[j]
+            # one-rank call of the per-run routine; the uniform-column rule is applied afterwards
+            out = _vb_iterate(eng, irun, mat, [ranks[k]], *common, False, nrun, 0, seed, inits, [])
+            done[(irun, k)] = {key: out[key][0] for key in out}
+            done[(irun, k)]["unif"] = out["unif_flag"][0]
+    gathered = [None] * world
+    dist.all_gather_object(gathered, done)
+    allres = {}
+    for d in gathered:
+        allres.update(d)
+    vb = []
+    for irun in range(1, nrun + 1):
+        out = dict(rdat=[-np.inf] * len(ranks), wdat=[None] * len(ranks), hdat=[None] * len(ranks),
+                   dwdat=[None] * len(ranks), dhdat=[None] * len(ranks),
+                   hyperp=[None] * len(ranks), nunif=[0] * len(ranks))
+        for k in range(len(ranks)):
+            res = allres[(irun, k)]
+            if res["unif"]:                                     # R/bayesian.R:370-378, post hoc
+                warnings.warn("Rank %d row/column constant." % ranks[k])
+                if unif_stop:
+                    warnings.warn("Rank scan stopped for rank >= %d" % ranks[k])
+                    if k == 0:
+                        raise RuntimeError("Rerun with lower ranks")
+                    break
+            for key in ("rdat", "wdat", "hdat", "dwdat", "dhdat", "hyperp", "nunif"):
+                out[key][k] = res[key]
+        if verbose >= 2:
+            for k in range(len(ranks)):
+                if out["hyperp"][k] is not None:
+                    print("Run %d Rank = %d: log(evidence) = %s" % (irun, ranks[k], out["rdat"][k]))
+        vb.append(out)
+    return vb
+
+
 def _vb_iterate(eng, irun, mat, ranks, ga, gb, initializer, Itmax, hyper_update, Tol, n0, dn,
                 connectivity, fudge, unif_stop, nrun, verbose, seed, inits, previous):
     """R/bayesian.R:303-390 for one run; the it-loop runs on the GPU."""
@@ -180,7 +251,8 @@ def _vb_iterate(eng, irun, mat, ranks, ga, gb, initializer, Itmax, hyper_update,
     nrank = len(ranks)
     out = dict(rdat=[-np.inf] * nrank, wdat=[None] * nrank, hdat=[None] * nrank,
                dwdat=[None] * nrank, dhdat=[None] * nrank, hyperp=[None] * nrank,
-               nunif=[0] * nrank, labels=[None] * nrank, niter=[0] * nrank)
+               nunif=[0] * nrank, labels=[None] * nrank, niter=[0] * nrank,
+               unif_flag=[False] * nrank)
     if verbose >= 2 and nrun > 1:
         print("Run %d" % irun)
     for irank, rank in enumerate(ranks):
@@ -216,6 +288,7 @@ def _vb_iterate(eng, irun, mat, ranks, ga, gb, initializer, Itmax, hyper_update,
                 rank, it, lk0, hyper["aw"], hyper["bw"], hyper["ah"], hyper["bh"])
             print(msg + (", dispersion = %s" % disp if connectivity else ""))
         unif = eng.uniform_columns(Tol)                         # :368-369
+        out["unif_flag"][irank] = bool(unif.sum() > 0)
         if unif.sum() > 0:
             warnings.warn("Rank %d row/column %s constant." % (
                 rank, ",".join(str(i + 1) for i in np.flatnonzero(unif))))

@@ -72,6 +72,17 @@ def main():
             relerr(out["h"], ref["h"][:, c0:c1]))
     assert e < 1e-9, ("ml", rank, e)
     eng.close()
+    # independent (run, rank) jobs farmed over the ranks == the serial front end, bit for bit
+    from ccfindr_b200 import api
+    Xc = load_counts("c1s2")
+    kw = dict(ranks=[2, 3, 4], nrun=2, verbose=0, Itmax=40, seed=3, device=local)
+    par = api.vb_factorize(api.scNMFSet(Xc), parallel=True, **kw)
+    ser = api.vb_factorize(api.scNMFSet(Xc), parallel=False, **kw)
+    assert list(par.ranks) == list(ser.ranks)
+    for key in ser.measure:
+        assert np.array_equal(par.measure[key], ser.measure[key]), key
+    for k in range(len(ser.ranks)):
+        assert np.array_equal(par.basis[k], ser.basis[k]) and np.array_equal(par.coeff[k], ser.coeff[k])
     t = torch.tensor([max(worst, e)], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:

@@ -77,3 +77,12 @@ def test_optimal_rank_types():
     assert out["type"] == 2 and 3.0 <= out["ropt"] <= 10.0
     with pytest.raises(ValueError):
         api.optimal_rank(dict(rank=ranks, lml=peak))
+
+
+def test_lpt_schedule_balances_rank_sweep():
+    ranks = list(range(2, 31)) * 5                       # BASELINE config 4: ranks 2..30 x 5 restarts
+    plan = api.lpt_schedule([float(r) for r in ranks], 8)
+    assert sorted(i for w in plan for i in w) == list(range(len(ranks)))
+    loads = [sum(ranks[i] for i in w) for w in plan]
+    assert max(loads) - min(loads) <= max(ranks)
+    assert api.lpt_schedule([3.0, 1.0], 4) == [[0], [1], [], []]
