@@ -22,6 +22,8 @@ LIB = os.path.join(HERE, "libvbnmf.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-I", INCLUDE]
+if os.environ.get("VBNMF_SWEEP_THREADS"):  # tuning experiments only
+    NVCC_FLAGS.append("-DVB_SWEEP_THREADS=" + os.environ["VBNMF_SWEEP_THREADS"])
 
 
 def _nvcc():

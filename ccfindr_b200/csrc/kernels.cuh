@@ -173,10 +173,21 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
 //
 // The build step orders the nonzeros of a segment so that 8 consecutive ones hit tile rows that
 // differ mod 8 -> with an odd row stride the 8 gathers of a group are bank-conflict free.
+#ifndef VB_SWEEP_THREADS
+#define VB_SWEEP_THREADS 512  // threads per sweep CTA for the narrow-rank configuration
+#endif
 template <int RP, typename PT>
 struct SweepCfg {
-    // register budget: own + acc + tile row = 3*RP values of PT, plus prefetched entries
-    static constexpr int kThreads = (RP * (int)sizeof(PT) <= 96) ? 512 : 256;
+    // Register budget per lane: own + acc + tile row = 3 * KL values of PT plus the prefetched
+    // entries.  Wide ranks are split over LPN = 2 lanes per nonzero (each lane takes every other
+    // 16-byte unit of the row), which keeps 512 threads (16 warps) per SM up to r = 24 in fp64.
+    static constexpr int kUE = 16 / (int)sizeof(PT);             // elements per 16-byte unit
+    static constexpr int kNU = (RP + kUE - 1) / kUE;             // units per row
+    static constexpr int kLPN = (RP * (int)sizeof(PT) > 96) ? 2 : 1;  // lanes per nonzero
+    static constexpr int kNUL = (kNU + kLPN - 1) / kLPN;         // units per lane
+    static constexpr int kKL = kNUL * kUE;                       // rank entries per lane
+    static constexpr int kNPG = kGroup / kLPN;                   // nonzeros per group step
+    static constexpr int kThreads = (kKL * (int)sizeof(PT) <= 96) ? VB_SWEEP_THREADS : 256;
     static constexpr int kGroups = kThreads / kGroup;
 };
 
@@ -281,19 +292,40 @@ __device__ __forceinline__ void load_entry<double>(const SweepTiledArgs &a, int6
     x = __ldcs(a.val + t);
 }
 
+// one 16-byte unit of a panel row from global memory (read-only path) / shared memory
+__device__ __forceinline__ void ldg_unit(const double *row, int u, double *out) {
+    const double2 v = __ldg(reinterpret_cast<const double2 *>(row) + u);
+    out[0] = v.x; out[1] = v.y;
+}
+__device__ __forceinline__ void ldg_unit(const float *row, int u, float *out) {
+    const float4 v = __ldg(reinterpret_cast<const float4 *>(row) + u);
+    out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
+}
+__device__ __forceinline__ void lds_unit(uint32_t addr, double *out) {
+    const double2 v = lds128(addr);
+    out[0] = v.x; out[1] = v.y;
+}
+__device__ __forceinline__ void lds_unit(uint32_t addr, float *out) {
+    const float4 v = lds128f(addr);
+    out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
+}
+
 template <int RP, typename VT, bool COLS, typename PT>
 __global__ void __launch_bounds__(SweepCfg<RP, PT>::kThreads, 1)
 sweep_tiled_kernel(const SweepTiledArgs a) {
+    using Cfg = SweepCfg<RP, PT>;
     constexpr int RS = row_stride(RP);          // stride of the fp64 Part rows
     constexpr int PS = panel_stride<PT>(RP);    // stride of the gathered / owner panels
-    constexpr int NT = SweepCfg<RP, PT>::kThreads;
-    constexpr int U = kUnroll;
+    constexpr int NT = Cfg::kThreads, U = kUnroll;
+    constexpr int UE = Cfg::kUE, NU = Cfg::kNU, LPN = Cfg::kLPN, NUL = Cfg::kNUL, KL = Cfg::kKL;
+    constexpr int NPG = Cfg::kNPG;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     PT *tile = reinterpret_cast<PT *>(smem_raw);
     const uint32_t tile_s = smem_u32(tile);
     __shared__ __align__(8) uint64_t mbar;
     __shared__ double red[NT / 32];
     const int gid = threadIdx.x / kGroup, gl = threadIdx.x % kGroup;
+    const int slot = gl / LPN, hf = gl % LPN;   // nonzero slot within the group step, rank half
     // the 4 groups of a warp run different trip counts: shuffles name only their own 8 lanes
     const unsigned gmask = 0xffu << ((threadIdx.x & 31) & ~(kGroup - 1));
     const int64_t e0 = a.split[blockIdx.x], e1 = a.split[blockIdx.x + 1];
@@ -314,23 +346,31 @@ sweep_tiled_kernel(const SweepTiledArgs a) {
         }
         mbar_wait(&mbar, parity);
         parity ^= 1;
-        for (int64_t e = ebase + gid; e < eend; e += SweepCfg<RP, PT>::kGroups) {
+        for (int64_t e = ebase + gid; e < eend; e += Cfg::kGroups) {
             const int64_t o = e - slab * a.NO;
             const int64_t beg = __ldg(a.ptr + e), end = __ldg(a.ptr + e + 1);
             // pull the entries of this group's NEXT segment from HBM into L2 while this one runs
-            if (sizeof(VT) == 4 && e + SweepCfg<RP, PT>::kGroups < eend) {
-                const int64_t nb = __ldg(a.ptr + e + SweepCfg<RP, PT>::kGroups);
-                const int64_t ne = __ldg(a.ptr + e + SweepCfg<RP, PT>::kGroups + 1);
+            if (sizeof(VT) == 4 && e + Cfg::kGroups < eend) {
+                const int64_t nb = __ldg(a.ptr + e + Cfg::kGroups);
+                const int64_t ne = __ldg(a.ptr + e + Cfg::kGroups + 1);
                 for (int64_t t = nb + gl * 16; t < ne; t += kGroup * 16)
                     prefetch_l2(reinterpret_cast<const int2 *>(a.ent) + t);
             }
-            PT acc[RP];
+            PT acc[KL];
             PT xls = 0;  // x log p of this segment in the arithmetic type
 #pragma unroll
-            for (int k = 0; k < RP; k++) acc[k] = 0;
+            for (int k = 0; k < KL; k++) acc[k] = 0;
             if (beg < end) {
-                PT own[RP];
-                load_row_t<RP>(a.owner, o, own);
+                // this lane's share of the owner row: units hf, hf + LPN, ...
+                PT own[KL];
+                const PT *orow = reinterpret_cast<const PT *>(a.owner) + o * PS;
+#pragma unroll
+                for (int c = 0; c < NUL; c++) {
+                    const int u = LPN * c + hf;
+#pragma unroll
+                    for (int j = 0; j < UE; j++) own[c * UE + j] = 0;
+                    if (u < NU) ldg_unit(orow, u, own + c * UE);
+                }
                 // software pipeline: the U index/count loads of the next chunk are issued before
                 // the current chunk is processed.  Slots past the end of the segment carry a zero
                 // count and tile row 0: they run through the same arithmetic and add nothing, so
@@ -340,14 +380,14 @@ sweep_tiled_kernel(const SweepTiledArgs a) {
                 double xv[U], xn[U];
 #pragma unroll
                 for (int u = 0; u < U; u++) {
-                    const int t = gl + u * kGroup;
+                    const int t = slot + u * NPG;
                     ti[u] = 0; xv[u] = 0.0;
                     if (t < len) load_entry<VT>(a, beg + t, ti[u], xv[u]);
                 }
-                for (int c = 0; c < len; c += U * kGroup) {
+                for (int c0 = 0; c0 < len; c0 += U * NPG) {
 #pragma unroll
                     for (int u = 0; u < U; u++) {
-                        const int t = c + U * kGroup + gl + u * kGroup;
+                        const int t = c0 + U * NPG + slot + u * NPG;
                         tn[u] = 0; xn[u] = 0.0;
                         if (t < len) load_entry<VT>(a, beg + t, tn[u], xn[u]);
                     }
@@ -355,43 +395,49 @@ sweep_tiled_kernel(const SweepTiledArgs a) {
                     for (int u = 0; u < U; u++) {
                         const PT x = (PT)xv[u];
                         const uint32_t raddr = tile_s + (uint32_t)ti[u] * (PS * (int)sizeof(PT));
-                        PT tr[RP];
-                        gather_row<RP>(raddr, tr);
+                        PT tr[KL];
+#pragma unroll
+                        for (int c = 0; c < NUL; c++) {
+                            const int uu = LPN * c + hf;
+                            if (LPN == 1 || uu < NU) {
+                                lds_unit(raddr + uu * 16, tr + c * UE);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < UE; j++) tr[c * UE + j] = 0;
+                            }
+                        }
                         PT p0 = 0, p1 = 0;
 #pragma unroll
-                        for (int k = 0; k < RP; k += 2) {
+                        for (int k = 0; k < KL; k += 2) {
                             p0 = fma(own[k], tr[k], p0);
                             p1 = fma(own[k + 1], tr[k + 1], p1);
                         }
-                        const PT p = p0 + p1;
+                        PT p = p0 + p1;
+                        if (LPN == 2) p += __shfl_xor_sync(gmask, p, 1);
                         const PT q = x * rcp_t(p);
 #pragma unroll
-                        for (int k = 0; k < RP; k++) acc[k] = fma(tr[k], q, acc[k]);
-                        if (COLS) xls = fma(x, log_t(p), xls);
+                        for (int k = 0; k < KL; k++) acc[k] = fma(tr[k], q, acc[k]);
+                        if (COLS) xls = fma(hf == 0 ? x : (PT)0, log_t(p), xls);
                     }
 #pragma unroll
                     for (int u = 0; u < U; u++) { ti[u] = tn[u]; xv[u] = xn[u]; }
                 }
                 if (COLS) xl += (double)xls;
             }
-            // sum over the 8 lanes of the group; lane gl keeps k = gl, gl+8, ...
-            constexpr int NH = (RP + kGroup - 1) / kGroup;
-            double mine[NH];
+            // sum over the lanes of the group that hold the same rank entries, in fp64
+            double *out = a.Part + e * RS;
 #pragma unroll
-            for (int h = 0; h < NH; h++) mine[h] = 0.0;
-#pragma unroll
-            for (int k = 0; k < RP; k++) {
+            for (int k = 0; k < KL; k++) {
                 double s = (double)acc[k];  // fp64 from here on (sums over lanes, slabs, ranks)
                 s += __shfl_xor_sync(gmask, s, 4);
                 s += __shfl_xor_sync(gmask, s, 2);
-                s += __shfl_xor_sync(gmask, s, 1);
-                if ((k % kGroup) == gl) mine[k / kGroup] = s;
-            }
-            double *out = a.Part + e * RS;
-#pragma unroll
-            for (int h = 0; h < NH; h++) {
-                const int kk = gl + kGroup * h;
-                if (kk < RP) out[kk] = mine[h];
+                if (LPN == 1) s += __shfl_xor_sync(gmask, s, 1);
+                const int kk = (LPN * (k / UE) + hf) * UE + (k % UE);  // rank index of entry k
+                if (LPN == 1) {
+                    if ((k % kGroup) == gl && kk < RP) out[kk] = s;
+                } else {
+                    if (slot == (k % NPG) && kk < RP) out[kk] = s;
+                }
             }
         }
         ebase = eend;

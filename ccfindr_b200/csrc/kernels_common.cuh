@@ -84,8 +84,10 @@ segment_ptr_kernel(int64_t E, int64_t nnz, const uint32_t *__restrict__ sorted_k
 
 // Gather one pass of the tiled layout through the sort permutation and order each segment for
 // conflict-free shared-memory gathers: the nonzeros of a segment are bucketed by (tile row mod 8)
-// and emitted round-robin, one from every non-empty bucket per round, so that 8 consecutive
-// nonzeros touch tile rows that differ mod 8 (until the smaller buckets run dry).
+// and emitted round-robin, one from every non-empty bucket per round in the residue order
+// 0,2,4,6,1,3,5,7: 8 consecutive nonzeros touch tile rows that differ mod 8, and 4 consecutive
+// ones rows of equal parity (what the 2-lanes-per-nonzero variant of the sweep needs), until the
+// smaller buckets run dry.
 // One thread per segment; the order inside a bucket is the sorted (stable) order.
 template <typename VT>
 __global__ void __launch_bounds__(kBlock)
@@ -105,7 +107,8 @@ build_segments_kernel(int64_t E, const int64_t *__restrict__ ptr,
         for (int64_t t = beg; t < end; t++) {
             const uint32_t s = perm[t];
             const int32_t d = cols_pass ? gene_dev[rowidx[s]] : cell_dev[colof[s]];
-            cnt[(d % T) & 7]++;
+            const int rr = (d % T) & 7;
+            cnt[(rr >> 1) | ((rr & 1) << 2)]++;  // bucket order 0,2,4,6,1,3,5,7
         }
         int seen[8];
 #pragma unroll
@@ -113,7 +116,7 @@ build_segments_kernel(int64_t E, const int64_t *__restrict__ ptr,
         for (int64_t t = beg; t < end; t++) {
             const uint32_t s = perm[t];
             const int32_t d = cols_pass ? gene_dev[rowidx[s]] : cell_dev[colof[s]];
-            const int local = d % T, b = local & 7;
+            const int local = d % T, rr = local & 7, b = (rr >> 1) | ((rr & 1) << 2);
             const int round = seen[b]++;
             // position = elements of all buckets in earlier rounds + earlier buckets in this round
             int64_t pos = 0;
