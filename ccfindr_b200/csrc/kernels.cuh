@@ -507,82 +507,83 @@ combine_kernel(int64_t NO, int nslabs, int r, const double *__restrict__ Part,
 //   out[RS+2]    : sum e                                               (R/bayesian.R:10-11)
 // One thread per panel row.  Rows are in device order: row d = slab*T + local holds the item at
 // sorted position local*S + slab, valid when that is < nvalid.  al is kept for ew/dw (eh/dh).
+// Thread mapping: a CTA of kPostLanes * RS threads covers kPostRows consecutive panel rows; thread
+// t always works on rank entry k = t % RS (so its be_k, log be_k and partial sums live in
+// registers) of rows t / RS, t / RS + kPostLanes, ...  Loads and stores are fully coalesced and a
+// panel of N rows exposes N * RS-way parallelism (the special functions dominate this kernel).
+constexpr int kPostRows = 96;   // rows per CTA
+__host__ __device__ constexpr int post_lanes(int rs) {   // rows in flight per CTA
+    return (1024 / rs) < 24 ? (1024 / rs) : 24;
+}
+__host__ __device__ constexpr int post_threads(int rs) {  // padded to whole warps
+    return ((post_lanes(rs) * rs + 31) / 32) * 32;
+}
+
 template <int RP>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(post_threads(row_stride(RP)))
 posterior_kernel(int64_t rows, int T, int S, int64_t nvalid, int r, double a, double b, double fud,
                  const double *__restrict__ osum, const double *__restrict__ SRaw,
                  double *__restrict__ l, double *__restrict__ al_out, double *__restrict__ part,
                  double *__restrict__ out, unsigned *counter, float *__restrict__ l32) {
     constexpr int RS = row_stride(RP);
-    __shared__ double sm[kWarpsPerBlock];
-    __shared__ double be[RP], lbe[RP];
-    if (threadIdx.x < RP) {
-        const double v = (threadIdx.x < r) ? a / b + osum[threadIdx.x] : 1.0;
-        be[threadIdx.x] = v;
-        lbe[threadIdx.x] = log(v);
+    constexpr int kPostLanes = post_lanes(RS);
+    constexpr int NT = post_threads(RS);
+    constexpr int W = RS + 3;
+    __shared__ double sm[NT / 32];
+    __shared__ double colbuf[4][NT];
+    const int k = threadIdx.x % RS, lane_row = threadIdx.x / RS;  // lane_row >= kPostLanes: idle
+    const bool kact = k < r;
+    const double be = kact ? a / b + osum[k] : 1.0;
+    const double lbe = log(be), aob = a / b;
+    double es = 0.0, prior = 0.0, sll = 0.0;
+    const int64_t row0 = (int64_t)blockIdx.x * kPostRows;
+#pragma unroll 1
+    for (int i = lane_row; i < kPostRows && lane_row < kPostLanes; i += kPostLanes) {
+        const int64_t row = row0 + i;
+        if (row >= rows) break;
+        const int64_t slab = row / T, local = row - slab * T;
+        const bool valid = local * S + slab < nvalid;
+        double ln = 0.0, al = 0.0;
+        if (valid && kact) {
+            al = a + l[row * RS + k] * SRaw[row * RS + k];
+            const double e = al / be;
+            const double tmp = exp(vb_digamma(al)) / be;
+            ln = tmp > fud ? tmp : fud;
+            es += e;
+            sll += log(ln);
+            prior += -aob * e + al * (1.0 - lbe) + lgamma(al);
+        }
+        if (valid) {
+            l[row * RS + k] = ln;
+            al_out[row * RS + k] = al;
+            if (l32 && k < row_stride_f32(RP)) l32[row * row_stride_f32(RP) + k] = (float)ln;
+        }
+    }
+    // per-rank-entry sums over the CTA's rows, in fixed order; then the three scalars
+    colbuf[0][threadIdx.x] = es;
+    colbuf[1][threadIdx.x] = prior;
+    colbuf[2][threadIdx.x] = sll;
+    __syncthreads();
+    double *mypart = part + (size_t)blockIdx.x * W;
+    if (threadIdx.x < RS) {
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+        for (int j = 0; j < kPostLanes; j++) {
+            s0 += colbuf[0][threadIdx.x + j * RS];
+            s1 += colbuf[1][threadIdx.x + j * RS];
+            s2 += colbuf[2][threadIdx.x + j * RS];
+        }
+        mypart[threadIdx.x] = s0;
+        colbuf[3][threadIdx.x] = s0;
+        colbuf[1][threadIdx.x] = s1;
+        colbuf[2][threadIdx.x] = s2;
     }
     __syncthreads();
-    const int64_t row = (int64_t)blockIdx.x * kBlock + threadIdx.x;
-    double es[RP];
-    double prior = 0.0, sll = 0.0, se = 0.0;
-#pragma unroll
-    for (int k = 0; k < RP; k++) es[k] = 0.0;
-    bool valid = row < rows;
-    if (valid) {
-        const int64_t slab = row / T, local = row - slab * T;
-        valid = local * S + slab < nvalid;
-    }
-    if (valid) {
-        double lv[RP], sv[RP];
-        load_row_d<RP>(l, row, lv);
-        load_row_d<RP>(SRaw, row, sv);
-        const double aob = a / b;
-#pragma unroll
-        for (int k = 0; k < RP; k++) {
-            if (k < r) {
-                const double al = a + lv[k] * sv[k];
-                const double e = al / be[k];
-                const double tmp = exp(vb_digamma(al)) / be[k];
-                const double ln = tmp > fud ? tmp : fud;
-                lv[k] = ln;
-                sv[k] = al;
-                es[k] = e;
-                se += e;
-                sll += log(ln);
-                prior += -aob * e + al * (1.0 - lbe[k]) + lgamma(al);
-            } else {
-                lv[k] = 0.0;
-                sv[k] = 0.0;
-            }
-        }
-        double2 *lp = reinterpret_cast<double2 *>(l + row * RS);
-        double2 *ap = reinterpret_cast<double2 *>(al_out + row * RS);
-#pragma unroll
-        for (int k = 0; k < RP / 2; k++) {
-            lp[k] = make_double2(lv[2 * k], lv[2 * k + 1]);
-            ap[k] = make_double2(sv[2 * k], sv[2 * k + 1]);
-        }
-        if (l32) {  // fp32 mirror read by the sweep in VBNMF_FP32_STORAGE mode
-#pragma unroll
-            for (int k = 0; k < RP; k++) l32[row * row_stride_f32(RP) + k] = (float)lv[k];
-        }
-    }
-    constexpr int W = RS + 3;
-    double *mypart = part + (size_t)blockIdx.x * W;
-#pragma unroll
-    for (int k = 0; k < RP; k++) {
-        const double s = block_sum(es[k], sm);
-        if (threadIdx.x == 0) mypart[k] = s;
-    }
-    if (threadIdx.x == 0)
-        for (int k = RP; k < RS; k++) mypart[k] = 0.0;
-    prior = block_sum(prior, sm);
-    sll = block_sum(sll, sm);
-    se = block_sum(se, sm);
     if (threadIdx.x == 0) {
-        mypart[RS + 0] = prior;
-        mypart[RS + 1] = sll;
-        mypart[RS + 2] = se;
+        double p = 0.0, q = 0.0, e = 0.0;
+        for (int j = 0; j < RS; j++) { p += colbuf[1][j]; q += colbuf[2][j]; e += colbuf[3][j]; }
+        mypart[RS + 0] = p;
+        mypart[RS + 1] = q;
+        mypart[RS + 2] = e;
     }
     last_block_reduce(part, W, out, counter, sm);
 }
@@ -590,53 +591,43 @@ posterior_kernel(int64_t rows, int T, int S, int64_t nvalid, int r, double a, do
 // ---- maximum-likelihood multiplicative updates (R/factorize.R:8-15 for h, :17-24 for w) ----
 //   v_new = max(v o SRaw / osum_k, eps);  out[0..RS) = sum over rows of v_new
 template <int RP>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(post_threads(row_stride(RP)))
 ml_update_kernel(int64_t rows, int T, int S, int64_t nvalid, int r, double eps,
                  const double *__restrict__ osum, const double *__restrict__ SRaw,
                  double *__restrict__ v, double *__restrict__ part, double *__restrict__ out,
                  unsigned *counter, float *__restrict__ l32) {
     constexpr int RS = row_stride(RP);
-    __shared__ double sm[kWarpsPerBlock];
-    const int64_t row = (int64_t)blockIdx.x * kBlock + threadIdx.x;
-    double es[RP];
-#pragma unroll
-    for (int k = 0; k < RP; k++) es[k] = 0.0;
-    bool valid = row < rows;
-    if (valid) {
+    constexpr int kPostLanes = post_lanes(RS);
+    constexpr int NT = post_threads(RS);
+    __shared__ double sm[NT / 32];
+    __shared__ double colbuf[NT];
+    const int k = threadIdx.x % RS, lane_row = threadIdx.x / RS;
+    const bool kact = k < r;
+    const double os = kact ? osum[k] : 1.0;
+    double es = 0.0;
+    const int64_t row0 = (int64_t)blockIdx.x * kPostRows;
+#pragma unroll 1
+    for (int i = lane_row; i < kPostRows && lane_row < kPostLanes; i += kPostLanes) {
+        const int64_t row = row0 + i;
+        if (row >= rows) break;
         const int64_t slab = row / T, local = row - slab * T;
-        valid = local * S + slab < nvalid;
-    }
-    if (valid) {
-        double lv[RP], sv[RP];
-        load_row_d<RP>(v, row, lv);
-        load_row_d<RP>(SRaw, row, sv);
-#pragma unroll
-        for (int k = 0; k < RP; k++) {
-            if (k < r) {
-                double x = lv[k] * sv[k] / osum[k];
-                if (x < eps) x = eps;
-                lv[k] = x;
-                es[k] = x;
-            } else {
-                lv[k] = 0.0;
-            }
+        if (local * S + slab >= nvalid) continue;
+        double x = 0.0;
+        if (kact) {
+            x = v[row * RS + k] * SRaw[row * RS + k] / os;
+            if (x < eps) x = eps;
+            es += x;
         }
-        double2 *lp = reinterpret_cast<double2 *>(v + row * RS);
-#pragma unroll
-        for (int k = 0; k < RP / 2; k++) lp[k] = make_double2(lv[2 * k], lv[2 * k + 1]);
-        if (l32) {
-#pragma unroll
-            for (int k = 0; k < RP; k++) l32[row * row_stride_f32(RP) + k] = (float)lv[k];
-        }
+        v[row * RS + k] = x;
+        if (l32 && k < row_stride_f32(RP)) l32[row * row_stride_f32(RP) + k] = (float)x;
     }
-    double *mypart = part + (size_t)blockIdx.x * RS;
-#pragma unroll
-    for (int k = 0; k < RP; k++) {
-        const double s = block_sum(es[k], sm);
-        if (threadIdx.x == 0) mypart[k] = s;
+    colbuf[threadIdx.x] = es;
+    __syncthreads();
+    if (threadIdx.x < RS) {
+        double s0 = 0.0;
+        for (int j = 0; j < kPostLanes; j++) s0 += colbuf[threadIdx.x + j * RS];
+        part[(size_t)blockIdx.x * RS + threadIdx.x] = s0;
     }
-    if (threadIdx.x == 0)
-        for (int k = RP; k < RS; k++) mypart[k] = 0.0;
     last_block_reduce(part, RS, out, counter, sm);
 }
 

@@ -56,12 +56,12 @@ void combine(const CombineArgs &a, cudaStream_t s) {
                                                  a.out, a.counter, a.xl_part, a.nxl);
 }
 void posterior(const PosteriorArgs &a, cudaStream_t s) {
-    posterior_kernel<RP><<<cdiv(a.rows, kBlock), kBlock, 0, s>>>(
+    posterior_kernel<RP><<<cdiv(a.rows, kPostRows), post_threads(RS), 0, s>>>(
         a.rows, a.T, a.S, a.nvalid, a.r, a.a, a.b, a.fud, a.osum, a.SRaw, a.l, a.al_out, a.part,
         a.out, a.counter, a.l32);
 }
 void ml_update(const MlUpdateArgs &a, cudaStream_t s) {
-    ml_update_kernel<RP><<<cdiv(a.rows, kBlock), kBlock, 0, s>>>(
+    ml_update_kernel<RP><<<cdiv(a.rows, kPostRows), post_threads(RS), 0, s>>>(
         a.rows, a.T, a.S, a.nvalid, a.r, a.eps, a.osum, a.SRaw, a.v, a.part, a.out, a.counter,
         a.l32);
 }

@@ -457,8 +457,11 @@ int alloc_panels(H *h, int r) {
     CK(vmalloc(h, &h->d_xl, (size_t)L->grid * 8));
     CK(vmalloc(h, &h->d_scal, (size_t)(rs + 8) * 8));
     h->gridC = h->num_sms * 4;
-    CK(vmalloc(h, &h->d_partW, (size_t)cdiv(L->NG, vb::kBlock) * (rs + 3) * 8));
-    CK(vmalloc(h, &h->d_partH, (size_t)cdiv(L->NC, vb::kBlock) * (rs + 3) * 8));
+    // per-CTA partial rows of the posterior / ML / column-sum kernels (the larger of the two grids)
+    const int64_t gw = std::max(cdiv(L->NG, vb::kPostRows), cdiv(L->NG, vb::kBlock));
+    const int64_t gh = std::max(cdiv(L->NC, vb::kPostRows), cdiv(L->NC, vb::kBlock));
+    CK(vmalloc(h, &h->d_partW, (size_t)gw * (rs + 3) * 8));
+    CK(vmalloc(h, &h->d_partH, (size_t)gh * (rs + 3) * 8));
     CK(vmalloc(h, &h->d_partC, (size_t)h->gridC * 2 * 8));
     CK(cudaMallocHost(&h->h_scal, (size_t)2 * (rs + 8) * 8));
     CK(cudaMemsetAsync(h->d_red, 0, (size_t)red_len(h) * 8, h->stream));
