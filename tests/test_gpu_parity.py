@@ -232,3 +232,84 @@ def test_fp32_mode_step_matches_oracle_random(Engine):
         st = eng.get_state()
     for k in ("ew", "eh"):
         assert _relerr_floor(st[k], ref[k], 1e-3 * float(np.abs(ref[k]).max())) < TOL32, k
+
+
+# ---- edge cases ------------------------------------------------------------------------------------
+def _check_steps(Engine, X, w0, h0, hyper, nsteps=3, tol=TOL):
+    from oracle import bindings as ob
+    from oracle import oracle_dense as od
+    ref = od.vb_init_from(w0, h0)
+    with Engine(X) as eng:
+        eng.set_state(w0, h0)
+        for it in range(nsteps):
+            ref = ob.sparse_vb_step(X, ref, hyper, od.EPS)
+            assert relerr(eng.step(hyper, od.EPS), ref["lkh"]) < tol, it
+        st = eng.get_state()
+    for k in FACT:
+        assert relerr(st[k], ref[k]) < tol, k
+
+
+def test_empty_rows_and_columns_at_the_abi_level(Engine):
+    """The front end rejects empty rows/columns (R/bayesian.R:244-247) but a shard of cells may
+    well contain genes without counts: the engine itself must handle them."""
+    rng = np.random.default_rng(2)
+    X = sp.random(60, 45, density=0.2, random_state=rng, format="lil",
+                  data_rvs=lambda k: rng.integers(1, 9, size=k).astype(float))
+    X[7, :] = 0; X[:, 11] = 0; X[59, :] = 0; X[:, 44] = 0
+    X = sp.csc_matrix(X); X.eliminate_zeros()
+    w0, h0 = rng.random((60, 3)) + 0.1, rng.random((3, 45)) + 0.1
+    _check_steps(Engine, X, w0, h0, dict(aw=1.0, bw=1.0, ah=1.0, bh=1.0))
+
+
+@pytest.mark.parametrize("n,m,r", [(3, 2, 2), (2, 5, 1), (1, 1, 1), (130, 9, 9)])
+def test_tiny_and_degenerate_shapes(Engine, n, m, r):
+    rng = np.random.default_rng(n * 100 + m)
+    X = sp.csc_matrix(rng.integers(1, 6, size=(n, m)).astype(float))
+    w0, h0 = rng.random((n, r)) + 0.1, rng.random((r, m)) + 0.1
+    _check_steps(Engine, X, w0, h0, dict(aw=0.5, bw=2.0, ah=2.0, bh=0.5))
+
+
+def test_large_and_non_fp32_counts(Engine):
+    """counts >= 64, >= 2^24 (not fp32-representable -> fp64 count storage) and fractional"""
+    rng = np.random.default_rng(9)
+    n, m, r = 80, 70, 4
+    X = sp.random(n, m, density=0.25, random_state=rng, format="csc",
+                  data_rvs=lambda k: rng.integers(1, 2000, size=k).astype(float))
+    from ccfindr_b200 import synth
+    X = synth.fix_empty(X, 1)
+    w0, h0 = rng.random((n, r)) + 0.1, rng.random((r, m)) + 0.1
+    hyper = dict(aw=1.0, bw=1.0, ah=1.0, bh=1.0)
+    _check_steps(Engine, X, w0, h0, hyper)
+    Y = X.copy(); Y.data[::7] = 2.0 ** 24 + 1.0; Y.data[3::11] += 0.37
+    _check_steps(Engine, Y, w0, h0, hyper)
+
+
+def test_nan_bound_stops_the_loop(Engine):
+    """fudge = 0 and a gene whose lw row is zero: p = 0 at its nonzeros -> NaN bound ->
+    `if(is.na(wh$lkh)) break` (R/bayesian.R:345): one iteration, lml stays at its initial 0."""
+    rng = np.random.default_rng(4)
+    X = sp.csc_matrix(rng.integers(1, 5, size=(20, 15)).astype(float))
+    w0, h0 = rng.random((20, 2)) + 0.1, rng.random((2, 15)) + 0.1
+    w0[3, :] = 0.0
+    with Engine(X) as eng:
+        eng.set_state(w0, h0)
+        res = eng.run(dict(aw=1.0, bw=1.0, ah=1.0, bh=1.0), Itmax=50, fudge=0.0)
+    assert res["stop_reason"] == 2 and res["niter"] == 1 and res["lml"] == 0.0
+    assert np.isnan(res["lkh_trace"][0])
+
+
+def test_itmax_one_and_rank_switching_on_one_handle(Engine):
+    from oracle import bindings as ob
+    X = load_counts("tiny")
+    n, m = X.shape
+    rng = np.random.default_rng(8)
+    hyper = dict(aw=1.0, bw=1.0, ah=1.0, bh=1.0)
+    with Engine(X) as eng:
+        for r in (2, 5, 3, 2):                      # the rank loop of vb_iterate reuses one handle
+            w0, h0 = rng.random((n, r)) + 0.1, rng.random((r, m)) + 0.1
+            eng.set_state(w0, h0)
+            res = eng.run(hyper, Itmax=1)
+            ref = ob.sparse_vb_run(X, w0, h0, hyper, Itmax=1)
+            assert res["niter"] == 1 and res["stop_reason"] == 0
+            assert relerr(res["lml"], ref["lml"]) < TOL
+            assert relerr(eng.get_state(("eh",))["eh"], ref["eh"]) < TOL
