@@ -208,7 +208,7 @@ def run_ours(args):
                   "ms_per_launch": {"sweep_cols": t32[1], "sweep_rows": t32[2]},
                   "roofline_frac": b32 / ((t32[1] + t32[2]) * 1e-3) / 1e9 / peaks()[0],
                   "algorithmic_bytes_per_launch": b32, "lkh_last": r32["lkh"],
-                  "rel_diff_lkh_vs_fp64_same_iteration_count": None,
+                  "rel_diff_lkh_vs_fp64_same_iteration_count": abs(r32["lkh"] - lkh_dev) / abs(lkh_dev),
                   "what": "panels lw/lh held in fp32, per-nonzero arithmetic fp32, every sum over "
                           "lanes/slabs/ranks and the posterior update in fp64 (tolerance 1e-4)"})
     eng.set_precision(0)
