@@ -51,6 +51,53 @@ class scNMFSet:
         return "scNMFSet(%d genes x %d cells, ranks=%s)" % (self.nrow(), self.ncol(), self.ranks)
 
 
+def remove_zeros(object):
+    """R/scNMF_class.R:636-656: drop genes and cells without any count."""
+    mat = object.counts
+    gi = np.flatnonzero(np.asarray(mat.sum(axis=1)).ravel() > 0)
+    ci = np.flatnonzero(np.asarray(mat.sum(axis=0)).ravel() > 0)
+    if len(gi) == mat.shape[0] and len(ci) == mat.shape[1]:
+        return object
+    out = scNMFSet(mat[gi][:, ci], rowData=[object.rowData[i] for i in gi],
+                   colData=[object.colData[j] for j in ci])
+    return out
+
+
+def read_10x(dir, count="matrix.mtx", genes="genes.tsv", barcodes="barcodes.tsv",
+             remove_zeros_=True):
+    """R/utils.R:28-54: MatrixMarket counts + gene / barcode tables -> scNMFSet whose counts are
+    CSC (the dgCMatrix of :34), ready for the device upload without densification."""
+    import os
+    import scipy.io
+    if not os.path.isdir(dir):
+        raise FileNotFoundError("Input directory %s does not exist" % dir)
+    for f in (count, genes, barcodes):
+        if not os.path.exists(os.path.join(dir, f)):
+            raise FileNotFoundError("Count file %s does not exist" % os.path.join(dir, f))
+    mat = sp.csc_matrix(scipy.io.mmread(os.path.join(dir, count)), dtype=np.float64)
+    glist = [ln.split() for ln in open(os.path.join(dir, genes)) if ln.strip()]
+    clist = [ln.split() for ln in open(os.path.join(dir, barcodes)) if ln.strip()]
+    if len(glist) != mat.shape[0] or len(clist) != mat.shape[1]:
+        raise ValueError("annotation tables do not match the matrix dimensions")
+    x = scNMFSet(mat, rowData=[tuple(g) for g in glist], colData=[tuple(c) for c in clist])
+    return remove_zeros(x) if remove_zeros_ else x
+
+
+def write_10x(object, dir, count="matrix.mtx", genes="genes.tsv", barcodes="barcodes.tsv"):
+    """R/utils.R:867-884."""
+    import os
+    import scipy.io
+    scipy.io.mmwrite(os.path.join(dir, count), sp.coo_matrix(object.counts), field="integer"
+                     if np.all(object.counts.data == np.round(object.counts.data)) else "real")
+    with open(os.path.join(dir, genes), "w") as f:
+        for g in object.rowData:
+            f.write(" ".join(str(v) for v in (g if isinstance(g, (tuple, list)) else (g,))) + "\n")
+    with open(os.path.join(dir, barcodes), "w") as f:
+        for c in object.colData:
+            f.write(" ".join(str(v) for v in (c if isinstance(c, (tuple, list)) else (c,))) + "\n")
+    return object
+
+
 def _check_no_empty(mat):
     """R/bayesian.R:242-247, R/factorize.R:147-150."""
     if int((np.asarray(mat.sum(axis=1)).ravel() == 0).sum()) > 0:

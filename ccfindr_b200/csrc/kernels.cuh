@@ -385,6 +385,7 @@ sweep_tiled_kernel(const SweepTiledArgs a) {
                     if (t < len) load_entry<VT>(a, beg + t, ti[u], xv[u]);
                 }
                 for (int c0 = 0; c0 < len; c0 += U * NPG) {
+                    PT pu[U], xu[U];  // LPN == 2: p and count of the chunk for the paired log
 #pragma unroll
                     for (int u = 0; u < U; u++) {
                         const int t = c0 + U * NPG + slot + u * NPG;
@@ -417,7 +418,19 @@ sweep_tiled_kernel(const SweepTiledArgs a) {
                         const PT q = x * rcp_t(p);
 #pragma unroll
                         for (int k = 0; k < KL; k++) acc[k] = fma(tr[k], q, acc[k]);
-                        if (COLS) xls = fma(hf == 0 ? x : (PT)0, log_t(p), xls);
+                        if (COLS) {
+                            if (LPN == 1) xls = fma(x, log_t(p), xls);
+                            else { pu[u] = p; xu[u] = x; }
+                        }
+                    }
+                    if (COLS && LPN == 2) {
+                        // both lanes of a pair hold p: each takes the log of every other nonzero
+#pragma unroll
+                        for (int v = 0; v < U / 2; v++) {
+                            const PT pm = hf ? pu[2 * v + 1] : pu[2 * v];
+                            const PT xm = hf ? xu[2 * v + 1] : xu[2 * v];
+                            xls = fma(xm, log_t(pm), xls);
+                        }
                     }
 #pragma unroll
                     for (int u = 0; u < U; u++) { ti[u] = tn[u]; xv[u] = xn[u]; }

@@ -86,3 +86,19 @@ def test_lpt_schedule_balances_rank_sweep():
     loads = [sum(ranks[i] for i in w) for w in plan]
     assert max(loads) - min(loads) <= max(ranks)
     assert api.lpt_schedule([3.0, 1.0], 4) == [[0], [1], [], []]
+
+
+def test_read_write_10x_roundtrip(tmp_path):
+    from conftest import load_counts
+    X = load_counts("tiny").tolil()
+    X[5, :] = 0                                            # an empty gene: dropped on read
+    s = api.scNMFSet(sp.csc_matrix(X), rowData=[("g%d" % i, "sym%d" % i) for i in range(X.shape[0])],
+                     colData=["cell%d" % j for j in range(X.shape[1])])
+    api.write_10x(s, str(tmp_path))
+    back = api.read_10x(str(tmp_path), remove_zeros_=False)
+    assert (back.counts != s.counts).nnz == 0 and back.rowData[3] == ("g3", "sym3")
+    clean = api.read_10x(str(tmp_path))
+    assert clean.nrow() == s.nrow() - 1 and ("g5", "sym5") not in clean.rowData
+    assert clean.counts.format == "csc" and clean.counts.dtype == np.float64
+    with pytest.raises(FileNotFoundError):
+        api.read_10x(str(tmp_path / "nope"))
