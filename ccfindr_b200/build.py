@@ -24,6 +24,8 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-I", INCLUDE]
 if os.environ.get("VBNMF_SWEEP_THREADS"):  # tuning experiments only
     NVCC_FLAGS.append("-DVB_SWEEP_THREADS=" + os.environ["VBNMF_SWEEP_THREADS"])
+if os.environ.get("VBNMF_UNROLL"):
+    NVCC_FLAGS.append("-DVB_UNROLL=" + os.environ["VBNMF_UNROLL"])
 
 
 def _nvcc():

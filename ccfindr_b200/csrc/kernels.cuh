@@ -173,6 +173,12 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
 //
 // The build step orders the nonzeros of a segment so that 8 consecutive ones hit tile rows that
 // differ mod 8 -> with an odd row stride the 8 gathers of a group are bank-conflict free.
+// nonzeros per lane whose index/count loads are in flight together and whose arithmetic chains are
+// interleaved: 6 for the fp64 single-lane configuration, 4 otherwise (measured on C2: fp64 1.81 ->
+// 1.76 ms with 6; the fp32 mode and the two-lane variant are faster with 4, 2 is slower everywhere)
+#ifndef VB_UNROLL
+#define VB_UNROLL 0
+#endif
 #ifndef VB_SWEEP_THREADS
 #define VB_SWEEP_THREADS 512  // threads per sweep CTA for the narrow-rank configuration
 #endif
@@ -188,10 +194,11 @@ struct SweepCfg {
     static constexpr int kKL = kNUL * kUE;                       // rank entries per lane
     static constexpr int kNPG = kGroup / kLPN;                   // nonzeros per group step
     static constexpr int kThreads = (kKL * (int)sizeof(PT) <= 96) ? VB_SWEEP_THREADS : 256;
+    static constexpr int kUnroll = VB_UNROLL ? VB_UNROLL : ((sizeof(PT) == 8 && kLPN == 1) ? 6 : 4);
     static constexpr int kGroups = kThreads / kGroup;
 };
 
-constexpr int kUnroll = 4;  // nonzeros per lane whose index/count loads are in flight together
+  // nonzeros per lane whose index/count loads are in flight together
 
 // log(p) for a positive normal double, ~1 ulp: p = 2^e m with m in [sqrt(1/2), sqrt(2)),
 // log m = 2 atanh(t), t = (m-1)/(m+1), |t| <= 0.1716, odd series through t^17 (next term < 3e-16).
@@ -316,7 +323,7 @@ sweep_tiled_kernel(const SweepTiledArgs a) {
     using Cfg = SweepCfg<RP, PT>;
     constexpr int RS = row_stride(RP);          // stride of the fp64 Part rows
     constexpr int PS = panel_stride<PT>(RP);    // stride of the gathered / owner panels
-    constexpr int NT = Cfg::kThreads, U = kUnroll;
+    constexpr int NT = Cfg::kThreads, U = Cfg::kUnroll;
     constexpr int UE = Cfg::kUE, NU = Cfg::kNU, LPN = Cfg::kLPN, NUL = Cfg::kNUL, KL = Cfg::kKL;
     constexpr int NPG = Cfg::kNPG;
     extern __shared__ __align__(128) unsigned char smem_raw[];
