@@ -194,7 +194,10 @@ struct SweepCfg {
     static constexpr int kKL = kNUL * kUE;                       // rank entries per lane
     static constexpr int kNPG = kGroup / kLPN;                   // nonzeros per group step
     static constexpr int kThreads = (kKL * (int)sizeof(PT) <= 96) ? VB_SWEEP_THREADS : 256;
-    static constexpr int kUnroll = VB_UNROLL ? VB_UNROLL : ((sizeof(PT) == 8 && kLPN == 1) ? 6 : 4);
+    // unroll of the chunk loop; the fp32 cell-owner pass (with its log) is the one that prefers 4
+    __host__ __device__ static constexpr int unroll(bool cols) {
+        return VB_UNROLL ? VB_UNROLL : ((kLPN == 1 && (sizeof(PT) == 8 || !cols)) ? 6 : 4);
+    }
     static constexpr int kGroups = kThreads / kGroup;
 };
 
@@ -323,7 +326,7 @@ sweep_tiled_kernel(const SweepTiledArgs a) {
     using Cfg = SweepCfg<RP, PT>;
     constexpr int RS = row_stride(RP);          // stride of the fp64 Part rows
     constexpr int PS = panel_stride<PT>(RP);    // stride of the gathered / owner panels
-    constexpr int NT = Cfg::kThreads, U = Cfg::kUnroll;
+    constexpr int NT = Cfg::kThreads, U = Cfg::unroll(COLS);
     constexpr int UE = Cfg::kUE, NU = Cfg::kNU, LPN = Cfg::kLPN, NUL = Cfg::kNUL, KL = Cfg::kKL;
     constexpr int NPG = Cfg::kNPG;
     extern __shared__ __align__(128) unsigned char smem_raw[];
