@@ -72,6 +72,8 @@ def _random_problem(n, m, r, density, seed, integer=True):
     (64, 2000, 13, 0.3, False),    # non-integer counts -> fp64 value storage
     (3000, 40, 20, 0.02, True),    # few cells, very short rows
     (500, 300, 33, 0.1, True),     # rank > 32 (padded to 40)
+    (260, 330, 64, 0.2, True),     # the widest supported rank
+    (900, 700, 24, 0.05, True),    # widest two-lane configuration that keeps 512 threads
 ])
 def test_steps_match_oracle(Engine, n, m, r, density, integer):
     from oracle import bindings as ob
@@ -313,3 +315,34 @@ def test_itmax_one_and_rank_switching_on_one_handle(Engine):
             assert res["niter"] == 1 and res["stop_reason"] == 0
             assert relerr(res["lml"], ref["lml"]) < TOL
             assert relerr(eng.get_state(("eh",))["eh"], ref["eh"]) < TOL
+
+
+def test_ml_path_in_fp32_storage_mode(Engine):
+    from ccfindr_b200 import synth
+    from oracle import bindings as ob
+    X = load_counts("pbmc")
+    n, m = X.shape
+    w0, h0 = synth.uniform_init(n, m, 5, 4)
+    ref = ob.sparse_ml_run(X, w0, h0, Itmax=20, Tol=0.0)
+    with Engine(X) as eng:
+        eng.set_precision(1)
+        res = eng.ml_run(w0, h0, Itmax=20, Tol=0.0)
+    assert res["niter"] == 20
+    assert relerr(res["lik_trace"], ref["lik_trace"]) < TOL32
+    assert _relerr_floor(res["h"], ref["h"], 1e-3 * float(np.abs(ref["h"]).max())) < TOL32
+
+
+def test_external_stream(Engine):
+    """vbnmf_set_stream: the engine runs on a caller-provided CUDA stream (a torch stream here)"""
+    import torch
+    from oracle import bindings as ob
+    from oracle import oracle_dense as od
+    X, w0, h0 = _random_problem(300, 200, 5, 0.1, seed=12)
+    hyper = dict(aw=1.0, bw=1.0, ah=1.0, bh=1.0)
+    ref = ob.sparse_vb_step(X, od.vb_init_from(w0, h0), hyper, od.EPS)
+    st = torch.cuda.Stream()
+    with Engine(X) as eng:
+        eng.set_stream(st.cuda_stream)
+        eng.set_state(w0, h0)
+        assert relerr(eng.step(hyper), ref["lkh"]) < TOL
+        st.synchronize()
