@@ -86,24 +86,6 @@ __device__ __forceinline__ void load_row_d(const double *__restrict__ base, int6
     }
 }
 
-template <int RP>
-__device__ __forceinline__ void load_row_t(const void *base, int64_t row, double (&out)[RP]) {
-    load_row_d<RP>(reinterpret_cast<const double *>(base), row, out);
-}
-template <int RP>
-__device__ __forceinline__ void load_row_t(const void *base, int64_t row, float (&out)[RP]) {
-    constexpr int RSF = row_stride_f32(RP);
-    const float4 *p = reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(base) + row * RSF);
-#pragma unroll
-    for (int c = 0; c < (RP + 3) / 4; c++) {
-        const float4 v = __ldg(p + c);
-        if (4 * c + 0 < RP) out[4 * c + 0] = v.x;
-        if (4 * c + 1 < RP) out[4 * c + 1] = v.y;
-        if (4 * c + 2 < RP) out[4 * c + 2] = v.z;
-        if (4 * c + 3 < RP) out[4 * c + 3] = v.w;
-    }
-}
-
 // 1/p to ~1 ulp: hardware seed (>= 20 bits) + two Newton steps.  p is a positive normal double
 // here (p >= r * fudge^2 > 0), so no special-case handling is needed.
 __device__ __forceinline__ double fast_rcp(double p) {
@@ -243,26 +225,6 @@ __device__ __forceinline__ float4 lds128f(uint32_t addr) {
                  : "r"(addr));
     return v;
 }
-template <int RP>
-__device__ __forceinline__ void gather_row(uint32_t raddr, double (&tr)[RP]) {
-#pragma unroll
-    for (int k = 0; k < RP / 2; k++) {
-        const double2 v = lds128(raddr + k * 16);
-        tr[2 * k] = v.x;
-        tr[2 * k + 1] = v.y;
-    }
-}
-template <int RP>
-__device__ __forceinline__ void gather_row(uint32_t raddr, float (&tr)[RP]) {
-#pragma unroll
-    for (int c = 0; c < (RP + 3) / 4; c++) {
-        const float4 v = lds128f(raddr + c * 16);
-        if (4 * c + 0 < RP) tr[4 * c + 0] = v.x;
-        if (4 * c + 1 < RP) tr[4 * c + 1] = v.y;
-        if (4 * c + 2 < RP) tr[4 * c + 2] = v.z;
-        if (4 * c + 3 < RP) tr[4 * c + 3] = v.w;
-    }
-}
 __device__ __forceinline__ double rcp_t(double p) { return fast_rcp(p); }
 __device__ __forceinline__ float rcp_t(float p) { return __frcp_rn(p); }
 __device__ __forceinline__ double log_t(double p) { return fast_log_pos(p); }
@@ -284,7 +246,15 @@ struct SweepTiledArgs {
     const void *tiles;       // tile panel, nslabs*T x stride
     double *Part;            // nslabs x NO x RS
     double *xl_part;         // COLS: gridDim.x partial sums of x log p
+    const double *ctl;       // device loop control block (see control_kernel) or nullptr
 };
+
+// Device loop control block (doubles).  When a kernel is given it and ctl[kCtlDone] != 0 the run
+// has ended (converged / NaN / Itmax) and the kernel returns at once, so iterations launched ahead
+// of the host's knowledge are no-ops.
+enum { kCtlDone = 0, kCtlIt = 1, kCtlLk0 = 2, kCtlReason = 3, kCtlHyper = 4 /*aw,bw,ah,bh*/,
+       kCtlHyperErr = 8, kCtlLkh = 9, kCtlAcc = 10 /*wacc[3], hacc[3]*/, kCtlBew = 16,
+       kCtlBeh = 16 + 64, kCtlEhsum = 16 + 128, kCtlLen = 16 + 192 };
 
 template <typename VT>
 __device__ __forceinline__ void load_entry(const SweepTiledArgs &a, int64_t t, int32_t &ti, double &x);
@@ -340,6 +310,7 @@ sweep_tiled_kernel(const SweepTiledArgs a) {
     const unsigned gmask = 0xffu << ((threadIdx.x & 31) & ~(kGroup - 1));
     const int64_t e0 = a.split[blockIdx.x], e1 = a.split[blockIdx.x + 1];
     const unsigned tile_bytes = (unsigned)a.T * PS * (unsigned)sizeof(PT);
+    if (a.ctl && a.ctl[kCtlDone] != 0.0) return;  // uniform over the grid: the run has ended
     if (threadIdx.x == 0) mbar_init(&mbar, 1);
     __syncthreads();
     unsigned parity = 0;
@@ -481,9 +452,10 @@ __global__ void __launch_bounds__(kBlock)
 combine_kernel(int64_t NO, int nslabs, int r, const double *__restrict__ Part,
                const double *__restrict__ l, double *__restrict__ SRaw, double *__restrict__ part,
                double *__restrict__ out, unsigned *counter, const double *__restrict__ xl_part,
-               int nxl) {
+               int nxl, const double *__restrict__ ctl) {
     constexpr int RS = row_stride(RP);
     __shared__ double sm[kWarpsPerBlock];
+    if (ctl && ctl[kCtlDone] != 0.0) return;
     double ent = 0.0;
     const int64_t tot = NO * (RS / 2);
     for (int64_t u = (int64_t)blockIdx.x * kBlock + threadIdx.x; u < tot;
@@ -547,11 +519,17 @@ __global__ void __launch_bounds__(post_threads(row_stride(RP)))
 posterior_kernel(int64_t rows, int T, int S, int64_t nvalid, int r, double a, double b, double fud,
                  const double *__restrict__ osum, const double *__restrict__ SRaw,
                  double *__restrict__ l, double *__restrict__ al_out, double *__restrict__ part,
-                 double *__restrict__ out, unsigned *counter, float *__restrict__ l32) {
+                 double *__restrict__ out, unsigned *counter, float *__restrict__ l32,
+                 const double *__restrict__ ctl, int hoff) {
     constexpr int RS = row_stride(RP);
     constexpr int kPostLanes = post_lanes(RS);
     constexpr int NT = post_threads(RS);
     constexpr int W = RS + 3;
+    if (ctl) {  // device-controlled loop: stop flag and the current hyper-parameters live on the GPU
+        if (ctl[kCtlDone] != 0.0) return;
+        a = ctl[kCtlHyper + hoff];
+        b = ctl[kCtlHyper + hoff + 1];
+    }
     __shared__ double sm[NT / 32];
     __shared__ double colbuf[4][NT];
     const int k = threadIdx.x % RS, lane_row = threadIdx.x / RS;  // lane_row >= kPostLanes: idle

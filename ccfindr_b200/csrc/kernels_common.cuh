@@ -7,7 +7,7 @@ namespace vb {
 // ---- one-time helpers ----------------------------------------------------------------------
 // sum over nonzeros of lgamma(x+1) (src/vbnmf_update.cpp:80-81; zeros contribute 0) and of
 // -x log x + x (R/factorize.R:45-46); out[0], out[1].  out[2] = number of values that are not
-// integers in [0, 2^31) (those force the general x*log(p) path of the sweep).
+// non-negative integers (informational).
 template <typename VT>
 __global__ void __launch_bounds__(kBlock)
 count_constants_kernel(int64_t nnz, const VT *__restrict__ val, double *__restrict__ part,
@@ -148,6 +148,68 @@ __global__ void split_kernel(int nparts, int64_t E, int64_t nnz, const int64_t *
         if (ptr[mid] < target) lo = mid + 1; else hi = mid;
     }
     split[b] = lo;
+}
+
+// One thread: the host half of an iteration moved onto the device.  Assembles the lower bound
+// (src/vbnmf_update.cpp:67-90 in its nonzero-only form) from the reduced scalars, then applies the
+// loop logic of vb_iterate (R/bayesian.R:342-348): hyper update, NaN stop, convergence test, lk0.
+struct ControlArgs {
+    double *ctl;
+    const double *scal;   // [ewsum rs | wprior, sum log lw, sum ew]
+    const double *tail;   // [ehsum rs | hprior, sum log lh, sum eh | enth, xlogp | entw]
+    double *trace, *htrace;
+    double n, m_global, lgx, tol;
+    int r, rs, itmax, n0, dn;
+    int flags[4];
+};
+
+__global__ void control_kernel(const ControlArgs a) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double *c = a.ctl;
+    if (c[kCtlDone] != 0.0) return;
+    const double aw = c[kCtlHyper + 0], bw = c[kCtlHyper + 1], ah = c[kCtlHyper + 2],
+                 bh = c[kCtlHyper + 3];
+    const double *ws = a.scal, *hs = a.tail;
+    const int r = a.r, rs = a.rs;
+    double U = 0.0;
+    for (int k = 0; k < r; k++) {
+        c[kCtlBew + k] = aw / bw + c[kCtlEhsum + k];   // what this iteration's W update used, :42-43
+        c[kCtlBeh + k] = ah / bh + ws[k];              // and its H update, :52-53
+        c[kCtlEhsum + k] = hs[k];                      // rowSums(eh_new) for the next iteration
+        U -= ws[k] * hs[k];                            // -sum(ew.eh), :78
+    }
+    U -= hs[rs + 5] + hs[rs + 3] - hs[rs + 4];         // -x((A+B)/wth - log wth), :74-78
+    U -= a.lgx;                                        // -lgamma(x+1), :81
+    const double nr = a.n * r, mr = a.m_global * r;
+    U += ws[rs + 0] + nr * (-lgamma(aw) + aw * log(aw / bw));   // :82-86
+    U += hs[rs + 0] + mr * (-lgamma(ah) + ah * log(ah / bh));   // :87-89
+    const double lkh = U / (a.n * a.m_global);                  // :90 (in double)
+    for (int q = 0; q < 3; q++) { c[kCtlAcc + q] = ws[rs + q]; c[kCtlAcc + 3 + q] = hs[rs + q]; }
+    const int it = (int)c[kCtlIt] + 1;
+    c[kCtlIt] = it;
+    c[kCtlLkh] = lkh;
+    double hyper[4] = {aw, bw, ah, bh};
+    if (it > a.n0 && it % a.dn == 0) {                 // R/bayesian.R:342-344
+        const double mn[4] = {ws[rs + 1] / nr, hs[rs + 1] / mr, ws[rs + 2] / nr, hs[rs + 2] / mr};
+        if (vb_hyper_update(a.flags, mn, hyper, 100, 1e-3)) {
+            c[kCtlHyperErr] = 1.0;
+            c[kCtlDone] = 1.0;
+            return;
+        }
+        for (int q = 0; q < 4; q++) c[kCtlHyper + q] = hyper[q];
+    }
+    if (a.trace) a.trace[it - 1] = lkh;
+    if (a.htrace)
+        for (int q = 0; q < 4; q++) a.htrace[4 * (it - 1) + q] = hyper[q];
+    const double lk0 = c[kCtlLk0];
+    if (isnan(lkh)) {                                  // :345
+        c[kCtlReason] = 2.0; c[kCtlDone] = 1.0;
+    } else if (it > 1 && it > a.n0 && lkh >= lk0 && fabs(1 - lkh / lk0) < a.tol) {  // :346-347
+        c[kCtlReason] = 1.0; c[kCtlDone] = 1.0;
+    } else {
+        c[kCtlLk0] = lkh;                              // :348
+        if (it >= a.itmax) { c[kCtlReason] = 0.0; c[kCtlDone] = 1.0; }
+    }
 }
 
 // cid[d] = 1 + index of the first maximum over k of alh[d][k] / beh[k]   (R/utils.R:906)

@@ -53,12 +53,12 @@ inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 void combine(const CombineArgs &a, cudaStream_t s) {
     combine_kernel<RP><<<a.grid, kBlock, 0, s>>>(a.NO, a.nslabs, a.r, a.Part, a.l, a.SRaw, a.part,
-                                                 a.out, a.counter, a.xl_part, a.nxl);
+                                                 a.out, a.counter, a.xl_part, a.nxl, a.ctl);
 }
 void posterior(const PosteriorArgs &a, cudaStream_t s) {
     posterior_kernel<RP><<<cdiv(a.rows, kPostRows), post_threads(RS), 0, s>>>(
         a.rows, a.T, a.S, a.nvalid, a.r, a.a, a.b, a.fud, a.osum, a.SRaw, a.l, a.al_out, a.part,
-        a.out, a.counter, a.l32);
+        a.out, a.counter, a.l32, a.ctl, a.hoff);
 }
 void ml_update(const MlUpdateArgs &a, cudaStream_t s) {
     ml_update_kernel<RP><<<cdiv(a.rows, kPostRows), post_threads(RS), 0, s>>>(

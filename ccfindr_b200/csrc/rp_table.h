@@ -17,6 +17,7 @@ struct CombineArgs {
     const double *xl_part;  // optional per-CTA partial sums folded into out[1]
     int nxl;
     int grid;
+    const double *ctl;      // device loop control block or nullptr
 };
 
 struct PosteriorArgs {
@@ -29,6 +30,8 @@ struct PosteriorArgs {
     double *l, *al_out, *part, *out;
     unsigned *counter;
     float *l32;  // fp32 mirror of l (fp32-storage mode) or nullptr
+    const double *ctl;  // device loop control block (hypers read from it) or nullptr
+    int hoff;           // 0: (aw, bw), 2: (ah, bh)
 };
 
 struct MlUpdateArgs {

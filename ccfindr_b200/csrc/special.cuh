@@ -39,3 +39,45 @@ VB_HD double vb_trigamma(double x) {
     for (int j = nstep - 1; j >= 0; j--) acc += 1.0 / ((x + (double)j) * (x + (double)j));
     return acc;
 }
+
+// hyper_update (R/bayesian.R:2-53): Newton iteration on the shapes aw, ah from the four means
+// mn = {mean log lw, mean log lh, mean ew, mean eh}; bw <- mean(ew) if flags[1]; bh <- mean(eh) in
+// BOTH branches of :50-51.  Returns 0, or 2 when `niter` steps are exhausted (:43).
+VB_HD int vb_hyper_update(const int *flags, const double *mn, double *hyper, int niter, double tol) {
+    if (flags[0] + flags[1] + flags[2] + flags[3] == 0) return 0;                 // :4
+    const double lwm = mn[0], lhm = mn[1], ewm = mn[2], ehm = mn[3];
+    double aw0 = hyper[0], ah0 = hyper[2];
+    const double bw0 = hyper[1], bh0 = hyper[3];
+    double aw1 = aw0, ah1 = ah0;
+    if (flags[0] + flags[2] > 0) {                                                 // :15
+        int i = 1;
+        while (i < niter) {                                                        // :17
+            double dw = 0.0, dh = 0.0;
+            if (flags[0])
+                dw = (log(aw0) - vb_digamma(aw0) - ewm / bw0 + 1.0 + lwm - log(bw0)) /
+                     (1.0 / aw0 - vb_trigamma(aw0));                               // :19-20
+            if (flags[2])
+                dh = (log(ah0) - vb_digamma(ah0) - ehm / bh0 + 1.0 + lhm - log(bh0)) /
+                     (1.0 / ah0 - vb_trigamma(ah0));                               // :23-24
+            aw1 = aw0 - dw;
+            ah1 = ah0 - dh;
+            // :28-35 halve the step until the shape is positive; the cap only matters for an
+            // infinite step, where the R loop would never end
+            for (int g = 0; aw1 <= 0 && g < 1200; g++) { dw = dw / 2; aw1 = aw0 - dw; }
+            for (int g = 0; ah1 <= 0 && g < 1200; g++) { dh = dh / 2; ah1 = ah0 - dh; }
+            if (aw1 <= 0 || ah1 <= 0) return 2;
+            const double df =
+                (1 - aw1 / aw0) * (1 - aw1 / aw0) + (1 - ah1 / ah0) * (1 - ah1 / ah0);  // :37
+            if (df < tol) break;                                                   // :38
+            aw0 = aw1;
+            ah0 = ah1;
+            i++;
+        }
+        if (i == niter) return 2;                                                  // :43
+    }
+    hyper[0] = aw1;
+    hyper[1] = flags[1] ? ewm : bw0;                                               // :48-49
+    hyper[2] = ah1;
+    hyper[3] = ehm;                                                                // :50-51
+    return 0;
+}

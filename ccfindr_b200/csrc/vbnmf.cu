@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <nccl.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -58,6 +59,13 @@ constexpr int kTileBytes = 204800;  // shared-memory budget of one staged slab
 const int kTileRows[] = {4096, 2560, 2048, 1536, 1152, 1024, 768, 512, 384, 256, 128};
 
 std::string g_create_error;
+
+// NVTX range around a phase of the iteration (visible in Nsight tools; header-only, no cost
+// without a profiler attached)
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 // VBNMF_TIMING=1 prints host-side stage times (setup paths only) to stderr
 struct StageTimer {
@@ -151,7 +159,7 @@ struct vbnmf_handle {
     int64_t n = 0, m = 0, nnz = 0, m_global = 0;
     int r = 0, rp = 0, rs = 0;
     int precision = VBNMF_FP64;
-    bool val_float = true, int_counts = true;
+    bool val_float = true;
     bool borrowed = false;
     // the count matrix as given (CSC); the tiled layouts are derived from it
     int64_t *d_colptr = nullptr;
@@ -173,6 +181,8 @@ struct vbnmf_handle {
     double *h_scal = nullptr;  // pinned mirror: [d_scal (rs+8) | tail of d_red (rs+8)]
     double *d_partW = nullptr, *d_partH = nullptr, *d_partC = nullptr;
     unsigned *d_counters = nullptr;
+    double *d_ctl = nullptr, *h_ctl = nullptr;  // device loop control block and its pinned mirror
+    const double *ctl = nullptr;                // = d_ctl while a device-controlled loop is running
     int gridC = 0;
     double lgx = 0.0, mlconst = 0.0;  // global sums over nonzeros
     // host copies of the small vectors
@@ -250,6 +260,7 @@ int choose_tile_rows(const H *h, int row_bytes) {
 
 int allreduce(H *h, double *buf, int64_t count) {
     if (h->nranks <= 1) return 0;
+    NvtxRange nv("vbnmf:allreduce");
     CKN(g_nccl.AllReduce(buf, buf, (size_t)count, ncclFloat64, ncclSum, h->comm, h->stream));
     h->launches += 1;
     return 0;
@@ -403,7 +414,6 @@ int scan_matrix_t(H *h) {
     vfree(h->stream, d_part); vfree(h->stream, d_out); vfree(h->stream, d_colof); vfree(h->stream, d_cnt);
     h->lgx = consts[0];
     h->mlconst = consts[1];
-    h->int_counts = h->val_float && consts[2] == 0.0;
     return 0;
 }
 
@@ -515,6 +525,7 @@ int download_panel(H *h, const double *src, std::vector<double> &tmp, bool wside
 
 // ---- one iteration --------------------------------------------------------------------------------
 int launch_posterior(H *h, bool wside, double a, double b, double fud) {
+    NvtxRange nv(wside ? "vbnmf:posterior_W" : "vbnmf:posterior_H");
     const Layout *L = h->L;
     double *tail = h->d_red + tail_off(h);
     vb::PosteriorArgs p;
@@ -532,6 +543,8 @@ int launch_posterior(H *h, bool wside, double a, double b, double fud) {
     p.out = wside ? h->d_scal : tail;
     p.counter = h->d_counters + (wside ? 0 : 1);
     p.l32 = wside ? h->d_lw32 : h->d_lh32;  // nullptr in fp64 mode
+    p.ctl = h->ctl;
+    p.hoff = wside ? 0 : 2;
     h->tab->posterior(p, h->stream);
     h->launches += 1;
     return 0;
@@ -539,16 +552,18 @@ int launch_posterior(H *h, bool wside, double a, double b, double fud) {
 
 // cell-owner pass: ShRaw, enth -> tail[rs+3], xlogp -> tail[rs+4]
 int launch_sweep_cols(H *h) {
+    NvtxRange nv("vbnmf:sweep_cell_owner");
     const Layout *L = h->L;
     double *tail = h->d_red + tail_off(h);
     const bool f32 = h->precision == VBNMF_FP32_STORAGE;
     vb::SweepTiledArgs a{L->NC, L->T, L->cols.d_split, L->cols.d_ptr, L->cols.d_ent,
                          L->cols.d_idx, (const double *)L->cols.d_val,
                          f32 ? (const void *)h->d_lh32 : (const void *)h->d_lh,
-                         f32 ? (const void *)h->d_lw32 : (const void *)h->d_lw, h->d_Part1, h->d_xl};
+                         f32 ? (const void *)h->d_lw32 : (const void *)h->d_lw, h->d_Part1, h->d_xl,
+                         h->ctl};
     h->tab->sweep(a, true, h->val_float, f32, L->grid, h->smem_bytes, h->stream);
     vb::CombineArgs c{L->NC, L->Sg, h->r, h->d_Part1, h->d_lh, h->d_ShRaw, h->d_partC,
-                      tail + h->rs + 3, h->d_counters + 2, h->d_xl, L->grid, h->gridC};
+                      tail + h->rs + 3, h->d_counters + 2, h->d_xl, L->grid, h->gridC, h->ctl};
     h->tab->combine(c, h->stream);
     h->launches += 2;
     return 0;
@@ -556,16 +571,18 @@ int launch_sweep_cols(H *h) {
 
 // gene-owner pass: SwRaw (local part) -> d_red, entw (local part) -> tail[rs+5]
 int launch_sweep_rows(H *h) {
+    NvtxRange nv("vbnmf:sweep_gene_owner");
     const Layout *L = h->L;
     double *tail = h->d_red + tail_off(h);
     const bool f32 = h->precision == VBNMF_FP32_STORAGE;
     vb::SweepTiledArgs a{L->NG, L->T, L->rows.d_split, L->rows.d_ptr, L->rows.d_ent,
                          L->rows.d_idx, (const double *)L->rows.d_val,
                          f32 ? (const void *)h->d_lw32 : (const void *)h->d_lw,
-                         f32 ? (const void *)h->d_lh32 : (const void *)h->d_lh, h->d_Part2, nullptr};
+                         f32 ? (const void *)h->d_lh32 : (const void *)h->d_lh, h->d_Part2, nullptr,
+                         h->ctl};
     h->tab->sweep(a, false, h->val_float, f32, L->grid, h->smem_bytes, h->stream);
     vb::CombineArgs c{L->NG, L->Sc, h->r, h->d_Part2, h->d_lw, h->d_red, h->d_partC,
-                      tail + h->rs + 5, h->d_counters + 3, nullptr, 0, h->gridC};
+                      tail + h->rs + 5, h->d_counters + 3, nullptr, 0, h->gridC, h->ctl};
     h->tab->combine(c, h->stream);
     h->launches += 2;
     return 0;
@@ -636,43 +653,6 @@ void means_of(const H *h, double *means) {
     means[1] = h->hacc[1] / mr;
     means[2] = h->wacc[2] / nr;
     means[3] = h->hacc[2] / mr;
-}
-
-// R/bayesian.R:2-53
-int hyper_update(const int *flags, const double *mn, double *hyper, int niter, double tol) {
-    if (flags[0] + flags[1] + flags[2] + flags[3] == 0) return 0;
-    const double lwm = mn[0], lhm = mn[1], ewm = mn[2], ehm = mn[3];
-    double aw0 = hyper[0], ah0 = hyper[2];
-    const double bw0 = hyper[1], bh0 = hyper[3];
-    double aw1 = aw0, ah1 = ah0;
-    if (flags[0] + flags[2] > 0) {
-        int i = 1;
-        while (i < niter) {
-            double dw = 0.0, dh = 0.0;
-            if (flags[0])
-                dw = (log(aw0) - vb_digamma(aw0) - ewm / bw0 + 1.0 + lwm - log(bw0)) /
-                     (1.0 / aw0 - vb_trigamma(aw0));
-            if (flags[2])
-                dh = (log(ah0) - vb_digamma(ah0) - ehm / bh0 + 1.0 + lhm - log(bh0)) /
-                     (1.0 / ah0 - vb_trigamma(ah0));
-            aw1 = aw0 - dw;
-            ah1 = ah0 - dh;
-            while (aw1 <= 0) { dw = dw / 2; aw1 = aw0 - dw; }
-            while (ah1 <= 0) { dh = dh / 2; ah1 = ah0 - dh; }
-            const double df =
-                (1 - aw1 / aw0) * (1 - aw1 / aw0) + (1 - ah1 / ah0) * (1 - ah1 / ah0);
-            if (df < tol) break;
-            aw0 = aw1;
-            ah0 = ah1;
-            i++;
-        }
-        if (i == niter) return VBNMF_ERR_HYPER;
-    }
-    hyper[0] = aw1;
-    hyper[1] = flags[1] ? ewm : bw0;
-    hyper[2] = ah1;
-    hyper[3] = ehm;  // R/bayesian.R:50-51 assigns ehm in both branches
-    return 0;
 }
 
 // Host -> device upload of a large array through two pinned staging buffers: worker threads
@@ -747,7 +727,10 @@ int init_common(H *h, int device) {
         }
     }
     CK(vmalloc(h, &h->d_counters, 16 * sizeof(unsigned)));
-    CK(cudaMemset(h->d_counters, 0, 16 * sizeof(unsigned)));
+    CK(cudaMemsetAsync(h->d_counters, 0, 16 * sizeof(unsigned), h->stream));
+    CK(vmalloc(h, &h->d_ctl, vb::kCtlLen * sizeof(double)));
+    CK(cudaMallocHost(&h->h_ctl, vb::kCtlLen * sizeof(double)));
+    CK(cudaStreamSynchronize(h->stream));
     h->m_global = h->m;
     return 0;
 }
@@ -770,6 +753,9 @@ void vbnmf_destroy(vbnmf_handle *h) {
         vfree(h->stream, h->d_colptr); vfree(h->stream, h->d_rowidx); vfree(h->stream, h->d_val);
     }
     vfree(h->stream, h->d_counters);
+    vfree(h->stream, h->d_ctl);
+    if (h->h_ctl) cudaFreeHost(h->h_ctl);
+    if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -1009,11 +995,115 @@ int vbnmf_step(vbnmf_handle *h, const double hyper[4], double fudge, double *lkh
     return iterate(h, hyper, fudge, lkh);
 }
 
+// The it-loop of vb_iterate with the loop control on the device: iterations are enqueued in
+// batches without a host round trip; control_kernel applies hyper_update, the NaN and convergence
+// rules after every iteration and raises the stop flag that turns the rest of the batch into
+// no-ops.  VBNMF_HOST_LOOP=1 selects the host-controlled loop (one sync per iteration) instead.
+static int run_device_loop(H *h, const vbnmf_cfg *cfg, double hyper[4], double *lkh_trace,
+                           double *hyper_trace, int *niter, double *lml, int *stop_reason,
+                           cudaEvent_t *ev /*optional: 4 events per iteration, bench*/) {
+    CK(cudaSetDevice(h->device));
+    int rc;
+    const int rs = h->rs, r = h->r, itmax = cfg->itmax;
+    if (!h->stats_valid) {
+        std::vector<double> keep((size_t)rs + 8, 0.0);
+        for (int k = 0; k < r; k++) keep[k] = h->ehsum[k];
+        if ((rc = sweep(h))) return rc;
+        CK(cudaMemcpyAsync(h->d_red + tail_off(h), keep.data(), (size_t)rs * 8,
+                           cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    // control block: hypers, lk0 = 0 (R/bayesian.R:336), rowSums(eh) of the loaded state
+    double *c = h->h_ctl;
+    for (int i = 0; i < vb::kCtlLen; i++) c[i] = 0.0;
+    for (int q = 0; q < 4; q++) c[vb::kCtlHyper + q] = hyper[q];
+    for (int k = 0; k < r; k++) c[vb::kCtlEhsum + k] = h->ehsum[k];
+    CK(cudaMemcpyAsync(h->d_ctl, c, vb::kCtlLen * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    double *d_trace = nullptr, *d_htrace = nullptr;
+    CK(vmalloc(h, &d_trace, (size_t)itmax * 8));
+    CK(vmalloc(h, &d_htrace, (size_t)itmax * 32));
+    vb::ControlArgs ca;
+    ca.ctl = h->d_ctl;
+    ca.scal = h->d_scal;
+    ca.tail = h->d_red + tail_off(h);
+    ca.trace = d_trace;
+    ca.htrace = d_htrace;
+    ca.n = (double)h->n; ca.m_global = (double)h->m_global; ca.lgx = h->lgx; ca.tol = cfg->tol;
+    ca.r = r; ca.rs = rs; ca.itmax = itmax; ca.n0 = cfg->n0; ca.dn = cfg->dn;
+    for (int q = 0; q < 4; q++) ca.flags[q] = cfg->hyper_update[q];
+    // from here on the kernels read the stop flag and the hypers from the control block; the
+    // guard restores the host-controlled mode on every exit path
+    struct CtlGuard {
+        H *h;
+        double *t0, *t1;
+        ~CtlGuard() {
+            h->ctl = nullptr;
+            vfree(h->stream, t0);
+            vfree(h->stream, t1);
+        }
+    } guard{h, d_trace, d_htrace};
+    h->ctl = h->d_ctl;
+    const int batch = 8;
+    int launched = 0, it = 0;
+    bool done = false;
+    auto finish = [&](int code) { return code; };
+    while (!done && launched < itmax) {
+        const int nb = std::min(batch, itmax - launched);
+        for (int b = 0; b < nb; b++) {
+            const int gi = launched + b;
+            if ((rc = launch_posterior(h, true, 0, 0, cfg->fudge))) return finish(rc);
+            if ((rc = launch_posterior(h, false, 0, 0, cfg->fudge))) return finish(rc);
+            if (ev) CK(cudaEventRecord(ev[4 * gi + 0], h->stream));
+            if ((rc = launch_sweep_cols(h))) return finish(rc);
+            if (ev) CK(cudaEventRecord(ev[4 * gi + 1], h->stream));
+            if (ev) CK(cudaEventRecord(ev[4 * gi + 2], h->stream));
+            if ((rc = launch_sweep_rows(h))) return finish(rc);
+            if (ev) CK(cudaEventRecord(ev[4 * gi + 3], h->stream));
+            if ((rc = allreduce(h, h->d_red, red_len(h)))) return finish(rc);
+            vb::control_kernel<<<1, 32, 0, h->stream>>>(ca);
+            h->launches += 1;
+        }
+        launched += nb;
+        CK(cudaMemcpyAsync(c, h->d_ctl, vb::kCtlLen * sizeof(double), cudaMemcpyDeviceToHost,
+                           h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        CK(cudaGetLastError());
+        done = c[vb::kCtlDone] != 0.0;
+        it = (int)c[vb::kCtlIt];
+    }
+    // results and the small host-side vectors the export functions use
+    if (lkh_trace && it > 0)
+        CK(cudaMemcpyAsync(lkh_trace, d_trace, (size_t)it * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (hyper_trace && it > 0)
+        CK(cudaMemcpyAsync(hyper_trace, d_htrace, (size_t)it * 32, cudaMemcpyDeviceToHost,
+                           h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int k = 0; k < r; k++) {
+        h->bew[k] = c[vb::kCtlBew + k];
+        h->beh[k] = c[vb::kCtlBeh + k];
+        h->ehsum[k] = c[vb::kCtlEhsum + k];
+    }
+    for (int q = 0; q < 3; q++) { h->wacc[q] = c[vb::kCtlAcc + q]; h->hacc[q] = c[vb::kCtlAcc + 3 + q]; }
+    for (int q = 0; q < 4; q++) hyper[q] = c[vb::kCtlHyper + q];
+    h->has_posterior = it > 0;
+    // iterations enqueued past the stop were no-ops except for the all-reduce of stale statistics
+    h->stats_valid = (launched == it || h->nranks == 1) && c[vb::kCtlHyperErr] == 0.0;
+    *niter = it;
+    *lml = c[vb::kCtlLk0];                                                  // R/bayesian.R:379
+    *stop_reason = (int)c[vb::kCtlReason];
+    if (c[vb::kCtlHyperErr] != 0.0)
+        return finish(fail(h, VBNMF_ERR_HYPER, "Hyper-parameter update failed to converge"));
+    return finish(0);
+}
+
 int vbnmf_run(vbnmf_handle *h, const vbnmf_cfg *cfg, double hyper[4], double *lkh_trace,
               double *hyper_trace, int *niter, double *lml, int *stop_reason) {
     if (!h || !cfg || !hyper || !niter || !lml || !stop_reason) return VBNMF_ERR_ARG;
     if (!h->d_lw) return fail(h, VBNMF_ERR_STATE, "vbnmf_set_state has not been called");
     if (cfg->itmax < 1 || cfg->dn < 1) return fail(h, VBNMF_ERR_ARG, "itmax and dn must be >= 1");
+    if (!getenv("VBNMF_HOST_LOOP"))
+        return run_device_loop(h, cfg, hyper, lkh_trace, hyper_trace, niter, lml, stop_reason,
+                               nullptr);
     double lk0 = 0.0, lkh = 0.0;  // R/bayesian.R:336
     int it, reason = VBNMF_STOP_ITMAX, rc = 0;
     for (it = 1; it <= cfg->itmax; it++) {                                  // :337
@@ -1021,7 +1111,7 @@ int vbnmf_run(vbnmf_handle *h, const vbnmf_cfg *cfg, double hyper[4], double *lk
         if (it > cfg->n0 && it % cfg->dn == 0) {                            // :342-344
             double mn[4];
             means_of(h, mn);
-            if ((rc = hyper_update(cfg->hyper_update, mn, hyper, 100, 1e-3)))
+            if ((rc = vb_hyper_update(cfg->hyper_update, mn, hyper, 100, 1e-3)))
                 return fail(h, rc, "Hyper-parameter update failed to converge");
         }
         if (lkh_trace) lkh_trace[it - 1] = lkh;
@@ -1143,27 +1233,23 @@ int vbnmf_bench_iterations(vbnmf_handle *h, const double hyper[4], double fudge,
     int rc;
     double lkh = 0.0;
     if (!h->stats_valid && (rc = vbnmf_step(h, hyper, fudge, &lkh))) return rc;
+    // exactly `iters` iterations of the product loop (run_device_loop) with the hyper-parameters
+    // held fixed and a tolerance that never triggers, CUDA events around the two sweep passes
     std::vector<cudaEvent_t> ev((size_t)iters * 4 + 2);
     for (auto &e : ev) CK(cudaEventCreate(&e));
+    vbnmf_cfg cfg;
+    cfg.itmax = iters; cfg.tol = -1.0; cfg.n0 = 1 << 30; cfg.dn = 1; cfg.fudge = fudge;
+    for (int q = 0; q < 4; q++) cfg.hyper_update[q] = 0;
+    double hy[4] = {hyper[0], hyper[1], hyper[2], hyper[3]}, lml = 0.0;
+    int niter = 0, why = 0;
     const int64_t l0 = h->launches;
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaEventRecord(ev[0], h->stream));
-    for (int it = 0; it < iters; it++) {
-        // same sequence as iterate(), with events around the two sweep passes
-        if ((rc = launch_posterior(h, true, hyper[0], hyper[1], fudge))) return rc;
-        if ((rc = launch_posterior(h, false, hyper[2], hyper[3], fudge))) return rc;
-        CK(cudaEventRecord(ev[2 + it * 4 + 0], h->stream));
-        if ((rc = launch_sweep_cols(h))) return rc;
-        CK(cudaEventRecord(ev[2 + it * 4 + 1], h->stream));
-        CK(cudaEventRecord(ev[2 + it * 4 + 2], h->stream));
-        if ((rc = launch_sweep_rows(h))) return rc;
-        CK(cudaEventRecord(ev[2 + it * 4 + 3], h->stream));
-        if ((rc = allreduce(h, h->d_red, red_len(h)))) return rc;
-        if ((rc = fetch_scalars(h))) return rc;  // the per-iteration host readback of the loop
-        lkh = absorb_scalars(h, hyper);
-    }
+    rc = run_device_loop(h, &cfg, hy, nullptr, nullptr, &niter, &lml, &why, ev.data() + 2);
+    if (rc) return rc;
     CK(cudaEventRecord(ev[1], h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    if (niter != iters) return fail(h, VBNMF_ERR_STATE, "bench loop stopped early (NaN bound)");
     float t = 0.f;
     CK(cudaEventElapsedTime(&t, ev[0], ev[1]));
     ms[0] = t;
@@ -1177,7 +1263,7 @@ int vbnmf_bench_iterations(vbnmf_handle *h, const double hyper[4], double fudge,
     ms[3] = ms[0] - ms[1] - ms[2];
     for (auto &e : ev) cudaEventDestroy(e);
     if (launches) *launches = h->launches - l0;
-    if (lkh_last) *lkh_last = lkh;
+    if (lkh_last) *lkh_last = h->h_ctl[vb::kCtlLkh];
     return 0;
 }
 
