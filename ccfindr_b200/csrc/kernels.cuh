@@ -234,6 +234,11 @@ __device__ __forceinline__ void prefetch_l2(const void *p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
+// storage formats of the nonzeros in the tiled layouts
+enum { kEntF32 = 0,   // 8 bytes {int32 tile row, float count}
+       kEntF64 = 1,   // int32 tile row + double count in two arrays (counts not exact in fp32)
+       kEntP16 = 2 }; // 4 bytes {count << 16 | tile row}: integer counts < 2^16 (sweep_p16_kernel)
+
 struct SweepTiledArgs {
     int64_t NO;              // owners per slab (device-ordered rows of the owner panel)
     int T;                   // tile rows
@@ -247,6 +252,7 @@ struct SweepTiledArgs {
     double *Part;            // nslabs x NO x RS
     double *xl_part;         // COLS: gridDim.x partial sums of x log p
     const double *ctl;       // device loop control block (see control_kernel) or nullptr
+    const uint32_t *ptr4;    // packed-16 layout: segment pointers in units of 4 entries (16 bytes)
 };
 
 // Device loop control block (doubles).  When a kernel is given it and ctl[kCtlDone] != 0 the run
@@ -437,6 +443,304 @@ sweep_tiled_kernel(const SweepTiledArgs a) {
         ebase = eend;
     }
     if (COLS) {
+        xl = block_sum(xl, red);
+        if (threadIdx.x == 0) a.xl_part[blockIdx.x] = xl;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Packed-16 variant of the tiled sweep (same maths, same outputs as sweep_tiled_kernel).
+//
+// When every count is an integer below 2^16 (true for raw UMI counts) a nonzero is ONE 32-bit word
+// {count << 16 | tile row}: half the bytes of the {int32, float} entries, and a lane fetches FOUR
+// nonzeros with one 128-bit load.  Segments are padded to a multiple of 4 entries with zero words
+// (row 0, count 0: they run through the arithmetic and add nothing), so every segment starts on a
+// 16-byte boundary and the pointers are 32-bit quad indices (ptr4).
+//
+// Placement inside a segment (build_segments_p16_kernel): the round-robin residue order of the
+// 8-byte layout is kept, but in blocks of 4*NPG entries item p goes to quad (p mod q), word
+// (p div q), q = quads of the block: the nonzeros the lanes of a group process in the same step
+// are consecutive items of that order -> the same conflict-free gathers.
+//
+// Latency: everything a segment needs first is already in registers when it starts -- its first
+// quad and its owner row were requested while the previous segment ran, its pointers one segment
+// before that -- and the rest of its entries were pulled into L2 by ONE bulk prefetch (TMA unit,
+// no LSU wavefronts).  Inside a segment the quads are loaded two chunks ahead.
+// The cross-lane sum of the per-lane accumulators is a recursive halving (each step a lane keeps
+// half of its values and sends the other half): KL/2 + KL/4 + .. shuffles instead of 3*KL.
+__device__ __forceinline__ void bulk_prefetch_l2(const void *p, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint4 ldcs_quad(const uint4 *p) { return __ldcs(p); }
+
+// one halving step over the lanes that differ in bit BIT of the group lane: N values -> ceil(N/2)
+template <int N, int BIT>
+__device__ __forceinline__ void halve_step(const double (&in)[N], double (&out)[(N + 1) / 2],
+                                           int gl, unsigned gmask) {
+    constexpr int Hh = (N + 1) / 2;
+    const bool hi = (gl & BIT) != 0;
+#pragma unroll
+    for (int k = 0; k < Hh; k++) {
+        const double lo_v = in[k];
+        const double hi_v = (Hh + k < N) ? in[Hh + k] : 0.0;
+        const double send = hi ? lo_v : hi_v;
+        const double keep = hi ? hi_v : lo_v;
+        out[k] = keep + __shfl_xor_sync(gmask, send, BIT);
+    }
+}
+
+// x log p of the fp64 cell-owner pass through products (integer counts): with p = 2^e m,
+//   sum x log p = ln2 * sum x e + sum_b 2^b log( prod_{bit b of x set} m ),   b < kLpBits,
+// so a nonzero costs kLpBits predicated multiplies and a few integer operations instead of a
+// log (~35 instructions).  The mantissa products stay below 2^(T/8) <= 2^512 within a segment and
+// are renormalised at its end.  Counts >= 2^kLpBits take the log in an out-of-line slow path.
+constexpr int kLpBits = 3;
+struct LogProd {
+    double P[kLpBits];
+    int E;          // sum x e of the current segment
+    double Es;      // ... of the finished ones (exact integer), and the slow-path terms
+    double slow;
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int b = 0; b < kLpBits; b++) P[b] = 1.0;
+        E = 0; Es = 0.0; slow = 0.0;
+    }
+    __device__ __forceinline__ void add(int xi, double p) {
+        const int hi = __double2hiint(p);
+        const int e = ((hi >> 20) & 0x7ff) - 1023;
+        const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(p));
+        const int xm = xi < (1 << kLpBits) ? xi : 0;
+        E += xm * e;
+#pragma unroll
+        for (int b = 0; b < kLpBits; b++)
+            if ((xm >> b) & 1) P[b] *= m;
+    }
+    // counts >= 2^kLpBits (rare): called once per chunk, inside a branch taken only if one occurred
+    __device__ __forceinline__ void add_slow(int xi, double p) {
+        if (xi >= (1 << kLpBits)) slow = fma((double)xi, fast_log_pos(p), slow);
+    }
+    __device__ __forceinline__ void end_segment() {
+#pragma unroll
+        for (int b = 0; b < kLpBits; b++) {
+            const int hi = __double2hiint(P[b]);
+            E += (((hi >> 20) & 0x7ff) - 1023) << b;
+            P[b] = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(P[b]));
+        }
+        Es += (double)E;
+        E = 0;
+    }
+    __device__ __forceinline__ double total() const {
+        double t = slow + Es * 0.6931471805599453094;
+#pragma unroll
+        for (int b = 0; b < kLpBits; b++) t += (double)(1 << b) * log(P[b]);
+        return t;
+    }
+};
+
+#ifndef VB_OWN_AHEAD
+#define VB_OWN_AHEAD(dflt) (dflt)
+#endif
+template <int RP, bool COLS, typename PT>
+__global__ void __launch_bounds__(SweepCfg<RP, PT>::kThreads, 1)
+sweep_p16_kernel(const SweepTiledArgs a) {
+    using Cfg = SweepCfg<RP, PT>;
+    constexpr int RS = row_stride(RP);
+    constexpr int PS = panel_stride<PT>(RP);
+    constexpr int NT = Cfg::kThreads;
+    constexpr int UE = Cfg::kUE, NU = Cfg::kNU, LPN = Cfg::kLPN, NUL = Cfg::kNUL, KL = Cfg::kKL;
+    constexpr int NPG = Cfg::kNPG;
+    constexpr int kGroups = Cfg::kGroups;
+    // the next owner row is requested one segment ahead where the register budget allows it
+    // (checked with -Xptxas -v: wider row shares, and the fp64 cell-owner pass with its log, spill)
+    constexpr int kRowShare = KL * (int)sizeof(PT);  // bytes of a row held per lane
+    constexpr bool kOwnAhead = VB_OWN_AHEAD(
+        kRowShare <= 48 || (kRowShare <= 80 && sizeof(PT) == 8 && !COLS && LPN == 1));
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    PT *tile = reinterpret_cast<PT *>(smem_raw);
+    const uint32_t tile_s = smem_u32(tile);
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ double red[NT / 32];
+    const int gid = threadIdx.x / kGroup, gl = threadIdx.x % kGroup;
+    const int slot = gl / LPN, hf = gl % LPN;
+    const unsigned gmask = 0xffu << ((threadIdx.x & 31) & ~(kGroup - 1));
+    const int64_t e0 = a.split[blockIdx.x], e1 = a.split[blockIdx.x + 1];
+    const unsigned tile_bytes = (unsigned)a.T * PS * (unsigned)sizeof(PT);
+    const uint4 *ent4 = reinterpret_cast<const uint4 *>(a.ent);
+    if (a.ctl && a.ctl[kCtlDone] != 0.0) return;
+    if (threadIdx.x == 0) mbar_init(&mbar, 1);
+    __syncthreads();
+    unsigned parity = 0;
+    double xl = 0.0;
+    constexpr bool kLogProd = COLS && sizeof(PT) == 8;  // fp64 cell-owner pass: log-product
+    LogProd lp;
+    if (kLogProd) lp.init();
+
+    // this lane's share of an owner row: units hf, hf + LPN, ...
+    auto load_owner = [&](int64_t o, PT(&dst)[KL]) {
+        const PT *orow = reinterpret_cast<const PT *>(a.owner) + o * PS;
+#pragma unroll
+        for (int c = 0; c < NUL; c++) {
+            const int u = LPN * c + hf;
+            if (LPN == 1 || u < NU) ldg_unit(orow, u, dst + c * UE);
+        }
+    };
+
+    for (int64_t ebase = e0; ebase < e1;) {
+        const int64_t slab = ebase / a.NO;
+        const int64_t eend = min(e1, (slab + 1) * a.NO);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(&mbar, tile_bytes);
+            bulk_g2s(tile, reinterpret_cast<const PT *>(a.tiles) + slab * (int64_t)a.T * PS,
+                     tile_bytes, &mbar);
+        }
+        // prime the group's pipeline while the tile lands: pointers of its first two segments,
+        // first quad and owner row of the first
+        int64_t e = ebase + gid;
+        uint32_t beg = 0, end = 0, nb = 0, ne = 0;
+        uint4 f0 = make_uint4(0u, 0u, 0u, 0u);
+        PT ownn[KL];
+#pragma unroll
+        for (int k = 0; k < KL; k++) ownn[k] = 0;
+        if (e < eend) {
+            beg = __ldg(a.ptr4 + e);
+            end = __ldg(a.ptr4 + e + 1);
+            if (e + kGroups < eend) {
+                nb = __ldg(a.ptr4 + e + kGroups);
+                ne = __ldg(a.ptr4 + e + kGroups + 1);
+            }
+            if (beg + slot < end) f0 = ldcs_quad(ent4 + beg + slot);
+            if (kOwnAhead && beg < end) load_owner(e - slab * a.NO, ownn);
+        }
+        mbar_wait(&mbar, parity);
+        parity ^= 1;
+        while (e < eend) {
+            const int64_t en = e + kGroups;
+            const int nq = (int)(end - beg);
+            const uint4 *eb = ent4 + beg;
+            uint4 cur = f0;
+            PT own[KL];
+#pragma unroll
+            for (int k = 0; k < KL; k++) own[k] = ownn[k];
+            if (!kOwnAhead && nq > 0) load_owner(e - slab * a.NO, own);
+            uint4 n1 = make_uint4(0u, 0u, 0u, 0u);
+            if (NPG + slot < nq) n1 = ldcs_quad(eb + NPG + slot);
+            // requests for the NEXT segment (pointers arrived during the previous one) and the
+            // pointers of the one after it
+            uint32_t nnb = 0, nne = 0;
+            f0 = make_uint4(0u, 0u, 0u, 0u);
+            if (en < eend) {
+                if (en + kGroups < eend) {
+                    nnb = __ldg(a.ptr4 + en + kGroups);
+                    nne = __ldg(a.ptr4 + en + kGroups + 1);
+                }
+                if (nb + slot < ne) f0 = ldcs_quad(ent4 + nb + slot);
+                if (kOwnAhead && nb < ne) load_owner(en - slab * a.NO, ownn);
+                if (gl == 0 && nb + NPG < ne)
+                    bulk_prefetch_l2(ent4 + nb + NPG, (ne - nb - NPG) * 16u);
+            }
+            PT acc[KL];
+            PT xls = 0;
+#pragma unroll
+            for (int k = 0; k < KL; k++) acc[k] = 0;
+            for (int c0 = 0; c0 < nq; c0 += NPG) {
+                uint4 n2 = make_uint4(0u, 0u, 0u, 0u);
+                if (c0 + 2 * NPG + slot < nq) n2 = ldcs_quad(eb + c0 + 2 * NPG + slot);
+                PT pu[4], xu[4];
+                uint32_t big = 0;  // kLogProd: OR of this lane's counts of the chunk
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t v = u == 0 ? cur.x : u == 1 ? cur.y : u == 2 ? cur.z : cur.w;
+                    const PT x = (PT)(int)(v >> 16);
+                    const uint32_t raddr = tile_s + (v & 0xffffu) * (uint32_t)(PS * sizeof(PT));
+                    PT tr[KL];
+#pragma unroll
+                    for (int c = 0; c < NUL; c++) {
+                        const int uu = LPN * c + hf;
+                        if (LPN == 1 || uu < NU) {
+                            lds_unit(raddr + uu * 16, tr + c * UE);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < UE; j++) tr[c * UE + j] = 0;
+                        }
+                    }
+                    PT p0 = 0, p1 = 0;
+#pragma unroll
+                    for (int k = 0; k < KL; k += 2) {
+                        p0 = fma(own[k], tr[k], p0);
+                        p1 = fma(own[k + 1], tr[k + 1], p1);
+                    }
+                    PT p = p0 + p1;
+                    if (LPN == 2) p += __shfl_xor_sync(gmask, p, 1);
+                    const PT q = x * rcp_t(p);
+#pragma unroll
+                    for (int k = 0; k < KL; k++) acc[k] = fma(tr[k], q, acc[k]);
+                    if (kLogProd) {
+                        // LPN == 2: both lanes of a pair hold p, each takes every other nonzero
+                        if (LPN == 1 || (u & 1) == hf) {
+                            lp.add((int)(v >> 16), (double)p);
+                            big |= v;
+                            pu[u] = p;
+                        }
+                    } else if (COLS) {
+                        if (LPN == 1) xls = fma(x, log_t(p), xls);
+                        else { pu[u] = p; xu[u] = x; }
+                    }
+                }
+                if (kLogProd && big >= (1u << (16 + kLpBits))) {
+                    const uint32_t cv[4] = {cur.x, cur.y, cur.z, cur.w};
+#pragma unroll 1
+                    for (int u = 0; u < 4; u++)
+                        if (LPN == 1 || (u & 1) == hf) lp.add_slow((int)(cv[u] >> 16), (double)pu[u]);
+                }
+                if (COLS && !kLogProd && LPN == 2) {
+#pragma unroll
+                    for (int v = 0; v < 2; v++) {
+                        const PT pm = hf ? pu[2 * v + 1] : pu[2 * v];
+                        const PT xm = hf ? xu[2 * v + 1] : xu[2 * v];
+                        xls = fma(xm, log_t(pm), xls);
+                    }
+                }
+                cur = n1;
+                n1 = n2;
+            }
+            if (kLogProd) lp.end_segment();
+            else if (COLS) xl += (double)xls;
+            // sum over the lanes that hold the same rank entries (fp64), recursive halving
+            double *out = a.Part + e * RS;
+            double v0[KL];
+#pragma unroll
+            for (int k = 0; k < KL; k++) v0[k] = (double)acc[k];
+            constexpr int H1 = (KL + 1) / 2, H2 = (H1 + 1) / 2, H3 = (H2 + 1) / 2;
+            double v1[H1], v2[H2];
+            halve_step<KL, 4>(v0, v1, gl, gmask);
+            halve_step<H1, 2>(v1, v2, gl, gmask);
+            const int o1 = (gl & 4) ? H1 : 0, o2 = (gl & 2) ? H2 : 0;
+            if (LPN == 1) {
+                double v3[H3];
+                halve_step<H2, 1>(v2, v3, gl, gmask);
+                const int o3 = (gl & 1) ? H3 : 0;
+#pragma unroll
+                for (int k = 0; k < H3; k++) {
+                    const int i2 = k + o3, i1 = i2 + o2, i0 = i1 + o1;  // entry index in acc[]
+                    if (i2 < H2 && i1 < H1 && i0 < KL && i0 < RP) out[i0] = v3[k];
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < H2; k++) {
+                    const int i1 = k + o2, i0 = i1 + o1;
+                    const int kk = (LPN * (i0 / UE) + hf) * UE + (i0 % UE);  // rank index
+                    if (i1 < H1 && i0 < KL && kk < RP) out[kk] = v2[k];
+                }
+            }
+            e = en;
+            beg = nb; end = ne;
+            nb = nnb; ne = nne;
+        }
+        ebase = eend;
+    }
+    if (COLS) {
+        if (kLogProd) xl = lp.total();
         xl = block_sum(xl, red);
         if (threadIdx.x == 0) a.xl_part[blockIdx.x] = xl;
     }

@@ -7,7 +7,7 @@ namespace vb {
 // ---- one-time helpers ----------------------------------------------------------------------
 // sum over nonzeros of lgamma(x+1) (src/vbnmf_update.cpp:80-81; zeros contribute 0) and of
 // -x log x + x (R/factorize.R:45-46); out[0], out[1].  out[2] = number of values that are not
-// non-negative integers (informational).
+// integers in [0, 65535] (0 -> the packed 16-bit layout of the sweep applies).
 template <typename VT>
 __global__ void __launch_bounds__(kBlock)
 count_constants_kernel(int64_t nnz, const VT *__restrict__ val, double *__restrict__ part,
@@ -19,7 +19,7 @@ count_constants_kernel(int64_t nnz, const VT *__restrict__ val, double *__restri
         const double x = (double)val[t];
         a += lgamma(x + 1.0);
         if (x > 0) b += -x * log(x) + x;
-        if (!(x >= 0.0 && x < 2147483648.0 && x == floor(x))) c += 1.0;
+        if (!(x >= 0.0 && x <= 65535.0 && x == floor(x))) c += 1.0;
     }
     a = block_sum(a, sm);
     b = block_sum(b, sm);
@@ -133,6 +133,86 @@ build_segments_kernel(int64_t E, const int64_t *__restrict__ ptr,
             }
         }
     }
+}
+
+// ---- packed-16 layout (sweep_p16_kernel) ----------------------------------------------------
+// quads (4 entries = 16 bytes) per segment, segments padded to a whole number of quads
+__global__ void __launch_bounds__(kBlock)
+quad_len_kernel(int64_t E, const int64_t *__restrict__ ptr, uint32_t *__restrict__ len4) {
+    for (int64_t e = (int64_t)blockIdx.x * kBlock + threadIdx.x; e <= E;
+         e += (int64_t)gridDim.x * kBlock)
+        len4[e] = e < E ? (uint32_t)((ptr[e + 1] - ptr[e] + 3) >> 2) : 0u;
+}
+
+// position of item p (round-robin residue order) of a segment of L4 entries (multiple of 4): in
+// blocks of B = 4*NPG entries, item p of a block with q quads -> quad p mod q, word p div q
+__device__ __forceinline__ int64_t p16_position(int64_t p, int64_t L4, int B) {
+    const int64_t blk = p / B;
+    const int pin = (int)(p - blk * B);
+    const int64_t rem = L4 - blk * B;
+    const int q = (int)(rem < B ? rem : B) >> 2;
+    return blk * B + 4 * (pin % q) + pin / q;
+}
+
+// One thread per segment, same bucketed round-robin order as build_segments_kernel, entries
+// written as {count << 16 | tile row} at their p16_position; the <= 3 padding items are zero words.
+template <typename VT>
+__global__ void __launch_bounds__(kBlock)
+build_segments_p16_kernel(int64_t E, const int64_t *__restrict__ ptr,
+                          const uint32_t *__restrict__ ptr4, const uint32_t *__restrict__ perm,
+                          const int32_t *__restrict__ rowidx, const int32_t *__restrict__ colof,
+                          const int32_t *__restrict__ gene_dev,
+                          const int32_t *__restrict__ cell_dev, const VT *__restrict__ val, int T,
+                          bool cols_pass, int B, uint32_t *__restrict__ ent_out) {
+    for (int64_t e = (int64_t)blockIdx.x * kBlock + threadIdx.x; e < E;
+         e += (int64_t)gridDim.x * kBlock) {
+        const int64_t beg = ptr[e], end = ptr[e + 1];
+        if (beg == end) continue;
+        const int64_t len = end - beg, L4 = (len + 3) & ~(int64_t)3;
+        uint32_t *dst = ent_out + (int64_t)ptr4[e] * 4;
+        int cnt[8];
+#pragma unroll
+        for (int b = 0; b < 8; b++) cnt[b] = 0;
+        for (int64_t t = beg; t < end; t++) {
+            const uint32_t s = perm[t];
+            const int32_t d = cols_pass ? gene_dev[rowidx[s]] : cell_dev[colof[s]];
+            const int rr = (d % T) & 7;
+            cnt[(rr >> 1) | ((rr & 1) << 2)]++;  // bucket order 0,2,4,6,1,3,5,7
+        }
+        int seen[8];
+#pragma unroll
+        for (int b = 0; b < 8; b++) seen[b] = 0;
+        for (int64_t t = beg; t < end; t++) {
+            const uint32_t s = perm[t];
+            const int32_t d = cols_pass ? gene_dev[rowidx[s]] : cell_dev[colof[s]];
+            const int local = d % T, rr = local & 7, b = (rr >> 1) | ((rr & 1) << 2);
+            const int round = seen[b]++;
+            int64_t pos = 0;
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                pos += min(cnt[c], round);
+                if (c < b && cnt[c] > round) pos++;
+            }
+            const uint32_t count = (uint32_t)val[s];
+            dst[p16_position(pos, L4, B)] = (count << 16) | (uint32_t)local;
+        }
+        for (int64_t p = len; p < L4; p++) dst[p16_position(p, L4, B)] = 0u;
+    }
+}
+
+// split[b] = first segment whose quad offset is >= b * total / nparts; split[nparts] = E
+__global__ void split_p16_kernel(int nparts, int64_t E, const uint32_t *__restrict__ ptr4,
+                                 int64_t *__restrict__ split) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > nparts) return;
+    if (b == nparts) { split[b] = E; return; }
+    const int64_t target = (int64_t)((double)ptr4[E] * b / nparts);
+    int64_t lo = 0, hi = E;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if ((int64_t)ptr4[mid] < target) lo = mid + 1; else hi = mid;
+    }
+    split[b] = lo;
 }
 
 // split[b] = first segment whose start offset is >= b * nnz / nparts; split[nparts] = E

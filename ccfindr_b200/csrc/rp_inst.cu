@@ -27,14 +27,22 @@ int sweep_prepare(int smem_bytes) {
     VB_OPT((sweep_tiled_kernel<RP, float, false, float>))
     VB_OPT((sweep_tiled_kernel<RP, double, true, float>))
     VB_OPT((sweep_tiled_kernel<RP, double, false, float>))
+    VB_OPT((sweep_p16_kernel<RP, true, double>))
+    VB_OPT((sweep_p16_kernel<RP, false, double>))
+    VB_OPT((sweep_p16_kernel<RP, true, float>))
+    VB_OPT((sweep_p16_kernel<RP, false, float>))
 #undef VB_OPT
     return e == cudaSuccess ? 0 : 1;
 }
 
 template <typename PT>
-void sweep_pt(const SweepTiledArgs &a, bool cols, bool vf, int grid, int smem, cudaStream_t s) {
+void sweep_pt(const SweepTiledArgs &a, bool cols, int fmt, int grid, int smem, cudaStream_t s) {
     constexpr int NT = SweepCfg<RP, PT>::kThreads;
-    if (cols) {
+    const bool vf = fmt == kEntF32;
+    if (fmt == kEntP16) {
+        if (cols) sweep_p16_kernel<RP, true, PT><<<grid, NT, smem, s>>>(a);
+        else sweep_p16_kernel<RP, false, PT><<<grid, NT, smem, s>>>(a);
+    } else if (cols) {
         if (vf) sweep_tiled_kernel<RP, float, true, PT><<<grid, NT, smem, s>>>(a);
         else sweep_tiled_kernel<RP, double, true, PT><<<grid, NT, smem, s>>>(a);
     } else {
@@ -43,10 +51,10 @@ void sweep_pt(const SweepTiledArgs &a, bool cols, bool vf, int grid, int smem, c
     }
 }
 
-void sweep(const SweepTiledArgs &a, bool cols, bool vf, bool pf32, int grid, int smem,
+void sweep(const SweepTiledArgs &a, bool cols, int fmt, bool pf32, int grid, int smem,
            cudaStream_t s) {
-    if (pf32) sweep_pt<float>(a, cols, vf, grid, smem, s);
-    else sweep_pt<double>(a, cols, vf, grid, smem, s);
+    if (pf32) sweep_pt<float>(a, cols, fmt, grid, smem, s);
+    else sweep_pt<double>(a, cols, fmt, grid, smem, s);
 }
 
 inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
@@ -77,7 +85,8 @@ void colsum(const ColsumArgs &a, cudaStream_t s) {
 
 extern const RpTable VB_CAT(rp_table_, VB_RP);
 const RpTable VB_CAT(rp_table_, VB_RP) = {
-    RP,      RS,        row_stride_f32(RP), SweepCfg<RP, double>::kThreads, sweep_prepare, sweep, mirror,
+    RP,      RS,        row_stride_f32(RP), SweepCfg<RP, double>::kThreads,
+    SweepCfg<RP, double>::kNPG, SweepCfg<RP, float>::kNPG, sweep_prepare, sweep, mirror,
     combine, posterior, ml_update,          colsum};
 
 }  // namespace vb

@@ -56,10 +56,11 @@ struct ColsumArgs {
 struct RpTable {
     int rp, rs, rsf;  // padded rank, fp64 panel stride (doubles), fp32 mirror stride (floats)
     int sweep_threads;
-    // cols: cell-owner pass; val_is_float selects the count storage type; int_counts = all counts
-    // are integers (enables the log-product path); grid = CTAs (one per SM, persistent)
+    int npg64, npg32;  // nonzeros per 8-lane group step of the sweep (fp64 / fp32 panels)
+    // cols: cell-owner pass; fmt = storage format of the nonzeros (kEnt*); grid = CTAs (one per
+    // SM, persistent)
     int (*sweep_prepare)(int smem_bytes);  // opt in to the dynamic shared memory size; 0 = ok
-    void (*sweep)(const SweepTiledArgs &, bool cols, bool val_is_float, bool panels_f32, int grid,
+    void (*sweep)(const SweepTiledArgs &, bool cols, int fmt, bool panels_f32, int grid,
                   int smem_bytes, cudaStream_t);
     void (*mirror)(int64_t rows, const double *v, float *v32, cudaStream_t);
     void (*combine)(const CombineArgs &, cudaStream_t);

@@ -118,19 +118,23 @@ struct PassLayout {
     int64_t *d_ptr = nullptr;   // E + 1
     int32_t *d_idx = nullptr;   // nnz (double counts only)
     void *d_val = nullptr;      // nnz (double counts only)
-    void *d_ent = nullptr;      // nnz packed {int32 tile row, float count} (float counts)
+    void *d_ent = nullptr;      // nnz packed {int32 tile row, float count} (float counts), or
+                                // the padded {count << 16 | tile row} words of the packed-16 layout
+    uint32_t *d_ptr4 = nullptr; // packed-16 layout: E + 1 segment pointers in quads (16 bytes)
     int64_t *d_split = nullptr; // grid + 1
     void release(cudaStream_t s) {
-        void *ps[] = {d_ptr, d_idx, d_val, d_ent, d_split};
+        void *ps[] = {d_ptr, d_idx, d_val, d_ent, d_ptr4, d_split};
         for (void *q : ps)
             if (q) cudaFreeAsync(q, s);
-        d_ptr = nullptr; d_idx = nullptr; d_val = nullptr; d_ent = nullptr; d_split = nullptr;
+        d_ptr = nullptr; d_idx = nullptr; d_val = nullptr; d_ent = nullptr; d_ptr4 = nullptr;
+        d_split = nullptr;
     }
 };
 
 // tiled layout for tile height T (cached per T; the rank only enters through T)
 struct Layout {
     int T = 0, Sg = 0, Sc = 0;
+    int npg = 0;  // packed-16 layout: nonzeros per group step it was ordered for (0: 8-byte layout)
     int64_t NG = 0, NC = 0;
     std::vector<int32_t> gene_dev, cell_dev;  // original index -> device row
     int32_t *d_gene_dev = nullptr, *d_cell_dev = nullptr;
@@ -160,6 +164,7 @@ struct vbnmf_handle {
     int r = 0, rp = 0, rs = 0;
     int precision = VBNMF_FP64;
     bool val_float = true;
+    bool p16 = false;  // all counts are integers < 2^16: packed-16 layouts (sweep_p16_kernel)
     bool borrowed = false;
     // the count matrix as given (CSC); the tiled layouts are derived from it
     int64_t *d_colptr = nullptr;
@@ -316,6 +321,38 @@ int build_pass(H *h, Layout *L, bool cols_pass, const int32_t *d_colof) {
     vb::segment_ptr_kernel<<<g, vb::kBlock, 0, h->stream>>>(P.E, nnz, k_out, P.d_ptr); }
     CK(cudaStreamSynchronize(h->stream));
     vfree(h->stream, d_tmp); vfree(h->stream, k_in); vfree(h->stream, k_out); vfree(h->stream, p_in);
+    if (L->npg > 0) {
+        // packed-16 layout: pad every segment to whole quads, scan the quad counts into ptr4
+        uint32_t *d_len4 = nullptr;
+        CK(vmalloc(h, &d_len4, (size_t)(P.E + 1) * 4));
+        CK(vmalloc(h, &P.d_ptr4, (size_t)(P.E + 1) * 4));
+        vb::quad_len_kernel<<<g, vb::kBlock, 0, h->stream>>>(P.E, P.d_ptr, d_len4);
+        size_t scan_bytes = 0;
+        CK(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, d_len4, P.d_ptr4, P.E + 1, h->stream));
+        void *d_scan = nullptr;
+        CK(vmalloc(h, &d_scan, scan_bytes));
+        CK(cub::DeviceScan::ExclusiveSum(d_scan, scan_bytes, d_len4, P.d_ptr4, P.E + 1, h->stream));
+        if (nnz + 3 * P.E >= ((int64_t)1 << 34))
+            return fail(h, VBNMF_ERR_ARG, "matrix too large for 32-bit quad pointers on one GPU");
+        uint32_t quads = 0;
+        CK(cudaMemcpyAsync(&quads, P.d_ptr4 + P.E, 4, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        vfree(h->stream, d_len4); vfree(h->stream, d_scan);
+        CK(vmalloc(h, &P.d_ent, (size_t)quads * 16));
+        { StageTimer t1("  build_segments(p16)");
+        vb::build_segments_p16_kernel<VT><<<g, vb::kBlock, 0, h->stream>>>(
+            P.E, P.d_ptr, P.d_ptr4, p_out, h->d_rowidx, d_colof, L->d_gene_dev, L->d_cell_dev,
+            (const VT *)h->d_val, L->T, cols_pass, 4 * L->npg, (uint32_t *)P.d_ent); }
+        CK(vmalloc(h, &P.d_split, (size_t)(L->grid + 1) * 8));
+        vb::split_p16_kernel<<<cdiv(L->grid + 1, 128), 128, 0, h->stream>>>(L->grid, P.E, P.d_ptr4,
+                                                                           P.d_split);
+        CK(cudaStreamSynchronize(h->stream));
+        CK(cudaGetLastError());
+        vfree(h->stream, p_out);
+        vfree(h->stream, P.d_ptr);
+        P.d_ptr = nullptr;
+        return 0;
+    }
     if (sizeof(VT) == 4) {
         CK(vmalloc(h, &P.d_ent, (size_t)nnz * 8));
     } else {
@@ -335,12 +372,14 @@ int build_pass(H *h, Layout *L, bool cols_pass, const int32_t *d_colof) {
     return 0;
 }
 
-int get_layout(H *h, int T, Layout **out) {
+int get_layout(H *h, int T, int npg, Layout **out) {
+    if (!h->p16) npg = 0;
     for (Layout *l : h->layouts)
-        if (l->T == T) { *out = l; return 0; }
+        if (l->T == T && l->npg == npg) { *out = l; return 0; }
     StageTimer tm("get_layout(total)");
     Layout *L = new Layout();
     L->T = T;
+    L->npg = npg;
     L->Sg = cdiv(h->n, T);
     L->Sc = cdiv(h->m, T);
     L->NG = (int64_t)L->Sg * T;
@@ -414,6 +453,8 @@ int scan_matrix_t(H *h) {
     vfree(h->stream, d_part); vfree(h->stream, d_out); vfree(h->stream, d_colof); vfree(h->stream, d_cnt);
     h->lgx = consts[0];
     h->mlconst = consts[1];
+    // VBNMF_NO_P16=1 keeps the 8-byte entries (A/B measurements, tests of that path)
+    h->p16 = h->val_float && consts[2] == 0.0 && !getenv("VBNMF_NO_P16");
     return 0;
 }
 
@@ -441,7 +482,7 @@ int alloc_panels(H *h, int r) {
     const int row_bytes = f32 ? tab->rsf * 4 : rs * 8;
     const int T = choose_tile_rows(h, row_bytes);
     Layout *L = nullptr;
-    int rc = get_layout(h, T, &L);
+    int rc = get_layout(h, T, f32 ? tab->npg32 : tab->npg64, &L);
     if (rc) return rc;
     if (rp == h->rp && L == h->L && h->d_lw && h->panel_precision == h->precision) {
         h->r = r;
@@ -524,6 +565,9 @@ int download_panel(H *h, const double *src, std::vector<double> &tmp, bool wside
 }
 
 // ---- one iteration --------------------------------------------------------------------------------
+inline int entry_format(const H *h) {
+    return h->L->npg > 0 ? vb::kEntP16 : (h->val_float ? vb::kEntF32 : vb::kEntF64);
+}
 int launch_posterior(H *h, bool wside, double a, double b, double fud) {
     NvtxRange nv(wside ? "vbnmf:posterior_W" : "vbnmf:posterior_H");
     const Layout *L = h->L;
@@ -560,8 +604,8 @@ int launch_sweep_cols(H *h) {
                          L->cols.d_idx, (const double *)L->cols.d_val,
                          f32 ? (const void *)h->d_lh32 : (const void *)h->d_lh,
                          f32 ? (const void *)h->d_lw32 : (const void *)h->d_lw, h->d_Part1, h->d_xl,
-                         h->ctl};
-    h->tab->sweep(a, true, h->val_float, f32, L->grid, h->smem_bytes, h->stream);
+                         h->ctl, L->cols.d_ptr4};
+    h->tab->sweep(a, true, entry_format(h), f32, L->grid, h->smem_bytes, h->stream);
     vb::CombineArgs c{L->NC, L->Sg, h->r, h->d_Part1, h->d_lh, h->d_ShRaw, h->d_partC,
                       tail + h->rs + 3, h->d_counters + 2, h->d_xl, L->grid, h->gridC, h->ctl};
     h->tab->combine(c, h->stream);
@@ -579,8 +623,8 @@ int launch_sweep_rows(H *h) {
                          L->rows.d_idx, (const double *)L->rows.d_val,
                          f32 ? (const void *)h->d_lw32 : (const void *)h->d_lw,
                          f32 ? (const void *)h->d_lh32 : (const void *)h->d_lh, h->d_Part2, nullptr,
-                         h->ctl};
-    h->tab->sweep(a, false, h->val_float, f32, L->grid, h->smem_bytes, h->stream);
+                         h->ctl, L->rows.d_ptr4};
+    h->tab->sweep(a, false, entry_format(h), f32, L->grid, h->smem_bytes, h->stream);
     vb::CombineArgs c{L->NG, L->Sc, h->r, h->d_Part2, h->d_lw, h->d_red, h->d_partC,
                       tail + h->rs + 5, h->d_counters + 3, nullptr, 0, h->gridC, h->ctl};
     h->tab->combine(c, h->stream);
