@@ -136,48 +136,187 @@ build_segments_kernel(int64_t E, const int64_t *__restrict__ ptr,
 }
 
 // ---- packed-16 layout (sweep_p16_kernel) ----------------------------------------------------
-// quads (4 entries = 16 bytes) per segment, segments padded to a whole number of quads
+// Conflict-aware schedule of one segment.  A group of the sweep processes NL nonzeros per step
+// (NL = 8, or 4 when two lanes share a nonzero) and a step costs as many shared-memory wavefronts
+// per gather as the largest number of its tile rows that fall into the same residue class
+// (row mod 8; with NL = 4 the four rows of a step must also have equal parity, so the even and the
+// odd residues are scheduled as two independent classes of NB = 4 buckets).  With bucket counts
+// c_b the cheapest schedule in K steps has max(K, max_b c_b) wavefronts.  It is reached by
+//   R "single" steps: step k holds the k-th nonzero of every bucket that still has one (lane =
+//     bucket, empty lanes are holes), conflict free;
+//   P "pair" steps of two half rows of <= NL/2 nonzeros with distinct buckets: the r_b = c_b - R
+//     nonzeros left in each bucket are dealt cyclically over the 2P half rows (r_b <= 2P, so no
+//     bucket repeats inside a half row) -> at most a 2-way conflict;
+// with R + P = K and P the smallest value for which L <= R + 2P and sum_b r_b <= NL * P.  K is the
+// number of steps the kernel executes anyway (whole chunks of 4 steps), so the schedule costs no
+// extra instructions.  Holes are zero-count words that point at a row of an unused residue class.
+struct SegPlan { int R, P; };
+
+template <int NB>
+__device__ __forceinline__ SegPlan plan_class(const int (&c)[NB], int NL, int K) {
+    int L = 0;
+#pragma unroll
+    for (int b = 0; b < NB; b++) L = max(L, c[b]);
+    SegPlan pl;
+    for (int P = max(0, L - K);; P++) {
+        const int R = K - P;
+        int rest = 0;
+#pragma unroll
+        for (int b = 0; b < NB; b++) rest += max(0, c[b] - R);
+        if (rest <= NL * P) { pl.R = R; pl.P = P; return pl; }
+    }
+}
+
+// steps of a class with n nonzeros, the fullest bucket holding L of them: enough for all of them
+// and for a 2-way conflict at worst (L <= 2K), rounded up to a multiple of `mult`
+__device__ __forceinline__ int class_steps(int n, int L, int NL, int mult) {
+    const int k0 = max((n + NL - 1) / NL, (L + 1) / 2);
+    return ((k0 + mult - 1) / mult) * mult;
+}
+
+// residue (tile row mod 8) -> (class, bucket) and back.  NL = 8: one class, bucket = residue.
+// NL = 4: class = parity, bucket = residue / 2.
+__device__ __forceinline__ int res_class(int rr, int NL) { return NL == 8 ? 0 : (rr & 1); }
+__device__ __forceinline__ int res_bucket(int rr, int NL) { return NL == 8 ? rr : (rr >> 1); }
+__device__ __forceinline__ int bucket_res(int cls, int b, int NL) { return NL == 8 ? b : 2 * b + cls; }
+
+struct SegSchedule {
+    int K[2];        // steps per class
+    SegPlan pl[2];
+    int offr[2][8];  // pair part: first dealt index of each bucket
+    int cnt[2][8];
+};
+
+// counts per residue -> schedule.  NL = 8: class 0 only, K a multiple of 4.  NL = 4: two classes
+// of K multiples of 2 (an odd number of step pairs gets one more pair of hole steps in class 1).
+__device__ __forceinline__ void make_schedule(const int (&cnt8)[8], int NL, SegSchedule &sc) {
+    const int ncls = NL == 8 ? 1 : 2, NB = NL;
+    for (int cl = 0; cl < 2; cl++) {
+        sc.K[cl] = 0; sc.pl[cl].R = 0; sc.pl[cl].P = 0;
+        for (int b = 0; b < 8; b++) { sc.cnt[cl][b] = 0; sc.offr[cl][b] = 0; }
+    }
+    for (int rr = 0; rr < 8; rr++) sc.cnt[res_class(rr, NL)][res_bucket(rr, NL)] = cnt8[rr];
+    for (int cl = 0; cl < ncls; cl++) {
+        int n = 0, L = 0;
+        for (int b = 0; b < NB; b++) { n += sc.cnt[cl][b]; L = max(L, sc.cnt[cl][b]); }
+        sc.K[cl] = class_steps(n, L, NL, NL == 8 ? 4 : 2);
+    }
+    if (ncls == 2 && ((sc.K[0] + sc.K[1]) & 3)) sc.K[1] += 2;
+    for (int cl = 0; cl < ncls; cl++) {
+        if (sc.K[cl] == 0) continue;
+        if (NL == 8) {
+            int c[8];
+            for (int b = 0; b < 8; b++) c[b] = sc.cnt[cl][b];
+            sc.pl[cl] = plan_class<8>(c, 8, sc.K[cl]);
+        } else {
+            int c[4];
+            for (int b = 0; b < 4; b++) c[b] = sc.cnt[cl][b];
+            sc.pl[cl] = plan_class<4>(c, 4, sc.K[cl]);
+        }
+        int acc = 0;
+        for (int b = 0; b < NB; b++) {
+            sc.offr[cl][b] = acc;
+            acc += max(0, sc.cnt[cl][b] - sc.pl[cl].R);
+        }
+    }
+}
+
+// item index (step * NL + lane, steps of class 1 after those of class 0) of the k-th nonzero of
+// residue rr
+__device__ __forceinline__ int schedule_item(const SegSchedule &sc, int NL, int rr, int k) {
+    const int cl = res_class(rr, NL), b = res_bucket(rr, NL);
+    const int R = sc.pl[cl].R, P = sc.pl[cl].P;
+    int step, lane;
+    if (k < R) {
+        step = k; lane = b;
+    } else {
+        const int t = sc.offr[cl][b] + (k - R);
+        const int row = t % (2 * P), level = t / (2 * P);
+        step = R + row % P;
+        lane = (row >= P) ? NL - 1 - level : level;
+    }
+    return ((cl ? sc.K[0] : 0) + step) * NL + lane;
+}
+
+__device__ __forceinline__ int tile_residue(int32_t d, int T) { return (d % T) & 7; }
+
+// quads (4 entries = 16 bytes) of every segment under the schedule above; len4[E] = 0
 __global__ void __launch_bounds__(kBlock)
-quad_len_kernel(int64_t E, const int64_t *__restrict__ ptr, uint32_t *__restrict__ len4) {
+plan_p16_kernel(int64_t E, const int64_t *__restrict__ ptr, const uint32_t *__restrict__ perm,
+                const int32_t *__restrict__ rowidx, const int32_t *__restrict__ colof,
+                const int32_t *__restrict__ gene_dev, const int32_t *__restrict__ cell_dev, int T,
+                bool cols_pass, int NL, uint32_t *__restrict__ len4) {
     for (int64_t e = (int64_t)blockIdx.x * kBlock + threadIdx.x; e <= E;
-         e += (int64_t)gridDim.x * kBlock)
-        len4[e] = e < E ? (uint32_t)((ptr[e + 1] - ptr[e] + 3) >> 2) : 0u;
-}
-
-// position of item p (round-robin residue order) of a segment of L4 entries (multiple of 4): in
-// blocks of B = 4*NPG entries, item p of a block with q quads -> quad p mod q, word p div q
-__device__ __forceinline__ int64_t p16_position(int64_t p, int64_t L4, int B) {
-    const int64_t blk = p / B;
-    const int pin = (int)(p - blk * B);
-    const int64_t rem = L4 - blk * B;
-    const int q = (int)(rem < B ? rem : B) >> 2;
-    return blk * B + 4 * (pin % q) + pin / q;
-}
-
-// One thread per segment, same bucketed round-robin order as build_segments_kernel, entries
-// written as {count << 16 | tile row} at their p16_position; the <= 3 padding items are zero words.
-template <typename VT>
-__global__ void __launch_bounds__(kBlock)
-build_segments_p16_kernel(int64_t E, const int64_t *__restrict__ ptr,
-                          const uint32_t *__restrict__ ptr4, const uint32_t *__restrict__ perm,
-                          const int32_t *__restrict__ rowidx, const int32_t *__restrict__ colof,
-                          const int32_t *__restrict__ gene_dev,
-                          const int32_t *__restrict__ cell_dev, const VT *__restrict__ val, int T,
-                          bool cols_pass, int B, uint32_t *__restrict__ ent_out) {
-    for (int64_t e = (int64_t)blockIdx.x * kBlock + threadIdx.x; e < E;
          e += (int64_t)gridDim.x * kBlock) {
+        if (e == E) { len4[e] = 0u; continue; }
         const int64_t beg = ptr[e], end = ptr[e + 1];
-        if (beg == end) continue;
-        const int64_t len = end - beg, L4 = (len + 3) & ~(int64_t)3;
-        uint32_t *dst = ent_out + (int64_t)ptr4[e] * 4;
+        if (beg == end) { len4[e] = 0u; continue; }
         int cnt[8];
 #pragma unroll
         for (int b = 0; b < 8; b++) cnt[b] = 0;
         for (int64_t t = beg; t < end; t++) {
             const uint32_t s = perm[t];
-            const int32_t d = cols_pass ? gene_dev[rowidx[s]] : cell_dev[colof[s]];
-            const int rr = (d % T) & 7;
-            cnt[(rr >> 1) | ((rr & 1) << 2)]++;  // bucket order 0,2,4,6,1,3,5,7
+            cnt[tile_residue(cols_pass ? gene_dev[rowidx[s]] : cell_dev[colof[s]], T)]++;
+        }
+        int n0 = 0, n1 = 0, L0 = 0, L1 = 0;
+        for (int rr = 0; rr < 8; rr++) {
+            if (res_class(rr, NL)) { n1 += cnt[rr]; L1 = max(L1, cnt[rr]); }
+            else { n0 += cnt[rr]; L0 = max(L0, cnt[rr]); }
+        }
+        int K = class_steps(n0, L0, NL, NL == 8 ? 4 : 2);
+        if (NL != 8) {
+            K += class_steps(n1, L1, NL, 2);
+            K = (K + 3) & ~3;
+        }
+        len4[e] = (uint32_t)(K * NL / 4);
+    }
+}
+
+// position of item p of a segment stored in blocks of B = 4*NL entries (4 steps): item p of a
+// block -> quad p mod NL, word p div NL, so that word u of the quads the NL lanes load in one
+// 128-bit access is step u of the block
+__device__ __forceinline__ int64_t p16_position(int64_t p, int NL) {
+    const int B = 4 * NL;
+    const int64_t blk = p / B;
+    const int pin = (int)(p - blk * B);
+    return blk * B + 4 * (pin % NL) + pin / NL;
+}
+
+// One thread per segment: fill the segment with hole words, then scatter the nonzeros to their
+// scheduled places as {count << 16 | tile row}.  nvalid / S: rows of the tile side that exist
+// (a hole must point at a real row: local * S + slab < nvalid; row 0 of a slab always is).
+template <typename VT>
+__global__ void __launch_bounds__(kBlock)
+build_segments_p16_kernel(int64_t E, int64_t NO, const int64_t *__restrict__ ptr,
+                          const uint32_t *__restrict__ ptr4, const uint32_t *__restrict__ perm,
+                          const int32_t *__restrict__ rowidx, const int32_t *__restrict__ colof,
+                          const int32_t *__restrict__ gene_dev,
+                          const int32_t *__restrict__ cell_dev, const VT *__restrict__ val, int T,
+                          bool cols_pass, int NL, int64_t nvalid, int S,
+                          uint32_t *__restrict__ ent_out) {
+    for (int64_t e = (int64_t)blockIdx.x * kBlock + threadIdx.x; e < E;
+         e += (int64_t)gridDim.x * kBlock) {
+        const int64_t beg = ptr[e], end = ptr[e + 1];
+        if (beg == end) continue;
+        uint32_t *dst = ent_out + (int64_t)ptr4[e] * 4;
+        const int nitems = (int)(ptr4[e + 1] - ptr4[e]) * 4;
+        const int64_t slab = e / NO;
+        int cnt[8];
+#pragma unroll
+        for (int b = 0; b < 8; b++) cnt[b] = 0;
+        for (int64_t t = beg; t < end; t++) {
+            const uint32_t s = perm[t];
+            cnt[tile_residue(cols_pass ? gene_dev[rowidx[s]] : cell_dev[colof[s]], T)]++;
+        }
+        SegSchedule sc;
+        make_schedule(cnt, NL, sc);
+        // holes: lane <-> bucket in the single steps, so the residue of the lane's bucket is free
+        for (int p = 0; p < nitems; p++) {
+            const int step = p / NL, lane = p - step * NL;
+            const int cl = (NL != 8 && step >= sc.K[0]) ? 1 : 0;
+            int rr = bucket_res(cl, lane, NL);
+            if ((int64_t)rr * S + slab >= nvalid) rr = 0;
+            dst[p16_position(p, NL)] = (uint32_t)rr;
         }
         int seen[8];
 #pragma unroll
@@ -185,18 +324,11 @@ build_segments_p16_kernel(int64_t E, const int64_t *__restrict__ ptr,
         for (int64_t t = beg; t < end; t++) {
             const uint32_t s = perm[t];
             const int32_t d = cols_pass ? gene_dev[rowidx[s]] : cell_dev[colof[s]];
-            const int local = d % T, rr = local & 7, b = (rr >> 1) | ((rr & 1) << 2);
-            const int round = seen[b]++;
-            int64_t pos = 0;
-#pragma unroll
-            for (int c = 0; c < 8; c++) {
-                pos += min(cnt[c], round);
-                if (c < b && cnt[c] > round) pos++;
-            }
+            const int local = d % T, rr = local & 7;
+            const int p = schedule_item(sc, NL, rr, seen[rr]++);
             const uint32_t count = (uint32_t)val[s];
-            dst[p16_position(pos, L4, B)] = (count << 16) | (uint32_t)local;
+            dst[p16_position(p, NL)] = (count << 16) | (uint32_t)local;
         }
-        for (int64_t p = len; p < L4; p++) dst[p16_position(p, L4, B)] = 0u;
     }
 }
 

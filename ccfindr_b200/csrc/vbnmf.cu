@@ -55,8 +55,9 @@ const RpTable *rp_table(int rp) {
 namespace {
 
 constexpr int kMaxRank = 64;
-constexpr int kTileBytes = 204800;  // shared-memory budget of one staged slab
-const int kTileRows[] = {4096, 2560, 2048, 1536, 1152, 1024, 768, 512, 384, 256, 128};
+// shared-memory budget of one staged slab: the 227 KB a CTA can opt in to minus the static part
+constexpr int kTileBytes = 231424;
+constexpr int kTileRowsMax = 4096, kTileRowsStep = 128;
 
 std::string g_create_error;
 
@@ -255,9 +256,9 @@ inline int64_t tail_off(const H *h) { return h->L->NG * h->rs; }
 inline int64_t red_len(const H *h) { return h->L->NG * h->rs + h->rs + 8; }
 
 int choose_tile_rows(const H *h, int row_bytes) {
-    int T = 128;
-    for (int t : kTileRows)
-        if ((int64_t)t * row_bytes <= kTileBytes) { T = t; break; }
+    // largest multiple of 128 rows that fits (ranks with the same row stride share a layout)
+    int T = (kTileBytes / row_bytes / kTileRowsStep) * kTileRowsStep;
+    T = std::max(kTileRowsStep, std::min(T, kTileRowsMax));
     const int64_t big = std::max(h->n, h->m);
     const int64_t cap = std::max<int64_t>(128, ((big + 127) / 128) * 128);
     return (int)std::min<int64_t>(T, cap);
@@ -326,13 +327,16 @@ int build_pass(H *h, Layout *L, bool cols_pass, const int32_t *d_colof) {
         uint32_t *d_len4 = nullptr;
         CK(vmalloc(h, &d_len4, (size_t)(P.E + 1) * 4));
         CK(vmalloc(h, &P.d_ptr4, (size_t)(P.E + 1) * 4));
-        vb::quad_len_kernel<<<g, vb::kBlock, 0, h->stream>>>(P.E, P.d_ptr, d_len4);
+        { StageTimer t1("  plan(p16)");
+        vb::plan_p16_kernel<<<g, vb::kBlock, 0, h->stream>>>(
+            P.E, P.d_ptr, p_out, h->d_rowidx, d_colof, L->d_gene_dev, L->d_cell_dev, L->T, cols_pass,
+            L->npg, d_len4); }
         size_t scan_bytes = 0;
         CK(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, d_len4, P.d_ptr4, P.E + 1, h->stream));
         void *d_scan = nullptr;
         CK(vmalloc(h, &d_scan, scan_bytes));
         CK(cub::DeviceScan::ExclusiveSum(d_scan, scan_bytes, d_len4, P.d_ptr4, P.E + 1, h->stream));
-        if (nnz + 3 * P.E >= ((int64_t)1 << 34))
+        if (2 * nnz + 32 * P.E >= ((int64_t)1 << 34))
             return fail(h, VBNMF_ERR_ARG, "matrix too large for 32-bit quad pointers on one GPU");
         uint32_t quads = 0;
         CK(cudaMemcpyAsync(&quads, P.d_ptr4 + P.E, 4, cudaMemcpyDeviceToHost, h->stream));
@@ -341,8 +345,9 @@ int build_pass(H *h, Layout *L, bool cols_pass, const int32_t *d_colof) {
         CK(vmalloc(h, &P.d_ent, (size_t)quads * 16));
         { StageTimer t1("  build_segments(p16)");
         vb::build_segments_p16_kernel<VT><<<g, vb::kBlock, 0, h->stream>>>(
-            P.E, P.d_ptr, P.d_ptr4, p_out, h->d_rowidx, d_colof, L->d_gene_dev, L->d_cell_dev,
-            (const VT *)h->d_val, L->T, cols_pass, 4 * L->npg, (uint32_t *)P.d_ent); }
+            P.E, NO, P.d_ptr, P.d_ptr4, p_out, h->d_rowidx, d_colof, L->d_gene_dev, L->d_cell_dev,
+            (const VT *)h->d_val, L->T, cols_pass, L->npg, cols_pass ? h->n : h->m,
+            cols_pass ? L->Sg : L->Sc, (uint32_t *)P.d_ent); }
         CK(vmalloc(h, &P.d_split, (size_t)(L->grid + 1) * 8));
         vb::split_p16_kernel<<<cdiv(L->grid + 1, 128), 128, 0, h->stream>>>(L->grid, P.E, P.d_ptr4,
                                                                            P.d_split);
