@@ -175,6 +175,7 @@ def run_ours(args):
         sampler.start()
     t0 = time.time()
     res = eng.bench_iterations(HYPER, args.steps)             # EXACTLY K iterations, CUDA events
+    res["layout"] = eng.layout_info()
     torch.cuda.synchronize()
     wall_ms = (time.time() - t0) * 1e3
     if world > 1:
@@ -292,21 +293,24 @@ def emit_line(args, wl, world, n, r, m_total, m_loc, nnz_loc, nnz_total, scale, 
                    "nnz_total": nnz_total, "rank": r, "precision": "fp64",
                    "sharding": "cells over %d GPU(s), 1 all-reduce/iter" % world,
                    "l2": "inputs larger than L2 (two tiled copies of X, %.2f GB per GPU vs 126 MB)"
-                         % (nnz_loc * 16 / 1e9),
+                         % (res["layout"]["bytes"] / 1e9),
+                   "layout": res["layout"],
                    "generator_scale": scale, "gen_seconds": round(t_gen, 2)},
         "clocks": clocks,
         "e2e": e2e,
         "gpu_launches": int(res["launches"]),
         "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
                      "frac": ach / peak, "traffic": traffic,
-                     "kernel": "sweep_tiled_kernel<COLS=1> + sweep_tiled_kernel<COLS=0> "
-                               "(the two passes of the nonzero sweep, incl. their combine kernels)",
+                     "kernel": "%s<COLS=1> + %s<COLS=0> (the two passes of the nonzero sweep, "
+                               "incl. their combine kernels)"
+                               % (("sweep_p16_kernel",) * 2 if res["layout"]["format"] == "p16"
+                                  else ("sweep_tiled_kernel",) * 2),
                      "algorithmic_bytes_per_launch": b_alg_local,
                      "ms_per_launch": {"sweep_cols": ms_cols / args.steps,
                                        "sweep_rows": ms_rows / args.steps},
                      "iteration_frac": b_alg_local / (ms_step * 1e-3) / 1e9 / peak,
-                     "limiter": "shared-memory gather wavefronts + FP64 issue, not HBM "
-                                "(DESIGN.md section 5)",
+                     "limiter": "shared-memory gather wavefronts (LSU data pipe ~90% busy in the "
+                                "gene-owner pass), not HBM (DESIGN.md section 5)",
                      "peak_source": peak_src},
         "cpu_baseline": cpu,
         "fp32_storage_mode": MIXED or None,

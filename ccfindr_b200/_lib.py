@@ -54,6 +54,7 @@ SIGNATURES = {
     "vbnmf_bench_iterations": (C.c_int, [C.c_void_p, c_dp, C.c_double, C.c_int, c_dp, c_i64p,
                                          c_dp]),
     "vbnmf_info": (C.c_int, [C.c_void_p, c_i64p]),
+    "vbnmf_layout_info": (C.c_int, [C.c_void_p, c_i64p]),
 }
 
 _lib = None

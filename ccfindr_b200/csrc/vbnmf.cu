@@ -116,6 +116,7 @@ NcclApi g_nccl;
 // one pass of the tiled count-matrix layout
 struct PassLayout {
     int64_t E = 0;              // segments = tile slabs * owners
+    int64_t nent = 0;           // entries stored (nonzeros, plus the schedule holes of packed-16)
     int64_t *d_ptr = nullptr;   // E + 1
     int32_t *d_idx = nullptr;   // nnz (double counts only)
     void *d_val = nullptr;      // nnz (double counts only)
@@ -343,6 +344,7 @@ int build_pass(H *h, Layout *L, bool cols_pass, const int32_t *d_colof) {
         CK(cudaStreamSynchronize(h->stream));
         vfree(h->stream, d_len4); vfree(h->stream, d_scan);
         CK(vmalloc(h, &P.d_ent, (size_t)quads * 16));
+        P.nent = (int64_t)quads * 4;
         { StageTimer t1("  build_segments(p16)");
         vb::build_segments_p16_kernel<VT><<<g, vb::kBlock, 0, h->stream>>>(
             P.E, NO, P.d_ptr, P.d_ptr4, p_out, h->d_rowidx, d_colof, L->d_gene_dev, L->d_cell_dev,
@@ -358,6 +360,7 @@ int build_pass(H *h, Layout *L, bool cols_pass, const int32_t *d_colof) {
         P.d_ptr = nullptr;
         return 0;
     }
+    P.nent = nnz;
     if (sizeof(VT) == 4) {
         CK(vmalloc(h, &P.d_ent, (size_t)nnz * 8));
     } else {
@@ -1320,6 +1323,20 @@ int vbnmf_info(const vbnmf_handle *h, int64_t info[8]) {
     if (!h || !info) return VBNMF_ERR_ARG;
     info[0] = h->n; info[1] = h->m; info[2] = h->nnz; info[3] = h->r; info[4] = h->rs;
     info[5] = h->precision; info[6] = h->nranks; info[7] = h->m_global;
+    return 0;
+}
+
+int vbnmf_layout_info(const vbnmf_handle *h, int64_t info[8]) {
+    if (!h || !info) return VBNMF_ERR_ARG;
+    if (!h->L) return VBNMF_ERR_STATE;
+    const Layout *L = h->L;
+    const int fmt = entry_format(h);
+    const int64_t ebytes = fmt == vb::kEntP16 ? 4 : (fmt == vb::kEntF32 ? 8 : 12);
+    const int64_t pbytes = fmt == vb::kEntP16 ? 4 : 8;
+    info[0] = fmt; info[1] = L->T; info[2] = L->Sg; info[3] = L->Sc;
+    info[4] = L->cols.nent; info[5] = L->rows.nent;
+    info[6] = fmt == vb::kEntP16 ? L->npg : 0;
+    info[7] = (L->cols.nent + L->rows.nent) * ebytes + (L->cols.E + L->rows.E + 2) * pbytes;
     return 0;
 }
 

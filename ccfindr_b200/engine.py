@@ -121,6 +121,16 @@ class Engine:
         self._ck(self.lib.vbnmf_info(self.handle, v))
         return dict(zip(("n", "m", "nnz", "r", "rs", "precision", "nranks", "m_global"), v))
 
+    def layout_info(self):
+        """Tiled device layout in use (after set_state): storage format of the nonzeros
+        ('f32', 'f64' or 'p16'), tile rows, slab counts, stored entries per pass, bytes."""
+        v = (C.c_int64 * 8)()
+        self._ck(self.lib.vbnmf_layout_info(self.handle, v))
+        d = dict(zip(("format", "tile_rows", "gene_slabs", "cell_slabs", "entries_cols",
+                      "entries_rows", "nonzeros_per_group_step", "bytes"), v))
+        d["format"] = ("f32", "f64", "p16")[d["format"]]
+        return d
+
     # -- state ---------------------------------------------------------------------------------
     def set_state(self, lw, lh, ew=None, eh=None):
         """wh list of vbnmf_update (src/vbnmf_update.cpp:22-25): lw, ew n x r; lh, eh r x m."""

@@ -142,6 +142,14 @@ VBNMF_API int vbnmf_bench_iterations(vbnmf_handle *h, const double hyper[4], dou
 
 /* shape / layout facts for the host side */
 VBNMF_API int vbnmf_info(const vbnmf_handle *h, int64_t info[8]); /* n, m, nnz, r, rs, precision, nranks, m_global */
+/* facts about the tiled device layout in use (valid after vbnmf_set_state / mlnmf_run):
+ * info[0] storage format of the nonzeros: 0 = {int32 row, float count} (8 bytes), 1 = int32 row +
+ *         double count (12 bytes; counts not exact in fp32), 2 = packed {count << 16 | row}
+ *         (4 bytes; integer counts below 2^16);
+ * info[1] tile rows T, info[2] gene slabs, info[3] cell slabs,
+ * info[4], info[5] entries stored for the cell-owner / gene-owner pass (nonzeros + schedule holes),
+ * info[6] nonzeros per 8-lane group step, info[7] bytes of both passes' entry and pointer arrays */
+VBNMF_API int vbnmf_layout_info(const vbnmf_handle *h, int64_t info[8]);
 
 #ifdef __cplusplus
 }

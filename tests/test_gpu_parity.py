@@ -346,3 +346,88 @@ def test_external_stream(Engine):
         eng.set_state(w0, h0)
         assert relerr(eng.step(hyper), ref["lkh"]) < TOL
         st.synchronize()
+
+
+# ---- storage formats of the nonzeros -----------------------------------
+def _check_format_steps(Engine, X, w0, h0, nsteps=3, expect_format=None):
+    from oracle import bindings as ob
+    from oracle import oracle_dense as od
+    hyper = dict(aw=0.9, bw=1.1, ah=1.2, bh=0.8)
+    ref = od.vb_init_from(w0, h0)
+    with Engine(X) as eng:
+        eng.set_state(w0, h0)
+        if expect_format is not None:
+            assert eng.layout_info()["format"] == expect_format
+        for it in range(nsteps):
+            ref = ob.sparse_vb_step(X, ref, hyper, od.EPS)
+            lkh = eng.step(hyper, od.EPS)
+            assert relerr(lkh, ref["lkh"]) < TOL, it
+        st = eng.get_state()
+        info = eng.layout_info()
+    for k in FACT:
+        assert relerr(st[k], ref[k]) < TOL, k
+    return info
+
+
+def test_integer_counts_use_the_packed16_layout(Engine):
+    X, w0, h0 = _random_problem(700, 900, 10, 0.08, seed=11)
+    info = _check_format_steps(Engine, X, w0, h0, expect_format="p16")
+    # segments are whole chunks of 4 steps x 8 nonzeros: stored entries >= nonzeros, multiple of 32
+    assert info["entries_cols"] >= X.nnz and info["entries_cols"] % 32 == 0
+    assert info["entries_rows"] >= X.nnz and info["entries_rows"] % 32 == 0
+
+
+def test_counts_beyond_16_bits_fall_back_to_float_entries(Engine):
+    X, w0, h0 = _random_problem(300, 250, 6, 0.1, seed=12)
+    X.data[::7] = 70000.0           # exact in fp32, not in 16 bits
+    X.data[1::11] = 65535.0         # the largest packed count
+    _check_format_steps(Engine, X, w0, h0, expect_format="f32")
+    Y = X.copy()
+    Y.data[Y.data > 65535.0] = 65535.0
+    _check_format_steps(Engine, Y, w0, h0, expect_format="p16")
+
+
+def test_packed16_large_counts_take_the_log_slow_path(Engine):
+    # counts >= 8 bypass the bit-sliced log-product of the fp64 cell-owner pass
+    X, w0, h0 = _random_problem(400, 350, 10, 0.15, seed=13)
+    rng = np.random.default_rng(5)
+    X.data[:] = rng.choice([1, 2, 3, 7, 8, 9, 15, 16, 255, 4096, 65535], size=X.nnz).astype(float)
+    _check_format_steps(Engine, X, w0, h0, expect_format="p16")
+
+
+@pytest.mark.parametrize("r", [10, 20])   # one / two lanes per nonzero in fp64
+def test_packed16_skewed_tile_row_residues(Engine, r):
+    """Nonzeros only in genes/cells whose index is a multiple of 8 (plus a few others): after the
+    count-sorted renumbering the residue classes of a segment are as unbalanced as they get, so the
+    schedule needs pair steps and hole steps everywhere."""
+    n, m = 640, 520
+    rng = np.random.default_rng(7)
+    D = np.zeros((n, m))
+    D[::8, :] = rng.integers(0, 4, size=(n // 8, m))
+    cols = np.arange(0, m, 8)
+    D[:, cols] += rng.integers(0, 3, size=(n, len(cols)))
+    D[rng.integers(0, n, 300), rng.integers(0, m, 300)] += 1
+    from ccfindr_b200 import synth
+    X = synth.fix_empty(sp.csc_matrix(D), 1)
+    w0 = rng.gamma(1.0, 1.0, size=(n, r)) + 1e-3
+    h0 = rng.gamma(1.0, 1.0, size=(r, m)) + 1e-3
+    _check_format_steps(Engine, X, w0, h0, expect_format="p16")
+
+
+def test_float_entry_layout_still_matches(Engine, monkeypatch):
+    """VBNMF_NO_P16=1 keeps the 8-byte {row, float} entries for integer counts (the path that
+    non-integer but fp32-exact counts take)."""
+    monkeypatch.setenv("VBNMF_NO_P16", "1")
+    X, w0, h0 = _random_problem(500, 400, 10, 0.1, seed=14)
+    _check_format_steps(Engine, X, w0, h0, expect_format="f32")
+    X.data[:] = np.round(X.data * 0.5, 1) + 0.5      # halves: exact in fp32, not integers
+    monkeypatch.delenv("VBNMF_NO_P16")
+    _check_format_steps(Engine, X, w0, h0, expect_format="f32")
+
+
+def test_packed16_tiny_matrix_holes_point_at_real_rows(Engine):
+    # fewer genes than residue classes: hole words must not read padding rows of the tile
+    X = sp.csc_matrix(np.array([[1.0, 0, 2, 0, 1], [0, 3, 0, 1, 0], [2, 0, 0, 0, 9]]))
+    rng = np.random.default_rng(1)
+    w0, h0 = rng.random((3, 2)) + 0.1, rng.random((2, 5)) + 0.1
+    _check_format_steps(Engine, X, w0, h0, expect_format="p16")
