@@ -53,6 +53,7 @@ SIGNATURES = {
                             c_ip]),
     "vbnmf_bench_iterations": (C.c_int, [C.c_void_p, c_dp, C.c_double, C.c_int, c_dp, c_i64p,
                                          c_dp]),
+    "vbnmf_init_random": (C.c_int, [C.c_void_p, C.c_int, c_dp, C.c_uint64, C.c_int64]),
     "vbnmf_info": (C.c_int, [C.c_void_p, c_i64p]),
     "vbnmf_layout_info": (C.c_int, [C.c_void_p, c_i64p]),
 }

@@ -184,7 +184,7 @@ def vb_factorize(object, ranks=2, nrun=1, verbose=2, progress_bar=True, initiali
                  Itmax=10000, hyper_update=(True,) * 4, gamma_a=1, gamma_b=1, Tol=1e-5,
                  hyper_update_n0=10, hyper_update_dn=1, connectivity=True, fudge=None, ncores=1,
                  useC=True, unif_stop=True, seed=1, device=0, inits=None, precision=0,
-                 parallel=False):
+                 parallel=False, device_init=False):
     """Bayesian NMF inference of a count matrix (R/bayesian.R:229-301).
 
     Arguments as in the reference (dots replaced by underscores).  Extras: `seed` keys the NumPy
@@ -192,6 +192,8 @@ def vb_factorize(object, ranks=2, nrun=1, verbose=2, progress_bar=True, initiali
     `inits[(irun, rank)] = (w0, h0)` overrides the draw; `device` is the CUDA ordinal.
     `ncores` and `useC` are accepted and ignored: the update always runs on the GPU.
     `precision`: 0 = fp64 (reference arithmetic), 1 = fp32-storage / fp64-accumulate.
+    `device_init=True`: the 'random' initializer is drawn on the GPU (Engine.init_random, a counter
+    RNG keyed by seed and matrix position) instead of on the host and uploaded.
     `parallel=True` (inside an initialised torch.distributed job, one process per GPU): the
     nrun x len(ranks) independent factorizations are spread over the ranks (the role of
     Rmpi::mpi.applyLB, R/bayesian.R:263), every rank holds a full copy of the matrix, results are
@@ -209,6 +211,10 @@ def vb_factorize(object, ranks=2, nrun=1, verbose=2, progress_bar=True, initiali
     ga = np.atleast_1d(np.asarray(gamma_a, dtype=np.float64))
     gb = np.atleast_1d(np.asarray(gamma_b, dtype=np.float64))
 
+    if device_init and initializer != "random":
+        raise ValueError("device_init applies to the 'random' initializer")
+    if device_init:
+        initializer = "random_device"
     common = (ga, gb, initializer, Itmax, hyper_update, Tol, hyper_update_n0, hyper_update_dn,
               connectivity, fudge)
     vb = []
@@ -308,10 +314,13 @@ def _vb_iterate(eng, irun, mat, ranks, ga, gb, initializer, Itmax, hyper_update,
         hyper = dict(aw=float(ga[0]), ah=float(ga[-1]), bw=float(gb[0]), bh=float(gb[-1]))  # :321-326
         if inits is not None and (irun, rank) in inits:
             w0, h0 = inits[(irun, rank)]
+            eng.set_state(w0, h0)                               # lw = ew = w, lh = eh = h (:170)
+        elif initializer == "random_device":
+            eng.init_random(rank, hyper, seed * 100003 + 1000 * rank + irun)
         else:
             w0, h0 = vb_init(nrow, ncol, mat, rank, hyper, initializer,
                              seed * 100003 + 1000 * rank + irun)
-        eng.set_state(w0, h0)                                   # lw = ew = w, lh = eh = h (:170)
+            eng.set_state(w0, h0)
         try:
             res = eng.run(hyper, Itmax=Itmax, Tol=Tol, hyper_update=hyper_update, n0=n0, dn=dn,
                           fudge=fudge)

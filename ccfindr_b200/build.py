@@ -24,6 +24,12 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-I", INCLUDE]
 if os.environ.get("VBNMF_SWEEP_THREADS"):  # tuning experiments only
     NVCC_FLAGS.append("-DVB_SWEEP_THREADS=" + os.environ["VBNMF_SWEEP_THREADS"])
+if os.environ.get("VBNMF_LPN_BYTES"):
+    NVCC_FLAGS.append("-DVB_LPN_BYTES=" + os.environ["VBNMF_LPN_BYTES"])
+if os.environ.get("VBNMF_MID_THREADS"):
+    NVCC_FLAGS.append("-DVB_MID_THREADS=" + os.environ["VBNMF_MID_THREADS"])
+if os.environ.get("VBNMF_WIDE_THREADS"):
+    NVCC_FLAGS.append("-DVB_WIDE_THREADS=" + os.environ["VBNMF_WIDE_THREADS"])
 if os.environ.get("VBNMF_UNROLL"):
     NVCC_FLAGS.append("-DVB_UNROLL=" + os.environ["VBNMF_UNROLL"])
 

@@ -164,18 +164,31 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
 #ifndef VB_SWEEP_THREADS
 #define VB_SWEEP_THREADS 512  // threads per sweep CTA for the narrow-rank configuration
 #endif
+#ifndef VB_LPN_BYTES
+#define VB_LPN_BYTES 160    // widest row a single lane gathers; wider rows are split over 2 lanes
+#endif
+#ifndef VB_MID_THREADS
+#define VB_MID_THREADS 384   // threads per sweep CTA when a lane holds 97..160 bytes of a row
+#endif
+#ifndef VB_WIDE_THREADS
+#define VB_WIDE_THREADS 256  // ... more than 160 bytes
+#endif
 template <int RP, typename PT>
 struct SweepCfg {
     // Register budget per lane: own + acc + tile row = 3 * KL values of PT plus the prefetched
-    // entries.  Wide ranks are split over LPN = 2 lanes per nonzero (each lane takes every other
-    // 16-byte unit of the row), which keeps 512 threads (16 warps) per SM up to r = 24 in fp64.
+    // entries.  A lane gathers rows of up to 160 bytes by itself (r <= 20 in fp64), with 512 threads
+    // per SM up to 96 bytes and 384 beyond; measured at C2 size, one lane per nonzero at 384
+    // threads beats two lanes at 512 by 25 % (r = 14) to 7 % (r = 20).  Wider rows are split over
+    // LPN = 2 lanes per nonzero (each lane takes every other 16-byte unit of the row).
     static constexpr int kUE = 16 / (int)sizeof(PT);             // elements per 16-byte unit
     static constexpr int kNU = (RP + kUE - 1) / kUE;             // units per row
-    static constexpr int kLPN = (RP * (int)sizeof(PT) > 96) ? 2 : 1;  // lanes per nonzero
+    static constexpr int kLPN = (RP * (int)sizeof(PT) > VB_LPN_BYTES) ? 2 : 1;  // lanes per nonzero
     static constexpr int kNUL = (kNU + kLPN - 1) / kLPN;         // units per lane
     static constexpr int kKL = kNUL * kUE;                       // rank entries per lane
     static constexpr int kNPG = kGroup / kLPN;                   // nonzeros per group step
-    static constexpr int kThreads = (kKL * (int)sizeof(PT) <= 96) ? VB_SWEEP_THREADS : 256;
+    static constexpr int kRowShare = kKL * (int)sizeof(PT);      // bytes of a row per lane
+    static constexpr int kThreads = kRowShare <= 96 ? VB_SWEEP_THREADS
+                                    : (kRowShare <= 160 ? VB_MID_THREADS : VB_WIDE_THREADS);
     // unroll of the chunk loop; the fp32 cell-owner pass (with its log) is the one that prefers 4
     __host__ __device__ static constexpr int unroll(bool cols) {
         return VB_UNROLL ? VB_UNROLL : ((kLPN == 1 && (sizeof(PT) == 8 || !cols)) ? 6 : 4);

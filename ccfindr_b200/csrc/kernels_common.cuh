@@ -424,6 +424,65 @@ __global__ void control_kernel(const ControlArgs a) {
     }
 }
 
+// ---- on-device 'random' initialiser (vb_init(initializer = 'random'), R/bayesian.R:111-115) ----
+// w_ik ~ Gamma(shape aw, scale bw/aw), h_kj ~ Gamma(shape ah, scale bh/ah).  R's RNG stream cannot be
+// reproduced, so the draw is DEFINED here by a counter RNG keyed by (seed, side, global row, k):
+// the same matrix entry gets the same value whatever the device layout or the sharding of the
+// cells.  ccfindr_b200/synth.py:device_random_init_reference restates it for the tests.
+//   stream:  state0 = mix(seed) ^ mix(id + 0x632BE59BD9B4E019), id = side << 62 | row << 6 | k;
+//            next() = mix(state += 0x9E3779B97F4A7C15)            (splitmix64)
+//   uniform: (next() >> 11 + 0.5) * 2^-53;  normal: sqrt(-2 ln u1) cos(2 pi u2) (Box-Muller)
+//   gamma(a >= 1): Marsaglia-Tsang (d = a - 1/3, c = 1/sqrt(9d)); a < 1: gamma(a + 1) * u^(1/a)
+VB_HD unsigned long long vb_mix64(unsigned long long z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+struct VbStream {
+    unsigned long long s;
+    VB_HD VbStream(unsigned long long seed, unsigned long long id)
+        : s(vb_mix64(seed) ^ vb_mix64(id + 0x632BE59BD9B4E019ull)) {}
+    VB_HD unsigned long long next() { s += 0x9E3779B97F4A7C15ull; return vb_mix64(s); }
+    VB_HD double uniform() { return ((double)(next() >> 11) + 0.5) * (1.0 / 9007199254740992.0); }
+    VB_HD double normal() {
+        const double u1 = uniform(), u2 = uniform();
+        return sqrt(-2.0 * log(u1)) * cos(6.283185307179586476925 * u2);
+    }
+    VB_HD double gamma(double a) {
+        const double a1 = a < 1.0 ? a + 1.0 : a;
+        const double d = a1 - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+        double g = 0.0;
+        for (int it = 0; it < 1000; it++) {
+            const double x = normal();
+            const double v0 = 1.0 + c * x;
+            const double u = uniform();
+            if (v0 <= 0.0) continue;
+            const double v = v0 * v0 * v0;
+            if (log(u) < 0.5 * x * x + d - d * v + d * log(v)) { g = d * v; break; }
+        }
+        if (a < 1.0) g *= pow(uniform(), 1.0 / a);
+        return g;
+    }
+};
+
+// one thread per (original row, k): panel[dev[row]][k] = scale * gamma(shape), also into `mirror`
+// (alw/alh hold ew/eh = w/h before the first update, R/bayesian.R:170)
+__global__ void __launch_bounds__(kBlock)
+init_random_kernel(int64_t rows, int r, int rs, const int32_t *__restrict__ dev, int side,
+                   int64_t row_offset, unsigned long long seed, double shape, double scale,
+                   double *__restrict__ panel, double *__restrict__ mirror) {
+    const int64_t t = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (t >= rows * r) return;
+    const int64_t row = t / r;
+    const int k = (int)(t - row * r);
+    VbStream st(seed, ((unsigned long long)side << 62) |
+                          ((unsigned long long)(row + row_offset) << 6) | (unsigned long long)k);
+    const double v = scale * st.gamma(shape);
+    const int64_t o = (int64_t)dev[row] * rs + k;
+    panel[o] = v;
+    mirror[o] = v;
+}
+
 // cid[d] = 1 + index of the first maximum over k of alh[d][k] / beh[k]   (R/utils.R:906)
 __global__ void __launch_bounds__(kBlock)
 cluster_id_kernel(int64_t rows, int RS, int r, const double *__restrict__ alh,

@@ -1030,6 +1030,53 @@ int vbnmf_set_state(vbnmf_handle *h, int r, const double *lw, const double *lh, 
     return 0;
 }
 
+int vbnmf_init_random(vbnmf_handle *h, int r, const double hyper[4], uint64_t seed,
+                      int64_t cell_offset) {
+    if (!h || !hyper) return VBNMF_ERR_ARG;
+    if (r < 1 || r > kMaxRank) return fail(h, VBNMF_ERR_ARG, "rank must be in 1..64");
+    if (!(hyper[0] > 0 && hyper[1] > 0 && hyper[2] > 0 && hyper[3] > 0) || cell_offset < 0)
+        return fail(h, VBNMF_ERR_ARG, "hyper-parameters must be positive");
+    CK(cudaSetDevice(h->device));
+    StageTimer tm("vbnmf_init_random(total)");
+    int rc;
+    if ((rc = alloc_panels(h, r))) return rc;
+    const Layout *L = h->L;
+    const int rs = h->rs;
+    const size_t gr = (size_t)L->NG * rs * 8, cr = (size_t)L->NC * rs * 8;
+    CK(cudaMemsetAsync(h->d_lw, 0, gr, h->stream));
+    CK(cudaMemsetAsync(h->d_alw, 0, gr, h->stream));
+    CK(cudaMemsetAsync(h->d_lh, 0, cr, h->stream));
+    CK(cudaMemsetAsync(h->d_alh, 0, cr, h->stream));
+    // w ~ Gamma(aw, scale bw/aw), h ~ Gamma(ah, scale bh/ah); lw = ew = w, lh = eh = h (:111-115,170)
+    vb::init_random_kernel<<<cdiv(h->n * r, vb::kBlock), vb::kBlock, 0, h->stream>>>(
+        h->n, r, rs, L->d_gene_dev, 0, 0, (unsigned long long)seed, hyper[0], hyper[1] / hyper[0],
+        h->d_lw, h->d_alw);
+    vb::init_random_kernel<<<cdiv(h->m * r, vb::kBlock), vb::kBlock, 0, h->stream>>>(
+        h->m, r, rs, L->d_cell_dev, 1, cell_offset, (unsigned long long)seed, hyper[2],
+        hyper[3] / hyper[2], h->d_lh, h->d_alh);
+    h->launches += 2;
+    if ((rc = refresh_mirrors(h))) return rc;
+    // rowSums(eh) of the initial state, over all shards
+    double *tail = h->d_red + tail_off(h);
+    CK(cudaMemsetAsync(tail, 0, (size_t)(rs + 8) * 8, h->stream));
+    vb::ColsumArgs ca{L->NC, h->d_lh, h->d_partH, tail, h->d_counters + 1};
+    h->tab->colsum(ca, h->stream);
+    h->launches += 1;
+    if ((rc = allreduce(h, tail, rs + 8))) return rc;
+    std::vector<double> s((size_t)rs + 8, 0.0);
+    CK(cudaMemcpyAsync(s.data(), tail, s.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+    for (int k = 0; k < kMaxRank; k++) {
+        h->ehsum[k] = k < r ? s[k] : 0.0;
+        h->ewsum[k] = 0.0;
+        h->bew[k] = h->beh[k] = 1.0;
+    }
+    h->stats_valid = false;
+    h->has_posterior = false;
+    return 0;
+}
+
 int vbnmf_step(vbnmf_handle *h, const double hyper[4], double fudge, double *lkh) {
     if (!h || !hyper || !lkh) return VBNMF_ERR_ARG;
     if (!h->d_lw) return fail(h, VBNMF_ERR_STATE, "vbnmf_set_state has not been called");

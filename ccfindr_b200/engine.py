@@ -144,6 +144,15 @@ class Engine:
         self._ck(self.lib.vbnmf_set_state(self.handle, r, _dp(lw), _dp(lh), _dp(ew), _dp(eh)))
         self.r = r
 
+    def init_random(self, rank, hyper, seed, cell_offset=0):
+        """vb_init(initializer='random') (R/bayesian.R:111-115) drawn on the device: no host
+        matrices, no upload.  The draw is keyed by (seed, gene / global cell index, k); see
+        synth.device_random_init_reference for the CPU restatement."""
+        hy = hyper_vec(hyper)
+        self._ck(self.lib.vbnmf_init_random(self.handle, int(rank), _dp(hy), int(seed),
+                                            int(cell_offset)))
+        self.r = int(rank)
+
     def get_state(self, which=("lw", "lh", "ew", "eh", "dw", "dh")):
         r = self.r
         out = {}

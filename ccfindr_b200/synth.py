@@ -132,3 +132,65 @@ def tenx_like_device(n, m, r_true, density, seed, device, col_start=0, col_end=N
     colptr = torch.zeros(cnt.numel() + 1, dtype=torch.int64, device=device)
     colptr[1:] = torch.cumsum(cnt, 0)
     return colptr, rowidx, values, s
+
+
+# ---- CPU restatement of the on-device 'random' initialiser (csrc/kernels_common.cuh) ---------
+_M64 = (1 << 64) - 1
+
+
+def _mix64(z):
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & _M64
+    return z ^ (z >> 31)
+
+
+class _Stream:
+    """splitmix64 counter stream of one matrix entry (VbStream)."""
+
+    def __init__(self, seed, ident):
+        self.s = _mix64(seed & _M64) ^ _mix64((ident + 0x632BE59BD9B4E019) & _M64)
+
+    def next(self):
+        self.s = (self.s + 0x9E3779B97F4A7C15) & _M64
+        return _mix64(self.s)
+
+    def uniform(self):
+        return (float(self.next() >> 11) + 0.5) * (1.0 / 9007199254740992.0)
+
+    def normal(self):
+        u1, u2 = self.uniform(), self.uniform()
+        return np.sqrt(-2.0 * np.log(u1)) * np.cos(6.283185307179586476925 * u2)
+
+    def gamma(self, a):
+        a1 = a + 1.0 if a < 1.0 else a
+        d = a1 - 1.0 / 3.0
+        c = 1.0 / np.sqrt(9.0 * d)
+        g = 0.0
+        for _ in range(1000):
+            x = self.normal()
+            v0 = 1.0 + c * x
+            u = self.uniform()
+            if v0 <= 0.0:
+                continue
+            v = v0 * v0 * v0
+            if np.log(u) < 0.5 * x * x + d - d * v + d * np.log(v):
+                g = d * v
+                break
+        if a < 1.0:
+            g *= self.uniform() ** (1.0 / a)
+        return g
+
+
+def device_random_init_reference(nrow, ncol, rank, hyper, seed, cell_offset=0):
+    """What Engine.init_random(rank, hyper, seed, cell_offset) puts on the device: w (nrow x rank),
+    h (rank x ncol).  Pure-Python loops: small cases only."""
+    w = np.zeros((nrow, rank))
+    h = np.zeros((rank, ncol))
+    for i in range(nrow):
+        for k in range(rank):
+            w[i, k] = hyper["bw"] / hyper["aw"] * _Stream(seed, (0 << 62) | (i << 6) | k).gamma(hyper["aw"])
+    for j in range(ncol):
+        for k in range(rank):
+            ident = (1 << 62) | ((j + cell_offset) << 6) | k
+            h[k, j] = hyper["bh"] / hyper["ah"] * _Stream(seed, ident).gamma(hyper["ah"])
+    return w, h

@@ -104,6 +104,15 @@ VBNMF_API int vbnmf_attach_comm(vbnmf_handle *h, vbnmf_comm *c);
 VBNMF_API int vbnmf_set_state(vbnmf_handle *h, int r, const double *lw, const double *lh, const double *ew,
                     const double *eh);
 
+/* vb_init(initializer = 'random') (R/bayesian.R:111-115,170) drawn on the device instead of
+ * vbnmf_set_state from host matrices: w_ik ~ Gamma(shape aw, scale bw/aw), h_kj ~ Gamma(shape ah,
+ * scale bh/ah), lw = ew = w, lh = eh = h.  R's RNG stream cannot be reproduced; the draw is defined
+ * by a counter RNG keyed by (seed, gene i or GLOBAL cell index cell_offset + j, k) (csrc/
+ * kernels_common.cuh, restated in ccfindr_b200/synth.py:device_random_init_reference), so it does
+ * not depend on the device layout or on how the cells are sharded.  hyper = {aw, bw, ah, bh}. */
+VBNMF_API int vbnmf_init_random(vbnmf_handle *h, int r, const double hyper[4], uint64_t seed,
+                                int64_t cell_offset);
+
 /* One call of vbnmf_update (src/vbnmf_update.cpp:16-102): state <- update(state); *lkh = bound. */
 VBNMF_API int vbnmf_step(vbnmf_handle *h, const double hyper[4], double fudge, double *lkh);
 

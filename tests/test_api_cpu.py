@@ -102,3 +102,21 @@ def test_read_write_10x_roundtrip(tmp_path):
     assert clean.counts.format == "csc" and clean.counts.dtype == np.float64
     with pytest.raises(FileNotFoundError):
         api.read_10x(str(tmp_path / "nope"))
+
+
+def test_device_random_init_reference_is_a_gamma_sampler():
+    """CPU restatement of the on-device initialiser (synth.device_random_init_reference): keyed by
+    (seed, position), so a shard of cells reproduces the same columns; moments of Gamma(a, scale b/a)."""
+    from ccfindr_b200 import synth
+    hyper = dict(aw=0.5, bw=2.0, ah=3.0, bh=0.7)
+    w, h = synth.device_random_init_reference(300, 40, 4, hyper, seed=7)
+    w2, h2 = synth.device_random_init_reference(300, 40, 4, hyper, seed=7)
+    assert np.array_equal(w, w2) and np.array_equal(h, h2)
+    _, hs = synth.device_random_init_reference(1, 15, 4, hyper, seed=7, cell_offset=25)
+    assert np.array_equal(hs, h[:, 25:40])
+    w3, _ = synth.device_random_init_reference(300, 1, 4, hyper, seed=8)
+    assert not np.array_equal(w, w3)
+    assert (w > 0).all() and (h > 0).all()
+    # mean b, variance b^2 / a (1200 and 160 draws: loose bounds)
+    assert abs(w.mean() - 2.0) < 0.35 and abs(w.var() - 8.0) < 3.0
+    assert abs(h.mean() - 0.7) < 0.12

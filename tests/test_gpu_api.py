@@ -61,3 +61,43 @@ def test_factorize_ml_matches_reference_loop():
         assert relerr(s.measure["likelihood"][k], best) < 1e-9
         assert relerr(s.basis[k], wb) < 1e-8 and relerr(s.coeff[k], hb) < 1e-8
     assert np.isfinite(s.measure["dispersion"]).all()
+
+
+def test_device_random_init_matches_its_cpu_restatement():
+    import scipy.sparse as sp
+    from ccfindr_b200 import synth
+    from ccfindr_b200.engine import Engine
+    rng = np.random.default_rng(3)
+    X = synth.fix_empty(sp.random(90, 70, density=0.2, random_state=rng, format="csc",
+                                  data_rvs=lambda k: rng.integers(1, 9, size=k).astype(float)), 1)
+    for hyper, r in ((dict(aw=0.4, bw=1.5, ah=2.5, bh=0.8), 5), (dict(aw=1.0, bw=1.0, ah=1.0, bh=1.0), 3)):
+        w, h = synth.device_random_init_reference(90, 70, r, hyper, seed=11)
+        with Engine(X) as eng:
+            eng.init_random(r, hyper, seed=11)
+            st = eng.get_state()
+            assert np.allclose(st["lw"], w, rtol=1e-12, atol=0) and np.allclose(st["lh"], h, rtol=1e-12, atol=0)
+            assert np.array_equal(st["ew"], st["lw"]) and np.array_equal(st["eh"], st["lh"])
+            assert not st["dw"].any() and not st["dh"].any()
+            a = eng.run(hyper, Itmax=15)
+            eng.set_state(st["lw"], st["lh"])
+            b = eng.run(hyper, Itmax=15)
+        # same state either way (rowSums(eh) is summed in a different order: not bitwise)
+        assert a["niter"] == b["niter"] and relerr(a["lkh_trace"], b["lkh_trace"]) < 1e-12
+    # a shard of cells draws the same columns (cell_offset = first global cell of the shard)
+    with Engine(X[:, 30:].tocsc()) as eng:
+        eng.init_random(3, hyper, seed=11, cell_offset=30)
+        hs = eng.get_state(("lh",))["lh"]
+    assert np.allclose(hs, h[:, 30:], rtol=1e-12, atol=0)
+
+
+def test_vb_factorize_with_device_init():
+    from ccfindr_b200 import api, synth
+    import scipy.sparse as sp
+    x = sp.csc_matrix(synth.simulate_whx(nrow=200, ncol=80, rank=3, seed=4)["x"])
+    a = api.vb_factorize(api.scNMFSet(count=x), ranks=[2, 3], nrun=2, verbose=0, Itmax=40,
+                         device_init=True, connectivity=False)
+    b = api.vb_factorize(api.scNMFSet(count=x), ranks=[2, 3], nrun=2, verbose=0, Itmax=40,
+                         device_init=True, connectivity=False)
+    assert a.ranks == [2, 3] and np.isfinite(a.measure["lml"]).all()
+    assert np.array_equal(a.measure["lml"], b.measure["lml"])      # same seeds, same draws
+    assert np.array_equal(a.basis[1], b.basis[1])
