@@ -55,18 +55,62 @@ def algorithmic_bytes(nnz, n, m, r, sp=8):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region: an NVML polling thread
+    (nvidia_ml_py, one sample per millisecond -- the timed region of the default run is ~40 ms);
+    falls back to an `nvidia-smi -lms` subprocess when NVML cannot be loaded."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.idx = gpu_index
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+        self.p = self.f = self.thread = None
+        self.sm, self.reasons, self.smax, self.stop_flag = [], set(), None, False
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            # CUDA_VISIBLE_DEVICES may renumber: resolve through the PCI bus id of the torch device
+            import torch
+            bus = torch.cuda.get_device_properties(gpu_index)
+            self.h = None
+            try:
+                pci = "%08x:%02x:%02x.0" % (bus.pci_domain_id, bus.pci_bus_id, bus.pci_device_id)
+                self.h = pynvml.nvmlDeviceGetHandleByPciBusId(pci.encode())
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
+
+    def _poll(self):
+        nv = self.nvml
+        bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                "sw_power_cap": 0x4}
+        while True:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                    nv.nvmlDeviceGetCurrentClocksThrottleReasons
+                r = int(get(self.h))
+                for nm, b in bits.items():
+                    if r & b:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            if self.stop_flag:
+                return
+            time.sleep(0.001)
 
     def start(self):
+        if self.nvml is not None:
+            import threading
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         try:
+            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
                                        "--format=csv,noheader,nounits", "-lms", "100"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
@@ -74,6 +118,13 @@ class ClockSampler:
             self.p = None
 
     def stop(self):
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            if not self.sm:
+                return None
+            return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.smax,
+                    "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml"}
         if self.p is None:
             return None
         time.sleep(0.15)
@@ -98,7 +149,7 @@ class ClockSampler:
         if not sm:
             return None
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)),
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 def env_rank():
@@ -232,20 +283,28 @@ def run_ours(args):
     torch.cuda.empty_cache()
     import scipy.sparse as sp
     csc = sp.csc_matrix((h_values, h_rowidx, h_colptr), shape=(n, m_loc))
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.time()
-    eng2 = Engine(csc, device=local_rank)                      # H2D of X + device layouts
-    if comm is not None:
-        eng2.attach_comm(comm)
-    eng2.set_state(w0, h0_loc)                                 # H2D of the initial factors
-    # Tol = 0 never satisfies |1 - lkh/lk0| < Tol: exactly K iterations with the reference's own
-    # loop (hyper updates from iteration 11 on, R/bayesian.R:342)
-    out = eng2.run(HYPER, Itmax=args.steps, Tol=0.0)
-    st = eng2.get_state(("ew", "eh"))                          # D2H of the result
-    torch.cuda.synchronize()
-    e2e_s = time.time() - t0
+    def e2e_pass():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.time()
+        eng2 = Engine(csc, device=local_rank)                  # H2D of X + device layouts
+        if comm is not None:
+            eng2.attach_comm(comm)
+        eng2.set_state(w0, h0_loc)                             # H2D of the initial factors
+        # Tol = 0 never satisfies |1 - lkh/lk0| < Tol: exactly K iterations with the reference's
+        # own loop (hyper updates from iteration 11 on, R/bayesian.R:342)
+        out = eng2.run(HYPER, Itmax=args.steps, Tol=0.0)
+        st = eng2.get_state(("ew", "eh"))                      # D2H of the result
+        torch.cuda.synchronize()
+        return time.time() - t0, eng2, out, st
+
+    # one untimed pass first (pinned staging buffers, memory pool, page cache of the host arrays),
+    # except for the workloads whose upload alone takes seconds
+    if nnz_loc < 5e8:
+        _, eng_w, _, _ = e2e_pass()
+        eng_w.close()
+    e2e_s, eng2, out, st = e2e_pass()
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -264,7 +323,8 @@ def run_ours(args):
     if rank == 0:
         e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps,
                "d2h_bytes_per_step": d2h / args.steps, "seconds": e2e_s, "iterations": args.steps,
-               "what": "vbnmf_create(host CSC) + set_state + vbnmf_run(K) + get_state(ew, eh)"}
+               "what": "vbnmf_create(host CSC) + set_state + vbnmf_run(K) + get_state(ew, eh); "
+                       "second of two identical passes (the first is the warm-up)"}
         emit_line(args, wl, world, n, r, m_total, m_loc, nnz_loc, nnz_total, scale, t_gen, value,
                   ms_step, ms_cols, ms_rows, wall_ms, clocks, res, e2e, cpu, lkh_dev)
     if world > 1:

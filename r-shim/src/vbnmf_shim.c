@@ -57,6 +57,14 @@ SEXP C_vbnmf_set_state(SEXP ptr, SEXP lw, SEXP lh, SEXP ew, SEXP eh) {
     return R_NilValue;
 }
 
+/* vb_init(initializer = 'random') drawn on the device (R/bayesian.R:111-115,170): no n x r and
+ * r x m matrices cross the bus.  hyper = c(aw, bw, ah, bh); seed: numeric(1) (an integer value) */
+SEXP C_vbnmf_init_random(SEXP ptr, SEXP rank, SEXP hyper, SEXP seed) {
+    vbnmf_handle *h = get_handle(ptr);
+    chk(vbnmf_init_random(h, Rf_asInteger(rank), REAL(hyper), (uint64_t)Rf_asReal(seed), 0), h);
+    return R_NilValue;
+}
+
 /* one vbnmf_update (src/vbnmf_update.cpp:16-102); hyper = c(aw, bw, ah, bh) */
 SEXP C_vbnmf_step(SEXP ptr, SEXP hyper, SEXP fudge) {
     vbnmf_handle *h = get_handle(ptr);
@@ -154,6 +162,7 @@ static const R_CallMethodDef CallEntries[] = {
     {"C_vbnmf_create", (DL_FUNC)&C_vbnmf_create, 5},
     {"C_vbnmf_destroy", (DL_FUNC)&C_vbnmf_destroy, 1},
     {"C_vbnmf_set_state", (DL_FUNC)&C_vbnmf_set_state, 5},
+    {"C_vbnmf_init_random", (DL_FUNC)&C_vbnmf_init_random, 4},
     {"C_vbnmf_step", (DL_FUNC)&C_vbnmf_step, 3},
     {"C_vbnmf_run", (DL_FUNC)&C_vbnmf_run, 8},
     {"C_vbnmf_get_state", (DL_FUNC)&C_vbnmf_get_state, 2},
