@@ -26,6 +26,8 @@ if os.environ.get("VBNMF_SWEEP_THREADS"):  # tuning experiments only
     NVCC_FLAGS.append("-DVB_SWEEP_THREADS=" + os.environ["VBNMF_SWEEP_THREADS"])
 if os.environ.get("VBNMF_LPN_BYTES"):
     NVCC_FLAGS.append("-DVB_LPN_BYTES=" + os.environ["VBNMF_LPN_BYTES"])
+if os.environ.get("VBNMF_SWEEP_THREADS_F32"):
+    NVCC_FLAGS.append("-DVB_SWEEP_THREADS_F32=" + os.environ["VBNMF_SWEEP_THREADS_F32"])
 if os.environ.get("VBNMF_MID_THREADS"):
     NVCC_FLAGS.append("-DVB_MID_THREADS=" + os.environ["VBNMF_MID_THREADS"])
 if os.environ.get("VBNMF_WIDE_THREADS"):

@@ -164,6 +164,10 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
 #ifndef VB_SWEEP_THREADS
 #define VB_SWEEP_THREADS 512  // threads per sweep CTA for the narrow-rank configuration
 #endif
+#ifndef VB_SWEEP_THREADS_F32
+#define VB_SWEEP_THREADS_F32 640  // ... of the fp32-storage kernels with rows of up to 48 bytes
+                                  // (C2: 0.98 -> 0.94 ms per iteration against 512; 768: 0.95)
+#endif
 #ifndef VB_LPN_BYTES
 #define VB_LPN_BYTES 160    // widest row a single lane gathers; wider rows are split over 2 lanes
 #endif
@@ -187,7 +191,8 @@ struct SweepCfg {
     static constexpr int kKL = kNUL * kUE;                       // rank entries per lane
     static constexpr int kNPG = kGroup / kLPN;                   // nonzeros per group step
     static constexpr int kRowShare = kKL * (int)sizeof(PT);      // bytes of a row per lane
-    static constexpr int kThreads = kRowShare <= 96 ? VB_SWEEP_THREADS
+    static constexpr int kThreads = kRowShare <= 96 ? (sizeof(PT) == 4 && kRowShare <= 48
+                                                           ? VB_SWEEP_THREADS_F32 : VB_SWEEP_THREADS)
                                     : (kRowShare <= 160 ? VB_MID_THREADS : VB_WIDE_THREADS);
     // unroll of the chunk loop; the fp32 cell-owner pass (with its log) is the one that prefers 4
     __host__ __device__ static constexpr int unroll(bool cols) {
@@ -486,6 +491,80 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void *p, unsigned bytes) 
 }
 __device__ __forceinline__ uint4 ldcs_quad(const uint4 *p) { return __ldcs(p); }
 
+// Packed fp32 arithmetic (Blackwell FFMA2: two fp32 FMAs per instruction on a 64-bit register
+// pair): 2*KL of the ~60 instructions per nonzero of the fp32-storage sweep are FMAs on pairs of
+// adjacent rank entries.  Measured at C2 it changes nothing (0.979 -> 0.988 ms per iteration at
+// 512 threads, 0.941 -> 0.939 at 640): the pass is not issue-limited.  Off by default (VB_FFMA2).
+__device__ __forceinline__ unsigned long long pack_f2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack_f2(unsigned long long v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b,
+                                                    unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+// p = sum_k own[k] tr[k];  acc[k] += tr[k] * x / p   (one nonzero; returns p)
+template <int KL>
+__device__ __forceinline__ double dot_rows(const double (&own)[KL], const double (&tr)[KL]) {
+    double p0 = 0, p1 = 0;
+#pragma unroll
+    for (int k = 0; k < KL; k += 2) {
+        p0 = fma(own[k], tr[k], p0);
+        p1 = fma(own[k + 1], tr[k + 1], p1);
+    }
+    return p0 + p1;
+}
+template <int KL>
+__device__ __forceinline__ void axpy_row(double (&acc)[KL], const double (&tr)[KL], double q) {
+#pragma unroll
+    for (int k = 0; k < KL; k++) acc[k] = fma(tr[k], q, acc[k]);
+}
+#ifndef VB_FFMA2
+#define VB_FFMA2 0
+#endif
+template <int KL>
+__device__ __forceinline__ float dot_rows(const float (&own)[KL], const float (&tr)[KL]) {
+    if (VB_FFMA2 && KL % 4 == 0) {
+        unsigned long long pa = 0ull, pb = 0ull;  // two chains of pairs
+#pragma unroll
+        for (int k = 0; k < KL; k += 4) {
+            pa = ffma2(pack_f2(own[k], own[k + 1]), pack_f2(tr[k], tr[k + 1]), pa);
+            pb = ffma2(pack_f2(own[k + 2], own[k + 3]), pack_f2(tr[k + 2], tr[k + 3]), pb);
+        }
+        float a0, a1, b0, b1;
+        unpack_f2(pa, a0, a1);
+        unpack_f2(pb, b0, b1);
+        return (a0 + a1) + (b0 + b1);
+    }
+    float p0 = 0, p1 = 0;
+#pragma unroll
+    for (int k = 0; k < KL; k += 2) {
+        p0 = fmaf(own[k], tr[k], p0);
+        p1 = fmaf(own[k + 1], tr[k + 1], p1);
+    }
+    return p0 + p1;
+}
+template <int KL>
+__device__ __forceinline__ void axpy_row(float (&acc)[KL], const float (&tr)[KL], float q) {
+    if (VB_FFMA2 && KL % 2 == 0) {
+        const unsigned long long qq = pack_f2(q, q);
+#pragma unroll
+        for (int k = 0; k < KL; k += 2) {
+            const unsigned long long r = ffma2(pack_f2(tr[k], tr[k + 1]), qq, pack_f2(acc[k], acc[k + 1]));
+            unpack_f2(r, acc[k], acc[k + 1]);
+        }
+        return;
+    }
+#pragma unroll
+    for (int k = 0; k < KL; k++) acc[k] = fmaf(tr[k], q, acc[k]);
+}
+
 // one halving step over the lanes that differ in bit BIT of the group lane: N values -> ceil(N/2)
 template <int N, int BIT>
 __device__ __forceinline__ void halve_step(const double (&in)[N], double (&out)[(N + 1) / 2],
@@ -677,17 +756,10 @@ sweep_p16_kernel(const SweepTiledArgs a) {
                             for (int j = 0; j < UE; j++) tr[c * UE + j] = 0;
                         }
                     }
-                    PT p0 = 0, p1 = 0;
-#pragma unroll
-                    for (int k = 0; k < KL; k += 2) {
-                        p0 = fma(own[k], tr[k], p0);
-                        p1 = fma(own[k + 1], tr[k + 1], p1);
-                    }
-                    PT p = p0 + p1;
+                    PT p = dot_rows<KL>(own, tr);
                     if (LPN == 2) p += __shfl_xor_sync(gmask, p, 1);
                     const PT q = x * rcp_t(p);
-#pragma unroll
-                    for (int k = 0; k < KL; k++) acc[k] = fma(tr[k], q, acc[k]);
+                    axpy_row<KL>(acc, tr, q);
                     if (kLogProd) {
                         // LPN == 2: both lanes of a pair hold p, each takes every other nonzero
                         if (LPN == 1 || (u & 1) == hf) {
