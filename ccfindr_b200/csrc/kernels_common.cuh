@@ -238,14 +238,28 @@ __device__ __forceinline__ int schedule_item(const SegSchedule &sc, int NL, int 
     return ((cl ? sc.K[0] : 0) + step) * NL + lane;
 }
 
-__device__ __forceinline__ int tile_residue(int32_t d, int T) { return (d % T) & 7; }
+// packed word {count << 16 | tile row} of every nonzero in sorted (segment-major) order: one
+// thread per nonzero, so the dependent gathers through the sort permutation run at full
+// parallelism once instead of three times inside the one-thread-per-segment kernels below
+template <typename VT>
+__global__ void __launch_bounds__(kBlock)
+gather_words_kernel(int64_t nnz, const uint32_t *__restrict__ perm,
+                    const int32_t *__restrict__ rowidx, const int32_t *__restrict__ colof,
+                    const int32_t *__restrict__ gene_dev, const int32_t *__restrict__ cell_dev,
+                    const VT *__restrict__ val, int T, bool cols_pass,
+                    uint32_t *__restrict__ words) {
+    for (int64_t t = (int64_t)blockIdx.x * kBlock + threadIdx.x; t < nnz;
+         t += (int64_t)gridDim.x * kBlock) {
+        const uint32_t s = perm[t];
+        const int32_t d = cols_pass ? gene_dev[rowidx[s]] : cell_dev[colof[s]];
+        words[t] = ((uint32_t)val[s] << 16) | (uint32_t)(d % T);
+    }
+}
 
 // quads (4 entries = 16 bytes) of every segment under the schedule above; len4[E] = 0
 __global__ void __launch_bounds__(kBlock)
-plan_p16_kernel(int64_t E, const int64_t *__restrict__ ptr, const uint32_t *__restrict__ perm,
-                const int32_t *__restrict__ rowidx, const int32_t *__restrict__ colof,
-                const int32_t *__restrict__ gene_dev, const int32_t *__restrict__ cell_dev, int T,
-                bool cols_pass, int NL, uint32_t *__restrict__ len4) {
+plan_p16_kernel(int64_t E, const int64_t *__restrict__ ptr, const uint32_t *__restrict__ words,
+                int NL, uint32_t *__restrict__ len4) {
     for (int64_t e = (int64_t)blockIdx.x * kBlock + threadIdx.x; e <= E;
          e += (int64_t)gridDim.x * kBlock) {
         if (e == E) { len4[e] = 0u; continue; }
@@ -254,10 +268,7 @@ plan_p16_kernel(int64_t E, const int64_t *__restrict__ ptr, const uint32_t *__re
         int cnt[8];
 #pragma unroll
         for (int b = 0; b < 8; b++) cnt[b] = 0;
-        for (int64_t t = beg; t < end; t++) {
-            const uint32_t s = perm[t];
-            cnt[tile_residue(cols_pass ? gene_dev[rowidx[s]] : cell_dev[colof[s]], T)]++;
-        }
+        for (int64_t t = beg; t < end; t++) cnt[words[t] & 7u]++;
         int n0 = 0, n1 = 0, L0 = 0, L1 = 0;
         for (int rr = 0; rr < 8; rr++) {
             if (res_class(rr, NL)) { n1 += cnt[rr]; L1 = max(L1, cnt[rr]); }
@@ -285,15 +296,10 @@ __device__ __forceinline__ int64_t p16_position(int64_t p, int NL) {
 // One thread per segment: fill the segment with hole words, then scatter the nonzeros to their
 // scheduled places as {count << 16 | tile row}.  nvalid / S: rows of the tile side that exist
 // (a hole must point at a real row: local * S + slab < nvalid; row 0 of a slab always is).
-template <typename VT>
 __global__ void __launch_bounds__(kBlock)
 build_segments_p16_kernel(int64_t E, int64_t NO, const int64_t *__restrict__ ptr,
-                          const uint32_t *__restrict__ ptr4, const uint32_t *__restrict__ perm,
-                          const int32_t *__restrict__ rowidx, const int32_t *__restrict__ colof,
-                          const int32_t *__restrict__ gene_dev,
-                          const int32_t *__restrict__ cell_dev, const VT *__restrict__ val, int T,
-                          bool cols_pass, int NL, int64_t nvalid, int S,
-                          uint32_t *__restrict__ ent_out) {
+                          const uint32_t *__restrict__ ptr4, const uint32_t *__restrict__ words,
+                          int NL, int64_t nvalid, int S, uint32_t *__restrict__ ent_out) {
     for (int64_t e = (int64_t)blockIdx.x * kBlock + threadIdx.x; e < E;
          e += (int64_t)gridDim.x * kBlock) {
         const int64_t beg = ptr[e], end = ptr[e + 1];
@@ -304,10 +310,7 @@ build_segments_p16_kernel(int64_t E, int64_t NO, const int64_t *__restrict__ ptr
         int cnt[8];
 #pragma unroll
         for (int b = 0; b < 8; b++) cnt[b] = 0;
-        for (int64_t t = beg; t < end; t++) {
-            const uint32_t s = perm[t];
-            cnt[tile_residue(cols_pass ? gene_dev[rowidx[s]] : cell_dev[colof[s]], T)]++;
-        }
+        for (int64_t t = beg; t < end; t++) cnt[words[t] & 7u]++;
         SegSchedule sc;
         make_schedule(cnt, NL, sc);
         // holes: lane <-> bucket in the single steps, so the residue of the lane's bucket is free
@@ -322,12 +325,9 @@ build_segments_p16_kernel(int64_t E, int64_t NO, const int64_t *__restrict__ ptr
 #pragma unroll
         for (int b = 0; b < 8; b++) seen[b] = 0;
         for (int64_t t = beg; t < end; t++) {
-            const uint32_t s = perm[t];
-            const int32_t d = cols_pass ? gene_dev[rowidx[s]] : cell_dev[colof[s]];
-            const int local = d % T, rr = local & 7;
-            const int p = schedule_item(sc, NL, rr, seen[rr]++);
-            const uint32_t count = (uint32_t)val[s];
-            dst[p16_position(p, NL)] = (count << 16) | (uint32_t)local;
+            const uint32_t w = words[t];
+            const int rr = (int)(w & 7u);
+            dst[p16_position(schedule_item(sc, NL, rr, seen[rr]++), NL)] = w;
         }
     }
 }

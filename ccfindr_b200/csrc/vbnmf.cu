@@ -288,8 +288,12 @@ void deal(const std::vector<unsigned long long> &cnt, int T, int S, std::vector<
     }
 }
 
+// scratch: 4 * nnz uint32 (sort keys/payloads in and out), owned by get_layout.  One arena instead
+// of a handful of GB-sized stream-ordered allocations per pass: the pool then sees the same few
+// sizes at every handle creation and hands the blocks back without mapping new memory (the
+// separate buffers cost 20-200 ms per layout, varying from run to run).
 template <typename VT>
-int build_pass(H *h, Layout *L, bool cols_pass, const int32_t *d_colof) {
+int build_pass(H *h, Layout *L, bool cols_pass, const int32_t *d_colof, uint32_t *scratch) {
     StageTimer tm(cols_pass ? "build_pass(cols)" : "build_pass(rows)");
     PassLayout &P = cols_pass ? L->cols : L->rows;
     const int64_t nnz = h->nnz;
@@ -299,11 +303,8 @@ int build_pass(H *h, Layout *L, bool cols_pass, const int32_t *d_colof) {
     if (P.E >= (int64_t)UINT32_MAX)
         return fail(h, VBNMF_ERR_ARG, "matrix too large for 32-bit segment keys on one GPU");
     const int g = h->num_sms * 8;
-    uint32_t *k_in = nullptr, *k_out = nullptr, *p_in = nullptr, *p_out = nullptr;
-    CK(vmalloc(h, &k_in, (size_t)nnz * 4));
-    CK(vmalloc(h, &k_out, (size_t)nnz * 4));
-    CK(vmalloc(h, &p_in, (size_t)nnz * 4));
-    CK(vmalloc(h, &p_out, (size_t)nnz * 4));
+    uint32_t *k_in = scratch, *k_out = scratch + nnz, *p_in = scratch + 2 * nnz,
+             *p_out = scratch + 3 * nnz;
     { StageTimer t1("  make_keys");
     vb::make_keys_kernel<<<g, vb::kBlock, 0, h->stream>>>(nnz, h->d_rowidx, d_colof, L->d_gene_dev,
                                                           L->d_cell_dev, L->T, NO, cols_pass, k_in,
@@ -322,16 +323,20 @@ int build_pass(H *h, Layout *L, bool cols_pass, const int32_t *d_colof) {
     { StageTimer t1("  segment_ptr");
     vb::segment_ptr_kernel<<<g, vb::kBlock, 0, h->stream>>>(P.E, nnz, k_out, P.d_ptr); }
     CK(cudaStreamSynchronize(h->stream));
-    vfree(h->stream, d_tmp); vfree(h->stream, k_in); vfree(h->stream, k_out); vfree(h->stream, p_in);
+    vfree(h->stream, d_tmp);
     if (L->npg > 0) {
         // packed-16 layout: pad every segment to whole quads, scan the quad counts into ptr4
         uint32_t *d_len4 = nullptr;
         CK(vmalloc(h, &d_len4, (size_t)(P.E + 1) * 4));
         CK(vmalloc(h, &P.d_ptr4, (size_t)(P.E + 1) * 4));
+        uint32_t *d_words = k_in;  // the unsorted keys are dead after the sort
+        { StageTimer t1("  gather_words");
+        vb::gather_words_kernel<VT><<<g, vb::kBlock, 0, h->stream>>>(
+            nnz, p_out, h->d_rowidx, d_colof, L->d_gene_dev, L->d_cell_dev, (const VT *)h->d_val,
+            L->T, cols_pass, d_words); }
         { StageTimer t1("  plan(p16)");
-        vb::plan_p16_kernel<<<g, vb::kBlock, 0, h->stream>>>(
-            P.E, P.d_ptr, p_out, h->d_rowidx, d_colof, L->d_gene_dev, L->d_cell_dev, L->T, cols_pass,
-            L->npg, d_len4); }
+        vb::plan_p16_kernel<<<g, vb::kBlock, 0, h->stream>>>(P.E, P.d_ptr, d_words, L->npg,
+                                                             d_len4); }
         size_t scan_bytes = 0;
         CK(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, d_len4, P.d_ptr4, P.E + 1, h->stream));
         void *d_scan = nullptr;
@@ -346,16 +351,14 @@ int build_pass(H *h, Layout *L, bool cols_pass, const int32_t *d_colof) {
         CK(vmalloc(h, &P.d_ent, (size_t)quads * 16));
         P.nent = (int64_t)quads * 4;
         { StageTimer t1("  build_segments(p16)");
-        vb::build_segments_p16_kernel<VT><<<g, vb::kBlock, 0, h->stream>>>(
-            P.E, NO, P.d_ptr, P.d_ptr4, p_out, h->d_rowidx, d_colof, L->d_gene_dev, L->d_cell_dev,
-            (const VT *)h->d_val, L->T, cols_pass, L->npg, cols_pass ? h->n : h->m,
+        vb::build_segments_p16_kernel<<<g, vb::kBlock, 0, h->stream>>>(
+            P.E, NO, P.d_ptr, P.d_ptr4, d_words, L->npg, cols_pass ? h->n : h->m,
             cols_pass ? L->Sg : L->Sc, (uint32_t *)P.d_ent); }
         CK(vmalloc(h, &P.d_split, (size_t)(L->grid + 1) * 8));
         vb::split_p16_kernel<<<cdiv(L->grid + 1, 128), 128, 0, h->stream>>>(L->grid, P.E, P.d_ptr4,
                                                                            P.d_split);
         CK(cudaStreamSynchronize(h->stream));
         CK(cudaGetLastError());
-        vfree(h->stream, p_out);
         vfree(h->stream, P.d_ptr);
         P.d_ptr = nullptr;
         return 0;
@@ -376,7 +379,6 @@ int build_pass(H *h, Layout *L, bool cols_pass, const int32_t *d_colof) {
                                                                    P.d_split);
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaGetLastError());
-    vfree(h->stream, p_out);
     return 0;
 }
 
@@ -393,29 +395,35 @@ int get_layout(H *h, int T, int npg, Layout **out) {
     L->NG = (int64_t)L->Sg * T;
     L->NC = (int64_t)L->Sc * T;
     L->grid = h->num_sms;
+    { StageTimer t1("  deal(host sort)");
     deal(h->row_count, T, L->Sg, L->gene_dev);
-    deal(h->col_count, T, L->Sc, L->cell_dev);
+    deal(h->col_count, T, L->Sc, L->cell_dev); }
     auto bail = [&](int rc) { L->release(h->stream); delete L; return rc; };
     auto body = [&]() -> int {
         CK(vmalloc(h, &L->d_gene_dev, (size_t)h->n * 4));
         CK(vmalloc(h, &L->d_cell_dev, (size_t)h->m * 4));
         CK(copy_sync(h, L->d_gene_dev, L->gene_dev.data(), (size_t)h->n * 4, cudaMemcpyHostToDevice));
         CK(copy_sync(h, L->d_cell_dev, L->cell_dev.data(), (size_t)h->m * 4, cudaMemcpyHostToDevice));
-        int32_t *d_colof = nullptr;
+        // one arena: [colof | 4 sort buffers], nnz 32-bit words each
+        uint32_t *arena = nullptr;
         unsigned long long *d_cnt = nullptr;
-        CK(vmalloc(h, &d_colof, (size_t)h->nnz * 4));
+        { StageTimer t1("  alloc(arena)");
+        CK(vmalloc(h, &arena, (size_t)h->nnz * 4 * 5)); }
+        int32_t *d_colof = (int32_t *)arena;
+        uint32_t *scratch = arena + h->nnz;
         CK(vmalloc(h, &d_cnt, (size_t)(h->n + h->m) * 8));
         CK(cudaMemsetAsync(d_cnt, 0, (size_t)(h->n + h->m) * 8, h->stream));
         { StageTimer t1("  expand_cols");
         vb::expand_cols_kernel<<<h->num_sms * 8, vb::kBlock, 0, h->stream>>>(
             h->m, h->d_colptr, h->d_rowidx, d_colof, d_cnt, d_cnt + h->n); }
-        int rc = h->val_float ? build_pass<float>(h, L, true, d_colof)
-                              : build_pass<double>(h, L, true, d_colof);
+        int rc = h->val_float ? build_pass<float>(h, L, true, d_colof, scratch)
+                              : build_pass<double>(h, L, true, d_colof, scratch);
         if (!rc)
-            rc = h->val_float ? build_pass<float>(h, L, false, d_colof)
-                              : build_pass<double>(h, L, false, d_colof);
-        vfree(h->stream, d_colof);
-        vfree(h->stream, d_cnt);
+            rc = h->val_float ? build_pass<float>(h, L, false, d_colof, scratch)
+                              : build_pass<double>(h, L, false, d_colof, scratch);
+        { StageTimer t1("  free(arena)");
+        vfree(h->stream, arena);
+        vfree(h->stream, d_cnt); }
         return rc;
     };
     int rc = body();
@@ -731,7 +739,7 @@ template <typename Src, typename Dst, typename Conv>
 int staged_upload(H *h, Dst *d_dst, const Src *src, int64_t count, Conv conv, bool *all_ok) {
     if (!g_staging.init()) return fail(h, VBNMF_ERR_CUDA, "cannot allocate pinned staging buffers");
     const int64_t per = (int64_t)(Staging::kBytes / sizeof(Dst));
-    const int nthr = (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+    const int nthr = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
     std::vector<char> good((size_t)nthr, 1);
     int slot = 0;
     for (int64_t lo = 0; lo < count; lo += per, slot ^= 1) {
