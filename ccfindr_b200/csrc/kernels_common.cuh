@@ -483,6 +483,77 @@ init_random_kernel(int64_t rows, int r, int rs, const int32_t *__restrict__ dev,
     mirror[o] = v;
 }
 
+// ---- all-reduce of the W-side statistics over NVLink peer memory -----------------------------
+// One process per GPU; every rank owns an exchange region [flags (kXchgFlags x u64) | buffer 0 |
+// buffer 1] that its peers map through CUDA IPC.  An all-reduce with sequence number seq is
+//   publish: copy the local vector into buffer seq & 1 of the own region, then (last CTA, after a
+//            system-scope fence) store seq into flags[my rank] of EVERY rank's region;
+//   reduce:  wait until flags[p] >= seq for all p in the own region, then out[i] = sum over
+//            p = 0..nranks-1 (fixed order -> bitwise identical on every rank) of buffer seq & 1
+//            of rank p, read straight from peer memory (NVLink P2P loads).
+// A rank can only publish seq + 2 (the next use of the same buffer) after its reduce of seq + 1,
+// which waits for every peer's publish of seq + 1, which follows that peer's reduce of seq in
+// stream order: double buffering is enough, no second barrier.  The payload is 1.6 MB at C2 (3.3 MB
+// at C3) per iteration.  Measured (profiles/r01_peer_allreduce_ab.txt): equal to NCCL on 2 GPUs,
+// 20 us per iteration slower on 8 (NCCL reduces in the switch), so it is opt-in
+// (VBNMF_PEER_ALLREDUCE=1) and the default stays one ncclAllReduce per iteration.
+constexpr int kXchgFlags = 16;   // u64 flags per region (>= ranks of one NVLink domain we use)
+struct XchgArgs {
+    unsigned long long *peer[kXchgFlags];  // base of every rank's region (own region at [rank])
+    int nranks, rank;
+    unsigned long long seq;
+    int64_t n2;                 // payload in double2 units
+    int64_t buf_stride;         // bytes between buffer 0 and buffer 1
+    const double *ctl;
+};
+__device__ __forceinline__ double2 *xchg_buf(unsigned long long *base, const XchgArgs &a) {
+    char *p = reinterpret_cast<char *>(base) + kXchgFlags * 8 + (a.seq & 1ull) * a.buf_stride;
+    return reinterpret_cast<double2 *>(p);
+}
+
+__global__ void __launch_bounds__(kBlock)
+xchg_publish_kernel(const XchgArgs a, const double2 *__restrict__ src, unsigned *counter) {
+    if (a.ctl && a.ctl[kCtlDone] != 0.0) return;
+    double2 *dst = xchg_buf(a.peer[a.rank], a);
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < a.n2;
+         i += (int64_t)gridDim.x * kBlock)
+        dst[i] = src[i];
+    __shared__ bool is_last;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicInc(counter, gridDim.x - 1) == gridDim.x - 1;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence_system();
+    if (threadIdx.x < a.nranks) {
+        volatile unsigned long long *f = a.peer[threadIdx.x] + a.rank;
+        *f = a.seq;
+    }
+}
+
+__global__ void __launch_bounds__(kBlock)
+xchg_reduce_kernel(const XchgArgs a, double2 *__restrict__ out) {
+    if (a.ctl && a.ctl[kCtlDone] != 0.0) return;
+    if (threadIdx.x < a.nranks) {
+        volatile unsigned long long *f = a.peer[a.rank] + threadIdx.x;
+        // bounded spin: a peer that never arrives traps this rank instead of hanging the GPU
+        for (unsigned long long spin = 0; *f < a.seq; spin++)
+            if (spin > (1ull << 31)) __trap();
+    }
+    __threadfence_system();
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < a.n2;
+         i += (int64_t)gridDim.x * kBlock) {
+        double2 s = make_double2(0.0, 0.0);
+        for (int p = 0; p < a.nranks; p++) {
+            const double2 v = __ldcv(xchg_buf(a.peer[p], a) + i);
+            s.x += v.x;
+            s.y += v.y;
+        }
+        out[i] = s;
+    }
+}
+
 // cid[d] = 1 + index of the first maximum over k of alh[d][k] / beh[k]   (R/utils.R:906)
 __global__ void __launch_bounds__(kBlock)
 cluster_id_kernel(int64_t rows, int RS, int r, const double *__restrict__ alh,

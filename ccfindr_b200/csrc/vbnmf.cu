@@ -91,6 +91,7 @@ struct NcclApi {
     decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
     decltype(&ncclCommInitRank) CommInitRank = nullptr;
     decltype(&ncclAllReduce) AllReduce = nullptr;
+    decltype(&ncclAllGather) AllGather = nullptr;
     decltype(&ncclCommDestroy) CommDestroy = nullptr;
     decltype(&ncclGetErrorString) GetErrorString = nullptr;
     bool load(std::string &err) {
@@ -102,6 +103,7 @@ struct NcclApi {
         GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
         CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
         AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+        AllGather = (decltype(AllGather))dlsym(lib, "ncclAllGather");
         CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
         GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
         if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy) {
@@ -199,6 +201,13 @@ struct vbnmf_handle {
     // NCCL
     int nranks = 1, rank = 0;
     ncclComm_t comm = nullptr;
+    // exchange region of the peer-memory all-reduce (kernels_common.cuh): own allocation, the
+    // peers' regions mapped through CUDA IPC, sequence number of the last all-reduce
+    unsigned long long *d_xchg = nullptr;
+    unsigned long long *xchg_peer[vb::kXchgFlags] = {};
+    int64_t xchg_stride = 0;
+    unsigned long long xchg_seq = 0;
+    bool peer_ok = false;
     int64_t launches = 0;
     std::string err;
 };
@@ -273,14 +282,129 @@ int allreduce(H *h, double *buf, int64_t count) {
     return 0;
 }
 
+// ---- all-reduce over NVLink peer memory (one process per GPU, CUDA IPC) -------------------------
+void free_xchg(H *h) {
+    if (!h->d_xchg) return;
+    for (int p = 0; p < h->nranks && p < vb::kXchgFlags; p++)
+        if (p != h->rank && h->xchg_peer[p]) cudaIpcCloseMemHandle(h->xchg_peer[p]);
+    cudaFree(h->d_xchg);
+    h->d_xchg = nullptr;
+    for (auto &q : h->xchg_peer) q = nullptr;
+    h->peer_ok = false;
+}
+
+// Collective over the ranks of the communicator (called from alloc_panels, which every rank runs
+// with the same rank argument).  Any failure on any rank -> every rank keeps the NCCL all-reduce.
+int setup_xchg(H *h) {
+    free_xchg(h);
+    if (h->nranks <= 1) return 0;
+    // Opt-in (VBNMF_PEER_ALLREDUCE=1, the same environment on every rank): measured on 8 B200s at
+    // C2 the NCCL all-reduce of the 1.6 MB vector (in-switch reduction) is 20 us per iteration
+    // FASTER than the two peer-memory launches (1.490 vs 1.510 ms per iteration, bitwise identical
+    // results), and equal on 2 GPUs (profiles/r01_peer_allreduce_ab.txt).
+    if (!getenv("VBNMF_PEER_ALLREDUCE")) return 0;
+    const bool want = h->nranks <= vb::kXchgFlags && g_nccl.AllGather;
+    int bad = want ? 0 : 1;
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof(mine));
+    h->xchg_stride = (((int64_t)red_len(h) * 8 + 255) / 256) * 256;
+    const size_t bytes = (size_t)vb::kXchgFlags * 8 + 2 * (size_t)h->xchg_stride;
+    if (!bad) {
+        if (cudaMalloc((void **)&h->d_xchg, bytes) != cudaSuccess) { h->d_xchg = nullptr; bad = 1; }
+        else if (cudaMemset(h->d_xchg, 0, bytes) != cudaSuccess) bad = 1;
+        else if (cudaIpcGetMemHandle(&mine, h->d_xchg) != cudaSuccess) bad = 1;
+        cudaGetLastError();
+    }
+    // all-gather the 64-byte handles (+ the per-rank failure flag in a 65th... kept separate below)
+    const int hb = (int)sizeof(cudaIpcMemHandle_t);
+    char *d_all = nullptr;
+    CK(vmalloc(h, &d_all, (size_t)hb * (h->nranks + 1)));
+    CK(cudaMemcpyAsync(d_all + (size_t)hb * h->nranks, &mine, hb, cudaMemcpyHostToDevice, h->stream));
+    if (g_nccl.AllGather) {
+        CKN(g_nccl.AllGather(d_all + (size_t)hb * h->nranks, d_all, (size_t)hb, ncclInt8, h->comm,
+                             h->stream));
+    }
+    std::vector<cudaIpcMemHandle_t> all((size_t)h->nranks);
+    CK(cudaMemcpyAsync(all.data(), d_all, (size_t)hb * h->nranks, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    vfree(h->stream, d_all);
+    if (!bad) {
+        h->xchg_peer[h->rank] = h->d_xchg;
+        for (int p = 0; p < h->nranks && !bad; p++) {
+            if (p == h->rank) continue;
+            void *q = nullptr;
+            if (cudaIpcOpenMemHandle(&q, all[(size_t)p], cudaIpcMemLazyEnablePeerAccess) !=
+                cudaSuccess) {
+                cudaGetLastError();
+                bad = 1;
+            } else {
+                h->xchg_peer[p] = (unsigned long long *)q;
+            }
+        }
+    }
+    // agree: the sum of the failure flags over the ranks must be zero
+    double *d_flag = nullptr, flag = (double)bad;
+    CK(vmalloc(h, &d_flag, 8));
+    CK(cudaMemcpyAsync(d_flag, &flag, 8, cudaMemcpyHostToDevice, h->stream));
+    int rc = allreduce(h, d_flag, 1);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(&flag, d_flag, 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    vfree(h->stream, d_flag);
+    if (flag != 0.0) { free_xchg(h); return 0; }
+    h->peer_ok = true;
+    h->xchg_seq = 0;
+    return 0;
+}
+
+// all-reduce of d_red (the W-side statistics and the scalars of the bound) inside the device-
+// controlled loop: peer memory when it is set up, NCCL otherwise
+int allreduce_red(H *h) {
+    if (h->nranks <= 1) return 0;
+    if (!h->peer_ok) return allreduce(h, h->d_red, red_len(h));
+    NvtxRange nv("vbnmf:allreduce(peer)");
+    vb::XchgArgs a;
+    for (int p = 0; p < vb::kXchgFlags; p++) a.peer[p] = h->xchg_peer[p];
+    a.nranks = h->nranks; a.rank = h->rank;
+    a.seq = ++h->xchg_seq;
+    a.n2 = red_len(h) / 2;
+    a.buf_stride = h->xchg_stride;
+    a.ctl = h->ctl;
+    vb::xchg_publish_kernel<<<64, vb::kBlock, 0, h->stream>>>(
+        a, reinterpret_cast<const double2 *>(h->d_red), h->d_counters + 8);
+    vb::xchg_reduce_kernel<<<128, vb::kBlock, 0, h->stream>>>(a,
+                                                              reinterpret_cast<double2 *>(h->d_red));
+    h->launches += 2;
+    return 0;
+}
+
+// every rank has left its device loop: nobody reads this rank's exchange region any more
+int peer_exit_barrier(H *h) {
+    if (!h->peer_ok) return 0;
+    CKN(g_nccl.AllReduce(h->d_counters + 12, h->d_counters + 12, 1, ncclInt32, ncclSum, h->comm,
+                         h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
 // ---- building the tiled layouts ---------------------------------------------------------------
 // sorted position -> device row for `count` items dealt over S slabs of T rows
 void deal(const std::vector<unsigned long long> &cnt, int T, int S, std::vector<int32_t> &dev) {
     const int64_t n = (int64_t)cnt.size();
+    // stable order by descending count: counting sort (counts are at most the other dimension)
+    unsigned long long maxc = 0;
+    for (auto c : cnt) maxc = std::max(maxc, c);
     std::vector<int64_t> order((size_t)n);
-    std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(),
-                     [&](int64_t a, int64_t b) { return cnt[a] > cnt[b]; });
+    if (maxc <= (unsigned long long)(8 * n + 1024)) {
+        std::vector<int64_t> start((size_t)maxc + 2, 0);
+        for (auto c : cnt) start[(size_t)(maxc - c) + 1]++;
+        for (size_t k = 1; k < start.size(); k++) start[k] += start[k - 1];
+        for (int64_t i = 0; i < n; i++) order[(size_t)start[(size_t)(maxc - cnt[(size_t)i])]++] = i;
+    } else {
+        std::iota(order.begin(), order.end(), 0);
+        std::stable_sort(order.begin(), order.end(),
+                         [&](int64_t a, int64_t b) { return cnt[a] > cnt[b]; });
+    }
     dev.resize((size_t)n);
     for (int64_t pos = 0; pos < n; pos++) {
         const int64_t slab = pos % S, local = pos / S;
@@ -476,6 +600,7 @@ int scan_matrix_t(H *h) {
 
 // ---- panels -------------------------------------------------------------------------------------
 void free_panels(H *h) {
+    free_xchg(h);
     double **ps[] = {&h->d_lw, &h->d_lh, &h->d_alw, &h->d_alh, &h->d_red, &h->d_ShRaw,
                      &h->d_Part1, &h->d_Part2, &h->d_xl, &h->d_scal, &h->d_partW, &h->d_partH,
                      &h->d_partC};
@@ -538,7 +663,7 @@ int alloc_panels(H *h, int r) {
         CK(vmalloc(h, &h->d_lw32, (size_t)L->NG * h->rsf * 4));
         CK(vmalloc(h, &h->d_lh32, (size_t)L->NC * h->rsf * 4));
     }
-    return 0;
+    return setup_xchg(h);
 }
 
 // fp32-storage mode: refresh the mirrors from the fp64 panels (after an upload)
@@ -1166,7 +1291,7 @@ static int run_device_loop(H *h, const vbnmf_cfg *cfg, double hyper[4], double *
             if (ev) CK(cudaEventRecord(ev[4 * gi + 2], h->stream));
             if ((rc = launch_sweep_rows(h))) return finish(rc);
             if (ev) CK(cudaEventRecord(ev[4 * gi + 3], h->stream));
-            if ((rc = allreduce(h, h->d_red, red_len(h)))) return finish(rc);
+            if ((rc = allreduce_red(h))) return finish(rc);
             vb::control_kernel<<<1, 32, 0, h->stream>>>(ca);
             h->launches += 1;
         }
@@ -1185,6 +1310,7 @@ static int run_device_loop(H *h, const vbnmf_cfg *cfg, double hyper[4], double *
         CK(cudaMemcpyAsync(hyper_trace, d_htrace, (size_t)it * 32, cudaMemcpyDeviceToHost,
                            h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    if ((rc = peer_exit_barrier(h))) return finish(rc);
     for (int k = 0; k < r; k++) {
         h->bew[k] = c[vb::kCtlBew + k];
         h->beh[k] = c[vb::kCtlBeh + k];
