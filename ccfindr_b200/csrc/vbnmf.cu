@@ -57,7 +57,7 @@ namespace {
 constexpr int kMaxRank = 64;
 // shared-memory budget of one staged slab: the 227 KB a CTA can opt in to minus the static part
 constexpr int kTileBytes = 231424;
-constexpr int kTileRowsMax = 4096, kTileRowsStep = 128;
+constexpr int kTileRowsMax = 4096, kTileRowsStep = 32;
 
 std::string g_create_error;
 
@@ -266,7 +266,7 @@ inline int64_t tail_off(const H *h) { return h->L->NG * h->rs; }
 inline int64_t red_len(const H *h) { return h->L->NG * h->rs + h->rs + 8; }
 
 int choose_tile_rows(const H *h, int row_bytes) {
-    // largest multiple of 128 rows that fits (ranks with the same row stride share a layout)
+    // largest multiple of 32 rows that fits (ranks with the same row stride share a layout)
     int T = (kTileBytes / row_bytes / kTileRowsStep) * kTileRowsStep;
     T = std::max(kTileRowsStep, std::min(T, kTileRowsMax));
     const int64_t big = std::max(h->n, h->m);
