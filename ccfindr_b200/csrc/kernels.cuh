@@ -155,9 +155,12 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
 //
 // The build step orders the nonzeros of a segment so that 8 consecutive ones hit tile rows that
 // differ mod 8 -> with an odd row stride the 8 gathers of a group are bank-conflict free.
-// nonzeros per lane whose index/count loads are in flight together and whose arithmetic chains are
-// interleaved: 6 for the fp64 single-lane configuration, 4 otherwise (measured on C2: fp64 1.81 ->
-// 1.76 ms with 6; the fp32 mode and the two-lane variant are faster with 4, 2 is slower everywhere)
+// This kernel serves the 8-byte {row, float} and the {row} + {double} entry formats; integer
+// counts below 2^16 take sweep_p16_kernel further down (same passes, same outputs).
+// VB_UNROLL: nonzeros per lane whose index/count loads are in flight together and whose arithmetic
+// chains are interleaved: 6 for the fp64 single-lane configuration, 4 otherwise (measured on C2:
+// fp64 1.81 -> 1.76 ms with 6; the fp32 mode and the two-lane variant are faster with 4, 2 is
+// slower everywhere)
 #ifndef VB_UNROLL
 #define VB_UNROLL 0
 #endif
@@ -201,7 +204,6 @@ struct SweepCfg {
     static constexpr int kGroups = kThreads / kGroup;
 };
 
-  // nonzeros per lane whose index/count loads are in flight together
 
 // log(p) for a positive normal double, ~1 ulp: p = 2^e m with m in [sqrt(1/2), sqrt(2)),
 // log m = 2 atanh(t), t = (m-1)/(m+1), |t| <= 0.1716, odd series through t^17 (next term < 3e-16).

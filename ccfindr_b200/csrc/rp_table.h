@@ -55,7 +55,6 @@ struct ColsumArgs {
 
 struct RpTable {
     int rp, rs, rsf;  // padded rank, fp64 panel stride (doubles), fp32 mirror stride (floats)
-    int sweep_threads;
     int npg64, npg32;  // nonzeros per 8-lane group step of the sweep (fp64 / fp32 panels)
     // cols: cell-owner pass; fmt = storage format of the nonzeros (kEnt*); grid = CTAs (one per
     // SM, persistent)
