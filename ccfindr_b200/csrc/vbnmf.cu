@@ -55,6 +55,7 @@ const RpTable *rp_table(int rp) {
 namespace {
 
 constexpr int kMaxRank = 64;
+constexpr int64_t kGraphMaxNnz = 20000000;  // below this the iteration loop is replayed as a CUDA graph
 // shared-memory budget of one staged slab: the 227 KB a CTA can opt in to minus the static part
 constexpr int kTileBytes = 231424;
 constexpr int kTileRowsMax = 4096, kTileRowsStep = 32;
@@ -1278,22 +1279,56 @@ static int run_device_loop(H *h, const vbnmf_cfg *cfg, double hyper[4], double *
     const int batch = 8;
     int launched = 0, it = 0;
     bool done = false;
+    // Small problems are launch-bound (an iteration of the 1,000 x 200 plumbing case is ~8 kernels
+    // of a few microseconds): there one batch of iterations is captured into a CUDA graph and
+    // replayed.  Every kernel argument is the same in every iteration (hypers and the stop flag
+    // live in the control block), and iterations replayed past the stop are no-ops.
+    struct GraphGuard {
+        cudaGraph_t g = nullptr;
+        cudaGraphExec_t x = nullptr;
+        ~GraphGuard() {
+            if (x) cudaGraphExecDestroy(x);
+            if (g) cudaGraphDestroy(g);
+        }
+    } gg;
+    const bool use_graph = !ev && h->nranks == 1 && itmax >= 4 * batch && h->nnz <= kGraphMaxNnz &&
+                           !getenv("VBNMF_NO_GRAPH");
     auto finish = [&](int code) { return code; };
+    auto enqueue = [&](int gi) -> int {
+        if ((rc = launch_posterior(h, true, 0, 0, cfg->fudge))) return rc;
+        if ((rc = launch_posterior(h, false, 0, 0, cfg->fudge))) return rc;
+        if (ev) CK(cudaEventRecord(ev[4 * gi + 0], h->stream));
+        if ((rc = launch_sweep_cols(h))) return rc;
+        if (ev) CK(cudaEventRecord(ev[4 * gi + 1], h->stream));
+        if (ev) CK(cudaEventRecord(ev[4 * gi + 2], h->stream));
+        if ((rc = launch_sweep_rows(h))) return rc;
+        if (ev) CK(cudaEventRecord(ev[4 * gi + 3], h->stream));
+        if ((rc = allreduce_red(h))) return rc;
+        vb::control_kernel<<<1, 32, 0, h->stream>>>(ca);
+        h->launches += 1;
+        return 0;
+    };
+    int64_t launches_per_batch = 0;
+    if (use_graph) {
+        const int64_t l0 = h->launches;
+        CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        rc = 0;
+        for (int b = 0; b < batch && !rc; b++) rc = enqueue(b);
+        cudaError_t ce = cudaStreamEndCapture(h->stream, &gg.g);
+        launches_per_batch = h->launches - l0;
+        h->launches = l0;
+        if (rc) return finish(rc);
+        CK(ce);
+        CK(cudaGraphInstantiate(&gg.x, gg.g, 0));
+    }
     while (!done && launched < itmax) {
-        const int nb = std::min(batch, itmax - launched);
-        for (int b = 0; b < nb; b++) {
-            const int gi = launched + b;
-            if ((rc = launch_posterior(h, true, 0, 0, cfg->fudge))) return finish(rc);
-            if ((rc = launch_posterior(h, false, 0, 0, cfg->fudge))) return finish(rc);
-            if (ev) CK(cudaEventRecord(ev[4 * gi + 0], h->stream));
-            if ((rc = launch_sweep_cols(h))) return finish(rc);
-            if (ev) CK(cudaEventRecord(ev[4 * gi + 1], h->stream));
-            if (ev) CK(cudaEventRecord(ev[4 * gi + 2], h->stream));
-            if ((rc = launch_sweep_rows(h))) return finish(rc);
-            if (ev) CK(cudaEventRecord(ev[4 * gi + 3], h->stream));
-            if ((rc = allreduce_red(h))) return finish(rc);
-            vb::control_kernel<<<1, 32, 0, h->stream>>>(ca);
-            h->launches += 1;
+        const int nb = use_graph ? batch : std::min(batch, itmax - launched);
+        if (use_graph) {
+            CK(cudaGraphLaunch(gg.x, h->stream));
+            h->launches += launches_per_batch;
+        } else {
+            for (int b = 0; b < nb; b++)
+                if ((rc = enqueue(launched + b))) return finish(rc);
         }
         launched += nb;
         CK(cudaMemcpyAsync(c, h->d_ctl, vb::kCtlLen * sizeof(double), cudaMemcpyDeviceToHost,
