@@ -27,6 +27,7 @@
 #include <cmath>
 #include <cub/cub.cuh>
 #include <numeric>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -860,9 +861,11 @@ struct Staging {
     }
 };
 Staging g_staging;
+std::mutex g_staging_mu;  // the staging buffers are shared by all handles of the process
 
 template <typename Src, typename Dst, typename Conv>
 int staged_upload(H *h, Dst *d_dst, const Src *src, int64_t count, Conv conv, bool *all_ok) {
+    std::lock_guard<std::mutex> lock(g_staging_mu);
     if (!g_staging.init()) return fail(h, VBNMF_ERR_CUDA, "cannot allocate pinned staging buffers");
     const int64_t per = (int64_t)(Staging::kBytes / sizeof(Dst));
     const int nthr = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
