@@ -52,18 +52,23 @@ expand_cols_kernel(int64_t m, const int64_t *__restrict__ colptr,
 }
 
 // sort key of every nonzero for one pass of the tiled layout:
-//   key = slab(tile side) * NO + owner(device row of the owner side),  payload = nonzero index
+//   key = slab(tile side) * NO + owner(device row of the owner side)
+//   payload = nonzero index, or (packed-16 layout, val != nullptr) the packed word
+//             {count << 16 | tile row} itself, so that the sorted payloads ARE the entries in
+//             segment-major order and nothing has to be gathered through a permutation afterwards
+template <typename VT>
 __global__ void __launch_bounds__(kBlock)
 make_keys_kernel(int64_t nnz, const int32_t *__restrict__ rowidx, const int32_t *__restrict__ colof,
                  const int32_t *__restrict__ gene_dev, const int32_t *__restrict__ cell_dev, int T,
-                 int64_t NO, bool cols_pass, uint32_t *__restrict__ key,
+                 int64_t NO, bool cols_pass, const VT *__restrict__ val, uint32_t *__restrict__ key,
                  uint32_t *__restrict__ payload) {
     for (int64_t t = (int64_t)blockIdx.x * kBlock + threadIdx.x; t < nnz;
          t += (int64_t)gridDim.x * kBlock) {
         const int64_t gd = gene_dev[rowidx[t]], cd = cell_dev[colof[t]];
         const int64_t k = cols_pass ? (gd / T) * NO + cd : (cd / T) * NO + gd;
         key[t] = (uint32_t)k;
-        payload[t] = (uint32_t)t;
+        payload[t] = val ? (((uint32_t)val[t] << 16) | (uint32_t)((cols_pass ? gd : cd) % T))
+                         : (uint32_t)t;
     }
 }
 
@@ -236,24 +241,6 @@ __device__ __forceinline__ int schedule_item(const SegSchedule &sc, int NL, int 
         lane = (row >= P) ? NL - 1 - level : level;
     }
     return ((cl ? sc.K[0] : 0) + step) * NL + lane;
-}
-
-// packed word {count << 16 | tile row} of every nonzero in sorted (segment-major) order: one
-// thread per nonzero, so the dependent gathers through the sort permutation run at full
-// parallelism once instead of three times inside the one-thread-per-segment kernels below
-template <typename VT>
-__global__ void __launch_bounds__(kBlock)
-gather_words_kernel(int64_t nnz, const uint32_t *__restrict__ perm,
-                    const int32_t *__restrict__ rowidx, const int32_t *__restrict__ colof,
-                    const int32_t *__restrict__ gene_dev, const int32_t *__restrict__ cell_dev,
-                    const VT *__restrict__ val, int T, bool cols_pass,
-                    uint32_t *__restrict__ words) {
-    for (int64_t t = (int64_t)blockIdx.x * kBlock + threadIdx.x; t < nnz;
-         t += (int64_t)gridDim.x * kBlock) {
-        const uint32_t s = perm[t];
-        const int32_t d = cols_pass ? gene_dev[rowidx[s]] : cell_dev[colof[s]];
-        words[t] = ((uint32_t)val[s] << 16) | (uint32_t)(d % T);
-    }
 }
 
 // quads (4 entries = 16 bytes) of every segment under the schedule above; len4[E] = 0

@@ -432,9 +432,9 @@ int build_pass(H *h, Layout *L, bool cols_pass, const int32_t *d_colof, uint32_t
     uint32_t *k_in = scratch, *k_out = scratch + nnz, *p_in = scratch + 2 * nnz,
              *p_out = scratch + 3 * nnz;
     { StageTimer t1("  make_keys");
-    vb::make_keys_kernel<<<g, vb::kBlock, 0, h->stream>>>(nnz, h->d_rowidx, d_colof, L->d_gene_dev,
-                                                          L->d_cell_dev, L->T, NO, cols_pass, k_in,
-                                                          p_in); }
+    vb::make_keys_kernel<VT><<<g, vb::kBlock, 0, h->stream>>>(
+        nnz, h->d_rowidx, d_colof, L->d_gene_dev, L->d_cell_dev, L->T, NO, cols_pass,
+        L->npg > 0 ? (const VT *)h->d_val : nullptr, k_in, p_in); }
     int bits = 1;
     while (((int64_t)1 << bits) < P.E) bits++;
     size_t tmp_bytes = 0;
@@ -455,11 +455,7 @@ int build_pass(H *h, Layout *L, bool cols_pass, const int32_t *d_colof, uint32_t
         uint32_t *d_len4 = nullptr;
         CK(vmalloc(h, &d_len4, (size_t)(P.E + 1) * 4));
         CK(vmalloc(h, &P.d_ptr4, (size_t)(P.E + 1) * 4));
-        uint32_t *d_words = k_in;  // the unsorted keys are dead after the sort
-        { StageTimer t1("  gather_words");
-        vb::gather_words_kernel<VT><<<g, vb::kBlock, 0, h->stream>>>(
-            nnz, p_out, h->d_rowidx, d_colof, L->d_gene_dev, L->d_cell_dev, (const VT *)h->d_val,
-            L->T, cols_pass, d_words); }
+        const uint32_t *d_words = p_out;  // the sorted payloads are the packed words
         { StageTimer t1("  plan(p16)");
         vb::plan_p16_kernel<<<g, vb::kBlock, 0, h->stream>>>(P.E, P.d_ptr, d_words, L->npg,
                                                              d_len4); }
