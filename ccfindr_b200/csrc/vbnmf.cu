@@ -172,6 +172,11 @@ struct vbnmf_handle {
     bool val_float = true;
     bool p16 = false;  // all counts are integers < 2^16: packed-16 layouts (sweep_p16_kernel)
     bool borrowed = false;
+    // Scratch arena of the first layout build (5 * nnz 32-bit words), reserved when the handle is
+    // created, BEFORE the smaller GB-sized buffers: the memory pool then hands the same blocks to
+    // the same requests at every handle creation instead of splitting the big block and mapping
+    // new memory for the arena later (tens of ms, varying from run to run).
+    uint32_t *d_arena = nullptr;
     // the count matrix as given (CSC); the tiled layouts are derived from it
     int64_t *d_colptr = nullptr;
     int32_t *d_rowidx = nullptr;
@@ -527,10 +532,10 @@ int get_layout(H *h, int T, int npg, Layout **out) {
         CK(copy_sync(h, L->d_gene_dev, L->gene_dev.data(), (size_t)h->n * 4, cudaMemcpyHostToDevice));
         CK(copy_sync(h, L->d_cell_dev, L->cell_dev.data(), (size_t)h->m * 4, cudaMemcpyHostToDevice));
         // one arena: [colof | 4 sort buffers], nnz 32-bit words each
-        uint32_t *arena = nullptr;
+        uint32_t *arena = h->d_arena;
+        h->d_arena = nullptr;
         unsigned long long *d_cnt = nullptr;
-        { StageTimer t1("  alloc(arena)");
-        CK(vmalloc(h, &arena, (size_t)h->nnz * 4 * 5)); }
+        if (!arena) CK(vmalloc(h, &arena, (size_t)h->nnz * 4 * 5));
         int32_t *d_colof = (int32_t *)arena;
         uint32_t *scratch = arena + h->nnz;
         CK(vmalloc(h, &d_cnt, (size_t)(h->n + h->m) * 8));
@@ -937,6 +942,7 @@ void vbnmf_destroy(vbnmf_handle *h) {
     if (!h->borrowed) {
         vfree(h->stream, h->d_colptr); vfree(h->stream, h->d_rowidx); vfree(h->stream, h->d_val);
     }
+    vfree(h->stream, h->d_arena);
     vfree(h->stream, h->d_counters);
     vfree(h->stream, h->d_ctl);
     if (h->h_ctl) cudaFreeHost(h->h_ctl);
@@ -972,6 +978,7 @@ int vbnmf_create(vbnmf_handle **out, int64_t n, int64_t m, int64_t nnz, const in
     auto up = [&]() -> int {
         StageTimer tu("  upload (staged, pinned)");
         bool ok = true;
+        CK(vmalloc(h, &h->d_arena, (size_t)nnz * 4 * 5));
         CK(vmalloc(h, &h->d_colptr, (size_t)(m + 1) * 8));
         CK(vmalloc(h, &h->d_rowidx, (size_t)nnz * 4));
         CK(copy_sync(h, h->d_colptr, cp.data(), (size_t)(m + 1) * 8, cudaMemcpyHostToDevice));
