@@ -101,3 +101,24 @@ def test_vb_factorize_with_device_init():
     assert a.ranks == [2, 3] and np.isfinite(a.measure["lml"]).all()
     assert np.array_equal(a.measure["lml"], b.measure["lml"])      # same seeds, same draws
     assert np.array_equal(a.basis[1], b.basis[1])
+
+
+def test_graph_replay_and_plain_launches_give_the_same_run(monkeypatch):
+    """Small problems replay batches of iterations as a CUDA graph; VBNMF_NO_GRAPH=1 launches the
+    kernels one by one.  Same kernels, same arguments: bitwise identical traces."""
+    import scipy.sparse as sp
+    from ccfindr_b200 import synth
+    from ccfindr_b200.engine import Engine
+    x = sp.csc_matrix(synth.simulate_whx(nrow=300, ncol=120, rank=3, seed=9)["x"])
+    hyper = dict(aw=1.0, bw=1.0, ah=1.0, bh=1.0)
+    w0, h0 = synth.random_init(*x.shape, 4, hyper, seed=5)
+    out = []
+    for no_graph in (False, True):
+        if no_graph:
+            monkeypatch.setenv("VBNMF_NO_GRAPH", "1")
+        with Engine(x) as eng:
+            eng.set_state(w0, h0)
+            out.append(eng.run(hyper, Itmax=70, Tol=1e-7))     # 70 is not a multiple of the batch
+    assert out[0]["niter"] == out[1]["niter"] and out[0]["stop_reason"] == out[1]["stop_reason"]
+    assert np.array_equal(out[0]["lkh_trace"], out[1]["lkh_trace"])
+    assert np.array_equal(out[0]["hyper_trace"], out[1]["hyper_trace"])
