@@ -897,12 +897,21 @@ combine_kernel(int64_t NO, int nslabs, int r, const double *__restrict__ Part,
 // t always works on rank entry k = t % RS (so its be_k, log be_k and partial sums live in
 // registers) of rows t / RS, t / RS + kPostLanes, ...  Loads and stores are fully coalesced and a
 // panel of N rows exposes N * RS-way parallelism (the special functions dominate this kernel).
-constexpr int kPostRows = 96;   // rows per CTA
+constexpr int kPostRows = 96;   // rows per CTA (posterior_kernel: at most; see post_rows_per_cta)
 __host__ __device__ constexpr int post_lanes(int rs) {   // rows in flight per CTA
     return (1024 / rs) < 24 ? (1024 / rs) : 24;
 }
 __host__ __device__ constexpr int post_threads(int rs) {  // padded to whole warps
     return ((post_lanes(rs) * rs + 31) / 32) * 32;
+}
+
+// rows per CTA of posterior_kernel: kPostRows for large panels; small panels (the special
+// functions of a row cost microseconds) are spread over about two CTAs per SM
+__host__ __device__ inline int post_rows_per_cta(int64_t rows, int rs, int num_sms) {
+    const int lanes = post_lanes(rs);
+    const int64_t per = (rows + 2 * (int64_t)num_sms * lanes - 1) / (2 * (int64_t)num_sms * lanes);
+    const int64_t r = per * lanes;
+    return (int)(r < kPostRows ? (r < lanes ? lanes : r) : kPostRows);
 }
 
 template <int RP>
@@ -911,7 +920,7 @@ posterior_kernel(int64_t rows, int T, int S, int64_t nvalid, int r, double a, do
                  const double *__restrict__ osum, const double *__restrict__ SRaw,
                  double *__restrict__ l, double *__restrict__ al_out, double *__restrict__ part,
                  double *__restrict__ out, unsigned *counter, float *__restrict__ l32,
-                 const double *__restrict__ ctl, int hoff) {
+                 const double *__restrict__ ctl, int hoff, int rows_per_cta) {
     constexpr int RS = row_stride(RP);
     constexpr int kPostLanes = post_lanes(RS);
     constexpr int NT = post_threads(RS);
@@ -928,9 +937,9 @@ posterior_kernel(int64_t rows, int T, int S, int64_t nvalid, int r, double a, do
     const double be = kact ? a / b + osum[k] : 1.0;
     const double lbe = log(be), aob = a / b;
     double es = 0.0, prior = 0.0, sll = 0.0;
-    const int64_t row0 = (int64_t)blockIdx.x * kPostRows;
+    const int64_t row0 = (int64_t)blockIdx.x * rows_per_cta;
 #pragma unroll 1
-    for (int i = lane_row; i < kPostRows && lane_row < kPostLanes; i += kPostLanes) {
+    for (int i = lane_row; i < rows_per_cta && lane_row < kPostLanes; i += kPostLanes) {
         const int64_t row = row0 + i;
         if (row >= rows) break;
         const int64_t slab = row / T, local = row - slab * T;

@@ -64,9 +64,9 @@ void combine(const CombineArgs &a, cudaStream_t s) {
                                                  a.out, a.counter, a.xl_part, a.nxl, a.ctl);
 }
 void posterior(const PosteriorArgs &a, cudaStream_t s) {
-    posterior_kernel<RP><<<cdiv(a.rows, kPostRows), post_threads(RS), 0, s>>>(
+    posterior_kernel<RP><<<cdiv(a.rows, a.rows_per_cta), post_threads(RS), 0, s>>>(
         a.rows, a.T, a.S, a.nvalid, a.r, a.a, a.b, a.fud, a.osum, a.SRaw, a.l, a.al_out, a.part,
-        a.out, a.counter, a.l32, a.ctl, a.hoff);
+        a.out, a.counter, a.l32, a.ctl, a.hoff, a.rows_per_cta);
 }
 void ml_update(const MlUpdateArgs &a, cudaStream_t s) {
     ml_update_kernel<RP><<<cdiv(a.rows, kPostRows), post_threads(RS), 0, s>>>(

@@ -32,6 +32,7 @@ struct PosteriorArgs {
     float *l32;  // fp32 mirror of l (fp32-storage mode) or nullptr
     const double *ctl;  // device loop control block (hypers read from it) or nullptr
     int hoff;           // 0: (aw, bw), 2: (ah, bh)
+    int rows_per_cta;   // post_rows_per_cta(rows, rs, SMs)
 };
 
 struct MlUpdateArgs {

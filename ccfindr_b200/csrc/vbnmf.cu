@@ -653,8 +653,10 @@ int alloc_panels(H *h, int r) {
     CK(vmalloc(h, &h->d_scal, (size_t)(rs + 8) * 8));
     h->gridC = h->num_sms * 4;
     // per-CTA partial rows of the posterior / ML / column-sum kernels (the larger of the two grids)
-    const int64_t gw = std::max(cdiv(L->NG, vb::kPostRows), cdiv(L->NG, vb::kBlock));
-    const int64_t gh = std::max(cdiv(L->NC, vb::kPostRows), cdiv(L->NC, vb::kBlock));
+    const int64_t gw = std::max(cdiv(L->NG, vb::post_rows_per_cta(L->NG, rs, h->num_sms)),
+                                std::max(cdiv(L->NG, vb::kPostRows), cdiv(L->NG, vb::kBlock)));
+    const int64_t gh = std::max(cdiv(L->NC, vb::post_rows_per_cta(L->NC, rs, h->num_sms)),
+                                std::max(cdiv(L->NC, vb::kPostRows), cdiv(L->NC, vb::kBlock)));
     CK(vmalloc(h, &h->d_partW, (size_t)gw * (rs + 3) * 8));
     CK(vmalloc(h, &h->d_partH, (size_t)gh * (rs + 3) * 8));
     CK(vmalloc(h, &h->d_partC, (size_t)h->gridC * 2 * 8));
@@ -733,6 +735,7 @@ int launch_posterior(H *h, bool wside, double a, double b, double fud) {
     p.l32 = wside ? h->d_lw32 : h->d_lh32;  // nullptr in fp64 mode
     p.ctl = h->ctl;
     p.hoff = wside ? 0 : 2;
+    p.rows_per_cta = vb::post_rows_per_cta(p.rows, h->rs, h->num_sms);
     h->tab->posterior(p, h->stream);
     h->launches += 1;
     return 0;
