@@ -1,0 +1,84 @@
+"""Python restatement of the conflict-aware segment schedule of the packed-16 layout
+(ccfindr_b200/csrc/kernels_common.cuh: class_steps, plan_class, make_schedule, schedule_item).
+Test infrastructure: it documents the algorithm and lets its invariants be checked on the CPU; the
+product builds the layout on the device."""
+import numpy as np
+
+
+def class_steps(n, L, NL, mult):
+    k0 = max((n + NL - 1) // NL, (L + 1) // 2)
+    return ((k0 + mult - 1) // mult) * mult
+
+
+def plan_class(c, NL, K):
+    """(R single steps, P pair steps), R + P = K, P minimal."""
+    L = max(c)
+    P = max(0, L - K)
+    while True:
+        R = K - P
+        if sum(max(0, x - R) for x in c) <= NL * P:
+            return R, P
+        P += 1
+
+
+def res_class(rr, NL):
+    return 0 if NL == 8 else rr & 1
+
+
+def res_bucket(rr, NL):
+    return rr if NL == 8 else rr >> 1
+
+
+def make_schedule(cnt8, NL):
+    ncls, NB = (1, 8) if NL == 8 else (2, 4)
+    sc = dict(K=[0, 0], pl=[(0, 0), (0, 0)], offr=[[0] * 8, [0] * 8], cnt=[[0] * 8, [0] * 8])
+    for rr in range(8):
+        sc["cnt"][res_class(rr, NL)][res_bucket(rr, NL)] = cnt8[rr]
+    for cl in range(ncls):
+        c = sc["cnt"][cl][:NB]
+        sc["K"][cl] = class_steps(sum(c), max(c), NL, 4 if NL == 8 else 2)
+    if ncls == 2 and ((sc["K"][0] + sc["K"][1]) & 3):
+        sc["K"][1] += 2
+    for cl in range(ncls):
+        if sc["K"][cl] == 0:
+            continue
+        c = sc["cnt"][cl][:NB]
+        sc["pl"][cl] = plan_class(c, NL, sc["K"][cl])
+        acc = 0
+        for b in range(NB):
+            sc["offr"][cl][b] = acc
+            acc += max(0, c[b] - sc["pl"][cl][0])
+    return sc
+
+
+def schedule_item(sc, NL, rr, k):
+    """Item index (step * NL + lane) of the k-th nonzero whose tile row has residue rr."""
+    cl, b = res_class(rr, NL), res_bucket(rr, NL)
+    R, P = sc["pl"][cl]
+    if k < R:
+        step, lane = k, b
+    else:
+        t = sc["offr"][cl][b] + (k - R)
+        row, level = t % (2 * P), t // (2 * P)
+        step = R + row % P
+        lane = NL - 1 - level if row >= P else level
+    return ((sc["K"][0] if cl else 0) + step) * NL + lane
+
+
+def wavefronts(cnt8, NL):
+    """(steps, wavefronts per gather) of the schedule for residue counts cnt8: a step costs the
+    largest number of its rows in one residue class (at least 1: hole steps still issue)."""
+    sc = make_schedule(cnt8, NL)
+    K = sc["K"][0] + sc["K"][1]
+    mult = np.zeros((K, 8), dtype=int)
+    seen = set()
+    for rr in range(8):
+        for k in range(cnt8[rr]):
+            p = schedule_item(sc, NL, rr, k)
+            assert 0 <= p < K * NL and p not in seen
+            seen.add(p)
+            mult[p // NL, rr] += 1
+    if NL == 4:      # the four rows of a step must have equal parity
+        for s in range(K):
+            assert not (mult[s, 0::2].any() and mult[s, 1::2].any())
+    return K, int(np.maximum(mult.max(axis=1), 1).sum())

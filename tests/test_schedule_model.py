@@ -1,0 +1,56 @@
+"""Invariants of the conflict-aware segment schedule (tests/schedule_model.py restates the device
+code of ccfindr_b200/csrc/kernels_common.cuh): every nonzero gets its own slot, the steps are whole
+chunks, and the wavefront count is the optimum max(K, largest bucket) for the K steps executed."""
+import numpy as np
+import pytest
+from hypothesis import given, settings, strategies as st
+
+from schedule_model import make_schedule, wavefronts
+
+counts = st.lists(st.integers(min_value=0, max_value=90), min_size=8, max_size=8).filter(lambda c: sum(c) > 0)
+
+
+@settings(max_examples=300, deadline=None)
+@given(counts)
+def test_one_lane_per_nonzero_schedule_is_collision_free_and_optimal(cnt):
+    K, w = wavefronts(cnt, 8)
+    R, P = make_schedule(cnt, 8)["pl"][0]
+    assert K % 4 == 0 and K * 8 >= sum(cnt) and R + P == K
+    # never below the bound, never above single steps + 2-way pair steps; P is the smallest number
+    # of pair steps whose 8 P slots hold what does not fit into R single steps
+    assert max(K, max(cnt)) <= w <= R + 2 * P
+    assert P == 0 or max(cnt) > R + 2 * P - 1 or sum(max(0, c - (R + 1)) for c in cnt) > 8 * (P - 1)
+
+
+@settings(max_examples=300, deadline=None)
+@given(counts)
+def test_two_lanes_per_nonzero_schedule(cnt):
+    K, w = wavefronts(cnt, 4)
+    sc = make_schedule(cnt, 4)
+    assert K % 4 == 0 and K == sc["K"][0] + sc["K"][1]
+    even, odd = cnt[0::2], cnt[1::2]
+    lo = max(sc["K"][0], max(even)) + max(sc["K"][1], max(odd))
+    hi = sum(R + 2 * P for R, P in sc["pl"])
+    assert lo <= w <= max(hi, lo)
+
+
+@pytest.mark.parametrize("cnt", [[9, 0, 0, 0, 0, 0, 0, 0], [0, 0, 0, 0, 0, 0, 0, 1],
+                                 [83, 79, 68, 53, 74, 61, 74, 195], [48, 50, 48, 48, 52, 39, 55, 36]])
+def test_skewed_segments(cnt):
+    for NL in (8, 4):
+        K, w = wavefronts(cnt, NL)
+        assert K % 4 == 0
+
+
+def test_typical_segment_beats_round_robin():
+    """~205 nonzeros per segment (C2): the schedule needs ~1.25 wavefronts per ideal wavefront,
+    the round-robin order of the 8-byte layouts ~1.4 (bank conflicts)."""
+    rng = np.random.default_rng(0)
+    tot_w = tot_ideal = 0
+    for _ in range(400):
+        rows = rng.choice(2880, size=rng.binomial(2880, 0.072), replace=False)
+        cnt = np.bincount(rows % 8, minlength=8).tolist()
+        _, w = wavefronts(cnt, 8)
+        tot_w += w
+        tot_ideal += sum(cnt) / 8
+    assert 1.15 < tot_w / tot_ideal < 1.32
