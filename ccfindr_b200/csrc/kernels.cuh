@@ -588,7 +588,11 @@ __device__ __forceinline__ void halve_step(const double (&in)[N], double (&out)[
 // so a nonzero costs kLpBits predicated multiplies and a few integer operations instead of a
 // log (~35 instructions).  The mantissa products stay below 2^(T/8) <= 2^512 within a segment and
 // are renormalised at its end.  Counts >= 2^kLpBits take the log in an out-of-line slow path.
-constexpr int kLpBits = 3;
+#ifndef VB_LP_BITS
+#define VB_LP_BITS 3   // 4 keeps counts up to 15 in the fast path (data with heavier tails) at no
+                       // cost at r = 10 and +3 % on the cell-owner pass at r = 20 (register spills)
+#endif
+constexpr int kLpBits = VB_LP_BITS;
 struct LogProd {
     double P[kLpBits];
     int E;          // sum x e of the current segment
