@@ -4,11 +4,23 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA engine
     python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU code (rank 0)
 
-A "step" is one VB iteration (posterior update of W and H, nonzero sweep, lower bound, the
-per-iteration host readback of the loop) over the whole synthetic matrix.  Workload at N GPUs
-(weak scaling): BASELINE config 2 per GPU -- 20,000 genes x 100,000 cells per GPU, ~8 % nonzero
-10x-shaped Poisson counts (SURVEY.md 8d generator), rank 10, fp64; cells sharded over the ranks,
-one NCCL all-reduce of the W-side statistics per iteration.  One JSON line on rank 0.
+Default workload = the north-star configuration C3 under STRONG scaling: 20,000 genes x 1,300,000
+cells, ~8 % nonzero 10x-shaped Poisson counts (SURVEY.md 8d generator), rank 20, fp64, the cells
+sharded over the N ranks by (expected) nonzero count, one NCCL all-reduce of the W-side statistics
+per iteration.  It fits one B200 (2.07e9 nonzeros), so N = 1 runs the same matrix.  BASELINE
+config 2 (20k x 100k cells per GPU, rank 10, weak scaling) is measured in the same run and nested
+under "secondary".
+
+A "step" is one VB iteration of the product loop (vbnmf_run's device-controlled loop): posterior
+update of W and H, the two passes of the nonzero sweep, the all-reduce, the lower bound and
+hyper_update + stop rules in the control kernel; the host reads the control block back once per 8
+iterations.  Timed iterations run with hyper_update after every iteration (the loop's steady state
+past hyper.update.n0 = 10, R/bayesian.R:342); the untimed warm-up holds the hypers fixed.
+
+The line also carries: `e2e` (host CSC -> vbnmf_create -> set_state -> vbnmf_run(K) -> get_state,
+cold and warm pass), `parity` (the same matrix through oracle/oracle_sparse.c on the host cores:
+per-iteration bound, factors, cluster ids; at N > 1 the sharded bound against a single-GPU run of
+the whole matrix), `cpu_baseline`, `roofline` and the fp32-storage mode.  One JSON line on rank 0.
 """
 import argparse
 import json
@@ -27,18 +39,22 @@ if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
     del os.environ["NCCL_DEBUG"]  # keeps NCCL's banner off stdout (one JSON line is the contract)
 
 WORKLOADS = {
-    # name: genes, cells per GPU, true rank, density, seed, fit rank
+    # name: genes, cells (per GPU = weak scaling, total = strong), true rank, density, seed, fit rank
     "c2": dict(n=20000, m_per_gpu=100000, r_true=10, density=0.08, seed=2, rank=10,
                label="C2: vb_factorize rank=10, 20k genes x 100k cells per GPU, ~8% nonzero"),
-    "c3": dict(n=20000, m_per_gpu=None, m_total=1300000, r_true=20, density=0.08, seed=3, rank=20,
-               label="C3: vb_factorize rank=20, 20k genes x 1.3M cells sharded over the GPUs"),
+    "c3": dict(n=20000, m_total=1300000, r_true=20, density=0.08, seed=3, rank=20,
+               label="C3: vb_factorize rank=20, 20k genes x 1.3M cells, ~8% nonzero, cells "
+                     "sharded over the GPUs (strong scaling)"),
     "small": dict(n=2000, m_per_gpu=8000, r_true=5, density=0.08, seed=4, rank=6,
                   label="small: plumbing check, 2k genes x 8k cells per GPU"),
+    "smallstrong": dict(n=2000, m_total=32000, r_true=5, density=0.08, seed=4, rank=6,
+                        label="smallstrong: plumbing check, 2k genes x 32k cells sharded"),
 }
 HYPER = dict(aw=1.0, bw=1.0, ah=1.0, bh=1.0)  # gamma.a = gamma.b = 1 (R/bayesian.R:231)
-MIXED = {}  # filled by run_ours: the fp32-storage mode measured beside the fp64 headline
+N0 = 10                                        # hyper.update.n0 (R/bayesian.R:233)
 METRIC = "VB-NMF nnz*rank updates/s per iteration"
 UNIT = "nnz*rank updates/s"
+SM_COUNT, SMEM_BYTES_PER_CLK = 148, 128        # shared-memory pipe: 128 B/clk/SM
 
 
 def peaks():
@@ -54,10 +70,27 @@ def algorithmic_bytes(nnz, n, m, r, sp=8):
     return nnz * 8 + 8 * (m + 1) + 2 * r * m * sp + 2 * n * r * sp
 
 
+def measured_traffic(name):
+    """dram bytes of the two sweep launches from the last `ncu --set full` capture
+    (profiles/traffic.json, written by profiles/ncu_traffic.py).  The file is stamped with the
+    hash of the kernel sources it was captured for; a stale stamp returns None."""
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(tp):
+        return None, "no capture"
+    t = json.load(open(tp))
+    try:
+        from ccfindr_b200 import build as vb_build
+        if t.get("source_hash") != vb_build.kernel_hash():
+            return None, "stale: profiles/traffic.json was captured for other kernel sources"
+    except Exception as e:  # pragma: no cover
+        return None, "cannot verify: %s" % e
+    return t.get(name), t.get("note")
+
+
 class ClockSampler:
     """SM clock and throttle reasons sampled DURING the timed region: an NVML polling thread
-    (nvidia_ml_py, one sample per millisecond -- the timed region of the default run is ~40 ms);
-    falls back to an `nvidia-smi -lms` subprocess when NVML cannot be loaded."""
+    (nvidia_ml_py, one sample per millisecond); falls back to an `nvidia-smi -lms` subprocess when
+    NVML cannot be loaded."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -157,14 +190,39 @@ def env_rank():
             int(os.environ.get("WORLD_SIZE", 1)))
 
 
-def shard_bounds(m_total, nranks, chunk):
-    """Contiguous cell ranges in whole generator chunks, as even as possible."""
-    nch = -(-m_total // chunk)
-    base, extra = divmod(nch, nranks)
-    b = [0]
-    for r in range(nranks):
-        b.append(min(m_total, b[-1] + (base + (1 if r < extra else 0)) * chunk))
-    return b
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def restore_omp_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU arms use all host cores."""
+    from oracle import bindings as ob
+    n = host_cores()
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    ob.set_omp_threads(n)
+    return n
+
+
+def shard_plan(wl, m_total, world, dev):
+    """Contiguous cell ranges in whole generator chunks with (nearly) equal EXPECTED numbers of
+    nonzeros (nnz-balanced), the same on every rank."""
+    from ccfindr_b200 import sharding, synth
+    nch = -(-m_total // synth.TENX_CHUNK)
+    if world == 1:
+        return [0, m_total], "single shard"
+    exp_nnz = synth.tenx_expected_nnz(wl["n"], m_total, wl["r_true"], wl["density"], wl["seed"], dev)
+    pseudo = np.concatenate([[0.0], np.cumsum(exp_nnz)])
+    cb = sharding.balanced_bounds(pseudo, world)
+    for i in range(1, world):           # every rank gets at least one chunk
+        cb[i] = max(cb[i], cb[i - 1] + 1)
+    for i in range(world - 1, 0, -1):
+        cb[i] = min(cb[i], cb[i + 1] - 1)
+    assert cb[0] == 0 and cb[-1] == nch and all(cb[i] < cb[i + 1] for i in range(world))
+    return [min(m_total, c * synth.TENX_CHUNK) for c in cb], \
+        "nnz-balanced (expected nonzeros per %d-cell generator chunk)" % synth.TENX_CHUNK
 
 
 def init_factors(n, m_total, rank, seed):
@@ -172,16 +230,301 @@ def init_factors(n, m_total, rank, seed):
     return synth.random_init(n, m_total, rank, HYPER, seed)  # vb_init 'random'
 
 
+def relerr(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)))
+
+
 # ------------------------------------------------------------------------------------------------
-def run_ours(args):
+def gpu_parity_run(eng, w0, h0_loc, iters, precision):
+    """`iters` iterations of the product loop from (w0, h0) on the engine: bound per iteration,
+    ew, eh and the cluster ids of the local cells."""
+    eng.set_precision(precision)
+    eng.set_state(w0, h0_loc)
+    out = eng.run(HYPER, Itmax=iters, Tol=0.0)   # Tol = 0 never converges: exactly `iters`
+    st = eng.get_state(("ew", "eh"))
+    return dict(lkh=out["lkh_trace"], ew=st["ew"], eh=st["eh"], cid=eng.cluster_id())
+
+
+def oracle_parity(n, m, colptr, rowidx, values, w0, h0, iters, gpu64, gpu32):
+    """The same matrix and start through oracle/oracle_sparse.c (fp64, OpenMP) on the host."""
+    from oracle import bindings as ob
+    from oracle import oracle_dense as od
+    threads = restore_omp_threads()
+    t0 = time.time()
+    ref = ob.sparse_vb_run((n, m, colptr, rowidx, values), w0, h0, HYPER, Itmax=iters, Tol=0.0)
+    sec = time.time() - t0
+    cid = od.cluster_id(ref["eh"])
+    blk = {"oracle": "oracle/oracle_sparse.c (fp64, OpenMP, %d threads) on the WHOLE matrix "
+                     "(%d cells, %d nonzeros), %d iterations from the same w0, h0"
+                     % (threads, m, len(rowidx), iters),
+           "iterations": iters, "oracle_seconds": round(sec, 2),
+           "lkh_oracle": [float(v) for v in ref["lkh_trace"]]}
+    for key, g in (("fp64", gpu64), ("fp32_storage", gpu32)):
+        if g is None:
+            continue
+        blk[key] = {"lkh": [float(v) for v in g["lkh"]],
+                    "lkh_rel_err": [abs(a - b) / abs(b) for a, b in zip(g["lkh"], ref["lkh_trace"])],
+                    "ew_max_rel_err": relerr(g["ew"], ref["ew"]),
+                    "eh_max_rel_err": relerr(g["eh"], ref["eh"]),
+                    "cid_mismatches": int(np.count_nonzero(g["cid"] != cid)), "cells": int(m)}
+    blk["lkh_rel_err"] = max(blk["fp64"]["lkh_rel_err"])
+    blk["cid_mismatches"] = blk["fp64"]["cid_mismatches"]
+    blk["tolerance"] = {"fp64": 1e-9, "fp32_storage": 1e-4}
+    cpu = {"value": len(rowidx) * w0.shape[1] / (sec / (iters + 1)), "unit": UNIT, "cores": threads,
+           "kind": "port",
+           "sample": "whole matrix (%d nonzeros): statistics pass + %d iterations of "
+                     "oracle_sparse.c (CSC, OpenMP, fp64), %.1f s" % (len(rowidx), iters, sec),
+           "seconds_per_iteration": sec / (iters + 1)}
+    return blk, cpu
+
+
+def cpu_baseline_port(n, r, colptr, rowidx, values, w0, h0, max_cols=24000, iters=2):
+    """oracle/oracle_sparse.c (OpenMP, all host threads) on the first max_cols cells."""
+    from oracle import bindings as ob
+    restore_omp_threads()
+    mc = min(max_cols, len(colptr) - 1)
+    end = int(colptr[mc])
+    arrays = (n, mc, np.ascontiguousarray(colptr[:mc + 1], dtype=np.int64),
+              np.ascontiguousarray(rowidx[:end], dtype=np.int32),
+              np.ascontiguousarray(values[:end], dtype=np.float64))
+    hy = np.array([HYPER[k] for k in ("aw", "bw", "ah", "bh")])
+    sec, lkh, threads = ob.sparse_time_iterations(arrays, w0, h0[:, :mc], hy,
+                                                  np.finfo(np.float64).eps, iters)
+    return {"value": end * r / sec, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "first %d cells (%d nnz) of rank 0's shard, %d iterations of "
+                      "oracle_sparse.c (CSC, OpenMP, fp64)" % (mc, end, iters),
+            "seconds_per_iteration": sec}
+
+
+def run_config(args, name, ctx):
+    """One workload through every leg.  Returns the record (rank 0) or None."""
     import torch
     import torch.distributed as dist
     from ccfindr_b200 import synth
-    from ccfindr_b200.engine import Comm, Engine
+    from ccfindr_b200.engine import Engine
+    rank, local_rank, world, dev, comm = ctx
+    wl = WORKLOADS[name]
+    n, r = wl["n"], wl["rank"]
+    strong = "m_total" in wl
+    m_total = wl["m_total"] if strong else wl["m_per_gpu"] * world
+    bounds, shard_how = shard_plan(wl, m_total, world, dev)
+    c0, c1 = bounds[rank], bounds[rank + 1]
+    t_gen = time.time()
+    colptr, rowidx, values, scale = synth.tenx_like_device(n, m_total, wl["r_true"], wl["density"],
+                                                           wl["seed"], dev, c0, c1)
+    torch.cuda.synchronize()
+    t_gen = time.time() - t_gen
+    m_loc, nnz_loc = c1 - c0, int(rowidx.numel())
+    w0, h0 = init_factors(n, m_total, r, seed=1000 * r + 1)
+    h0_loc = np.asfortranarray(h0[:, c0:c1])
+    P = args.parity_iters
+
+    def allmax(vals):
+        t = torch.tensor(vals, dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t.tolist()]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm: inputs already in HBM when the timed region starts --------------
+    eng = Engine.from_device_csc(n, m_loc, nnz_loc, colptr, rowidx, values, device=local_rank)
+    if comm is not None:
+        eng.attach_comm(comm)
+    nnz_t = torch.tensor([float(nnz_loc)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(nnz_t)
+    nnz_total = int(nnz_t.item())
+
+    def timed(precision, sample_clocks):
+        eng.set_precision(precision)
+        eng.set_state(w0, h0_loc)
+        # untimed: hyper.update.n0 iterations with fixed hypers (at least the requested warm-up)
+        eng.bench_iterations(HYPER, max(args.warmup, N0), hyper_on=False)
+        sampler = ClockSampler(local_rank) if (sample_clocks and rank == 0) else None
+        barrier()
+        if sampler:
+            sampler.start()
+        t0 = time.time()
+        res = eng.bench_iterations(HYPER, args.steps, hyper_on=True)   # EXACTLY K iterations
+        torch.cuda.synchronize()
+        wall = (time.time() - t0) * 1e3
+        barrier()
+        clocks = sampler.stop() if sampler else None
+        tot, tc, tr, wall = allmax([res["ms_total"], res["ms_cols"], res["ms_rows"], wall])
+        return dict(res=res, ms_step=tot / args.steps, ms_cols=tc / args.steps,
+                    ms_rows=tr / args.steps, wall_ms=wall / args.steps, clocks=clocks)
+
+    t64 = timed(0, True)
+    layout = eng.layout_info()
+    value = nnz_total * r / (t64["ms_step"] * 1e-3)
+    gp64 = gpu_parity_run(eng, w0, h0_loc, P, 0) if P else None
+    t32 = timed(1, False)
+    layout32 = eng.layout_info()
+    gp32 = gpu_parity_run(eng, w0, h0_loc, P, 1) if P else None
+    eng.set_precision(0)
+    peak, peak_src = peaks()
+    b32 = algorithmic_bytes(nnz_loc, n, m_loc, r, sp=4)
+    mixed = {"value": nnz_total * r / (t32["ms_step"] * 1e-3), "unit": UNIT,
+             "ms_per_step": t32["ms_step"],
+             "ms_per_launch": {"sweep_cols": t32["ms_cols"], "sweep_rows": t32["ms_rows"]},
+             "roofline_frac": b32 / ((t32["ms_cols"] + t32["ms_rows"]) * 1e-3) / 1e9 / peak,
+             "algorithmic_bytes_per_launch": b32, "lkh_last": t32["res"]["lkh"],
+             "tile_rows": layout32["tile_rows"],
+             "what": "panels lw/lh held in fp32, per-nonzero arithmetic fp32, every sum over "
+                     "lanes/slabs/ranks and the posterior update in fp64 (tolerance 1e-4)"}
+    eng.close()
+
+    # ---- end-to-end arm: HOST buffers through the C ABI, copies inside the timed region ---------
+    e2e = parity = cpu = None
+    h_colptr = h_rowidx = h_values = None
+    if not args.no_e2e or (P and world == 1):
+        h_colptr = colptr.cpu().numpy()
+        h_rowidx = rowidx.cpu().numpy()
+        h_values = values.double().cpu().numpy()                  # dgCMatrix @x is double
+    del colptr, rowidx, values
+    torch.cuda.empty_cache()
+    if not args.no_e2e:
+        import scipy.sparse as sp
+        csc = sp.csc_matrix((h_values, h_rowidx, h_colptr), shape=(n, m_loc))
+        csc.has_sorted_indices = True                             # generator output is sorted
+
+        def e2e_pass():
+            barrier()
+            t0 = time.time()
+            eng2 = Engine(csc, device=local_rank)                 # H2D of X + device layouts
+            if comm is not None:
+                eng2.attach_comm(comm)
+            eng2.set_state(w0, h0_loc)                            # H2D of the initial factors
+            # Tol = 0 never satisfies |1 - lkh/lk0| < Tol: exactly K iterations of the reference's
+            # own loop (hyper updates from iteration 11 on, R/bayesian.R:342)
+            out = eng2.run(HYPER, Itmax=args.steps, Tol=0.0)
+            st = eng2.get_state(("ew", "eh"))                     # D2H of the result
+            torch.cuda.synchronize()
+            sec = time.time() - t0
+            assert out["niter"] == args.steps and np.isfinite(st["ew"]).all()
+            d2h = st["ew"].nbytes + st["eh"].nbytes + 5 * 8 * args.steps
+            eng2.close()
+            return allmax([sec])[0], d2h, out
+
+        cold_s, _, _ = e2e_pass()   # pays pinned-buffer creation and first-touch of the memory pool
+        warm_s, d2h, out = e2e_pass()
+        h2d = (h_values.nbytes + h_rowidx.nbytes + h_colptr.nbytes + w0.nbytes + h0_loc.nbytes)
+        e2e = {"value": nnz_total * r * args.steps / warm_s, "unit": UNIT,
+               "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
+               "seconds": warm_s, "seconds_cold": cold_s, "iterations": args.steps,
+               "value_cold": nnz_total * r * args.steps / cold_s,
+               "host_threads": max(1, host_cores() // world),
+               "lkh_first": [float(v) for v in out["lkh_trace"][:3]],
+               "what": "vbnmf_create(host CSC: fp64 values, int32 indices) + set_state + "
+                       "vbnmf_run(K, reference loop defaults) + get_state(ew, eh), max over ranks; "
+                       "`seconds` = second (warm) of two identical passes, `seconds_cold` = the "
+                       "first, which also creates the pinned staging buffers and maps the device "
+                       "memory pool"}
+        del csc
+
+    # ---- parity ------------------------------------------------------------------------------
+    if P and world == 1 and not args.no_parity:
+        parity, cpu = oracle_parity(n, m_loc, h_colptr, h_rowidx, h_values, w0, h0_loc, P, gp64, gp32)
+    elif P and world > 1 and not args.no_parity:
+        # sharded bound against ONE GPU holding the whole matrix (rank 0), same start
+        parity = {"iterations": P, "lkh_sharded": [float(v) for v in gp64["lkh"]]}
+        if rank == 0 and strong and nnz_total < 3.5e9:
+            fc, fr, fv, _ = synth.tenx_like_device(n, m_total, wl["r_true"], wl["density"],
+                                                   wl["seed"], dev, 0, m_total)
+            e1 = Engine.from_device_csc(n, m_total, int(fr.numel()), fc, fr, fv, device=local_rank)
+            one = gpu_parity_run(e1, w0, np.asfortranarray(h0), P, 0)
+            e1.close()
+            del fc, fr, fv
+            torch.cuda.empty_cache()
+            parity.update({
+                "lkh_single_gpu": [float(v) for v in one["lkh"]],
+                "lkh_rel_err_vs_single_gpu": [abs(a - b) / abs(b)
+                                              for a, b in zip(gp64["lkh"], one["lkh"])],
+                "ew_max_rel_err_vs_single_gpu": relerr(gp64["ew"], one["ew"]),
+                "eh_max_rel_err_vs_single_gpu": relerr(gp64["eh"], one["eh"][:, c0:c1]),
+                "cid_mismatches_vs_single_gpu": int(np.count_nonzero(gp64["cid"] !=
+                                                                     one["cid"][c0:c1])),
+                "what": "the %d-rank sharded run against a single-GPU run of the whole matrix on "
+                        "rank 0 (same w0, h0); the single-GPU path is checked against the CPU "
+                        "oracle in the N = 1 line" % world})
+            parity["lkh_rel_err"] = max(parity["lkh_rel_err_vs_single_gpu"])
+            parity["cid_mismatches"] = parity["cid_mismatches_vs_single_gpu"]
+        barrier()
+    if cpu is None and rank == 0 and not args.no_cpu and h_colptr is not None:
+        cpu = cpu_baseline_port(n, r, h_colptr, h_rowidx, h_values, w0, h0_loc)
+    barrier()
+    if rank != 0:
+        return None
+
+    b_alg = algorithmic_bytes(nnz_loc, n, m_loc, r)
+    t_sweep = (t64["ms_cols"] + t64["ms_rows"]) * 1e-3
+    ach = b_alg / t_sweep / 1e9
+    traffic, traffic_note = measured_traffic(name)
+    clk = (t64["clocks"] or {}).get("sm_mhz") or 1965.0
+    smem_peak = SM_COUNT * SMEM_BYTES_PER_CLK * clk * 1e6 / 1e9          # GB/s at the sampled clock
+    smem_ach = 2.0 * nnz_loc * r * 8 / t_sweep / 1e9
+    p16 = layout["format"] == "p16"
+    kname = "sweep_p16_kernel" if p16 else "sweep_tiled_kernel"
+    return {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t64["ms_step"], "higher_is_better": True,
+        "scaling": "strong" if strong else "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["label"], "genes": n, "cells_total": m_total,
+                   "nnz_total": nnz_total, "rank": r, "precision": "fp64",
+                   "sharding": "cells over %d GPU(s), %s; 1 all-reduce/iter" % (world, shard_how),
+                   "shard_cells_rank0": m_loc, "shard_nnz_rank0": nnz_loc,
+                   "loop": "device-controlled product loop; %d untimed iterations with fixed "
+                           "hyper-parameters (hyper.update.n0), then K timed iterations with "
+                           "hyper_update after each; one control readback per 8 iterations"
+                           % max(args.warmup, N0),
+                   "l2": "inputs larger than L2 (two tiled copies of X, %.2f GB per GPU vs 126 MB)"
+                         % (layout["bytes"] / 1e9),
+                   "layout": layout, "generator_scale": scale, "gen_seconds": round(t_gen, 2)},
+        "clocks": t64["clocks"],
+        "e2e": e2e,
+        "gpu_launches": int(t64["res"]["launches"]),
+        "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                     "frac": ach / peak, "traffic": traffic, "traffic_note": traffic_note,
+                     "kernel": "%s<COLS=1> + %s<COLS=0> (the two passes of the nonzero sweep, "
+                               "incl. their combine kernels)" % (kname, kname),
+                     "algorithmic_bytes_per_launch": b_alg,
+                     "ms_per_launch": {"sweep_cols": t64["ms_cols"], "sweep_rows": t64["ms_rows"]},
+                     "iteration_frac": b_alg / (t64["ms_step"] * 1e-3) / 1e9 / peak,
+                     "secondary": {"bound": "smem", "achieved": smem_ach, "peak": smem_peak,
+                                   "unit": "GB/s", "frac": smem_ach / smem_peak,
+                                   "what": "rank-r fp64 rows gathered from shared memory: 2 passes x "
+                                           "nnz x r x 8 B against 148 SMs x 128 B/clk at the "
+                                           "sampled SM clock (the pipe that limits this "
+                                           "formulation, DESIGN.md section 5)"},
+                     "limiter": "shared-memory gather wavefronts (LSU data pipe), not HBM "
+                                "(DESIGN.md section 5)",
+                     "peak_source": peak_src},
+        "cpu_baseline": cpu,
+        "parity": parity,
+        "fp32_storage_mode": mixed,
+        "wall_ms_per_step": t64["wall_ms"],
+        "lkh_last": t64["res"]["lkh"],
+        "hyper_last": t64["res"]["hyper"],
+    }
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from ccfindr_b200.engine import Comm, Engine, set_host_threads
 
     rank, local_rank, world = env_rank()
     if args.gpus != world and world > 1:
         raise SystemExit("--gpus must equal WORLD_SIZE under torchrun")
+    if args.workload.startswith("small"):   # plumbing matrices: a 2,000-gene matrix has empty genes
+        os.environ.setdefault("VBNMF_ALLOW_EMPTY", "1")
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -193,208 +536,21 @@ def run_ours(args):
             uid = torch.tensor(list(Engine.nccl_unique_id()), dtype=torch.uint8, device=dev)
         dist.broadcast(uid, 0)
         comm = Comm(world, rank, bytes(uid.cpu().tolist()), device=local_rank)
-
-    wl = WORKLOADS[args.workload]
-    n, r = wl["n"], wl["rank"]
-    m_total = wl["m_per_gpu"] * world if wl.get("m_per_gpu") else wl["m_total"]
-    bounds = shard_bounds(m_total, world, synth.TENX_CHUNK)
-    c0, c1 = bounds[rank], bounds[rank + 1]
-    t_gen = time.time()
-    colptr, rowidx, values, scale = synth.tenx_like_device(n, m_total, wl["r_true"], wl["density"],
-                                                           wl["seed"], dev, c0, c1)
-    torch.cuda.synchronize()
-    t_gen = time.time() - t_gen
-    m_loc, nnz_loc = c1 - c0, int(rowidx.numel())
-    w0, h0 = init_factors(n, m_total, r, seed=1000 * r + 1)
-    h0_loc = np.asfortranarray(h0[:, c0:c1])
-
-    # ---- device-resident arm: inputs already in HBM when the timed region starts --------------
-    eng = Engine.from_device_csc(n, m_loc, nnz_loc, colptr, rowidx, values, device=local_rank)
-    if comm is not None:
-        eng.attach_comm(comm)
-    eng.set_state(w0, h0_loc)
-    eng.bench_iterations(HYPER, max(args.warmup, 1))          # warm-up (untimed)
-    nnz_t = torch.tensor([float(nnz_loc)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(nnz_t)
-    nnz_total = int(nnz_t.item())
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    if sampler:
-        sampler.start()
-    t0 = time.time()
-    res = eng.bench_iterations(HYPER, args.steps)             # EXACTLY K iterations, CUDA events
-    res["layout"] = eng.layout_info()
-    torch.cuda.synchronize()
-    wall_ms = (time.time() - t0) * 1e3
-    if world > 1:
-        dist.barrier()
-    clocks = sampler.stop() if sampler else None
-    tms = torch.tensor([res["ms_total"], res["ms_cols"], res["ms_rows"], wall_ms],
-                       dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms_total, ms_cols, ms_rows, wall_ms = [float(v) for v in tms.tolist()]
-    ms_step = ms_total / args.steps
-    value = nnz_total * r / (ms_step * 1e-3)
-    lkh_dev = res["lkh"]
-
-    # ---- same measurement in the fp32-storage / fp64-accumulate mode (reported beside fp64) -----
-    eng.set_precision(1)
-    eng.set_state(w0, h0_loc)
-    eng.bench_iterations(HYPER, max(args.warmup, 1))
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    r32 = eng.bench_iterations(HYPER, args.steps)
-    torch.cuda.synchronize()
-    t32 = torch.tensor([r32["ms_total"], r32["ms_cols"], r32["ms_rows"]], dtype=torch.float64,
-                       device=dev)
-    if world > 1:
-        dist.all_reduce(t32, op=dist.ReduceOp.MAX)
-    t32 = [float(v) / args.steps for v in t32.tolist()]
-    b32 = algorithmic_bytes(nnz_loc, n, m_loc, r, sp=4)
-    MIXED.update({"value": nnz_total * r / (t32[0] * 1e-3), "unit": UNIT, "ms_per_step": t32[0],
-                  "ms_per_launch": {"sweep_cols": t32[1], "sweep_rows": t32[2]},
-                  "roofline_frac": b32 / ((t32[1] + t32[2]) * 1e-3) / 1e9 / peaks()[0],
-                  "algorithmic_bytes_per_launch": b32, "lkh_last": r32["lkh"],
-                  "rel_diff_lkh_vs_fp64_same_iteration_count": abs(r32["lkh"] - lkh_dev) / abs(lkh_dev),
-                  "what": "panels lw/lh held in fp32, per-nonzero arithmetic fp32, every sum over "
-                          "lanes/slabs/ranks and the posterior update in fp64 (tolerance 1e-4)"})
-    eng.set_precision(0)
-
-    if args.no_e2e:
-        if rank == 0:
-            emit_line(args, wl, world, n, r, m_total, m_loc, nnz_loc, nnz_total, scale, t_gen,
-                      value, ms_step, ms_cols, ms_rows, wall_ms, clocks, res, None, None, lkh_dev)
-        if world > 1:
-            dist.barrier()
-            comm.close()
-            dist.destroy_process_group()
-        return
-    # ---- end-to-end arm: HOST buffers through the C ABI, copies inside the timed region ---------
-    h_colptr = colptr.cpu().numpy()
-    h_rowidx = rowidx.cpu().numpy()
-    h_values = values.cpu().numpy().astype(np.float64)        # dgCMatrix @x is double
-    eng.close()
-    del colptr, rowidx, values
-    torch.cuda.empty_cache()
-    import scipy.sparse as sp
-    csc = sp.csc_matrix((h_values, h_rowidx, h_colptr), shape=(n, m_loc))
-    def e2e_pass():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        t0 = time.time()
-        eng2 = Engine(csc, device=local_rank)                  # H2D of X + device layouts
-        if comm is not None:
-            eng2.attach_comm(comm)
-        eng2.set_state(w0, h0_loc)                             # H2D of the initial factors
-        # Tol = 0 never satisfies |1 - lkh/lk0| < Tol: exactly K iterations with the reference's
-        # own loop (hyper updates from iteration 11 on, R/bayesian.R:342)
-        out = eng2.run(HYPER, Itmax=args.steps, Tol=0.0)
-        st = eng2.get_state(("ew", "eh"))                      # D2H of the result
-        torch.cuda.synchronize()
-        return time.time() - t0, eng2, out, st
-
-    # one untimed pass first (pinned staging buffers, memory pool, page cache of the host arrays),
-    # except for the workloads whose upload alone takes seconds
-    if nnz_loc < 5e8:
-        _, eng_w, _, _ = e2e_pass()
-        eng_w.close()
-    e2e_s, eng2, out, st = e2e_pass()
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_s = float(te.item())
-    assert out["niter"] == args.steps and np.isfinite(st["ew"]).all()
-    h2d = (h_values.nbytes + h_rowidx.nbytes + h_colptr.nbytes + w0.nbytes + h0_loc.nbytes)
-    d2h = st["ew"].nbytes + st["eh"].nbytes + 5 * 8 * args.steps
-    e2e_value = nnz_total * r * args.steps / e2e_s
-    eng2.close()
-
-    # ---- CPU baseline on rank 0 (bounded sample of the same workload) -------------------------
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        cpu = cpu_baseline_port(n, r, h_colptr, h_rowidx, h_values, w0, h0_loc)
-
+    # the ranks of one box share its cores: staging threads = cores / ranks
+    set_host_threads(max(1, min(16, host_cores() // world)))
+    ctx = (rank, local_rank, world, dev, comm)
+    line = run_config(args, args.workload, ctx)
+    sec = None
+    if args.secondary != "none" and args.secondary != args.workload:
+        sec = run_config(args, args.secondary, ctx)
     if rank == 0:
-        e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps,
-               "d2h_bytes_per_step": d2h / args.steps, "seconds": e2e_s, "iterations": args.steps,
-               "what": "vbnmf_create(host CSC) + set_state + vbnmf_run(K) + get_state(ew, eh); "
-                       "second of two identical passes (the first is the warm-up)"}
-        emit_line(args, wl, world, n, r, m_total, m_loc, nnz_loc, nnz_total, scale, t_gen, value,
-                  ms_step, ms_cols, ms_rows, wall_ms, clocks, res, e2e, cpu, lkh_dev)
+        if sec is not None:
+            line["secondary"] = sec
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
-        if comm is not None:
-            comm.close()
+        comm.close()
         dist.destroy_process_group()
-
-
-def emit_line(args, wl, world, n, r, m_total, m_loc, nnz_loc, nnz_total, scale, t_gen, value,
-              ms_step, ms_cols, ms_rows, wall_ms, clocks, res, e2e, cpu, lkh_dev):
-    peak, peak_src = peaks()
-    b_alg_local = algorithmic_bytes(nnz_loc, n, m_loc, r)
-    t_sweep = (ms_cols + ms_rows) / args.steps * 1e-3
-    ach = b_alg_local / t_sweep / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
-        traffic = json.load(open(tp)).get(args.workload)
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-        "scaling": "weak" if wl.get("m_per_gpu") else "strong", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl["label"], "genes": n, "cells_total": m_total,
-                   "nnz_total": nnz_total, "rank": r, "precision": "fp64",
-                   "sharding": "cells over %d GPU(s), 1 all-reduce/iter" % world,
-                   "l2": "inputs larger than L2 (two tiled copies of X, %.2f GB per GPU vs 126 MB)"
-                         % (res["layout"]["bytes"] / 1e9),
-                   "layout": res["layout"],
-                   "generator_scale": scale, "gen_seconds": round(t_gen, 2)},
-        "clocks": clocks,
-        "e2e": e2e,
-        "gpu_launches": int(res["launches"]),
-        "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                     "frac": ach / peak, "traffic": traffic,
-                     "kernel": "%s<COLS=1> + %s<COLS=0> (the two passes of the nonzero sweep, "
-                               "incl. their combine kernels)"
-                               % (("sweep_p16_kernel",) * 2 if res["layout"]["format"] == "p16"
-                                  else ("sweep_tiled_kernel",) * 2),
-                     "algorithmic_bytes_per_launch": b_alg_local,
-                     "ms_per_launch": {"sweep_cols": ms_cols / args.steps,
-                                       "sweep_rows": ms_rows / args.steps},
-                     "iteration_frac": b_alg_local / (ms_step * 1e-3) / 1e9 / peak,
-                     "limiter": "shared-memory gather wavefronts (LSU data pipe ~90% busy in the "
-                                "gene-owner pass), not HBM (DESIGN.md section 5)",
-                     "peak_source": peak_src},
-        "cpu_baseline": cpu,
-        "fp32_storage_mode": MIXED or None,
-        "wall_ms_per_step": wall_ms / args.steps,
-        "lkh_last": lkh_dev,
-    }
-    print(json.dumps(line), flush=True)
-
-
-def cpu_baseline_port(n, r, colptr, rowidx, values, w0, h0, max_cols=24000, iters=2):
-    """oracle/oracle_sparse.c (OpenMP, all host threads) on the first max_cols cells."""
-    from oracle import bindings as ob
-    mc = min(max_cols, len(colptr) - 1)
-    end = int(colptr[mc])
-    arrays = (n, mc, np.ascontiguousarray(colptr[:mc + 1], dtype=np.int64),
-              np.ascontiguousarray(rowidx[:end], dtype=np.int32),
-              np.ascontiguousarray(values[:end], dtype=np.float64))
-    hy = np.array([HYPER[k] for k in ("aw", "bw", "ah", "bh")])
-    sec, lkh, threads = ob.sparse_time_iterations(arrays, w0, h0[:, :mc], hy,
-                                                  np.finfo(np.float64).eps, iters)
-    return {"value": end * r / sec, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": "first %d cells (%d nnz) of the same matrix, %d iterations of "
-                      "oracle_sparse.c (CSC, OpenMP, fp64)" % (mc, end, iters),
-            "seconds_per_iteration": sec}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -407,9 +563,10 @@ def run_reference(args):
     import torch
     from ccfindr_b200 import synth
     from oracle import bindings as ob
+    cores = restore_omp_threads()
     wl = WORKLOADS[args.workload]
     n, r = wl["n"], wl["rank"]
-    m_total = wl["m_per_gpu"] * max(world, args.gpus) if wl.get("m_per_gpu") else wl["m_total"]
+    m_total = wl["m_total"] if "m_total" in wl else wl["m_per_gpu"] * max(world, args.gpus)
     ms = min(args.ref_cells, synth.TENX_CHUNK, m_total)
     # first generator chunk of the same matrix (sampled on the CPU here), first ms cells
     colptr, rowidx, values, _ = synth.tenx_like_device(n, m_total, wl["r_true"], wl["density"],
@@ -424,13 +581,13 @@ def run_reference(args):
     have_ref = ob.ref_lib() is not None
     if have_ref:
         X = np.asfortranarray(csc.toarray())
-        kind, cores = "reference", ob.sparse_lib().osp_num_threads()
+        kind = "reference"
         wh = dict(lw=w0, lh=h0, ew=w0, eh=h0)
         step = lambda wh: ob.ref_vbnmf_update(X, wh, HYPER, np.finfo(np.float64).eps)
         what = ("src/vbnmf_update.cpp compiled in place (oracle/_ref; stand-in Eigen/Rcpp/GSL "
                 "headers, GEMM loops OpenMP-parallel, the rest serial as in the reference)")
     else:
-        kind, cores = "port", ob.sparse_lib().osp_num_threads()
+        kind = "port"
         wh = dict(lw=w0, lh=h0, ew=w0, eh=h0)
         step = lambda wh: ob.sparse_vb_step(csc, wh, HYPER, np.finfo(np.float64).eps)
         what = "oracle_sparse.c osp_vb_step (oracle/_ref not available)"
@@ -445,13 +602,15 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
         "n_gpus": max(world, args.gpus), "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": sec * 1e3, "higher_is_better": True,
-        "scaling": "weak" if wl.get("m_per_gpu") else "strong", "vs_baseline": None,
+        "scaling": "strong" if "m_total" in wl else "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": wl["label"], "genes": n, "cells_total": m_total, "rank": r,
                    "precision": "fp64"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
                          "sample": "dense slab: first %d cells (%d nnz) of the same matrix per "
-                                   "step; %s" % (ms, end, what)},
+                                   "step (the reference densifies X, R/bayesian.R:339; the whole "
+                                   "matrix would need %.0f GB per n x m temporary); %s"
+                                   % (ms, end, n * m_total * 8 / 1e9, what)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "lkh_last": float(wh["lkh"]),
     }
@@ -461,15 +620,22 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--secondary", default=None,
+                    help="second workload nested under 'secondary' (default: c2 beside c3; 'none')")
+    ap.add_argument("--parity-iters", type=int, default=3,
+                    help="iterations compared with the CPU oracle (0: skip the parity block)")
     ap.add_argument("--ref-cells", type=int, default=400,
                     help="cells in the dense slab one reference step processes")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg")
+    ap.add_argument("--no-parity", action="store_true", help="skip the CPU-oracle comparison")
     args = ap.parse_args()
+    if args.secondary is None:
+        args.secondary = "c2" if args.workload == "c3" else "none"
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":

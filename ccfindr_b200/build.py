@@ -34,6 +34,8 @@ if os.environ.get("VBNMF_WIDE_THREADS"):
     NVCC_FLAGS.append("-DVB_WIDE_THREADS=" + os.environ["VBNMF_WIDE_THREADS"])
 if os.environ.get("VBNMF_UNROLL"):
     NVCC_FLAGS.append("-DVB_UNROLL=" + os.environ["VBNMF_UNROLL"])
+if os.environ.get("VBNMF_LP_BITS"):   # count bits of the log-product bound term (kernels.cuh)
+    NVCC_FLAGS.append("-DVB_LP_BITS=" + os.environ["VBNMF_LP_BITS"])
 
 
 def _nvcc():
@@ -58,6 +60,18 @@ def _source_hash():
             hsh.update(open(p, "rb").read())
     hsh.update(" ".join(NVCC_FLAGS).encode())
     return hsh.hexdigest()
+
+
+def kernel_hash():
+    """Hash of the CUDA sources alone (profiles/traffic.json is stamped with it: an ncu capture
+    describes the kernels it was taken from)."""
+    hsh = hashlib.sha256()
+    for f in sorted(os.listdir(CSRC)):
+        p = os.path.join(CSRC, f)
+        if os.path.isfile(p) and p.endswith((".cu", ".cuh", ".h")):
+            hsh.update(f.encode())
+            hsh.update(open(p, "rb").read())
+    return hsh.hexdigest()[:16]
 
 
 def _run(cmd, verbose):

@@ -7,6 +7,10 @@
 
 #include "special.cuh"
 
+#ifndef VB_LPN_BYTES
+#define VB_LPN_BYTES 160    // widest row a single lane gathers; wider rows are split over 2 lanes
+#endif
+
 namespace vb {
 
 constexpr int kBlock = 256;  // threads per CTA of the elementwise / reduction kernels
@@ -28,6 +32,23 @@ __host__ __device__ constexpr int row_stride_f32(int rp) {
 template <typename PT>
 __host__ __device__ constexpr int panel_stride(int rp) {
     return sizeof(PT) == 8 ? row_stride(rp) : row_stride_f32(rp);
+}
+
+// ---- split layout of the gathered fp64 panels (lw, lh) -----------------------------------------
+// Rows of at least 8 sixteen-byte units (RP >= 16) gathered by one lane per nonzero are stored per
+// slab of T rows as two blocks, A = T x 16 doubles (units 0..7, row stride exactly 128 bytes) then
+// B = T x (RS - 16) doubles (the remaining units; stride an odd number of units or a single unit).
+// In block A every row presents the 8 bank groups of shared memory identically, so the 8 lanes of
+// a group, reading unit (c XOR lane) of THEIR row in step c, hit 8 different bank groups whatever
+// the rows are: conflict free with no scheduling at all.  Only block B (2 of the 10 units at
+// r = 20) still depends on the residue schedule of the segment.  tsplit = T selects this layout
+// (0: plain row-major rows of RS doubles).
+__host__ __device__ constexpr bool split_rank(int rp) { return rp >= 16 && rp * 8 <= VB_LPN_BYTES; }
+__host__ __device__ __forceinline__ int64_t panel_ofs(int64_t row, int k, int rs, int tsplit) {
+    if (tsplit == 0) return row * rs + k;
+    const int64_t slab = row / tsplit, local = row - slab * tsplit;
+    return slab * tsplit * rs +
+           (k < 16 ? local * 16 + k : (int64_t)tsplit * 16 + local * (rs - 16) + (k - 16));
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -170,9 +191,6 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
 #ifndef VB_SWEEP_THREADS_F32
 #define VB_SWEEP_THREADS_F32 640  // ... of the fp32-storage kernels with rows of up to 48 bytes
                                   // (C2: 0.98 -> 0.94 ms per iteration against 512; 768: 0.95)
-#endif
-#ifndef VB_LPN_BYTES
-#define VB_LPN_BYTES 160    // widest row a single lane gathers; wider rows are split over 2 lanes
 #endif
 #ifndef VB_MID_THREADS
 #define VB_MID_THREADS 384   // threads per sweep CTA when a lane holds 97..160 bytes of a row
@@ -583,6 +601,24 @@ __device__ __forceinline__ void halve_step(const double (&in)[N], double (&out)[
     }
 }
 
+// sum of N per-lane values over the 8 lanes of a group by recursive halving, then out[i] = sum_i
+// for i < limit: every lane ends up with at most ceil(N/8) of the sums and stores those
+template <int N>
+__device__ __forceinline__ void halve_reduce_store(const double (&v0)[N], int gl, unsigned gmask,
+                                                   double *out, int limit) {
+    constexpr int H1 = (N + 1) / 2, H2 = (H1 + 1) / 2, H3 = (H2 + 1) / 2;
+    double v1[H1], v2[H2], v3[H3];
+    halve_step<N, 4>(v0, v1, gl, gmask);
+    halve_step<H1, 2>(v1, v2, gl, gmask);
+    halve_step<H2, 1>(v2, v3, gl, gmask);
+    const int o1 = (gl & 4) ? H1 : 0, o2 = (gl & 2) ? H2 : 0, o3 = (gl & 1) ? H3 : 0;
+#pragma unroll
+    for (int k = 0; k < H3; k++) {
+        const int i2 = k + o3, i1 = i2 + o2, i0 = i1 + o1;  // index in v0[]
+        if (i2 < H2 && i1 < H1 && i0 < N && i0 < limit) out[i0] = v3[k];
+    }
+}
+
 // x log p of the fp64 cell-owner pass through products (integer counts): with p = 2^e m,
 //   sum x log p = ln2 * sum x e + sum_b 2^b log( prod_{bit b of x set} m ),   b < kLpBits,
 // so a nonzero costs kLpBits predicated multiplies and a few integer operations instead of a
@@ -638,12 +674,22 @@ struct LogProd {
 #ifndef VB_OWN_AHEAD
 #define VB_OWN_AHEAD(dflt) (dflt)
 #endif
-template <int RP, bool COLS, typename PT>
+// SPLIT (fp64 panels, one lane per nonzero, rows of >= 8 units; see split_rank / panel_ofs): the
+// tile is stored as block A (T x 128 bytes) + block B; lane gl gathers unit c ^ gl of block A in
+// step c -- conflict free for ANY 8 rows -- and holds its owner row and accumulators in the same
+// rotated order; the cross-lane sum un-rotates for free (partner gl ^ b holds my unit of register
+// c in its register c ^ b).  Entries with count 0 (schedule holes) skip their gathers: the lane
+// keeps the previous row, and x = 0 adds nothing.
+template <int RP, bool COLS, typename PT, bool SPLIT = false>
 __global__ void __launch_bounds__(SweepCfg<RP, PT>::kThreads, 1)
 sweep_p16_kernel(const SweepTiledArgs a) {
     using Cfg = SweepCfg<RP, PT>;
     constexpr int RS = row_stride(RP);
     constexpr int PS = panel_stride<PT>(RP);
+    static_assert(!SPLIT || (sizeof(PT) == 8 && Cfg::kLPN == 1 && Cfg::kNU >= 8 && Cfg::kNU <= 15),
+                  "split layout: fp64 panels, one lane per nonzero, 8..15 units per row");
+    constexpr int NUB = SPLIT ? Cfg::kNU - 8 : 0;            // units of block B
+    constexpr int BSB = SPLIT ? (RS - 16) * 8 : 0;           // bytes per row of block B
     constexpr int NT = Cfg::kThreads;
     constexpr int UE = Cfg::kUE, NU = Cfg::kNU, LPN = Cfg::kLPN, NUL = Cfg::kNUL, KL = Cfg::kKL;
     constexpr int NPG = Cfg::kNPG;
@@ -673,15 +719,32 @@ sweep_p16_kernel(const SweepTiledArgs a) {
     LogProd lp;
     if (kLogProd) lp.init();
 
+    const uint32_t tileB_s = tile_s + (uint32_t)a.T * 128u;
+    const uint32_t rot = (uint32_t)gl << 4;
+    if (SPLIT && (tile_s & 127u)) __trap();  // block A rows must start on 128-byte boundaries
+
     // this lane's share of an owner row: units hf, hf + LPN, ...
     auto load_owner = [&](int64_t o, PT(&dst)[KL]) {
-        const PT *orow = reinterpret_cast<const PT *>(a.owner) + o * PS;
+        if constexpr (SPLIT) {
+            const uint32_t so = (uint32_t)o / (uint32_t)a.T, lo = (uint32_t)o - so * (uint32_t)a.T;
+            const PT *blk = reinterpret_cast<const PT *>(a.owner) + (int64_t)so * a.T * PS;
+            const PT *ra = blk + (int64_t)lo * 16, *rb = blk + (int64_t)a.T * 16 + (int64_t)lo * (RS - 16);
 #pragma unroll
-        for (int c = 0; c < NUL; c++) {
-            const int u = LPN * c + hf;
-            if (LPN == 1 || u < NU) ldg_unit(orow, u, dst + c * UE);
+            for (int c = 0; c < 8; c++) ldg_unit(ra, c ^ gl, dst + c * UE);
+#pragma unroll
+            for (int c = 0; c < NUB; c++) ldg_unit(rb, c, dst + (8 + c) * UE);
+        } else {
+            const PT *orow = reinterpret_cast<const PT *>(a.owner) + o * PS;
+#pragma unroll
+            for (int c = 0; c < NUL; c++) {
+                const int u = LPN * c + hf;
+                if (LPN == 1 || u < NU) ldg_unit(orow, u, dst + c * UE);
+            }
         }
     };
+    PT tr[KL];  // the gathered row; SPLIT: kept by hole entries (overwritten in full otherwise)
+#pragma unroll
+    for (int k = 0; k < KL; k++) tr[k] = 1;
 
     for (int64_t ebase = e0; ebase < e1;) {
         const int64_t slab = ebase / a.NO;
@@ -750,16 +813,27 @@ sweep_p16_kernel(const SweepTiledArgs a) {
                 for (int u = 0; u < 4; u++) {
                     const uint32_t v = u == 0 ? cur.x : u == 1 ? cur.y : u == 2 ? cur.z : cur.w;
                     const PT x = (PT)(int)(v >> 16);
-                    const uint32_t raddr = tile_s + (v & 0xffffu) * (uint32_t)(PS * sizeof(PT));
-                    PT tr[KL];
+                    if constexpr (SPLIT) {
+                        if (v >> 16) {  // a hole keeps the previous row: no shared-memory traffic
+                            const uint32_t row = v & 0xffffu;
+                            const uint32_t ra = (tile_s + row * 128u) ^ rot;
+                            const uint32_t rb = tileB_s + row * (uint32_t)BSB;
 #pragma unroll
-                    for (int c = 0; c < NUL; c++) {
-                        const int uu = LPN * c + hf;
-                        if (LPN == 1 || uu < NU) {
-                            lds_unit(raddr + uu * 16, tr + c * UE);
-                        } else {
+                            for (int c = 0; c < 8; c++) lds_unit(ra ^ (uint32_t)(c << 4), tr + c * UE);
 #pragma unroll
-                            for (int j = 0; j < UE; j++) tr[c * UE + j] = 0;
+                            for (int c = 0; c < NUB; c++) lds_unit(rb + c * 16, tr + (8 + c) * UE);
+                        }
+                    } else {
+                        const uint32_t raddr = tile_s + (v & 0xffffu) * (uint32_t)(PS * sizeof(PT));
+#pragma unroll
+                        for (int c = 0; c < NUL; c++) {
+                            const int uu = LPN * c + hf;
+                            if (LPN == 1 || uu < NU) {
+                                lds_unit(raddr + uu * 16, tr + c * UE);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < UE; j++) tr[c * UE + j] = 0;
+                            }
                         }
                     }
                     PT p = dot_rows<KL>(own, tr);
@@ -802,6 +876,24 @@ sweep_p16_kernel(const SweepTiledArgs a) {
             double v0[KL];
 #pragma unroll
             for (int k = 0; k < KL; k++) v0[k] = (double)acc[k];
+            if constexpr (SPLIT) {
+                // block A: register unit c of lane gl is rank unit c ^ gl; the partner gl ^ b
+                // holds the same rank unit in its register unit c ^ b
+                double a1[8], a2[4], a3[2];
+#pragma unroll
+                for (int k = 0; k < 8; k++) a1[k] = v0[k] + __shfl_xor_sync(gmask, v0[k + 8], 4);
+#pragma unroll
+                for (int k = 0; k < 4; k++) a2[k] = a1[k] + __shfl_xor_sync(gmask, a1[k + 4], 2);
+#pragma unroll
+                for (int k = 0; k < 2; k++) a3[k] = a2[k] + __shfl_xor_sync(gmask, a2[k + 2], 1);
+                *reinterpret_cast<double2 *>(out + 2 * gl) = make_double2(a3[0], a3[1]);
+                if constexpr (NUB > 0) {
+                    double vb[2 * NUB];
+#pragma unroll
+                    for (int k = 0; k < 2 * NUB; k++) vb[k] = v0[16 + k];
+                    halve_reduce_store<2 * NUB>(vb, gl, gmask, out + 16, RP - 16);
+                }
+            } else {
             constexpr int H1 = (KL + 1) / 2, H2 = (H1 + 1) / 2, H3 = (H2 + 1) / 2;
             double v1[H1], v2[H2];
             halve_step<KL, 4>(v0, v1, gl, gmask);
@@ -823,6 +915,7 @@ sweep_p16_kernel(const SweepTiledArgs a) {
                     const int kk = (LPN * (i0 / UE) + hf) * UE + (i0 % UE);  // rank index
                     if (i1 < H1 && i0 < KL && kk < RP) out[kk] = v2[k];
                 }
+            }
             }
             e = en;
             beg = nb; end = ne;
@@ -847,7 +940,7 @@ __global__ void __launch_bounds__(kBlock)
 combine_kernel(int64_t NO, int nslabs, int r, const double *__restrict__ Part,
                const double *__restrict__ l, double *__restrict__ SRaw, double *__restrict__ part,
                double *__restrict__ out, unsigned *counter, const double *__restrict__ xl_part,
-               int nxl, const double *__restrict__ ctl) {
+               int nxl, const double *__restrict__ ctl, int tsplit) {
     constexpr int RS = row_stride(RP);
     __shared__ double sm[kWarpsPerBlock];
     if (ctl && ctl[kCtlDone] != 0.0) return;
@@ -866,7 +959,7 @@ combine_kernel(int64_t NO, int nslabs, int r, const double *__restrict__ Part,
         }
         if (k2 >= RP) s = make_double2(0.0, 0.0);
         *reinterpret_cast<double2 *>(SRaw + o * RS + k2) = s;
-        const double2 lv = *reinterpret_cast<const double2 *>(l + o * RS + k2);
+        const double2 lv = *reinterpret_cast<const double2 *>(l + panel_ofs(o, k2, RS, tsplit));
         if (k2 < r && lv.x > 0.0) ent += log(lv.x) * lv.x * s.x;
         if (k2 + 1 < r && lv.y > 0.0) ent += log(lv.y) * lv.y * s.y;
     }
@@ -924,7 +1017,7 @@ posterior_kernel(int64_t rows, int T, int S, int64_t nvalid, int r, double a, do
                  const double *__restrict__ osum, const double *__restrict__ SRaw,
                  double *__restrict__ l, double *__restrict__ al_out, double *__restrict__ part,
                  double *__restrict__ out, unsigned *counter, float *__restrict__ l32,
-                 const double *__restrict__ ctl, int hoff, int rows_per_cta) {
+                 const double *__restrict__ ctl, int hoff, int rows_per_cta, int tsplit) {
     constexpr int RS = row_stride(RP);
     constexpr int kPostLanes = post_lanes(RS);
     constexpr int NT = post_threads(RS);
@@ -949,8 +1042,9 @@ posterior_kernel(int64_t rows, int T, int S, int64_t nvalid, int r, double a, do
         const int64_t slab = row / T, local = row - slab * T;
         const bool valid = local * S + slab < nvalid;
         double ln = 0.0, al = 0.0;
+        const int64_t lo = panel_ofs(row, k, RS, tsplit);
         if (valid && kact) {
-            al = a + l[row * RS + k] * SRaw[row * RS + k];
+            al = a + l[lo] * SRaw[row * RS + k];
             const double e = al / be;
             const double tmp = exp(vb_digamma(al)) / be;
             ln = tmp > fud ? tmp : fud;
@@ -959,7 +1053,7 @@ posterior_kernel(int64_t rows, int T, int S, int64_t nvalid, int r, double a, do
             prior += -aob * e + al * (1.0 - lbe) + lgamma(al);
         }
         if (valid) {
-            l[row * RS + k] = ln;
+            l[lo] = ln;
             al_out[row * RS + k] = al;
             if (l32 && k < row_stride_f32(RP)) l32[row * row_stride_f32(RP) + k] = (float)ln;
         }
@@ -1000,7 +1094,7 @@ __global__ void __launch_bounds__(post_threads(row_stride(RP)))
 ml_update_kernel(int64_t rows, int T, int S, int64_t nvalid, int r, double eps,
                  const double *__restrict__ osum, const double *__restrict__ SRaw,
                  double *__restrict__ v, double *__restrict__ part, double *__restrict__ out,
-                 unsigned *counter, float *__restrict__ l32) {
+                 unsigned *counter, float *__restrict__ l32, int tsplit) {
     constexpr int RS = row_stride(RP);
     constexpr int kPostLanes = post_lanes(RS);
     constexpr int NT = post_threads(RS);
@@ -1018,12 +1112,13 @@ ml_update_kernel(int64_t rows, int T, int S, int64_t nvalid, int r, double eps,
         const int64_t slab = row / T, local = row - slab * T;
         if (local * S + slab >= nvalid) continue;
         double x = 0.0;
+        const int64_t lo = panel_ofs(row, k, RS, tsplit);
         if (kact) {
-            x = v[row * RS + k] * SRaw[row * RS + k] / os;
+            x = v[lo] * SRaw[row * RS + k] / os;
             if (x < eps) x = eps;
             es += x;
         }
-        v[row * RS + k] = x;
+        v[lo] = x;
         if (l32 && k < row_stride_f32(RP)) l32[row * row_stride_f32(RP) + k] = (float)x;
     }
     colbuf[threadIdx.x] = es;
@@ -1051,14 +1146,21 @@ mirror_kernel(int64_t rows, const double *__restrict__ v, float *__restrict__ v3
 template <int RP>
 __global__ void __launch_bounds__(kBlock)
 panel_colsum_kernel(int64_t rows, const double *__restrict__ v, double *__restrict__ part,
-                    double *__restrict__ out, unsigned *counter) {
+                    double *__restrict__ out, unsigned *counter, int tsplit) {
     constexpr int RS = row_stride(RP);
     __shared__ double sm[kWarpsPerBlock];
     const int64_t row = (int64_t)blockIdx.x * kBlock + threadIdx.x;
     double lv[RP];
 #pragma unroll
     for (int k = 0; k < RP; k++) lv[k] = 0.0;
-    if (row < rows) load_row_d<RP>(v, row, lv);
+    if (row < rows) {
+#pragma unroll
+        for (int k = 0; k < RP; k += 2) {
+            const double2 t = __ldg(reinterpret_cast<const double2 *>(v + panel_ofs(row, k, RS, tsplit)));
+            lv[k] = t.x;
+            lv[k + 1] = t.y;
+        }
+    }
     double *mypart = part + (size_t)blockIdx.x * RS;
 #pragma unroll
     for (int k = 0; k < RP; k++) {

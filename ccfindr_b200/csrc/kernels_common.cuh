@@ -7,47 +7,154 @@ namespace vb {
 // ---- one-time helpers ----------------------------------------------------------------------
 // sum over nonzeros of lgamma(x+1) (src/vbnmf_update.cpp:80-81; zeros contribute 0) and of
 // -x log x + x (R/factorize.R:45-46); out[0], out[1].  out[2] = number of values that are not
-// integers in [0, 65535] (0 -> the packed 16-bit layout of the sweep applies).
+// integers in [0, 65535] (0 -> the packed 16-bit layout of the sweep applies); out[3] = number of
+// negative or non-finite values (the handle is refused: the reference's bound would be NaN).
 template <typename VT>
 __global__ void __launch_bounds__(kBlock)
 count_constants_kernel(int64_t nnz, const VT *__restrict__ val, double *__restrict__ part,
                        double *__restrict__ out, unsigned *counter) {
     __shared__ double sm[kWarpsPerBlock];
-    double a = 0.0, b = 0.0, c = 0.0;
+    double a = 0.0, b = 0.0, c = 0.0, d = 0.0;
     for (int64_t t = (int64_t)blockIdx.x * kBlock + threadIdx.x; t < nnz;
          t += (int64_t)gridDim.x * kBlock) {
         const double x = (double)val[t];
+        if (!(x >= 0.0 && x <= 1.7e308)) { d += 1.0; continue; }
         a += lgamma(x + 1.0);
         if (x > 0) b += -x * log(x) + x;
-        if (!(x >= 0.0 && x <= 65535.0 && x == floor(x))) c += 1.0;
+        if (!(x <= 65535.0 && x == floor(x))) c += 1.0;
     }
     a = block_sum(a, sm);
     b = block_sum(b, sm);
     c = block_sum(c, sm);
+    d = block_sum(d, sm);
     if (threadIdx.x == 0) {
-        part[blockIdx.x * 3 + 0] = a;
-        part[blockIdx.x * 3 + 1] = b;
-        part[blockIdx.x * 3 + 2] = c;
+        part[blockIdx.x * 4 + 0] = a;
+        part[blockIdx.x * 4 + 1] = b;
+        part[blockIdx.x * 4 + 2] = c;
+        part[blockIdx.x * 4 + 3] = d;
     }
-    last_block_reduce(part, 3, out, counter, sm);
+    last_block_reduce(part, 4, out, counter, sm);
 }
 
-// expand CSC column pointers into a per-nonzero column index; count nonzeros per row and column
+// expand CSC column pointers into a per-nonzero column index.  With counts != nullptr (first
+// call for a matrix) also: count the entries with a non-zero value per row and column (an explicit
+// zero does not make a row non-empty: the reference tests rowSums/colSums == 0,
+// R/bayesian.R:244-247) and flag row indices outside [0, n) in bad[0] (those are not counted).
+template <typename VT>
 __global__ void __launch_bounds__(kBlock)
-expand_cols_kernel(int64_t m, const int64_t *__restrict__ colptr,
-                   const int32_t *__restrict__ rowidx, int32_t *__restrict__ colof,
-                   unsigned long long *__restrict__ row_count,
-                   unsigned long long *__restrict__ col_count) {
+expand_cols_kernel(int64_t m, int64_t n, const int64_t *__restrict__ colptr,
+                   const int32_t *__restrict__ rowidx, const VT *__restrict__ val,
+                   int32_t *__restrict__ colof, unsigned long long *__restrict__ row_count,
+                   unsigned long long *__restrict__ col_count, unsigned *__restrict__ bad) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * kBlock + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * kBlock) >> 5;
     for (int64_t j = warp; j < m; j += nwarps) {
         const int64_t beg = colptr[j], end = colptr[j + 1];
-        if (lane == 0) col_count[j] = (unsigned long long)(end - beg);
+        unsigned cc = 0;
         for (int64_t t = beg + lane; t < end; t += 32) {
             colof[t] = (int32_t)j;
-            atomicAdd(row_count + rowidx[t], 1ull);
+            if (row_count) {
+                const int32_t i = rowidx[t];
+                if (i < 0 || i >= n) { *bad = 1u; continue; }
+                if (val[t] != (VT)0) { atomicAdd(row_count + i, 1ull); cc++; }
+            }
         }
+        if (row_count) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) cc += __shfl_xor_sync(kFull, cc, o);
+            if (lane == 0) col_count[j] = cc;
+        }
+    }
+}
+
+// ---- renumbering on the device ----------------------------------------------------------------
+// sort key for "descending count, stable": key = 2^31 - 1 - count (counts are < 2^31)
+__global__ void __launch_bounds__(kBlock)
+order_keys_kernel(int64_t count, const unsigned long long *__restrict__ cnt,
+                  uint32_t *__restrict__ key, uint32_t *__restrict__ idx,
+                  unsigned *__restrict__ nzero) {
+    const int64_t t = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (t >= count) return;
+    const unsigned long long c = cnt[t];
+    key[t] = 0x7fffffffu - (uint32_t)(c > 0x7fffffffull ? 0x7fffffffull : c);
+    idx[t] = (uint32_t)t;
+    if (c == 0ull && nzero) atomicAdd(nzero, 1u);
+}
+// sorted position pos (descending count) -> device row: dealt round-robin over S slabs of T rows
+__global__ void __launch_bounds__(kBlock)
+deal_kernel(int64_t count, int S, int T, const uint32_t *__restrict__ order,
+            int32_t *__restrict__ dev) {
+    const int64_t pos = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (pos >= count) return;
+    dev[order[pos]] = (int32_t)((pos % S) * T + pos / S);
+}
+
+// ---- panels between the caller's layout and the device layout -----------------------------------
+// caller: W side src[k * cnt + i] (cnt x r, column-major), H side src[j * r + k] (r x cnt)
+// device: panel[dev[i] * rs + k], rows/entries not addressed stay as they are (zeroed before)
+// dst1 is an l panel (layout tsplit, panel_ofs), dst2 a row-major one
+__global__ void __launch_bounds__(kBlock)
+scatter_panel_kernel(int64_t cnt, int r, int rs, const int32_t *__restrict__ dev,
+                     const double *__restrict__ src, bool wside, double *__restrict__ dst1,
+                     double *__restrict__ dst2, int tsplit) {
+    const int64_t t = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (t >= cnt * r) return;
+    int64_t i; int k;
+    if (wside) { k = (int)(t / cnt); i = t - (int64_t)k * cnt; }
+    else { i = t / r; k = (int)(t - i * r); }
+    const double v = src[t];
+    const int64_t d = dev[i];
+    if (dst1) dst1[panel_ofs(d, k, rs, tsplit)] = v;
+    if (dst2) dst2[d * rs + k] = v;
+}
+// mode 0: out = panel; 1: out = panel / be_k; 2: out = panel / be_k^2 (0 when !has_post)
+__global__ void __launch_bounds__(kBlock)
+gather_panel_kernel(int64_t cnt, int r, int rs, const int32_t *__restrict__ dev,
+                    const double *__restrict__ panel, bool wside, const double *__restrict__ be,
+                    int mode, double *__restrict__ out, int tsplit) {
+    const int64_t t = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (t >= cnt * r) return;
+    int64_t i; int k;
+    if (wside) { k = (int)(t / cnt); i = t - (int64_t)k * cnt; }
+    else { i = t / r; k = (int)(t - i * r); }
+    double v = panel[panel_ofs(dev[i], k, rs, tsplit)];
+    if (mode >= 1) v = v / be[k];
+    if (mode == 2) v = v / be[k];
+    out[t] = v;
+}
+__global__ void __launch_bounds__(kBlock)
+gather_i32_kernel(int64_t cnt, const int32_t *__restrict__ dev, const int32_t *__restrict__ src,
+                  int32_t *__restrict__ out) {
+    const int64_t t = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (t < cnt) out[t] = src[dev[t]];
+}
+// flags[k] = |max_i e_ik - min_i e_ik| < tol over the valid rows, e = al / be_k (R/bayesian.R:368-369)
+// one CTA per k
+__global__ void __launch_bounds__(kBlock)
+uniform_columns_kernel(int64_t rows, int T, int S, int64_t nvalid, int rs,
+                       const double *__restrict__ al, const double *__restrict__ be, double tol,
+                       int32_t *__restrict__ flags) {
+    __shared__ double smx[kWarpsPerBlock], smn[kWarpsPerBlock];
+    const int k = blockIdx.x;
+    double mx = -INFINITY, mn = INFINITY;
+    for (int64_t row = threadIdx.x; row < rows; row += kBlock) {
+        const int64_t slab = row / T, local = row - slab * T;
+        if (local * S + slab >= nvalid) continue;
+        const double v = al[row * rs + k] / be[k];
+        mx = v > mx ? v : mx;
+        mn = v < mn ? v : mn;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mx = fmax(mx, __shfl_xor_sync(kFull, mx, o));
+        mn = fmin(mn, __shfl_xor_sync(kFull, mn, o));
+    }
+    if ((threadIdx.x & 31) == 0) { smx[threadIdx.x >> 5] = mx; smn[threadIdx.x >> 5] = mn; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < kWarpsPerBlock; w++) { mx = fmax(mx, smx[w]); mn = fmin(mn, smn[w]); }
+        flags[k] = fabs(mx - mn) < tol ? 1 : 0;
     }
 }
 
@@ -192,9 +299,13 @@ struct SegSchedule {
     int cnt[2][8];
 };
 
-// counts per residue -> schedule.  NL = 8: class 0 only, K a multiple of 4.  NL = 4: two classes
-// of K multiples of 2 (an odd number of step pairs gets one more pair of hole steps in class 1).
-__device__ __forceinline__ void make_schedule(const int (&cnt8)[8], int NL, SegSchedule &sc) {
+// counts per residue -> schedule.  NL = 8: class 0 only, K a multiple of kmult (4: every stored
+// step is scheduled; 1: the schedule uses the fewest steps and the rest of the last stored chunk
+// of 4 steps is all holes, which kernels that skip the gathers of hole entries get for free).
+// NL = 4: two classes of K multiples of 2 (an odd number of step pairs gets one more pair of hole
+// steps in class 1).
+__device__ __forceinline__ void make_schedule(const int (&cnt8)[8], int NL, int kmult,
+                                              SegSchedule &sc) {
     const int ncls = NL == 8 ? 1 : 2, NB = NL;
     for (int cl = 0; cl < 2; cl++) {
         sc.K[cl] = 0; sc.pl[cl].R = 0; sc.pl[cl].P = 0;
@@ -204,7 +315,7 @@ __device__ __forceinline__ void make_schedule(const int (&cnt8)[8], int NL, SegS
     for (int cl = 0; cl < ncls; cl++) {
         int n = 0, L = 0;
         for (int b = 0; b < NB; b++) { n += sc.cnt[cl][b]; L = max(L, sc.cnt[cl][b]); }
-        sc.K[cl] = class_steps(n, L, NL, NL == 8 ? 4 : 2);
+        sc.K[cl] = class_steps(n, L, NL, NL == 8 ? kmult : 2);
     }
     if (ncls == 2 && ((sc.K[0] + sc.K[1]) & 3)) sc.K[1] += 2;
     for (int cl = 0; cl < ncls; cl++) {
@@ -243,30 +354,44 @@ __device__ __forceinline__ int schedule_item(const SegSchedule &sc, int NL, int 
     return ((cl ? sc.K[0] : 0) + step) * NL + lane;
 }
 
-// quads (4 entries = 16 bytes) of every segment under the schedule above; len4[E] = 0
+// residue counts of a segment's words, one warp per segment (every lane gets all 8 counts)
+__device__ __forceinline__ void warp_residue_counts(const uint32_t *__restrict__ words,
+                                                    int64_t beg, int64_t end, int lane,
+                                                    int (&cnt)[8]) {
+#pragma unroll
+    for (int b = 0; b < 8; b++) cnt[b] = 0;
+    for (int64_t base = beg; base < end; base += 32) {
+        const int64_t t = base + lane;
+        const int rr = t < end ? (int)(words[t] & 7u) : 8;
+#pragma unroll
+        for (int b = 0; b < 8; b++) cnt[b] += __popc(__ballot_sync(kFull, rr == b));
+    }
+}
+
+// quads (4 entries = 16 bytes) of every segment under the schedule above; len4[E] = 0.
+// One warp per segment.
 __global__ void __launch_bounds__(kBlock)
 plan_p16_kernel(int64_t E, const int64_t *__restrict__ ptr, const uint32_t *__restrict__ words,
-                int NL, uint32_t *__restrict__ len4) {
-    for (int64_t e = (int64_t)blockIdx.x * kBlock + threadIdx.x; e <= E;
-         e += (int64_t)gridDim.x * kBlock) {
-        if (e == E) { len4[e] = 0u; continue; }
+                int NL, int kmult, uint32_t *__restrict__ len4) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * kBlock + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * kBlock) >> 5;
+    if (warp == 0 && lane == 0) len4[E] = 0u;
+    for (int64_t e = warp; e < E; e += nwarps) {
         const int64_t beg = ptr[e], end = ptr[e + 1];
-        if (beg == end) { len4[e] = 0u; continue; }
+        if (beg == end) { if (lane == 0) len4[e] = 0u; continue; }
         int cnt[8];
-#pragma unroll
-        for (int b = 0; b < 8; b++) cnt[b] = 0;
-        for (int64_t t = beg; t < end; t++) cnt[words[t] & 7u]++;
+        warp_residue_counts(words, beg, end, lane, cnt);
         int n0 = 0, n1 = 0, L0 = 0, L1 = 0;
+#pragma unroll
         for (int rr = 0; rr < 8; rr++) {
             if (res_class(rr, NL)) { n1 += cnt[rr]; L1 = max(L1, cnt[rr]); }
             else { n0 += cnt[rr]; L0 = max(L0, cnt[rr]); }
         }
-        int K = class_steps(n0, L0, NL, NL == 8 ? 4 : 2);
-        if (NL != 8) {
-            K += class_steps(n1, L1, NL, 2);
-            K = (K + 3) & ~3;
-        }
-        len4[e] = (uint32_t)(K * NL / 4);
+        int K = class_steps(n0, L0, NL, NL == 8 ? kmult : 2);
+        if (NL != 8) K += class_steps(n1, L1, NL, 2);
+        K = (K + 3) & ~3;
+        if (lane == 0) len4[e] = (uint32_t)(K * NL / 4);
     }
 }
 
@@ -280,42 +405,56 @@ __device__ __forceinline__ int64_t p16_position(int64_t p, int NL) {
     return blk * B + 4 * (pin % NL) + pin / NL;
 }
 
-// One thread per segment: fill the segment with hole words, then scatter the nonzeros to their
-// scheduled places as {count << 16 | tile row}.  nvalid / S: rows of the tile side that exist
-// (a hole must point at a real row: local * S + slab < nvalid; row 0 of a slab always is).
+// One warp per segment: fill the segment with hole words, then scatter the nonzeros to their
+// scheduled places as {count << 16 | tile row} (the k-th word of a residue in sorted order is the
+// k-th nonzero of its bucket).  nvalid / S: rows of the tile side that exist (a hole must point
+// at a real row: local * S + slab < nvalid; row 0 of a slab always is).
 __global__ void __launch_bounds__(kBlock)
 build_segments_p16_kernel(int64_t E, int64_t NO, const int64_t *__restrict__ ptr,
                           const uint32_t *__restrict__ ptr4, const uint32_t *__restrict__ words,
-                          int NL, int64_t nvalid, int S, uint32_t *__restrict__ ent_out) {
-    for (int64_t e = (int64_t)blockIdx.x * kBlock + threadIdx.x; e < E;
-         e += (int64_t)gridDim.x * kBlock) {
+                          int NL, int kmult, int64_t nvalid, int S,
+                          uint32_t *__restrict__ ent_out) {
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const int64_t warp = ((int64_t)blockIdx.x * kBlock + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * kBlock) >> 5;
+    for (int64_t e = warp; e < E; e += nwarps) {
         const int64_t beg = ptr[e], end = ptr[e + 1];
         if (beg == end) continue;
         uint32_t *dst = ent_out + (int64_t)ptr4[e] * 4;
         const int nitems = (int)(ptr4[e + 1] - ptr4[e]) * 4;
         const int64_t slab = e / NO;
         int cnt[8];
-#pragma unroll
-        for (int b = 0; b < 8; b++) cnt[b] = 0;
-        for (int64_t t = beg; t < end; t++) cnt[words[t] & 7u]++;
+        warp_residue_counts(words, beg, end, lane, cnt);
         SegSchedule sc;
-        make_schedule(cnt, NL, sc);
+        make_schedule(cnt, NL, kmult, sc);
         // holes: lane <-> bucket in the single steps, so the residue of the lane's bucket is free
-        for (int p = 0; p < nitems; p++) {
-            const int step = p / NL, lane = p - step * NL;
+        for (int p = lane; p < nitems; p += 32) {
+            const int step = p / NL, ln = p - step * NL;
             const int cl = (NL != 8 && step >= sc.K[0]) ? 1 : 0;
-            int rr = bucket_res(cl, lane, NL);
+            int rr = bucket_res(cl, ln, NL);
             if ((int64_t)rr * S + slab >= nvalid) rr = 0;
             dst[p16_position(p, NL)] = (uint32_t)rr;
         }
+        __syncwarp();
         int seen[8];
 #pragma unroll
         for (int b = 0; b < 8; b++) seen[b] = 0;
-        for (int64_t t = beg; t < end; t++) {
-            const uint32_t w = words[t];
-            const int rr = (int)(w & 7u);
-            dst[p16_position(schedule_item(sc, NL, rr, seen[rr]++), NL)] = w;
+        for (int64_t base = beg; base < end; base += 32) {
+            const int64_t t = base + lane;
+            const bool valid = t < end;
+            const uint32_t w = valid ? words[t] : 0u;
+            const int rr = valid ? (int)(w & 7u) : 8;
+            int k = 0;
+#pragma unroll
+            for (int b = 0; b < 8; b++) {
+                const unsigned mk = __ballot_sync(kFull, rr == b);
+                if (rr == b) k = seen[b] + __popc(mk & lt);
+                seen[b] += __popc(mk);
+            }
+            if (valid) dst[p16_position(schedule_item(sc, NL, rr, k), NL)] = w;
         }
+        __syncwarp();
     }
 }
 
@@ -457,7 +596,7 @@ struct VbStream {
 __global__ void __launch_bounds__(kBlock)
 init_random_kernel(int64_t rows, int r, int rs, const int32_t *__restrict__ dev, int side,
                    int64_t row_offset, unsigned long long seed, double shape, double scale,
-                   double *__restrict__ panel, double *__restrict__ mirror) {
+                   double *__restrict__ panel, double *__restrict__ mirror, int tsplit) {
     const int64_t t = (int64_t)blockIdx.x * kBlock + threadIdx.x;
     if (t >= rows * r) return;
     const int64_t row = t / r;
@@ -465,9 +604,9 @@ init_random_kernel(int64_t rows, int r, int rs, const int32_t *__restrict__ dev,
     VbStream st(seed, ((unsigned long long)side << 62) |
                           ((unsigned long long)(row + row_offset) << 6) | (unsigned long long)k);
     const double v = scale * st.gamma(shape);
-    const int64_t o = (int64_t)dev[row] * rs + k;
-    panel[o] = v;
-    mirror[o] = v;
+    const int64_t d = dev[row];
+    panel[panel_ofs(d, k, rs, tsplit)] = v;
+    mirror[d * rs + k] = v;
 }
 
 // ---- all-reduce of the W-side statistics over NVLink peer memory -----------------------------

@@ -31,14 +31,26 @@ int sweep_prepare(int smem_bytes) {
     VB_OPT((sweep_p16_kernel<RP, false, double>))
     VB_OPT((sweep_p16_kernel<RP, true, float>))
     VB_OPT((sweep_p16_kernel<RP, false, float>))
+    if constexpr (split_rank(RP)) {
+        VB_OPT((sweep_p16_kernel<RP, true, double, true>))
+        VB_OPT((sweep_p16_kernel<RP, false, double, true>))
+    }
 #undef VB_OPT
     return e == cudaSuccess ? 0 : 1;
 }
 
 template <typename PT>
-void sweep_pt(const SweepTiledArgs &a, bool cols, int fmt, int grid, int smem, cudaStream_t s) {
+void sweep_pt(const SweepTiledArgs &a, bool cols, int fmt, bool split, int grid, int smem,
+              cudaStream_t s) {
     constexpr int NT = SweepCfg<RP, PT>::kThreads;
     const bool vf = fmt == kEntF32;
+    if constexpr (split_rank(RP) && sizeof(PT) == 8) {
+        if (fmt == kEntP16 && split) {
+            if (cols) sweep_p16_kernel<RP, true, PT, true><<<grid, NT, smem, s>>>(a);
+            else sweep_p16_kernel<RP, false, PT, true><<<grid, NT, smem, s>>>(a);
+            return;
+        }
+    }
     if (fmt == kEntP16) {
         if (cols) sweep_p16_kernel<RP, true, PT><<<grid, NT, smem, s>>>(a);
         else sweep_p16_kernel<RP, false, PT><<<grid, NT, smem, s>>>(a);
@@ -51,34 +63,35 @@ void sweep_pt(const SweepTiledArgs &a, bool cols, int fmt, int grid, int smem, c
     }
 }
 
-void sweep(const SweepTiledArgs &a, bool cols, int fmt, bool pf32, int grid, int smem,
+void sweep(const SweepTiledArgs &a, bool cols, int fmt, bool pf32, bool split, int grid, int smem,
            cudaStream_t s) {
-    if (pf32) sweep_pt<float>(a, cols, fmt, grid, smem, s);
-    else sweep_pt<double>(a, cols, fmt, grid, smem, s);
+    if (pf32) sweep_pt<float>(a, cols, fmt, false, grid, smem, s);
+    else sweep_pt<double>(a, cols, fmt, split, grid, smem, s);
 }
 
 inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 void combine(const CombineArgs &a, cudaStream_t s) {
     combine_kernel<RP><<<a.grid, kBlock, 0, s>>>(a.NO, a.nslabs, a.r, a.Part, a.l, a.SRaw, a.part,
-                                                 a.out, a.counter, a.xl_part, a.nxl, a.ctl);
+                                                 a.out, a.counter, a.xl_part, a.nxl, a.ctl,
+                                                 a.tsplit);
 }
 void posterior(const PosteriorArgs &a, cudaStream_t s) {
     posterior_kernel<RP><<<cdiv(a.rows, a.rows_per_cta), post_threads(RS), 0, s>>>(
         a.rows, a.T, a.S, a.nvalid, a.r, a.a, a.b, a.fud, a.osum, a.SRaw, a.l, a.al_out, a.part,
-        a.out, a.counter, a.l32, a.ctl, a.hoff, a.rows_per_cta);
+        a.out, a.counter, a.l32, a.ctl, a.hoff, a.rows_per_cta, a.tsplit);
 }
 void ml_update(const MlUpdateArgs &a, cudaStream_t s) {
     ml_update_kernel<RP><<<cdiv(a.rows, kPostRows), post_threads(RS), 0, s>>>(
         a.rows, a.T, a.S, a.nvalid, a.r, a.eps, a.osum, a.SRaw, a.v, a.part, a.out, a.counter,
-        a.l32);
+        a.l32, a.tsplit);
 }
 void mirror(int64_t rows, const double *v, float *v32, cudaStream_t s) {
     mirror_kernel<RP><<<cdiv(rows, kBlock), kBlock, 0, s>>>(rows, v, v32);
 }
 void colsum(const ColsumArgs &a, cudaStream_t s) {
     panel_colsum_kernel<RP><<<cdiv(a.rows, kBlock), kBlock, 0, s>>>(a.rows, a.v, a.part, a.out,
-                                                                   a.counter);
+                                                                   a.counter, a.tsplit);
 }
 
 }  // namespace
@@ -86,7 +99,8 @@ void colsum(const ColsumArgs &a, cudaStream_t s) {
 extern const RpTable VB_CAT(rp_table_, VB_RP);
 const RpTable VB_CAT(rp_table_, VB_RP) = {
     RP,      RS,        row_stride_f32(RP),
-    SweepCfg<RP, double>::kNPG, SweepCfg<RP, float>::kNPG, sweep_prepare, sweep, mirror,
+    SweepCfg<RP, double>::kNPG, SweepCfg<RP, float>::kNPG, split_rank(RP) ? 1 : 0, sweep_prepare,
+    sweep, mirror,
     combine, posterior, ml_update,          colsum};
 
 }  // namespace vb

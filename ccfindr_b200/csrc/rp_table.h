@@ -18,6 +18,7 @@ struct CombineArgs {
     int nxl;
     int grid;
     const double *ctl;      // device loop control block or nullptr
+    int tsplit;             // layout of l (panel_ofs)
 };
 
 struct PosteriorArgs {
@@ -33,6 +34,7 @@ struct PosteriorArgs {
     const double *ctl;  // device loop control block (hypers read from it) or nullptr
     int hoff;           // 0: (aw, bw), 2: (ah, bh)
     int rows_per_cta;   // post_rows_per_cta(rows, rs, SMs)
+    int tsplit;         // layout of l (panel_ofs)
 };
 
 struct MlUpdateArgs {
@@ -45,6 +47,7 @@ struct MlUpdateArgs {
     double *v, *part, *out;
     unsigned *counter;
     float *l32;
+    int tsplit;  // layout of v (panel_ofs)
 };
 
 struct ColsumArgs {
@@ -52,15 +55,17 @@ struct ColsumArgs {
     const double *v;
     double *part, *out;
     unsigned *counter;
+    int tsplit;  // layout of v (panel_ofs)
 };
 
 struct RpTable {
     int rp, rs, rsf;  // padded rank, fp64 panel stride (doubles), fp32 mirror stride (floats)
     int npg64, npg32;  // nonzeros per 8-lane group step of the sweep (fp64 / fp32 panels)
+    int split64;       // 1: the fp64 packed-16 sweep reads lw/lh in the split layout (panel_ofs)
     // cols: cell-owner pass; fmt = storage format of the nonzeros (kEnt*); grid = CTAs (one per
     // SM, persistent)
     int (*sweep_prepare)(int smem_bytes);  // opt in to the dynamic shared memory size; 0 = ok
-    void (*sweep)(const SweepTiledArgs &, bool cols, int fmt, bool panels_f32, int grid,
+    void (*sweep)(const SweepTiledArgs &, bool cols, int fmt, bool panels_f32, bool split, int grid,
                   int smem_bytes, cudaStream_t);
     void (*mirror)(int64_t rows, const double *v, float *v32, cudaStream_t);
     void (*combine)(const CombineArgs &, cudaStream_t);

@@ -26,6 +26,9 @@
 #include <algorithm>
 #include <cmath>
 #include <cub/cub.cuh>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
 #include <numeric>
 #include <mutex>
 #include <string>
@@ -61,7 +64,7 @@ constexpr int64_t kGraphMaxNnz = 20000000;  // below this the iteration loop is 
 constexpr int kTileBytes = 231424;
 constexpr int kTileRowsMax = 4096, kTileRowsStep = 32;
 
-std::string g_create_error;
+thread_local std::string g_create_error;  // error text of the last failed create on this thread
 
 // NVTX range around a phase of the iteration (visible in Nsight tools; header-only, no cost
 // without a profiler attached)
@@ -141,9 +144,9 @@ struct PassLayout {
 struct Layout {
     int T = 0, Sg = 0, Sc = 0;
     int npg = 0;  // packed-16 layout: nonzeros per group step it was ordered for (0: 8-byte layout)
+    int kmult = 4;  // packed-16 layout: the schedule's step count is a multiple of this (4 or 1)
     int64_t NG = 0, NC = 0;
-    std::vector<int32_t> gene_dev, cell_dev;  // original index -> device row
-    int32_t *d_gene_dev = nullptr, *d_cell_dev = nullptr;
+    int32_t *d_gene_dev = nullptr, *d_cell_dev = nullptr;  // original index -> device row
     PassLayout cols, rows;
     int grid = 0;
     void release(cudaStream_t s) {
@@ -181,7 +184,11 @@ struct vbnmf_handle {
     int64_t *d_colptr = nullptr;
     int32_t *d_rowidx = nullptr;
     void *d_val = nullptr;
-    std::vector<unsigned long long> row_count, col_count;  // row counts are global once sharded
+    // entries with a non-zero value per gene (n) and per cell (m); the gene counts are global once
+    // the cells are sharded (vbnmf_attach_comm)
+    unsigned long long *d_cnt = nullptr;
+    bool colof_in_arena = false;  // d_arena[0, nnz) holds the column of every entry (scan_matrix)
+    int64_t empty_rows = 0, empty_cols = 0;
     std::vector<Layout *> layouts;
     Layout *L = nullptr;
     const vb::RpTable *tab = nullptr;
@@ -190,6 +197,8 @@ struct vbnmf_handle {
     double *d_lw = nullptr, *d_lh = nullptr, *d_alw = nullptr, *d_alh = nullptr;
     float *d_lw32 = nullptr, *d_lh32 = nullptr;  // fp32 mirrors read by the sweep (fp32-storage mode)
     int rsf = 0, panel_precision = -1;
+    int tsplit = 0;  // layout of d_lw / d_lh: 0 row-major, else the tile height T of the split
+                     // layout (kernels.cuh panel_ofs) read by the split variant of the p16 sweep
     // d_red = [SwRaw NG*rs | ehsum rs | hprior, sumloglh, sumeh | enth, xlogp | entw, - | pad]
     double *d_red = nullptr;
     double *d_ShRaw = nullptr, *d_Part1 = nullptr, *d_Part2 = nullptr, *d_xl = nullptr;
@@ -416,28 +425,24 @@ int peer_exit_barrier(H *h) {
 }
 
 // ---- building the tiled layouts ---------------------------------------------------------------
-// sorted position -> device row for `count` items dealt over S slabs of T rows
-void deal(const std::vector<unsigned long long> &cnt, int T, int S, std::vector<int32_t> &dev) {
-    const int64_t n = (int64_t)cnt.size();
-    // stable order by descending count: counting sort (counts are at most the other dimension)
-    unsigned long long maxc = 0;
-    for (auto c : cnt) maxc = std::max(maxc, c);
-    std::vector<int64_t> order((size_t)n);
-    if (maxc <= (unsigned long long)(8 * n + 1024)) {
-        std::vector<int64_t> start((size_t)maxc + 2, 0);
-        for (auto c : cnt) start[(size_t)(maxc - c) + 1]++;
-        for (size_t k = 1; k < start.size(); k++) start[k] += start[k - 1];
-        for (int64_t i = 0; i < n; i++) order[(size_t)start[(size_t)(maxc - cnt[(size_t)i])]++] = i;
-    } else {
-        std::iota(order.begin(), order.end(), 0);
-        std::stable_sort(order.begin(), order.end(),
-                         [&](int64_t a, int64_t b) { return cnt[a] > cnt[b]; });
-    }
-    dev.resize((size_t)n);
-    for (int64_t pos = 0; pos < n; pos++) {
-        const int64_t slab = pos % S, local = pos / S;
-        dev[(size_t)order[pos]] = (int32_t)(slab * T + local);
-    }
+// device row of every item: stable sort by descending count (cub radix sort of 2^31-1-count),
+// then sorted position pos -> slab pos % S, local row pos / S.  scratch: 4 * count uint32.
+int deal_device(H *h, const unsigned long long *d_cnt, int64_t count, int T, int S,
+                int32_t *d_dev, uint32_t *scratch) {
+    uint32_t *k_in = scratch, *k_out = scratch + count, *v_in = scratch + 2 * count,
+             *v_out = scratch + 3 * count;
+    const int g = cdiv(count, vb::kBlock);
+    vb::order_keys_kernel<<<g, vb::kBlock, 0, h->stream>>>(count, d_cnt, k_in, v_in, nullptr);
+    size_t tmp_bytes = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in, k_out, v_in, v_out, count, 0, 31,
+                                       h->stream));
+    void *d_tmp = nullptr;
+    CK(vmalloc(h, &d_tmp, tmp_bytes));
+    CK(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, k_in, k_out, v_in, v_out, count, 0, 31,
+                                       h->stream));
+    vb::deal_kernel<<<g, vb::kBlock, 0, h->stream>>>(count, S, T, v_out, d_dev);
+    vfree(h->stream, d_tmp);
+    return 0;
 }
 
 // scratch: 4 * nnz uint32 (sort keys/payloads in and out), owned by get_layout.  One arena instead
@@ -484,7 +489,7 @@ int build_pass(H *h, Layout *L, bool cols_pass, const int32_t *d_colof, uint32_t
         const uint32_t *d_words = p_out;  // the sorted payloads are the packed words
         { StageTimer t1("  plan(p16)");
         vb::plan_p16_kernel<<<g, vb::kBlock, 0, h->stream>>>(P.E, P.d_ptr, d_words, L->npg,
-                                                             d_len4); }
+                                                             L->kmult, d_len4); }
         size_t scan_bytes = 0;
         CK(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, d_len4, P.d_ptr4, P.E + 1, h->stream));
         void *d_scan = nullptr;
@@ -500,7 +505,7 @@ int build_pass(H *h, Layout *L, bool cols_pass, const int32_t *d_colof, uint32_t
         P.nent = (int64_t)quads * 4;
         { StageTimer t1("  build_segments(p16)");
         vb::build_segments_p16_kernel<<<g, vb::kBlock, 0, h->stream>>>(
-            P.E, NO, P.d_ptr, P.d_ptr4, d_words, L->npg, cols_pass ? h->n : h->m,
+            P.E, NO, P.d_ptr, P.d_ptr4, d_words, L->npg, L->kmult, cols_pass ? h->n : h->m,
             cols_pass ? L->Sg : L->Sc, (uint32_t *)P.d_ent); }
         CK(vmalloc(h, &P.d_split, (size_t)(L->grid + 1) * 8));
         vb::split_p16_kernel<<<cdiv(L->grid + 1, 128), 128, 0, h->stream>>>(L->grid, P.E, P.d_ptr4,
@@ -530,48 +535,67 @@ int build_pass(H *h, Layout *L, bool cols_pass, const int32_t *d_colof, uint32_t
     return 0;
 }
 
-int get_layout(H *h, int T, int npg, Layout **out) {
+template <typename VT>
+void launch_expand_cols(H *h, int32_t *d_colof, unsigned long long *d_cnt, unsigned *d_bad) {
+    vb::expand_cols_kernel<VT><<<h->num_sms * 8, vb::kBlock, 0, h->stream>>>(
+        h->m, h->n, h->d_colptr, h->d_rowidx, (const VT *)h->d_val, d_colof, d_cnt,
+        d_cnt ? d_cnt + h->n : nullptr, d_bad);
+}
+
+int get_layout(H *h, int T, int npg, int kmult, Layout **out) {
     if (!h->p16) npg = 0;
+    if (npg != 8) kmult = 4;
     for (Layout *l : h->layouts)
-        if (l->T == T && l->npg == npg) { *out = l; return 0; }
+        if (l->T == T && l->npg == npg && l->kmult == kmult) { *out = l; return 0; }
     StageTimer tm("get_layout(total)");
     Layout *L = new Layout();
     L->T = T;
     L->npg = npg;
+    L->kmult = kmult;
     L->Sg = cdiv(h->n, T);
     L->Sc = cdiv(h->m, T);
     L->NG = (int64_t)L->Sg * T;
     L->NC = (int64_t)L->Sc * T;
     L->grid = h->num_sms;
-    { StageTimer t1("  deal(host sort)");
-    deal(h->row_count, T, L->Sg, L->gene_dev);
-    deal(h->col_count, T, L->Sc, L->cell_dev); }
     auto bail = [&](int rc) { L->release(h->stream); delete L; return rc; };
     auto body = [&]() -> int {
         CK(vmalloc(h, &L->d_gene_dev, (size_t)h->n * 4));
         CK(vmalloc(h, &L->d_cell_dev, (size_t)h->m * 4));
-        CK(copy_sync(h, L->d_gene_dev, L->gene_dev.data(), (size_t)h->n * 4, cudaMemcpyHostToDevice));
-        CK(copy_sync(h, L->d_cell_dev, L->cell_dev.data(), (size_t)h->m * 4, cudaMemcpyHostToDevice));
-        // one arena: [colof | 4 sort buffers], nnz 32-bit words each
+        // one arena: [colof | 4 sort buffers], nnz 32-bit words each (also the scratch of the
+        // two small sorts that renumber the genes and the cells)
+        const int64_t words = std::max<int64_t>(h->nnz * 5, 4 * std::max(h->n, h->m));
         uint32_t *arena = h->d_arena;
+        const bool have_colof = arena && h->colof_in_arena;
         h->d_arena = nullptr;
-        unsigned long long *d_cnt = nullptr;
-        if (!arena) CK(vmalloc(h, &arena, (size_t)h->nnz * 4 * 5));
+        h->colof_in_arena = false;
+        if (!arena) CK(vmalloc(h, &arena, (size_t)words * 4));
         int32_t *d_colof = (int32_t *)arena;
         uint32_t *scratch = arena + h->nnz;
-        CK(vmalloc(h, &d_cnt, (size_t)(h->n + h->m) * 8));
-        CK(cudaMemsetAsync(d_cnt, 0, (size_t)(h->n + h->m) * 8, h->stream));
-        { StageTimer t1("  expand_cols");
-        vb::expand_cols_kernel<<<h->num_sms * 8, vb::kBlock, 0, h->stream>>>(
-            h->m, h->d_colptr, h->d_rowidx, d_colof, d_cnt, d_cnt + h->n); }
-        int rc = h->val_float ? build_pass<float>(h, L, true, d_colof, scratch)
+        int rc = 0;
+        { StageTimer t1("  deal(device sort)");
+        // (the scratch of the small sorts must not overlap colof: needs 4 * max(n, m) words)
+        uint32_t *dscr = scratch;
+        uint32_t *own = nullptr;
+        if (4 * std::max(h->n, h->m) > 4 * h->nnz) {
+            CK(vmalloc(h, &own, (size_t)4 * std::max(h->n, h->m) * 4));
+            dscr = own;
+        }
+        rc = deal_device(h, h->d_cnt, h->n, T, L->Sg, L->d_gene_dev, dscr);
+        if (!rc) rc = deal_device(h, h->d_cnt + h->n, h->m, T, L->Sc, L->d_cell_dev, dscr);
+        vfree(h->stream, own); }
+        if (!rc && !have_colof) {
+            StageTimer t1("  expand_cols");
+            if (h->val_float) launch_expand_cols<float>(h, d_colof, nullptr, nullptr);
+            else launch_expand_cols<double>(h, d_colof, nullptr, nullptr);
+        }
+        if (!rc)
+            rc = h->val_float ? build_pass<float>(h, L, true, d_colof, scratch)
                               : build_pass<double>(h, L, true, d_colof, scratch);
         if (!rc)
             rc = h->val_float ? build_pass<float>(h, L, false, d_colof, scratch)
                               : build_pass<double>(h, L, false, d_colof, scratch);
         { StageTimer t1("  free(arena)");
-        vfree(h->stream, arena);
-        vfree(h->stream, d_cnt); }
+        vfree(h->stream, arena); }
         return rc;
     };
     int rc = body();
@@ -587,34 +611,53 @@ void drop_layouts(H *h) {
     h->L = nullptr;
 }
 
-// nonzero counts per gene / cell and the constants over the nonzeros
+// nonzero counts per gene / cell (kept on the device), validation, the constants over the nonzeros
 template <typename VT>
 int scan_matrix_t(H *h) {
     StageTimer tm("scan_matrix");
     const int64_t n = h->n, m = h->m, nnz = h->nnz;
     const int gridK = h->num_sms * 8;
     double *d_part = nullptr, *d_out = nullptr;
-    CK(vmalloc(h, &d_part, (size_t)gridK * 3 * 8));
-    CK(vmalloc(h, &d_out, 3 * 8));
+    unsigned *d_flags = nullptr;  // [bad row index, empty rows, empty cols]
+    CK(vmalloc(h, &d_part, (size_t)gridK * 4 * 8));
+    CK(vmalloc(h, &d_out, 4 * 8));
+    CK(vmalloc(h, &d_flags, 4 * sizeof(unsigned)));
+    CK(cudaMemsetAsync(d_flags, 0, 4 * sizeof(unsigned), h->stream));
     vb::count_constants_kernel<VT><<<gridK, vb::kBlock, 0, h->stream>>>(
         nnz, (const VT *)h->d_val, d_part, d_out, h->d_counters + 4);
-    double consts[3];
-    CK(cudaMemcpyAsync(consts, d_out, 24, cudaMemcpyDeviceToHost, h->stream));
-    int32_t *d_colof = nullptr;
-    unsigned long long *d_cnt = nullptr;
-    CK(vmalloc(h, &d_colof, (size_t)nnz * 4));
-    CK(vmalloc(h, &d_cnt, (size_t)(n + m) * 8));
-    CK(cudaMemsetAsync(d_cnt, 0, (size_t)(n + m) * 8, h->stream));
-    vb::expand_cols_kernel<<<h->num_sms * 8, vb::kBlock, 0, h->stream>>>(
-        m, h->d_colptr, h->d_rowidx, d_colof, d_cnt, d_cnt + n);
-    h->row_count.resize((size_t)n);
-    h->col_count.resize((size_t)m);
-    CK(cudaMemcpyAsync(h->row_count.data(), d_cnt, (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(h->col_count.data(), d_cnt + n, (size_t)m * 8, cudaMemcpyDeviceToHost,
-                       h->stream));
+    double consts[4];
+    unsigned flags[4];
+    CK(cudaMemcpyAsync(consts, d_out, 32, cudaMemcpyDeviceToHost, h->stream));
+    // the column of every entry goes into the arena the first layout build sorts in (so that it
+    // is expanded once), or into a temporary when the handle has no arena
+    int32_t *d_colof = (int32_t *)h->d_arena;
+    if (!d_colof) CK(vmalloc(h, &d_colof, (size_t)nnz * 4));
+    CK(vmalloc(h, &h->d_cnt, (size_t)(n + m) * 8));
+    CK(cudaMemsetAsync(h->d_cnt, 0, (size_t)(n + m) * 8, h->stream));
+    launch_expand_cols<VT>(h, d_colof, h->d_cnt, d_flags);
+    h->colof_in_arena = h->d_arena != nullptr;
+    // empty genes / cells: counted by the kernel that makes the sort keys (scratch discarded)
+    uint32_t *d_scr = nullptr;
+    CK(vmalloc(h, &d_scr, (size_t)2 * std::max(n, m) * 4));
+    vb::order_keys_kernel<<<cdiv(n, vb::kBlock), vb::kBlock, 0, h->stream>>>(
+        n, h->d_cnt, d_scr, d_scr + std::max(n, m), d_flags + 1);
+    vb::order_keys_kernel<<<cdiv(m, vb::kBlock), vb::kBlock, 0, h->stream>>>(
+        m, h->d_cnt + n, d_scr, d_scr + std::max(n, m), d_flags + 2);
+    CK(cudaMemcpyAsync(flags, d_flags, sizeof(flags), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaGetLastError());
-    vfree(h->stream, d_part); vfree(h->stream, d_out); vfree(h->stream, d_colof); vfree(h->stream, d_cnt);
+    vfree(h->stream, d_part); vfree(h->stream, d_out); vfree(h->stream, d_flags);
+    vfree(h->stream, d_scr);
+    if (!h->d_arena) vfree(h->stream, d_colof);
+    if (flags[0]) return fail(h, VBNMF_ERR_ARG, "row index out of range");
+    if (consts[3] != 0.0)
+        return fail(h, VBNMF_ERR_ARG, "counts must be finite and non-negative");
+    h->empty_rows = flags[1];
+    h->empty_cols = flags[2];
+    // R/bayesian.R:244-247.  Empty genes of ONE shard are legal (the test is on the whole matrix:
+    // vbnmf_attach_comm repeats it on the all-reduced gene counts), empty cells never are.
+    if (h->empty_cols && !getenv("VBNMF_ALLOW_EMPTY"))
+        return fail(h, VBNMF_ERR_EMPTY, "Input matrix contains empty columns");
     h->lgx = consts[0];
     h->mlconst = consts[1];
     // VBNMF_NO_P16=1 keeps the 8-byte entries (A/B measurements, tests of that path)
@@ -645,9 +688,14 @@ int alloc_panels(H *h, int r) {
     const int rs = tab->rs;
     const bool f32 = h->precision == VBNMF_FP32_STORAGE;
     const int row_bytes = f32 ? tab->rsf * 4 : rs * 8;
+    // R/bayesian.R:244-245 (for a sharded matrix the test was made on the global gene counts)
+    if (h->empty_rows && !getenv("VBNMF_ALLOW_EMPTY"))
+        return fail(h, VBNMF_ERR_EMPTY, "Input matrix contains empty rows");
     const int T = choose_tile_rows(h, row_bytes);
+    // split layout + conflict-free rotated gathers: fp64 panels, packed-16 entries, 8..10 units
+    const bool split = !f32 && h->p16 && tab->split64 && !getenv("VBNMF_NO_SPLIT");
     Layout *L = nullptr;
-    int rc = get_layout(h, T, f32 ? tab->npg32 : tab->npg64, &L);
+    int rc = get_layout(h, T, f32 ? tab->npg32 : tab->npg64, split ? 1 : 4, &L);
     if (rc) return rc;
     if (rp == h->rp && L == h->L && h->d_lw && h->panel_precision == h->precision) {
         h->r = r;
@@ -656,10 +704,14 @@ int alloc_panels(H *h, int r) {
     free_panels(h);
     h->tab = tab;
     h->L = L;
+    h->tsplit = split ? T : 0;
     h->r = r; h->rp = rp; h->rs = rs; h->rsf = tab->rsf;
     h->panel_precision = h->precision;
     h->smem_bytes = T * row_bytes;
-    if (tab->sweep_prepare(h->smem_bytes))
+    // The opt-in is per kernel and device, i.e. shared by every handle of the process: always ask
+    // for the largest tile so that a second handle with a smaller tile cannot lower the limit
+    // under this one.
+    if (tab->sweep_prepare(kTileBytes))
         return fail(h, VBNMF_ERR_CUDA, "cannot opt in to the shared-memory tile size");
     const size_t gr = (size_t)L->NG * rs * 8, cr = (size_t)L->NC * rs * 8;
     CK(vmalloc(h, &h->d_lw, gr));
@@ -702,34 +754,10 @@ int refresh_mirrors(H *h) {
     return 0;
 }
 
-// host column-major (rows x r, `rows` genes) or r x cols (cells; contiguous r per cell) -> device
-// panel in device order, zero padded
-int upload_panel(H *h, double *dst, const double *src, bool wside, int r) {
-    const Layout *L = h->L;
-    const int rs = h->rs;
-    const int64_t cnt = wside ? h->n : h->m, N = wside ? L->NG : L->NC;
-    const std::vector<int32_t> &dev = wside ? L->gene_dev : L->cell_dev;
-    std::vector<double> tmp((size_t)N * rs, 0.0);
-    if (wside) {
-        for (int k = 0; k < r; k++)
-            for (int64_t i = 0; i < cnt; i++)
-                tmp[(size_t)dev[i] * rs + k] = src[(size_t)k * cnt + i];
-    } else {
-        for (int64_t j = 0; j < cnt; j++)
-            for (int k = 0; k < r; k++) tmp[(size_t)dev[j] * rs + k] = src[(size_t)j * r + k];
-    }
-    CK(cudaMemcpyAsync(dst, tmp.data(), tmp.size() * 8, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    return 0;
-}
-
-int download_panel(H *h, const double *src, std::vector<double> &tmp, bool wside) {
-    const Layout *L = h->L;
-    const int64_t N = wside ? L->NG : L->NC;
-    tmp.resize((size_t)N * h->rs);
-    CK(copy_sync(h, tmp.data(), src, tmp.size() * 8, cudaMemcpyDeviceToHost));
-    return 0;
-}
+// caller's matrix (n x r column-major for the W side, r x m for the H side) -> device panel(s) in
+// device order, zero padded.  The matrix goes up as it is (staged through pinned memory by the
+// worker pool) and is permuted on the device.
+int upload_panel(H *h, double *dst1, double *dst2, const double *src, bool wside, int r);
 
 // ---- one iteration --------------------------------------------------------------------------------
 inline int entry_format(const H *h) {
@@ -757,6 +785,7 @@ int launch_posterior(H *h, bool wside, double a, double b, double fud) {
     p.ctl = h->ctl;
     p.hoff = wside ? 0 : 2;
     p.rows_per_cta = vb::post_rows_per_cta(p.rows, h->rs, h->num_sms);
+    p.tsplit = h->tsplit;
     h->tab->posterior(p, h->stream);
     h->launches += 1;
     return 0;
@@ -773,9 +802,10 @@ int launch_sweep_cols(H *h) {
                          f32 ? (const void *)h->d_lh32 : (const void *)h->d_lh,
                          f32 ? (const void *)h->d_lw32 : (const void *)h->d_lw, h->d_Part1, h->d_xl,
                          h->ctl, L->cols.d_ptr4};
-    h->tab->sweep(a, true, entry_format(h), f32, L->grid, h->smem_bytes, h->stream);
+    h->tab->sweep(a, true, entry_format(h), f32, h->tsplit != 0, L->grid, h->smem_bytes, h->stream);
     vb::CombineArgs c{L->NC, L->Sg, h->r, h->d_Part1, h->d_lh, h->d_ShRaw, h->d_partC,
-                      tail + h->rs + 3, h->d_counters + 2, h->d_xl, L->grid, h->gridC, h->ctl};
+                      tail + h->rs + 3, h->d_counters + 2, h->d_xl, L->grid, h->gridC, h->ctl,
+                      h->tsplit};
     h->tab->combine(c, h->stream);
     h->launches += 2;
     return 0;
@@ -792,9 +822,10 @@ int launch_sweep_rows(H *h) {
                          f32 ? (const void *)h->d_lw32 : (const void *)h->d_lw,
                          f32 ? (const void *)h->d_lh32 : (const void *)h->d_lh, h->d_Part2, nullptr,
                          h->ctl, L->rows.d_ptr4};
-    h->tab->sweep(a, false, entry_format(h), f32, L->grid, h->smem_bytes, h->stream);
+    h->tab->sweep(a, false, entry_format(h), f32, h->tsplit != 0, L->grid, h->smem_bytes, h->stream);
     vb::CombineArgs c{L->NG, L->Sc, h->r, h->d_Part2, h->d_lw, h->d_red, h->d_partC,
-                      tail + h->rs + 5, h->d_counters + 3, nullptr, 0, h->gridC, h->ctl};
+                      tail + h->rs + 5, h->d_counters + 3, nullptr, 0, h->gridC, h->ctl,
+                      h->tsplit};
     h->tab->combine(c, h->stream);
     h->launches += 2;
     return 0;
@@ -867,17 +898,98 @@ void means_of(const H *h, double *means) {
     means[3] = h->hacc[2] / mr;
 }
 
-// Host -> device upload of a large array through two pinned staging buffers: worker threads
-// convert/validate a chunk into one buffer while the copy engine drains the other.  `conv` maps
+// ---- host worker pool ---------------------------------------------------------------------------
+// Persistent threads that copy / convert host arrays into the pinned staging buffers (creating
+// and joining threads per 32 MB chunk cost more than the conversion).  The number of workers is
+// min(16, hardware threads), VBNMF_HOST_THREADS, or vbnmf_set_host_threads(): with one process
+// per GPU the host side should pass cores / processes.
+class WorkerPool {
+public:
+    void set_threads(int n) {
+        std::lock_guard<std::mutex> lk(mu_);
+        want_ = std::max(1, std::min(n, 64));
+    }
+    int threads() {
+        std::lock_guard<std::mutex> lk(mu_);
+        return want_;
+    }
+    // fn(part, nparts) for part in [0, nparts), nparts = current number of workers; returns when
+    // all parts are done.  The calling thread runs part 0.
+    void run(const std::function<void(int, int)> &fn) {
+        std::unique_lock<std::mutex> lk(mu_);
+        const int np = want_;
+        while ((int)th_.size() < np - 1) {
+            const int id = (int)th_.size() + 1;
+            th_.emplace_back([this, id] { loop(id); });
+        }
+        fn_ = &fn;
+        nparts_ = np;
+        pending_ = np - 1;
+        gen_++;
+        lk.unlock();
+        cv_.notify_all();
+        fn(0, np);
+        lk.lock();
+        done_.wait(lk, [this] { return pending_ == 0; });
+        fn_ = nullptr;
+    }
+    WorkerPool() {
+        unsigned hw = std::thread::hardware_concurrency();
+        want_ = (int)std::max(1u, std::min(16u, hw ? hw : 1u));
+        if (const char *e = getenv("VBNMF_HOST_THREADS")) want_ = std::max(1, std::min(atoi(e), 64));
+    }
+    ~WorkerPool() {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+            gen_++;
+        }
+        cv_.notify_all();
+        for (auto &t : th_) t.join();
+    }
+
+private:
+    void loop(int id) {
+        uint64_t seen = 0;
+        for (;;) {
+            std::unique_lock<std::mutex> lk(mu_);
+            cv_.wait(lk, [&] { return gen_ != seen; });
+            seen = gen_;
+            if (stop_) return;
+            if (id >= nparts_ || !fn_) continue;
+            const std::function<void(int, int)> *fn = fn_;
+            const int np = nparts_;
+            lk.unlock();
+            (*fn)(id, np);
+            lk.lock();
+            if (--pending_ == 0) done_.notify_all();
+        }
+    }
+    std::mutex mu_;
+    std::condition_variable cv_, done_;
+    std::vector<std::thread> th_;
+    const std::function<void(int, int)> *fn_ = nullptr;
+    int want_ = 1, nparts_ = 0, pending_ = 0;
+    uint64_t gen_ = 0;
+    bool stop_ = false;
+};
+WorkerPool &pool() {
+    static WorkerPool *p = new WorkerPool();  // leaked on purpose: no join at process exit
+    return *p;
+}
+
+// Host -> device upload of a large array through pinned staging buffers: the pool converts /
+// validates a chunk into one buffer while the copy engine drains the others.  `conv` maps
 // src[i] -> dst element and returns false for an invalid element.
 struct Staging {
     static constexpr size_t kBytes = (size_t)32 << 20;
-    void *buf[2] = {nullptr, nullptr};
-    cudaEvent_t ev[2];
+    static constexpr int kSlots = 3;
+    void *buf[kSlots] = {};
+    cudaEvent_t ev[kSlots];
     bool ok = false;
     bool init() {
         if (ok) return true;
-        for (int i = 0; i < 2; i++) {
+        for (int i = 0; i < kSlots; i++) {
             if (cudaMallocHost(&buf[i], kBytes) != cudaSuccess) return false;
             if (cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) return false;
         }
@@ -886,37 +998,82 @@ struct Staging {
     }
 };
 Staging g_staging;
-std::mutex g_staging_mu;  // the staging buffers are shared by all handles of the process
+std::mutex g_staging_mu;  // the staging buffers and the pool are shared by all handles of the process
 
 template <typename Src, typename Dst, typename Conv>
 int staged_upload(H *h, Dst *d_dst, const Src *src, int64_t count, Conv conv, bool *all_ok) {
     std::lock_guard<std::mutex> lock(g_staging_mu);
     if (!g_staging.init()) return fail(h, VBNMF_ERR_CUDA, "cannot allocate pinned staging buffers");
     const int64_t per = (int64_t)(Staging::kBytes / sizeof(Dst));
-    const int nthr = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-    std::vector<char> good((size_t)nthr, 1);
+    std::atomic<int> bad{0};
     int slot = 0;
-    for (int64_t lo = 0; lo < count; lo += per, slot ^= 1) {
+    for (int64_t lo = 0; lo < count; lo += per, slot = (slot + 1) % Staging::kSlots) {
         const int64_t len = std::min(per, count - lo);
         CK(cudaEventSynchronize(g_staging.ev[slot]));  // the copy that last used this buffer is done
         Dst *out = (Dst *)g_staging.buf[slot];
-        auto work = [&](int t) {
-            const int64_t a = len * t / nthr, b = len * (t + 1) / nthr;
+        const Src *in = src + lo;
+        pool().run([&](int t, int nt) {
+            const int64_t a = len * t / nt, b = len * (t + 1) / nt;
             bool okk = true;
-            for (int64_t i = a; i < b; i++) okk &= conv(src[lo + i], out[i]);
-            if (!okk) good[(size_t)t] = 0;
-        };
-        std::vector<std::thread> th;
-        for (int t = 1; t < nthr; t++) th.emplace_back(work, t);
-        work(0);
-        for (auto &x : th) x.join();
+            for (int64_t i = a; i < b; i++) okk &= conv(in[i], out[i]);
+            if (!okk) bad.store(1, std::memory_order_relaxed);
+        });
         CK(cudaMemcpyAsync(d_dst + lo, out, (size_t)len * sizeof(Dst), cudaMemcpyHostToDevice,
                            h->stream));
         CK(cudaEventRecord(g_staging.ev[slot], h->stream));
     }
     CK(cudaStreamSynchronize(h->stream));
-    *all_ok = true;
-    for (char c : good) *all_ok = *all_ok && c;
+    *all_ok = bad.load() == 0;
+    return 0;
+}
+
+// device -> host of a large array into pageable memory, through the same pinned buffers
+int staged_download(H *h, double *dst, const double *d_src, int64_t count) {
+    std::lock_guard<std::mutex> lock(g_staging_mu);
+    if (!g_staging.init()) return fail(h, VBNMF_ERR_CUDA, "cannot allocate pinned staging buffers");
+    const int64_t per = (int64_t)(Staging::kBytes / 8);
+    const int64_t nch = (count + per - 1) / per;
+    auto drain = [&](int64_t c) -> int {
+        const int sl = (int)(c % Staging::kSlots);
+        const int64_t lo = c * per, len = std::min(per, count - lo);
+        CK(cudaEventSynchronize(g_staging.ev[sl]));
+        const double *in = (const double *)g_staging.buf[sl];
+        pool().run([&](int t, int nt) {
+            const int64_t a = len * t / nt, b = len * (t + 1) / nt;
+            memcpy(dst + lo + a, in + a, (size_t)(b - a) * 8);
+        });
+        return 0;
+    };
+    for (int64_t c = 0; c < nch; c++) {
+        const int sl = (int)(c % Staging::kSlots);
+        if (c >= Staging::kSlots) {  // the slot still holds chunk c - kSlots: move it out first
+            int rc = drain(c - Staging::kSlots);
+            if (rc) return rc;
+        }
+        const int64_t lo = c * per, len = std::min(per, count - lo);
+        CK(cudaMemcpyAsync(g_staging.buf[sl], d_src + lo, (size_t)len * 8, cudaMemcpyDeviceToHost,
+                           h->stream));
+        CK(cudaEventRecord(g_staging.ev[sl], h->stream));
+    }
+    for (int64_t c = std::max<int64_t>(0, nch - Staging::kSlots); c < nch; c++) {
+        int rc = drain(c);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+int upload_panel(H *h, double *dst1, double *dst2, const double *src, bool wside, int r) {
+    const Layout *L = h->L;
+    const int64_t cnt = wside ? h->n : h->m;
+    double *d_raw = nullptr;
+    CK(vmalloc(h, &d_raw, (size_t)cnt * r * 8));
+    bool ok = true;
+    int rc = staged_upload(h, d_raw, src, cnt * r, [](double v, double &o) { o = v; return true; },
+                           &ok);
+    if (rc) { vfree(h->stream, d_raw); return rc; }
+    vb::scatter_panel_kernel<<<cdiv(cnt * r, vb::kBlock), vb::kBlock, 0, h->stream>>>(
+        cnt, r, h->rs, wside ? L->d_gene_dev : L->d_cell_dev, d_raw, wside, dst1, dst2, h->tsplit);
+    vfree(h->stream, d_raw);
     return 0;
 }
 
@@ -932,12 +1089,16 @@ int init_common(H *h, int device) {
     h->num_sms = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     h->own_stream = true;
-    {   // keep freed blocks in the device's default pool (VBNMF_POOL_KEEP_GB, default 32 GB)
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    {   // Keep freed blocks in the device's default pool.  With a finite threshold a large
+        // factorization (the layout build of a 2e9-nonzero matrix cycles through ~60 GB of
+        // scratch) has the driver unmap and remap tens of GB at every synchronisation: measured
+        // 2 s for ONE free and 3.5 s per layout build against 0.4 s of kernels.  Default: keep
+        // everything (VBNMF_POOL_KEEP_GB sets a limit; vbnmf_trim_pool() returns the memory).
+        cudaMemPool_t mp;
+        if (cudaDeviceGetDefaultMemPool(&mp, device) == cudaSuccess) {
             const char *env = getenv("VBNMF_POOL_KEEP_GB");
-            uint64_t keep = (uint64_t)(env ? atof(env) : 32.0) << 30;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            uint64_t keep = env ? (uint64_t)(atof(env) * 1073741824.0) : UINT64_MAX;
+            cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &keep);
         }
     }
     CK(vmalloc(h, &h->d_counters, 16 * sizeof(unsigned)));
@@ -967,12 +1128,27 @@ void vbnmf_destroy(vbnmf_handle *h) {
         vfree(h->stream, h->d_colptr); vfree(h->stream, h->d_rowidx); vfree(h->stream, h->d_val);
     }
     vfree(h->stream, h->d_arena);
+    vfree(h->stream, h->d_cnt);
     vfree(h->stream, h->d_counters);
     vfree(h->stream, h->d_ctl);
     if (h->h_ctl) cudaFreeHost(h->h_ctl);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
+}
+
+int vbnmf_set_host_threads(int nthreads) {
+    if (nthreads < 1) return VBNMF_ERR_ARG;
+    pool().set_threads(nthreads);
+    return 0;
+}
+
+int vbnmf_trim_pool(int device) {
+    cudaMemPool_t mp;
+    if (cudaSetDevice(device) != cudaSuccess) return VBNMF_ERR_CUDA;
+    if (cudaDeviceSynchronize() != cudaSuccess) return VBNMF_ERR_CUDA;
+    if (cudaDeviceGetDefaultMemPool(&mp, device) != cudaSuccess) return VBNMF_ERR_CUDA;
+    return cudaMemPoolTrimTo(mp, 0) == cudaSuccess ? 0 : VBNMF_ERR_CUDA;
 }
 
 int vbnmf_create(vbnmf_handle **out, int64_t n, int64_t m, int64_t nnz, const int32_t *colptr32,
@@ -988,30 +1164,52 @@ int vbnmf_create(vbnmf_handle **out, int64_t n, int64_t m, int64_t nnz, const in
     StageTimer tm("vbnmf_create(total)");
     if (n <= 0 || m <= 0 || nnz <= 0 || (!colptr32 == !colptr64) || !rowidx || !values)
         return bail(fail(h, VBNMF_ERR_ARG, "vbnmf_create: bad arguments"));
+    if (n > INT32_MAX || m > INT32_MAX)
+        return bail(fail(h, VBNMF_ERR_ARG, "n and m must be below 2^31 (int32 row/column indices)"));
     if (nnz >= (int64_t)UINT32_MAX)
         return bail(fail(h, VBNMF_ERR_ARG, "nnz per GPU must be < 2^32-1"));
     h->n = n; h->m = m; h->nnz = nnz;
     int rc = init_common(h, device);
     if (rc) return bail(rc);
-    std::vector<int64_t> cp((size_t)m + 1);
-    for (int64_t j = 0; j <= m; j++) cp[j] = colptr64 ? colptr64[j] : (int64_t)colptr32[j];
-    if (cp[0] != 0 || cp[m] != nnz) return bail(fail(h, VBNMF_ERR_ARG, "colptr does not span nnz"));
-    for (int64_t j = 0; j < m; j++)
-        if (cp[j] > cp[j + 1]) return bail(fail(h, VBNMF_ERR_ARG, "colptr is not non-decreasing"));
     bool as_float = true;
     auto up = [&]() -> int {
         StageTimer tu("  upload (staged, pinned)");
         bool ok = true;
-        CK(vmalloc(h, &h->d_arena, (size_t)nnz * 4 * 5));
+        std::atomic<int> unsorted{0};
+        CK(vmalloc(h, &h->d_arena, (size_t)std::max<int64_t>(nnz * 5, 4 * std::max(n, m)) * 4));
         CK(vmalloc(h, &h->d_colptr, (size_t)(m + 1) * 8));
         CK(vmalloc(h, &h->d_rowidx, (size_t)nnz * 4));
-        CK(copy_sync(h, h->d_colptr, cp.data(), (size_t)(m + 1) * 8, cudaMemcpyHostToDevice));
-        const int32_t nn = (int32_t)n;
-        int rc2 = staged_upload(h, h->d_rowidx, rowidx, nnz,
-                                [nn](int32_t v, int32_t &o) { o = v; return v >= 0 && v < nn; }, &ok);
+        // column pointers: widened to 64 bits and checked on the way (first = 0, last = nnz,
+        // non-decreasing: element j is compared with element j + 1, which the caller's array holds)
+        int rc2;
+        if (colptr64) {
+            if (colptr64[0] != 0 || colptr64[m] != nnz) return fail(h, VBNMF_ERR_ARG, "colptr does not span nnz");
+            rc2 = staged_upload(h, h->d_colptr, colptr64, m + 1,
+                                [](const int64_t &v, int64_t &o) { o = v; return true; }, &ok);
+            if (rc2) return rc2;
+            pool().run([&](int t, int nt) {
+                bool g = true;
+                for (int64_t j = m * t / nt; j < m * (t + 1) / nt; j++) g &= colptr64[j] <= colptr64[j + 1];
+                if (!g) unsorted.store(1);
+            });
+        } else {
+            if (colptr32[0] != 0 || (int64_t)colptr32[m] != nnz) return fail(h, VBNMF_ERR_ARG, "colptr does not span nnz");
+            rc2 = staged_upload(h, h->d_colptr, colptr32, m + 1,
+                                [](const int32_t &v, int64_t &o) { o = v; return true; }, &ok);
+            if (rc2) return rc2;
+            pool().run([&](int t, int nt) {
+                bool g = true;
+                for (int64_t j = m * t / nt; j < m * (t + 1) / nt; j++) g &= colptr32[j] <= colptr32[j + 1];
+                if (!g) unsorted.store(1);
+            });
+        }
+        if (unsorted.load()) return fail(h, VBNMF_ERR_ARG, "colptr is not non-decreasing");
+        // row indices: plain copy, range-checked on the device (scan_matrix)
+        rc2 = staged_upload(h, h->d_rowidx, rowidx, nnz,
+                            [](int32_t v, int32_t &o) { o = v; return true; }, &ok);
         if (rc2) return rc2;
-        if (!ok) return fail(h, VBNMF_ERR_ARG, "row index out of range");
         // counts go to the device as fp32 when every one of them is exactly representable
+        // (NaN compares unequal: it takes the fp64 path and is refused by scan_matrix)
         float *dv = nullptr;
         CK(vmalloc(h, &dv, (size_t)nnz * 4));
         rc2 = staged_upload(h, dv, values, nnz,
@@ -1052,6 +1250,8 @@ int vbnmf_create_from_device(vbnmf_handle **out, int64_t n, int64_t m, int64_t n
     };
     if (n <= 0 || m <= 0 || nnz <= 0 || !d_colptr || !d_rowidx || !d_values)
         return bail(fail(h, VBNMF_ERR_ARG, "vbnmf_create_from_device: bad arguments"));
+    if (n > INT32_MAX || m > INT32_MAX)
+        return bail(fail(h, VBNMF_ERR_ARG, "n and m must be below 2^31 (int32 row/column indices)"));
     if (nnz >= (int64_t)UINT32_MAX)
         return bail(fail(h, VBNMF_ERR_ARG, "nnz per GPU must be < 2^32-1"));
     h->n = n; h->m = m; h->nnz = nnz;
@@ -1139,25 +1339,58 @@ int vbnmf_attach_comm(vbnmf_handle *h, vbnmf_comm *c) {
     h->rank = c->rank;
     // global quantities: total cells, the sums over nonzeros, and the per-gene nonzero counts
     // (every rank must derive the same gene renumbering)
-    const int64_t len = 3 + h->n;
-    std::vector<double> hv((size_t)len);
-    hv[0] = (double)h->m; hv[1] = h->lgx; hv[2] = h->mlconst;
-    for (int64_t i = 0; i < h->n; i++) hv[3 + i] = (double)h->row_count[i];
+    double hv[3] = {(double)h->m, h->lgx, h->mlconst};
     double *dv = nullptr;
-    CK(vmalloc(h, &dv, (size_t)len * 8));
-    CK(cudaMemcpyAsync(dv, hv.data(), (size_t)len * 8, cudaMemcpyHostToDevice, h->stream));
-    int rc = allreduce(h, dv, len);
+    unsigned *d_flag = nullptr;
+    uint32_t *d_scr = nullptr;
+    CK(vmalloc(h, &dv, 3 * 8));
+    CK(vmalloc(h, &d_flag, 4));
+    CK(vmalloc(h, &d_scr, (size_t)2 * h->n * 4));
+    CK(cudaMemsetAsync(d_flag, 0, 4, h->stream));
+    CK(cudaMemcpyAsync(dv, hv, 3 * 8, cudaMemcpyHostToDevice, h->stream));
+    int rc = allreduce(h, dv, 3);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(hv.data(), dv, (size_t)len * 8, cudaMemcpyDeviceToHost, h->stream));
+    CKN(g_nccl.AllReduce(h->d_cnt, h->d_cnt, (size_t)h->n, ncclUint64, ncclSum, h->comm, h->stream));
+    vb::order_keys_kernel<<<cdiv(h->n, vb::kBlock), vb::kBlock, 0, h->stream>>>(
+        h->n, h->d_cnt, d_scr, d_scr + h->n, d_flag);
+    unsigned nzero = 0;
+    CK(cudaMemcpyAsync(hv, dv, 3 * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(&nzero, d_flag, 4, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    vfree(h->stream, dv);
+    vfree(h->stream, dv); vfree(h->stream, d_flag); vfree(h->stream, d_scr);
     h->m_global = (int64_t)llround(hv[0]);
     h->lgx = hv[1];
     h->mlconst = hv[2];
-    for (int64_t i = 0; i < h->n; i++) h->row_count[i] = (unsigned long long)llround(hv[3 + i]);
+    h->empty_rows = nzero;  // of the whole matrix now (R/bayesian.R:244); tested at set_state
     free_panels(h);
     drop_layouts(h);
     h->stats_valid = false;
+    return 0;
+}
+
+// rowSums(eh) of the state just loaded (alh holds eh before the first update), over all shards,
+// into the tail of the reduce buffer and the host vectors
+static int initial_ehsum(H *h) {
+    const Layout *L = h->L;
+    const int rs = h->rs, r = h->r;
+    int rc;
+    double *tail = h->d_red + tail_off(h);
+    CK(cudaMemsetAsync(tail, 0, (size_t)(rs + 8) * 8, h->stream));
+    vb::ColsumArgs ca{L->NC, h->d_alh, h->d_partH, tail, h->d_counters + 1, 0};
+    h->tab->colsum(ca, h->stream);
+    h->launches += 1;
+    if ((rc = allreduce(h, tail, rs + 8))) return rc;
+    double s[kMaxRank + 16];  // rs + 8 <= 66 + 8
+    CK(cudaMemcpyAsync(s, tail, (size_t)(rs + 8) * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+    for (int k = 0; k < kMaxRank; k++) {
+        h->ehsum[k] = k < r ? s[k] : 0.0;
+        h->ewsum[k] = 0.0;
+        h->bew[k] = h->beh[k] = 1.0;
+    }
+    h->stats_valid = false;
+    h->has_posterior = false;
     return 0;
 }
 
@@ -1169,29 +1402,21 @@ int vbnmf_set_state(vbnmf_handle *h, int r, const double *lw, const double *lh, 
     StageTimer tm("vbnmf_set_state(total)");
     int rc;
     if ((rc = alloc_panels(h, r))) return rc;
-    if ((rc = upload_panel(h, h->d_lw, lw, true, r))) return rc;
-    if ((rc = upload_panel(h, h->d_lh, lh, false, r))) return rc;
-    // before the first update ew/eh are whatever the caller holds (vb_init: ew = w, eh = h)
-    if ((rc = upload_panel(h, h->d_alw, ew ? ew : lw, true, r))) return rc;
-    if ((rc = upload_panel(h, h->d_alh, eh ? eh : lh, false, r))) return rc;
+    const Layout *L = h->L;
+    const size_t gr = (size_t)L->NG * h->rs * 8, cr = (size_t)L->NC * h->rs * 8;
+    CK(cudaMemsetAsync(h->d_lw, 0, gr, h->stream));
+    CK(cudaMemsetAsync(h->d_alw, 0, gr, h->stream));
+    CK(cudaMemsetAsync(h->d_lh, 0, cr, h->stream));
+    CK(cudaMemsetAsync(h->d_alh, 0, cr, h->stream));
+    // before the first update ew/eh are whatever the caller holds (vb_init: ew = w, eh = h); a
+    // matrix passed twice goes up once
+    const bool ew_same = !ew || ew == lw, eh_same = !eh || eh == lh;
+    if ((rc = upload_panel(h, h->d_lw, ew_same ? h->d_alw : nullptr, lw, true, r))) return rc;
+    if (!ew_same && (rc = upload_panel(h, h->d_alw, nullptr, ew, true, r))) return rc;
+    if ((rc = upload_panel(h, h->d_lh, eh_same ? h->d_alh : nullptr, lh, false, r))) return rc;
+    if (!eh_same && (rc = upload_panel(h, h->d_alh, nullptr, eh, false, r))) return rc;
     if ((rc = refresh_mirrors(h))) return rc;
-    const double *e = eh ? eh : lh;
-    double *tail = h->d_red + tail_off(h);
-    std::vector<double> s((size_t)h->rs + 8, 0.0);
-    for (int64_t j = 0; j < h->m; j++)
-        for (int k = 0; k < r; k++) s[k] += e[(size_t)j * r + k];
-    CK(cudaMemcpyAsync(tail, s.data(), s.size() * 8, cudaMemcpyHostToDevice, h->stream));
-    if ((rc = allreduce(h, tail, h->rs + 8))) return rc;
-    CK(cudaMemcpyAsync(s.data(), tail, s.size() * 8, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    for (int k = 0; k < kMaxRank; k++) {
-        h->ehsum[k] = k < r ? s[k] : 0.0;
-        h->ewsum[k] = 0.0;
-        h->bew[k] = h->beh[k] = 1.0;
-    }
-    h->stats_valid = false;
-    h->has_posterior = false;
-    return 0;
+    return initial_ehsum(h);
 }
 
 int vbnmf_init_random(vbnmf_handle *h, int r, const double hyper[4], uint64_t seed,
@@ -1214,31 +1439,13 @@ int vbnmf_init_random(vbnmf_handle *h, int r, const double hyper[4], uint64_t se
     // w ~ Gamma(aw, scale bw/aw), h ~ Gamma(ah, scale bh/ah); lw = ew = w, lh = eh = h (:111-115,170)
     vb::init_random_kernel<<<cdiv(h->n * r, vb::kBlock), vb::kBlock, 0, h->stream>>>(
         h->n, r, rs, L->d_gene_dev, 0, 0, (unsigned long long)seed, hyper[0], hyper[1] / hyper[0],
-        h->d_lw, h->d_alw);
+        h->d_lw, h->d_alw, h->tsplit);
     vb::init_random_kernel<<<cdiv(h->m * r, vb::kBlock), vb::kBlock, 0, h->stream>>>(
         h->m, r, rs, L->d_cell_dev, 1, cell_offset, (unsigned long long)seed, hyper[2],
-        hyper[3] / hyper[2], h->d_lh, h->d_alh);
+        hyper[3] / hyper[2], h->d_lh, h->d_alh, h->tsplit);
     h->launches += 2;
     if ((rc = refresh_mirrors(h))) return rc;
-    // rowSums(eh) of the initial state, over all shards
-    double *tail = h->d_red + tail_off(h);
-    CK(cudaMemsetAsync(tail, 0, (size_t)(rs + 8) * 8, h->stream));
-    vb::ColsumArgs ca{L->NC, h->d_lh, h->d_partH, tail, h->d_counters + 1};
-    h->tab->colsum(ca, h->stream);
-    h->launches += 1;
-    if ((rc = allreduce(h, tail, rs + 8))) return rc;
-    std::vector<double> s((size_t)rs + 8, 0.0);
-    CK(cudaMemcpyAsync(s.data(), tail, s.size() * 8, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    CK(cudaGetLastError());
-    for (int k = 0; k < kMaxRank; k++) {
-        h->ehsum[k] = k < r ? s[k] : 0.0;
-        h->ewsum[k] = 0.0;
-        h->bew[k] = h->beh[k] = 1.0;
-    }
-    h->stats_valid = false;
-    h->has_posterior = false;
-    return 0;
+    return initial_ehsum(h);
 }
 
 int vbnmf_step(vbnmf_handle *h, const double hyper[4], double fudge, double *lkh) {
@@ -1442,42 +1649,42 @@ int vbnmf_get_state(vbnmf_handle *h, double *lw, double *lh, double *ew, double 
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
     StageTimer tm("vbnmf_get_state(total)");
-    const int r = h->r, rs = h->rs;
+    // the panels are brought into the caller's layout (and divided by bew / beh, :44,46,54,56) on
+    // the device, then copied out
+    const int r = h->r;
     const int64_t n = h->n, m = h->m;
     const Layout *L = h->L;
-    std::vector<double> tmp;
-    int rc;
-    if (lw) {
-        if ((rc = download_panel(h, h->d_lw, tmp, true))) return rc;
-        for (int k = 0; k < r; k++)
-            for (int64_t i = 0; i < n; i++)
-                lw[(size_t)k * n + i] = tmp[(size_t)L->gene_dev[i] * rs + k];
-    }
-    if (ew || dw) {
-        if ((rc = download_panel(h, h->d_alw, tmp, true))) return rc;
-        for (int k = 0; k < r; k++)
-            for (int64_t i = 0; i < n; i++) {
-                const double a = tmp[(size_t)L->gene_dev[i] * rs + k], b = h->bew[k];
-                if (ew) ew[(size_t)k * n + i] = a / b;                               // :44
-                if (dw) dw[(size_t)k * n + i] = h->has_posterior ? a / b / b : 0.0;  // :46
-            }
-    }
-    if (lh) {
-        if ((rc = download_panel(h, h->d_lh, tmp, false))) return rc;
-        for (int64_t j = 0; j < m; j++)
-            for (int k = 0; k < r; k++)
-                lh[(size_t)j * r + k] = tmp[(size_t)L->cell_dev[j] * rs + k];
-    }
-    if (eh || dh) {
-        if ((rc = download_panel(h, h->d_alh, tmp, false))) return rc;
-        for (int64_t j = 0; j < m; j++)
-            for (int k = 0; k < r; k++) {
-                const double a = tmp[(size_t)L->cell_dev[j] * rs + k], b = h->beh[k];
-                if (eh) eh[(size_t)j * r + k] = a / b;                               // :54
-                if (dh) dh[(size_t)j * r + k] = h->has_posterior ? a / b / b : 0.0;  // :56
-            }
-    }
-    return 0;
+    double *d_be = nullptr, *d_tmp = nullptr;
+    CK(vmalloc(h, &d_be, 2 * kMaxRank * 8));
+    CK(vmalloc(h, &d_tmp, (size_t)std::max(n, m) * r * 8));
+    CK(cudaMemcpyAsync(d_be, h->bew, kMaxRank * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_be + kMaxRank, h->beh, kMaxRank * 8, cudaMemcpyHostToDevice, h->stream));
+    auto one = [&](const double *panel, bool wside, int mode, double *out) -> int {
+        if (!out) return 0;
+        const int64_t cnt = wside ? n : m;
+        if (mode == 2 && !h->has_posterior) {  // dw = dh = 0 before the first update (vb_init)
+            memset(out, 0, (size_t)cnt * r * 8);
+            return 0;
+        }
+        vb::gather_panel_kernel<<<cdiv(cnt * r, vb::kBlock), vb::kBlock, 0, h->stream>>>(
+            cnt, r, h->rs, wside ? L->d_gene_dev : L->d_cell_dev, panel, wside,
+            wside ? d_be : d_be + kMaxRank, mode, d_tmp, mode == 0 ? h->tsplit : 0);
+        if (cnt * r * 8 >= (int64_t)(8 << 20)) return staged_download(h, out, d_tmp, cnt * r);
+        CK(cudaMemcpyAsync(out, d_tmp, (size_t)cnt * r * 8, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        return 0;
+    };
+    int rc = 0;
+    if (!rc) rc = one(h->d_lw, true, 0, lw);
+    if (!rc) rc = one(h->d_alw, true, 1, ew);
+    if (!rc) rc = one(h->d_alw, true, 2, dw);
+    if (!rc) rc = one(h->d_lh, false, 0, lh);
+    if (!rc) rc = one(h->d_alh, false, 1, eh);
+    if (!rc) rc = one(h->d_alh, false, 2, dh);
+    vfree(h->stream, d_be);
+    vfree(h->stream, d_tmp);
+    if (!rc) CK(cudaGetLastError());
+    return rc;
 }
 
 int vbnmf_cluster_id(vbnmf_handle *h, int32_t *cid) {
@@ -1486,18 +1693,21 @@ int vbnmf_cluster_id(vbnmf_handle *h, int32_t *cid) {
     CK(cudaSetDevice(h->device));
     const Layout *L = h->L;
     double *d_beh = nullptr;
-    int32_t *d_cid = nullptr;
-    std::vector<int32_t> tmp((size_t)L->NC);
+    int32_t *d_cid = nullptr, *d_out = nullptr;
     CK(vmalloc(h, &d_beh, kMaxRank * 8));
     CK(vmalloc(h, &d_cid, (size_t)L->NC * 4));
+    CK(vmalloc(h, &d_out, (size_t)h->m * 4));
     CK(cudaMemcpyAsync(d_beh, h->beh, kMaxRank * 8, cudaMemcpyHostToDevice, h->stream));
     vb::cluster_id_kernel<<<cdiv(L->NC, vb::kBlock), vb::kBlock, 0, h->stream>>>(
         L->NC, h->rs, h->r, h->d_alh, d_beh, d_cid);
-    CK(cudaMemcpyAsync(tmp.data(), d_cid, (size_t)L->NC * 4, cudaMemcpyDeviceToHost, h->stream));
+    vb::gather_i32_kernel<<<cdiv(h->m, vb::kBlock), vb::kBlock, 0, h->stream>>>(
+        h->m, L->d_cell_dev, d_cid, d_out);
+    CK(cudaMemcpyAsync(cid, d_out, (size_t)h->m * 4, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     vfree(h->stream, d_beh);
     vfree(h->stream, d_cid);
-    for (int64_t j = 0; j < h->m; j++) cid[j] = tmp[(size_t)L->cell_dev[j]];
+    vfree(h->stream, d_out);
+    CK(cudaGetLastError());
     return 0;
 }
 
@@ -1505,39 +1715,40 @@ int vbnmf_uniform_columns(vbnmf_handle *h, double tol, int32_t *flags) {
     if (!h || !flags) return VBNMF_ERR_ARG;
     if (!h->d_lw) return fail(h, VBNMF_ERR_STATE, "vbnmf_set_state has not been called");
     CK(cudaSetDevice(h->device));
-    CK(cudaStreamSynchronize(h->stream));
-    const int r = h->r, rs = h->rs;
     const Layout *L = h->L;
-    std::vector<double> tmp;
-    int rc;
-    if ((rc = download_panel(h, h->d_alw, tmp, true))) return rc;
-    for (int k = 0; k < r; k++) {
-        double mx = -INFINITY, mn = INFINITY;
-        for (int64_t i = 0; i < h->n; i++) {
-            const double v = tmp[(size_t)L->gene_dev[i] * rs + k] / h->bew[k];
-            mx = v > mx ? v : mx;
-            mn = v < mn ? v : mn;
-        }
-        flags[k] = fabs(mx - mn) < tol ? 1 : 0;  // R/bayesian.R:368-369
-    }
+    double *d_bew = nullptr;
+    int32_t *d_fl = nullptr;
+    CK(vmalloc(h, &d_bew, kMaxRank * 8));
+    CK(vmalloc(h, &d_fl, kMaxRank * 4));
+    CK(cudaMemcpyAsync(d_bew, h->bew, kMaxRank * 8, cudaMemcpyHostToDevice, h->stream));
+    vb::uniform_columns_kernel<<<h->r, vb::kBlock, 0, h->stream>>>(
+        L->NG, L->T, L->Sg, h->n, h->rs, h->d_alw, d_bew, tol, d_fl);
+    CK(cudaMemcpyAsync(flags, d_fl, (size_t)h->r * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    vfree(h->stream, d_bew);
+    vfree(h->stream, d_fl);
+    CK(cudaGetLastError());
     return 0;
 }
 
-int vbnmf_bench_iterations(vbnmf_handle *h, const double hyper[4], double fudge, int iters,
-                           double ms[4], int64_t *launches, double *lkh_last) {
+int vbnmf_bench_iterations(vbnmf_handle *h, double hyper[4], double fudge, int iters,
+                           int hyper_on, double ms[4], int64_t *launches, double *lkh_last) {
     if (!h || !hyper || !ms || iters < 1) return VBNMF_ERR_ARG;
     if (!h->d_lw) return fail(h, VBNMF_ERR_STATE, "vbnmf_set_state has not been called");
     CK(cudaSetDevice(h->device));
     int rc;
     double lkh = 0.0;
     if (!h->stats_valid && (rc = vbnmf_step(h, hyper, fudge, &lkh))) return rc;
-    // exactly `iters` iterations of the product loop (run_device_loop) with the hyper-parameters
-    // held fixed and a tolerance that never triggers, CUDA events around the two sweep passes
+    // exactly `iters` iterations of the product loop (run_device_loop) with a tolerance that never
+    // triggers, CUDA events around the two sweep passes.  hyper_on = 1: hyper_update after every
+    // iteration, i.e. the steady state of the reference loop past hyper.update.n0
+    // (R/bayesian.R:342), hyper[] is updated; 0: hyper-parameters held fixed.
     std::vector<cudaEvent_t> ev((size_t)iters * 4 + 2);
     for (auto &e : ev) CK(cudaEventCreate(&e));
     vbnmf_cfg cfg;
-    cfg.itmax = iters; cfg.tol = -1.0; cfg.n0 = 1 << 30; cfg.dn = 1; cfg.fudge = fudge;
-    for (int q = 0; q < 4; q++) cfg.hyper_update[q] = 0;
+    cfg.itmax = iters; cfg.tol = -1.0; cfg.n0 = hyper_on ? 0 : 1 << 30; cfg.dn = 1;
+    cfg.fudge = fudge;
+    for (int q = 0; q < 4; q++) cfg.hyper_update[q] = hyper_on ? 1 : 0;
     double hy[4] = {hyper[0], hyper[1], hyper[2], hyper[3]}, lml = 0.0;
     int niter = 0, why = 0;
     const int64_t l0 = h->launches;
@@ -1560,6 +1771,7 @@ int vbnmf_bench_iterations(vbnmf_handle *h, const double hyper[4], double fudge,
     }
     ms[3] = ms[0] - ms[1] - ms[2];
     for (auto &e : ev) cudaEventDestroy(e);
+    for (int q = 0; q < 4; q++) hyper[q] = hy[q];
     if (launches) *launches = h->launches - l0;
     if (lkh_last) *lkh_last = h->h_ctl[vb::kCtlLkh];
     return 0;
@@ -1593,8 +1805,10 @@ int mlnmf_run(vbnmf_handle *h, int r, const double *w0, const double *h0, int it
     CK(cudaSetDevice(h->device));
     int rc;
     if ((rc = alloc_panels(h, r))) return rc;
-    if ((rc = upload_panel(h, h->d_lw, w0, true, r))) return rc;
-    if ((rc = upload_panel(h, h->d_lh, h0, false, r))) return rc;
+    CK(cudaMemsetAsync(h->d_lw, 0, (size_t)h->L->NG * h->rs * 8, h->stream));
+    CK(cudaMemsetAsync(h->d_lh, 0, (size_t)h->L->NC * h->rs * 8, h->stream));
+    if ((rc = upload_panel(h, h->d_lw, nullptr, w0, true, r))) return rc;
+    if ((rc = upload_panel(h, h->d_lh, nullptr, h0, false, r))) return rc;
     if ((rc = refresh_mirrors(h))) return rc;
     h->stats_valid = false;
     h->has_posterior = false;
@@ -1605,7 +1819,7 @@ int mlnmf_run(vbnmf_handle *h, int r, const double *w0, const double *h0, int it
     auto colsum = [&](bool wside) -> int {
         vb::ColsumArgs a{wside ? L->NG : L->NC, wside ? h->d_lw : h->d_lh,
                          wside ? h->d_partW : h->d_partH, wside ? h->d_scal : tail,
-                         h->d_counters + (wside ? 0 : 1)};
+                         h->d_counters + (wside ? 0 : 1), h->tsplit};
         h->tab->colsum(a, h->stream);
         h->launches += 1;
         return 0;
@@ -1615,7 +1829,8 @@ int mlnmf_run(vbnmf_handle *h, int r, const double *w0, const double *h0, int it
                            wside ? h->n : h->m, r, eps, wside ? tail : h->d_scal,
                            wside ? h->d_red : h->d_ShRaw, wside ? h->d_lw : h->d_lh,
                            wside ? h->d_partW : h->d_partH, wside ? h->d_scal : tail,
-                           h->d_counters + (wside ? 0 : 1), wside ? h->d_lw32 : h->d_lh32};
+                           h->d_counters + (wside ? 0 : 1), wside ? h->d_lw32 : h->d_lh32,
+                           h->tsplit};
         h->tab->ml_update(a, h->stream);
         h->launches += 1;
         return 0;

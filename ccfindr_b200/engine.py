@@ -221,15 +221,29 @@ class Engine:
         return dict(w=w, h=h, niter=it, lik_trace=trace[:it].copy(), lik=float(trace[it - 1]))
 
     # -- measurement ---------------------------------------------------------------------------
-    def bench_iterations(self, hyper, iters, fudge=EPS):
+    def bench_iterations(self, hyper, iters, fudge=EPS, hyper_on=False):
+        """`iters` iterations of the device-controlled product loop, CUDA-event timed.  hyper_on:
+        hyper_update after every iteration (the loop's steady state past hyper.update.n0); the
+        updated hyper-parameters come back in the result."""
         hy = hyper_vec(hyper)
         ms = np.zeros(4)
         launches = C.c_int64(0)
         lkh = C.c_double(0.0)
         self._ck(self.lib.vbnmf_bench_iterations(self.handle, _dp(hy), float(fudge), int(iters),
-                                                 _dp(ms), C.byref(launches), C.byref(lkh)))
+                                                 int(bool(hyper_on)), _dp(ms), C.byref(launches),
+                                                 C.byref(lkh)))
         return dict(ms_total=ms[0], ms_cols=ms[1], ms_rows=ms[2], ms_other=ms[3],
-                    launches=launches.value, lkh=lkh.value)
+                    launches=launches.value, lkh=lkh.value, hyper=hyper_dict(hy))
+
+
+def set_host_threads(n):
+    """Threads that stage host -> device uploads (process-wide); pass cores / processes when one
+    process drives each GPU."""
+    _lib.check(_lib.load().vbnmf_set_host_threads(int(n)))
+
+
+def trim_pool(device=0):
+    _lib.check(_lib.load().vbnmf_trim_pool(int(device)))
 
 
 class Comm:

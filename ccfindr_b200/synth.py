@@ -120,6 +120,10 @@ def tenx_like_device(n, m, r_true, density, seed, device, col_start=0, col_end=N
         gen = torch.Generator(device=device)
         gen.manual_seed((int(seed) << 32) + c0 // TENX_CHUNK)
         x = torch.poisson(lam, generator=gen)
+        # a cell without counts gets one (the API rejects empty columns)
+        empty = torch.nonzero(x.sum(dim=1) == 0).flatten()
+        if empty.numel():
+            x[empty, (empty + c0) % n] = 1.0
         nz = torch.nonzero(x)                                # sorted by (cell, gene) = CSC order
         rows.append(nz[:, 1].to(torch.int32))
         vals.append(x[nz[:, 0], nz[:, 1]].to(torch.float32))
@@ -132,6 +136,24 @@ def tenx_like_device(n, m, r_true, density, seed, device, col_start=0, col_end=N
     colptr = torch.zeros(cnt.numel() + 1, dtype=torch.int64, device=device)
     colptr[1:] = torch.cumsum(cnt, 0)
     return colptr, rowidx, values, s
+
+
+def tenx_expected_nnz(n, m, r_true, density, seed, device):
+    """Expected number of nonzeros of every TENX_CHUNK-cell chunk of G(n, m, r_true, density,
+    seed): sum_ij (1 - exp(-s d_j (W H)_ij)).  Cheap (no sampling) and identical on every rank:
+    the basis of the nnz-balanced shard boundaries of a multi-GPU run."""
+    import torch
+    W, H, d = tenx_factors(n, m, r_true, seed)
+    s = tenx_scale(W, H, d, density, seed, device)
+    Wt = torch.from_numpy(W).to(device)
+    out = []
+    for c0 in range(0, m, TENX_CHUNK):
+        c1 = min(c0 + TENX_CHUNK, m)
+        Hc = torch.from_numpy(H[c0:c1]).to(device)
+        dc = torch.from_numpy(d[c0:c1]).to(device) * float(s)
+        lam = (Hc @ Wt.T) * dc[:, None]
+        out.append(float((1.0 - torch.exp(-lam)).sum(dtype=torch.float64)))
+    return np.array(out)
 
 
 # ---- CPU restatement of the on-device 'random' initialiser (csrc/kernels_common.cuh) ---------

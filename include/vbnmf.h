@@ -79,6 +79,14 @@ VBNMF_API int vbnmf_create_from_device(vbnmf_handle **out, int64_t n, int64_t m,
                              const int64_t *d_colptr, const int32_t *d_rowidx, const float *d_values,
                              int device);
 
+/* Host threads that stage uploads (copy / fp64 -> fp32 conversion into pinned buffers).  Default
+ * min(16, hardware threads) or VBNMF_HOST_THREADS; with one process per GPU pass cores / processes.
+ * Process-wide.  (The reference holds X in R memory; this replaces as.matrix(), R/bayesian.R:339.) */
+VBNMF_API int vbnmf_set_host_threads(int nthreads);
+
+/* Return the device memory the engine's stream-ordered pool keeps cached to the driver. */
+VBNMF_API int vbnmf_trim_pool(int device);
+
 VBNMF_API void vbnmf_destroy(vbnmf_handle *h);
 VBNMF_API const char *vbnmf_last_error(const vbnmf_handle *h); /* h may be NULL: error of the last create */
 
@@ -145,9 +153,11 @@ VBNMF_API int mlnmf_run(vbnmf_handle *h, int r, const double *w0, const double *
 /* Measurement hooks (bench.py).  Runs `iters` steady-state VB iterations (posterior update +
  * nonzero sweep [+ all-reduce]) with fixed hypers and reports CUDA-event times in ms:
  * ms[0] = whole timed region, ms[1] = sum over the column-sweep kernel, ms[2] = row-sweep kernel,
- * ms[3] = everything else.  launches = kernels launched inside the timed region. */
-VBNMF_API int vbnmf_bench_iterations(vbnmf_handle *h, const double hyper[4], double fudge, int iters,
-                           double ms[4], int64_t *launches, double *lkh_last);
+ * ms[3] = everything else.  launches = kernels launched inside the timed region.
+ * hyper_on = 1: hyper_update (R/bayesian.R:2-53) after every iteration as in the reference loop past
+ * hyper.update.n0, hyper[] in/out; 0: hyper-parameters held fixed. */
+VBNMF_API int vbnmf_bench_iterations(vbnmf_handle *h, double hyper[4], double fudge, int iters,
+                           int hyper_on, double ms[4], int64_t *launches, double *lkh_last);
 
 /* shape / layout facts for the host side */
 VBNMF_API int vbnmf_info(const vbnmf_handle *h, int64_t info[8]); /* n, m, nnz, r, rs, precision, nranks, m_global */

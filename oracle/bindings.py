@@ -142,11 +142,29 @@ def sparse_vb_step(csc, wh, hyper, fudge):
     return dict(w=ew, h=eh, lw=lw, lh=lh, ew=ew, eh=eh, dw=dw, dh=dh, lkh=lkh.value, means=means)
 
 
+def set_omp_threads(nthreads):
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arms of bench.py restore the
+    host's thread count (process-wide libgomp setting)."""
+    for name in ("libgomp.so.1", "libgomp.so"):
+        try:
+            C.CDLL(name).omp_set_num_threads(int(nthreads))
+            return True
+        except OSError:
+            continue
+    return False
+
+
 def sparse_vb_run(csc, w0, h0, hyper, *, Itmax=10000, hyper_update_flags=(True,) * 4, Tol=1e-5,
                   n0=10, dn=1, fudge=np.finfo(np.float64).eps):
-    """oracle_sparse.c osp_vb_run: the loop of vb_iterate for one rank (R/bayesian.R:336-352)."""
+    """oracle_sparse.c osp_vb_run: the loop of vb_iterate for one rank (R/bayesian.R:336-352).
+    csc: a scipy.sparse matrix, or the tuple (n, m, colptr int64, rowidx int32, val float64) of
+    sorted CSC arrays (no copies are made: matrices of 2e9 nonzeros)."""
     lib = sparse_lib()
-    n, m, colptr, rowidx, val = _csc_args(csc)
+    if isinstance(csc, tuple):
+        n, m, colptr, rowidx, val = csc
+        assert colptr.dtype == np.int64 and rowidx.dtype == np.int32 and val.dtype == np.float64
+    else:
+        n, m, colptr, rowidx, val = _csc_args(csc)
     lw = np.array(w0, dtype=np.float64, order="F")
     lh = np.array(h0, dtype=np.float64, order="F")
     r = lw.shape[1]

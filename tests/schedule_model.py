@@ -29,14 +29,16 @@ def res_bucket(rr, NL):
     return rr if NL == 8 else rr >> 1
 
 
-def make_schedule(cnt8, NL):
+def make_schedule(cnt8, NL, kmult=4):
+    """kmult (NL = 8 only): the step count is a multiple of it -- 4: every stored step is
+    scheduled; 1: fewest steps, the rest of the last stored chunk of 4 steps is all holes."""
     ncls, NB = (1, 8) if NL == 8 else (2, 4)
     sc = dict(K=[0, 0], pl=[(0, 0), (0, 0)], offr=[[0] * 8, [0] * 8], cnt=[[0] * 8, [0] * 8])
     for rr in range(8):
         sc["cnt"][res_class(rr, NL)][res_bucket(rr, NL)] = cnt8[rr]
     for cl in range(ncls):
         c = sc["cnt"][cl][:NB]
-        sc["K"][cl] = class_steps(sum(c), max(c), NL, 4 if NL == 8 else 2)
+        sc["K"][cl] = class_steps(sum(c), max(c), NL, kmult if NL == 8 else 2)
     if ncls == 2 and ((sc["K"][0] + sc["K"][1]) & 3):
         sc["K"][1] += 2
     for cl in range(ncls):
@@ -65,10 +67,10 @@ def schedule_item(sc, NL, rr, k):
     return ((sc["K"][0] if cl else 0) + step) * NL + lane
 
 
-def wavefronts(cnt8, NL):
+def wavefronts(cnt8, NL, kmult=4):
     """(steps, wavefronts per gather) of the schedule for residue counts cnt8: a step costs the
     largest number of its rows in one residue class (at least 1: hole steps still issue)."""
-    sc = make_schedule(cnt8, NL)
+    sc = make_schedule(cnt8, NL, kmult)
     K = sc["K"][0] + sc["K"][1]
     mult = np.zeros((K, 8), dtype=int)
     seen = set()

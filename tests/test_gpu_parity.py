@@ -251,16 +251,80 @@ def _check_steps(Engine, X, w0, h0, hyper, nsteps=3, tol=TOL):
         assert relerr(st[k], ref[k]) < tol, k
 
 
-def test_empty_rows_and_columns_at_the_abi_level(Engine):
-    """The front end rejects empty rows/columns (R/bayesian.R:244-247) but a shard of cells may
-    well contain genes without counts: the engine itself must handle them."""
+def test_empty_rows_and_columns_at_the_abi_level(Engine, monkeypatch):
+    """The C ABI itself refuses empty rows / columns with VBNMF_ERR_EMPTY, as vb_factorize does
+    (R/bayesian.R:244-247: rowSums / colSums == 0, so an explicit zero does not count), and
+    negative or non-finite counts.  A SHARD of cells may well contain genes without counts, so the
+    kernels must still handle them: VBNMF_ALLOW_EMPTY=1 lifts the gene test."""
+    from ccfindr_b200._lib import VbnmfError
     rng = np.random.default_rng(2)
     X = sp.random(60, 45, density=0.2, random_state=rng, format="lil",
                   data_rvs=lambda k: rng.integers(1, 9, size=k).astype(float))
-    X[7, :] = 0; X[:, 11] = 0; X[59, :] = 0; X[:, 44] = 0
-    X = sp.csc_matrix(X); X.eliminate_zeros()
+    X[7, :] = 0; X[59, :] = 0
+    Xr = sp.csc_matrix(X); Xr.eliminate_zeros()
+    Xr = synth_fix_cols(Xr)
     w0, h0 = rng.random((60, 3)) + 0.1, rng.random((3, 45)) + 0.1
-    _check_steps(Engine, X, w0, h0, dict(aw=1.0, bw=1.0, ah=1.0, bh=1.0))
+    hyper = dict(aw=1.0, bw=1.0, ah=1.0, bh=1.0)
+    with Engine(Xr) as eng:                                    # empty genes: refused at set_state
+        with pytest.raises(VbnmfError, match="empty rows") as ei:
+            eng.set_state(w0, h0)
+        assert ei.value.code == 6
+    Xc = Xr.tolil(); Xc[:, 11] = 0; Xc = sp.csc_matrix(Xc); Xc.eliminate_zeros()
+    with pytest.raises(VbnmfError, match="empty columns") as ei:
+        Engine(Xc)
+    assert ei.value.code == 6
+    Xz = Xr.copy().tolil(); Xz[7, 3] = 1.0; Xz = sp.csc_matrix(Xz)
+    Xz.data[Xz.indices == 7] = 0.0                             # explicit zero only: still empty
+    with Engine(Xz) as eng:
+        with pytest.raises(VbnmfError, match="empty rows"):
+            eng.set_state(w0, h0)
+    Xn = Xr.copy(); Xn.data[5] = -1.0
+    with pytest.raises(VbnmfError, match="non-negative"):
+        Engine(Xn)
+    Xn.data[5] = np.nan
+    with pytest.raises(VbnmfError, match="non-negative"):
+        Engine(Xn)
+    monkeypatch.setenv("VBNMF_ALLOW_EMPTY", "1")
+    _check_steps(Engine, Xr, w0, h0, hyper)
+
+
+def synth_fix_cols(X):
+    """one count into every empty column (rows are left alone)"""
+    X = X.tolil()
+    for j in np.flatnonzero(np.asarray(X.sum(axis=0)).ravel() == 0):
+        X[(3 * j) % X.shape[0] if (3 * j) % X.shape[0] not in (7, 59) else 1, j] = 1.0
+    return sp.csc_matrix(X)
+
+
+def test_two_engines_with_different_tiles_alive_together(Engine):
+    """The dynamic shared-memory opt-in is per kernel and device, i.e. shared by all handles: a
+    second handle with a smaller tile at the same padded rank must not break the first."""
+    from ccfindr_b200 import synth
+    from oracle import bindings as ob
+    from oracle import oracle_dense as od
+    rng = np.random.default_rng(12)
+    hyper = dict(aw=1.0, bw=1.0, ah=1.0, bh=1.0)
+    big = synth.fix_empty(sp.random(6000, 5000, density=0.05, random_state=rng, format="csc",
+                                    data_rvs=lambda k: rng.integers(1, 9, size=k).astype(float)), 1)
+    small = synth.fix_empty(sp.random(70, 50, density=0.3, random_state=rng, format="csc",
+                                      data_rvs=lambda k: rng.integers(1, 9, size=k).astype(float)), 1)
+    r = 4
+    wb, hb = rng.random((6000, r)) + 0.1, rng.random((r, 5000)) + 0.1
+    ws, hs = rng.random((70, r)) + 0.1, rng.random((r, 50)) + 0.1
+    with Engine(big) as e1:
+        e1.set_state(wb, hb)
+        l1 = e1.step(hyper)
+        with Engine(small) as e2:
+            e2.set_state(ws, hs)
+            assert e2.layout_info()["tile_rows"] < e1.layout_info()["tile_rows"]
+            ls = e2.step(hyper)
+            l2 = e1.step(hyper)                                # first handle, after the second's opt-in
+            ref = ob.sparse_vb_step(small, od.vb_init_from(ws, hs), hyper, od.EPS)
+            assert relerr(ls, ref["lkh"]) < 1e-9
+    refb = ob.sparse_vb_step(big, od.vb_init_from(wb, hb), hyper, od.EPS)
+    assert relerr(l1, refb["lkh"]) < 1e-9
+    refb2 = ob.sparse_vb_step(big, refb, hyper, od.EPS)
+    assert relerr(l2, refb2["lkh"]) < 1e-9
 
 
 @pytest.mark.parametrize("n,m,r", [(3, 2, 2), (2, 5, 1), (1, 1, 1), (130, 9, 9)])

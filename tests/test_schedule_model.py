@@ -54,3 +54,34 @@ def test_typical_segment_beats_round_robin():
         tot_w += w
         tot_ideal += sum(cnt) / 8
     assert 1.15 < tot_w / tot_ideal < 1.32
+
+
+@settings(max_examples=300, deadline=None)
+@given(counts)
+def test_fewest_steps_schedule_for_the_split_layout(cnt):
+    """kmult = 1 (kernels that skip the gathers of hole entries): the schedule uses
+    max(ceil(n/8), ceil(L/2)) steps, still collision free, and every nonzero sits inside them (the
+    rest of the stored chunk of 4 steps is all holes)."""
+    K, w = wavefronts(cnt, 8, kmult=1)
+    sc = make_schedule(cnt, 8, kmult=1)
+    R, P = sc["pl"][0]
+    n, L = sum(cnt), max(cnt)
+    assert K == max((n + 7) // 8, (L + 1) // 2) and R + P == K
+    assert max(K, L) <= w <= R + 2 * P
+
+
+def test_split_layout_cost_model():
+    """Wavefronts per segment at r = 20 (10 units per row, ~105 nonzeros per segment): block A
+    (8 units) costs one wavefront per executed step whatever the rows, block B (2 units) follows
+    the residue schedule.  Against the lock-step layout (all 10 units pay the schedule)."""
+    rng = np.random.default_rng(1)
+    old = new = ideal = 0.0
+    for _ in range(400):
+        rows = rng.choice(1312, size=rng.binomial(1312, 0.08), replace=False)
+        cnt = np.bincount(rows % 8, minlength=8).tolist()
+        _, w4 = wavefronts(cnt, 8, kmult=4)
+        K1, w1 = wavefronts(cnt, 8, kmult=1)
+        old += 10 * w4
+        new += 8 * K1 + 2 * w1
+        ideal += 10 * sum(cnt) / 8
+    assert old / ideal > 1.30 and new / ideal < 1.15
