@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libvbnmf.so")
+LIB_PATH = os.path.join(HERE, os.environ.get("VBNMF_LIB_NAME", "libvbnmf.so"))  # experiments: variants
 
 c_dp = C.POINTER(C.c_double)
 c_ip = C.POINTER(C.c_int)

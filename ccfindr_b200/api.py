@@ -184,7 +184,7 @@ def vb_factorize(object, ranks=2, nrun=1, verbose=2, progress_bar=True, initiali
                  Itmax=10000, hyper_update=(True,) * 4, gamma_a=1, gamma_b=1, Tol=1e-5,
                  hyper_update_n0=10, hyper_update_dn=1, connectivity=True, fudge=None, ncores=1,
                  useC=True, unif_stop=True, seed=1, device=0, inits=None, precision=0,
-                 parallel=False, device_init=False):
+                 parallel=False, device_init=False, shard_cells=False):
     """Bayesian NMF inference of a count matrix (R/bayesian.R:229-301).
 
     Arguments as in the reference (dots replaced by underscores).  Extras: `seed` keys the NumPy
@@ -198,6 +198,11 @@ def vb_factorize(object, ranks=2, nrun=1, verbose=2, progress_bar=True, initiali
     nrun x len(ranks) independent factorizations are spread over the ranks (the role of
     Rmpi::mpi.applyLB, R/bayesian.R:263), every rank holds a full copy of the matrix, results are
     all-gathered and every rank returns the same object.
+    `shard_cells=True` (same setting): ONE factorization at a time on all GPUs -- every rank keeps
+    an nnz-balanced contiguous range of the cells on its GPU, the W-side statistics are all-reduced
+    once per iteration, and the coeff / dcoeff columns are gathered at the end, so
+    every rank returns the same full object.  For matrices that do not fit one GPU, or to cut the
+    time of one large factorization.
     """
     if fudge is None:
         fudge = EPS                                             # :238
@@ -218,7 +223,13 @@ def vb_factorize(object, ranks=2, nrun=1, verbose=2, progress_bar=True, initiali
     common = (ga, gb, initializer, Itmax, hyper_update, Tol, hyper_update_n0, hyper_update_dn,
               connectivity, fudge)
     vb = []
-    if parallel:
+    if parallel and shard_cells:
+        raise ValueError("parallel (independent jobs per GPU) and shard_cells (one job on all GPUs) "
+                         "are alternatives")
+    if shard_cells:
+        vb = _vb_sharded(mat, ranks, nrun, common, unif_stop, verbose, seed, inits, device,
+                         precision)
+    elif parallel:
         vb = _vb_parallel(mat, ranks, nrun, common, unif_stop, verbose, seed, inits, device,
                           precision)
     else:
@@ -249,6 +260,52 @@ def vb_factorize(object, ranks=2, nrun=1, verbose=2, progress_bar=True, initiali
     object.coeff, object.dcoeff = coeff, dcoeff
     object.measure = {k: np.array(v) for k, v in cols.items()}
     return object
+
+
+def dist_comm(device):
+    """A libvbnmf NCCL communicator over the ranks of the initialised torch.distributed group:
+    rank 0 makes the unique id, the group broadcasts it (the role Rmpi would play for the R shim)."""
+    import torch
+    import torch.distributed as dist
+    from .engine import Comm
+    if not (dist.is_available() and dist.is_initialized()):
+        raise RuntimeError("needs an initialised torch.distributed process group")
+    world, me = dist.get_world_size(), dist.get_rank()
+    box = [Engine.nccl_unique_id() if me == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    return Comm(world, me, box[0], device=device)
+
+
+def _vb_sharded(mat, ranks, nrun, common, unif_stop, verbose, seed, inits, device, precision):
+    """vb_iterate for every run with the cells sharded over the ranks of torch.distributed."""
+    import torch.distributed as dist
+    from . import sharding
+    from .engine import set_host_threads
+    comm = dist_comm(device)
+    world, me = comm.nranks, comm.rank
+    b = sharding.balanced_bounds(mat.indptr, world)
+    c0, c1 = b[me], b[me + 1]
+    if c1 <= c0:
+        raise ValueError("more GPUs than cells to shard")
+    vb = []
+    try:
+        with Engine(sharding.shard_csc(mat, c0, c1), device=device) as eng:
+            eng.set_precision(precision)
+            eng.attach_comm(comm)
+            for irun in range(1, nrun + 1):
+                out = _vb_iterate(eng, irun, mat, ranks, *common, unif_stop, nrun,
+                                  verbose if me == 0 else 0, seed, inits, vb, cols=(c0, c1))
+                # coeff / dcoeff: this rank's columns -> all columns on every rank
+                parts = [None] * world
+                dist.all_gather_object(parts, (out["hdat"], out["dhdat"]))
+                for k in range(len(ranks)):
+                    if out["hdat"][k] is not None:
+                        out["hdat"][k] = np.concatenate([p[0][k] for p in parts], axis=1)
+                        out["dhdat"][k] = np.concatenate([p[1][k] for p in parts], axis=1)
+                vb.append(out)
+    finally:
+        comm.close()
+    return vb
 
 
 def _vb_parallel(mat, ranks, nrun, common, unif_stop, verbose, seed, inits, device, precision):
@@ -298,9 +355,13 @@ def _vb_parallel(mat, ranks, nrun, common, unif_stop, verbose, seed, inits, devi
 
 
 def _vb_iterate(eng, irun, mat, ranks, ga, gb, initializer, Itmax, hyper_update, Tol, n0, dn,
-                connectivity, fudge, unif_stop, nrun, verbose, seed, inits, previous):
-    """R/bayesian.R:303-390 for one run; the it-loop runs on the GPU."""
+                connectivity, fudge, unif_stop, nrun, verbose, seed, inits, previous, cols=None):
+    """R/bayesian.R:303-390 for one run; the it-loop runs on the GPU.  cols = (c0, c1): the engine
+    holds the cells [c0, c1) of `mat` and the calls are collective over the shards."""
     nrow, ncol = mat.shape
+    c0, c1 = cols if cols is not None else (0, ncol)
+    if cols is not None:
+        connectivity = False      # the dispersion print needs the labels of all cells
     nrank = len(ranks)
     out = dict(rdat=[-np.inf] * nrank, wdat=[None] * nrank, hdat=[None] * nrank,
                dwdat=[None] * nrank, dhdat=[None] * nrank, hyperp=[None] * nrank,
@@ -314,13 +375,13 @@ def _vb_iterate(eng, irun, mat, ranks, ga, gb, initializer, Itmax, hyper_update,
         hyper = dict(aw=float(ga[0]), ah=float(ga[-1]), bw=float(gb[0]), bh=float(gb[-1]))  # :321-326
         if inits is not None and (irun, rank) in inits:
             w0, h0 = inits[(irun, rank)]
-            eng.set_state(w0, h0)                               # lw = ew = w, lh = eh = h (:170)
+            eng.set_state(w0, h0[:, c0:c1])                     # lw = ew = w, lh = eh = h (:170)
         elif initializer == "random_device":
-            eng.init_random(rank, hyper, seed * 100003 + 1000 * rank + irun)
+            eng.init_random(rank, hyper, seed * 100003 + 1000 * rank + irun, cell_offset=c0)
         else:
             w0, h0 = vb_init(nrow, ncol, mat, rank, hyper, initializer,
                              seed * 100003 + 1000 * rank + irun)
-            eng.set_state(w0, h0)
+            eng.set_state(w0, h0[:, c0:c1])
         try:
             res = eng.run(hyper, Itmax=Itmax, Tol=Tol, hyper_update=hyper_update, n0=n0, dn=dn,
                           fudge=fudge)

@@ -16,9 +16,9 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(CSRC, "_obj")
+OBJ = os.path.join(CSRC, "_obj" + os.environ.get("VBNMF_OBJ_SUFFIX", ""))
 INCLUDE = os.path.join(HERE, "..", "include")
-LIB = os.path.join(HERE, "libvbnmf.so")
+LIB = os.path.join(HERE, os.environ.get("VBNMF_LIB_NAME", "libvbnmf.so"))  # experiments: variants
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-I", INCLUDE]
@@ -34,6 +34,12 @@ if os.environ.get("VBNMF_WIDE_THREADS"):
     NVCC_FLAGS.append("-DVB_WIDE_THREADS=" + os.environ["VBNMF_WIDE_THREADS"])
 if os.environ.get("VBNMF_UNROLL"):
     NVCC_FLAGS.append("-DVB_UNROLL=" + os.environ["VBNMF_UNROLL"])
+if os.environ.get("VBNMF_SPLIT_PRED"):
+    NVCC_FLAGS.append("-DVB_SPLIT_PRED=" + os.environ["VBNMF_SPLIT_PRED"])
+if os.environ.get("VBNMF_SKIP_DEAD"):
+    NVCC_FLAGS.append("-DVB_SKIP_DEAD=" + os.environ["VBNMF_SKIP_DEAD"])
+if os.environ.get("VBNMF_DOT_CHAINS"):
+    NVCC_FLAGS.append("-DVB_DOT_CHAINS=" + os.environ["VBNMF_DOT_CHAINS"])
 if os.environ.get("VBNMF_LP_BITS"):   # count bits of the log-product bound term (kernels.cuh)
     NVCC_FLAGS.append("-DVB_LP_BITS=" + os.environ["VBNMF_LP_BITS"])
 

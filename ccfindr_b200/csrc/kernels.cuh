@@ -7,6 +7,18 @@
 
 #include "special.cuh"
 
+#ifndef VB_SPLIT_PRED
+#define VB_SPLIT_PRED 0   // split kernels: entries with count 0 (holes) skip their gathers.  Measured
+                          // SLOWER (C3-shaped, r = 20: cell-owner pass 3.09 -> 3.49 ms): the branch
+                          // around the gathers costs more than the wavefronts it saves
+#endif
+#ifndef VB_SKIP_DEAD
+#define VB_SKIP_DEAD 1    // split kernels: skip the all-hole steps at the end of a segment (their
+                          // number rides in the low 2 bits of the segment's quad pointer)
+#endif
+#ifndef VB_DOT_CHAINS
+#define VB_DOT_CHAINS 2   // independent FMA chains of the rank-r dot product (fp64)
+#endif
 #ifndef VB_LPN_BYTES
 #define VB_LPN_BYTES 160    // widest row a single lane gathers; wider rows are split over 2 lanes
 #endif
@@ -532,6 +544,17 @@ __device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsign
 // p = sum_k own[k] tr[k];  acc[k] += tr[k] * x / p   (one nonzero; returns p)
 template <int KL>
 __device__ __forceinline__ double dot_rows(const double (&own)[KL], const double (&tr)[KL]) {
+    if (VB_DOT_CHAINS == 4 && KL % 4 == 0) {
+        double p0 = 0, p1 = 0, p2 = 0, p3 = 0;
+#pragma unroll
+        for (int k = 0; k < KL; k += 4) {
+            p0 = fma(own[k], tr[k], p0);
+            p1 = fma(own[k + 1], tr[k + 1], p1);
+            p2 = fma(own[k + 2], tr[k + 2], p2);
+            p3 = fma(own[k + 3], tr[k + 3], p3);
+        }
+        return (p0 + p1) + (p2 + p3);
+    }
     double p0 = 0, p1 = 0;
 #pragma unroll
     for (int k = 0; k < KL; k += 2) {
@@ -674,6 +697,7 @@ struct LogProd {
 #ifndef VB_OWN_AHEAD
 #define VB_OWN_AHEAD(dflt) (dflt)
 #endif
+
 // SPLIT (fp64 panels, one lane per nonzero, rows of >= 8 units; see split_rank / panel_ofs): the
 // tile is stored as block A (T x 128 bytes) + block B; lane gl gathers unit c ^ gl of block A in
 // step c -- conflict free for ANY 8 rows -- and holds its owner row and accumulators in the same
@@ -759,16 +783,20 @@ sweep_p16_kernel(const SweepTiledArgs a) {
         // first quad and owner row of the first
         int64_t e = ebase + gid;
         uint32_t beg = 0, end = 0, nb = 0, ne = 0;
+        uint32_t dead = 0, ndead = 0, nndead = 0;  // all-hole steps at the end of the segment (SPLIT)
+        constexpr uint32_t kTag = SPLIT ? 3u : 0u;
         uint4 f0 = make_uint4(0u, 0u, 0u, 0u);
         PT ownn[KL];
 #pragma unroll
         for (int k = 0; k < KL; k++) ownn[k] = 0;
         if (e < eend) {
             beg = __ldg(a.ptr4 + e);
-            end = __ldg(a.ptr4 + e + 1);
+            end = __ldg(a.ptr4 + e + 1) & ~kTag;
+            dead = beg & kTag; beg &= ~kTag;
             if (e + kGroups < eend) {
                 nb = __ldg(a.ptr4 + e + kGroups);
-                ne = __ldg(a.ptr4 + e + kGroups + 1);
+                ne = __ldg(a.ptr4 + e + kGroups + 1) & ~kTag;
+                ndead = nb & kTag; nb &= ~kTag;
             }
             if (beg + slot < end) f0 = ldcs_quad(ent4 + beg + slot);
             if (kOwnAhead && beg < end) load_owner(e - slab * a.NO, ownn);
@@ -793,7 +821,8 @@ sweep_p16_kernel(const SweepTiledArgs a) {
             if (en < eend) {
                 if (en + kGroups < eend) {
                     nnb = __ldg(a.ptr4 + en + kGroups);
-                    nne = __ldg(a.ptr4 + en + kGroups + 1);
+                    nne = __ldg(a.ptr4 + en + kGroups + 1) & ~kTag;
+                    nndead = nnb & kTag; nnb &= ~kTag;
                 }
                 if (nb + slot < ne) f0 = ldcs_quad(ent4 + nb + slot);
                 if (kOwnAhead && nb < ne) load_owner(en - slab * a.NO, ownn);
@@ -809,12 +838,16 @@ sweep_p16_kernel(const SweepTiledArgs a) {
                 if (c0 + 2 * NPG + slot < nq) n2 = ldcs_quad(eb + c0 + 2 * NPG + slot);
                 PT pu[4], xu[4];
                 uint32_t big = 0;  // kLogProd: OR of this lane's counts of the chunk
+                // steps of this chunk that hold nonzeros (the last chunk of a segment may end in
+                // all-hole steps)
+                const int ulive = (SPLIT && VB_SKIP_DEAD && c0 + NPG >= nq) ? 4 - (int)dead : 4;
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
+                    if (SPLIT && VB_SKIP_DEAD && u > 0 && u >= ulive) break;
                     const uint32_t v = u == 0 ? cur.x : u == 1 ? cur.y : u == 2 ? cur.z : cur.w;
                     const PT x = (PT)(int)(v >> 16);
                     if constexpr (SPLIT) {
-                        if (v >> 16) {  // a hole keeps the previous row: no shared-memory traffic
+                        if (!VB_SPLIT_PRED || (v >> 16)) {  // a hole keeps the previous row: no shared-memory traffic
                             const uint32_t row = v & 0xffffu;
                             const uint32_t ra = (tile_s + row * 128u) ^ rot;
                             const uint32_t rb = tileB_s + row * (uint32_t)BSB;
@@ -918,8 +951,8 @@ sweep_p16_kernel(const SweepTiledArgs a) {
             }
             }
             e = en;
-            beg = nb; end = ne;
-            nb = nnb; ne = nne;
+            beg = nb; end = ne; dead = ndead;
+            nb = nnb; ne = nne; ndead = nndead;
         }
         ebase = eend;
     }

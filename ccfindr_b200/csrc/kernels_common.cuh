@@ -372,14 +372,14 @@ __device__ __forceinline__ void warp_residue_counts(const uint32_t *__restrict__
 // One warp per segment.
 __global__ void __launch_bounds__(kBlock)
 plan_p16_kernel(int64_t E, const int64_t *__restrict__ ptr, const uint32_t *__restrict__ words,
-                int NL, int kmult, uint32_t *__restrict__ len4) {
+                int NL, int kmult, uint32_t *__restrict__ len4, uint8_t *__restrict__ dead) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * kBlock + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * kBlock) >> 5;
     if (warp == 0 && lane == 0) len4[E] = 0u;
     for (int64_t e = warp; e < E; e += nwarps) {
         const int64_t beg = ptr[e], end = ptr[e + 1];
-        if (beg == end) { if (lane == 0) len4[e] = 0u; continue; }
+        if (beg == end) { if (lane == 0) { len4[e] = 0u; if (dead) dead[e] = 0; } continue; }
         int cnt[8];
         warp_residue_counts(words, beg, end, lane, cnt);
         int n0 = 0, n1 = 0, L0 = 0, L1 = 0;
@@ -390,8 +390,11 @@ plan_p16_kernel(int64_t E, const int64_t *__restrict__ ptr, const uint32_t *__re
         }
         int K = class_steps(n0, L0, NL, NL == 8 ? kmult : 2);
         if (NL != 8) K += class_steps(n1, L1, NL, 2);
-        K = (K + 3) & ~3;
-        if (lane == 0) len4[e] = (uint32_t)(K * NL / 4);
+        const int Kst = (K + 3) & ~3;  // stored steps: whole chunks of 4
+        if (lane == 0) {
+            len4[e] = (uint32_t)(Kst * NL / 4);
+            if (dead) dead[e] = (uint8_t)(Kst - K);  // all-hole steps at the end (kmult = 1)
+        }
     }
 }
 
@@ -458,17 +461,29 @@ build_segments_p16_kernel(int64_t E, int64_t NO, const int64_t *__restrict__ ptr
     }
 }
 
-// split[b] = first segment whose quad offset is >= b * total / nparts; split[nparts] = E
+// ptr4[e] |= number of all-hole steps at the end of segment e (0..3; quad pointers are multiples
+// of 8, the sweep kernels of the split layout mask the tag off)
+__global__ void __launch_bounds__(kBlock)
+tag_dead_kernel(int64_t E, const uint8_t *__restrict__ dead, uint32_t *__restrict__ ptr4) {
+    const int64_t e = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (e < E) ptr4[e] |= (uint32_t)dead[e];
+}
+
+// Work split of a packed-16 pass over the persistent CTAs: split[b] = first segment whose cost
+// prefix is >= b * total / nparts, split[nparts] = E.  Cost of a segment = its quads + kappa: the
+// per-segment part (pointers, owner row, cross-lane sum, store) is worth a few quads of gathers, so
+// a CTA whose range holds the short segments of a slab (the owners are sorted by count) would be
+// late under an equal-entries split (measured: sm__cycles_elapsed.max 5.7 % above the mean).
 __global__ void split_p16_kernel(int nparts, int64_t E, const uint32_t *__restrict__ ptr4,
-                                 int64_t *__restrict__ split) {
+                                 double kappa, int64_t *__restrict__ split) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b > nparts) return;
     if (b == nparts) { split[b] = E; return; }
-    const int64_t target = (int64_t)((double)ptr4[E] * b / nparts);
+    const double target = ((double)ptr4[E] + kappa * (double)E) * b / nparts;
     int64_t lo = 0, hi = E;
     while (lo < hi) {
         const int64_t mid = (lo + hi) >> 1;
-        if ((int64_t)ptr4[mid] < target) lo = mid + 1; else hi = mid;
+        if ((double)ptr4[mid] + kappa * (double)mid < target) lo = mid + 1; else hi = mid;
     }
     split[b] = lo;
 }

@@ -63,6 +63,7 @@ constexpr int64_t kGraphMaxNnz = 20000000;  // below this the iteration loop is 
 // shared-memory budget of one staged slab: the 227 KB a CTA can opt in to minus the static part
 constexpr int kTileBytes = 231424;
 constexpr int kTileRowsMax = 4096, kTileRowsStep = 32;
+constexpr double kSplitKappa = 0.0;  // cost of a segment beyond its entries, in quads (split_p16_kernel)
 
 thread_local std::string g_create_error;  // error text of the last failed create on this thread
 
@@ -484,12 +485,14 @@ int build_pass(H *h, Layout *L, bool cols_pass, const int32_t *d_colof, uint32_t
     if (L->npg > 0) {
         // packed-16 layout: pad every segment to whole quads, scan the quad counts into ptr4
         uint32_t *d_len4 = nullptr;
+        uint8_t *d_dead = nullptr;
         CK(vmalloc(h, &d_len4, (size_t)(P.E + 1) * 4));
+        if (L->kmult == 1) CK(vmalloc(h, &d_dead, (size_t)P.E));
         CK(vmalloc(h, &P.d_ptr4, (size_t)(P.E + 1) * 4));
         const uint32_t *d_words = p_out;  // the sorted payloads are the packed words
         { StageTimer t1("  plan(p16)");
         vb::plan_p16_kernel<<<g, vb::kBlock, 0, h->stream>>>(P.E, P.d_ptr, d_words, L->npg,
-                                                             L->kmult, d_len4); }
+                                                             L->kmult, d_len4, d_dead); }
         size_t scan_bytes = 0;
         CK(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, d_len4, P.d_ptr4, P.E + 1, h->stream));
         void *d_scan = nullptr;
@@ -508,10 +511,17 @@ int build_pass(H *h, Layout *L, bool cols_pass, const int32_t *d_colof, uint32_t
             P.E, NO, P.d_ptr, P.d_ptr4, d_words, L->npg, L->kmult, cols_pass ? h->n : h->m,
             cols_pass ? L->Sg : L->Sc, (uint32_t *)P.d_ent); }
         CK(vmalloc(h, &P.d_split, (size_t)(L->grid + 1) * 8));
+        // per-segment overhead in quads (VBNMF_SPLIT_KAPPA: tuning)
+        const char *kenv = getenv("VBNMF_SPLIT_KAPPA");
+        const double kappa = kenv ? atof(kenv) : kSplitKappa;
         vb::split_p16_kernel<<<cdiv(L->grid + 1, 128), 128, 0, h->stream>>>(L->grid, P.E, P.d_ptr4,
-                                                                           P.d_split);
+                                                                           kappa, P.d_split);
+        if (d_dead)
+            vb::tag_dead_kernel<<<cdiv(P.E, vb::kBlock), vb::kBlock, 0, h->stream>>>(P.E, d_dead,
+                                                                                    P.d_ptr4);
         CK(cudaStreamSynchronize(h->stream));
         CK(cudaGetLastError());
+        vfree(h->stream, d_dead);
         vfree(h->stream, P.d_ptr);
         P.d_ptr = nullptr;
         return 0;
@@ -695,7 +705,9 @@ int alloc_panels(H *h, int r) {
     // split layout + conflict-free rotated gathers: fp64 panels, packed-16 entries, 8..10 units
     const bool split = !f32 && h->p16 && tab->split64 && !getenv("VBNMF_NO_SPLIT");
     Layout *L = nullptr;
-    int rc = get_layout(h, T, f32 ? tab->npg32 : tab->npg64, split ? 1 : 4, &L);
+    int kmult = split ? 1 : 4;
+    if (const char *e = getenv("VBNMF_KMULT")) kmult = atoi(e) == 1 ? 1 : 4;  // experiments
+    int rc = get_layout(h, T, f32 ? tab->npg32 : tab->npg64, kmult, &L);
     if (rc) return rc;
     if (rp == h->rp && L == h->L && h->d_lw && h->panel_precision == h->precision) {
         h->r = r;

@@ -21,5 +21,6 @@ w0, h0 = bench.init_factors(n, m, r, seed=1000 * r + 1)
 eng = Engine.from_device_csc(n, m, int(rowidx.numel()), colptr, rowidx, values)
 eng.set_precision(a.precision)
 eng.set_state(w0, h0)
+eng.bench_iterations(bench.HYPER, 3)
 res = eng.bench_iterations(bench.HYPER, a.iters)
-print(res)
+print({k: (round(v / a.iters, 4) if k.startswith('ms_') else v) for k, v in res.items()}, eng.layout_info())

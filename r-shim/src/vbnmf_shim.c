@@ -1,6 +1,8 @@
-/* R .Call shim over libvbnmf (include/vbnmf.h).  SOURCE ONLY: R is not installed in the build
- * environment of this repository, so this file has not been compiled there; it uses nothing beyond
- * the documented R C API (Rinternals.h, R_ext/Rdynload.h).
+/* R .Call shim over libvbnmf (include/vbnmf.h).  R is not installed in the build environment of
+ * this repository: there this file is compiled, linked against libvbnmf.so and EXECUTED against
+ * stand-in headers and a minimal runtime for the R C API subset it uses (tests/rstub/,
+ * tests/test_rshim.py); it uses nothing beyond the documented API (Rinternals.h,
+ * R_ext/Rdynload.h).
  *
  * It replaces, in ccfindR, the generated glue src/RcppExports.cpp:11-32 (one .Call per ITERATION,
  * `_ccfindR_vbnmf_update`) by one .Call per RUN of iterations on a device-resident handle.
@@ -101,12 +103,11 @@ SEXP C_vbnmf_run(SEXP ptr, SEXP hyper, SEXP itmax, SEXP tol, SEXP hyper_update, 
 }
 
 /* list(lw, lh, ew, eh, dw, dh) with the shapes of src/vbnmf_update.cpp:92-100 */
-SEXP C_vbnmf_get_state(SEXP ptr, SEXP dims) {
+SEXP C_vbnmf_get_state(SEXP ptr) {
     vbnmf_handle *h = get_handle(ptr);
     int64_t info[8];
     chk(vbnmf_info(h, info), h);
     const int n = (int)info[0], m = (int)info[1], r = (int)info[3];
-    (void)dims;
     const char *names[] = {"lw", "lh", "ew", "eh", "dw", "dh", ""};
     SEXP out = PROTECT(Rf_mkNamed(VECSXP, names));
     for (int k = 0; k < 6; k++) {
@@ -158,6 +159,60 @@ SEXP C_mlnmf_run(SEXP ptr, SEXP w0, SEXP h0, SEXP itmax, SEXP tol) {
     return out;
 }
 
+/* 0 = fp64 (the reference's arithmetic), 1 = fp32 storage / fp64 accumulation */
+SEXP C_vbnmf_set_precision(SEXP ptr, SEXP precision) {
+    vbnmf_handle *h = get_handle(ptr);
+    chk(vbnmf_set_precision(h, Rf_asInteger(precision)), h);
+    return R_NilValue;
+}
+
+SEXP C_vbnmf_set_host_threads(SEXP nthreads) {
+    if (vbnmf_set_host_threads(Rf_asInteger(nthreads)) != 0) Rf_error("libvbnmf: bad thread count");
+    return R_NilValue;
+}
+
+/* ---- cells sharded over several GPUs: one R process per GPU (the processes the reference would
+ * start through Rmpi, R/bayesian.R:263), each holding a contiguous range of the columns --------- */
+static void comm_finalizer(SEXP ptr) {
+    vbnmf_comm *c = (vbnmf_comm *)R_ExternalPtrAddr(ptr);
+    if (c) vbnmf_comm_destroy(c);
+    R_ClearExternalPtr(ptr);
+}
+
+/* raw(128): the ncclUniqueId made on rank 0, to be broadcast by the host side (e.g. Rmpi::mpi.bcast) */
+SEXP C_vbnmf_nccl_unique_id(void) {
+    SEXP out = PROTECT(Rf_allocVector(RAWSXP, 128));
+    if (vbnmf_nccl_unique_id(RAW(out)) != 0) Rf_error("libvbnmf: %s", vbnmf_last_error(NULL));
+    UNPROTECT(1);
+    return out;
+}
+
+SEXP C_vbnmf_comm_create(SEXP nranks, SEXP rank, SEXP uid, SEXP device) {
+    vbnmf_comm *c = NULL;
+    if (XLENGTH(uid) != 128) Rf_error("libvbnmf: the unique id must be raw(128)");
+    if (vbnmf_comm_create(&c, Rf_asInteger(nranks), Rf_asInteger(rank), RAW(uid),
+                          Rf_asInteger(device)) != 0)
+        Rf_error("libvbnmf: %s", vbnmf_last_error(NULL));
+    SEXP ptr = PROTECT(R_MakeExternalPtr(c, R_NilValue, R_NilValue));
+    R_RegisterCFinalizerEx(ptr, comm_finalizer, TRUE);
+    UNPROTECT(1);
+    return ptr;
+}
+
+SEXP C_vbnmf_comm_destroy(SEXP ptr) {
+    comm_finalizer(ptr);
+    return R_NilValue;
+}
+
+/* the handle holds the columns of ONE shard; collective over the ranks of the communicator */
+SEXP C_vbnmf_attach_comm(SEXP ptr, SEXP comm) {
+    vbnmf_handle *h = get_handle(ptr);
+    vbnmf_comm *c = (vbnmf_comm *)R_ExternalPtrAddr(comm);
+    if (!c) Rf_error("libvbnmf: communicator has been released");
+    chk(vbnmf_attach_comm(h, c), h);
+    return R_NilValue;
+}
+
 static const R_CallMethodDef CallEntries[] = {
     {"C_vbnmf_create", (DL_FUNC)&C_vbnmf_create, 5},
     {"C_vbnmf_destroy", (DL_FUNC)&C_vbnmf_destroy, 1},
@@ -165,10 +220,16 @@ static const R_CallMethodDef CallEntries[] = {
     {"C_vbnmf_init_random", (DL_FUNC)&C_vbnmf_init_random, 4},
     {"C_vbnmf_step", (DL_FUNC)&C_vbnmf_step, 3},
     {"C_vbnmf_run", (DL_FUNC)&C_vbnmf_run, 8},
-    {"C_vbnmf_get_state", (DL_FUNC)&C_vbnmf_get_state, 2},
+    {"C_vbnmf_get_state", (DL_FUNC)&C_vbnmf_get_state, 1},
     {"C_vbnmf_uniform_columns", (DL_FUNC)&C_vbnmf_uniform_columns, 2},
     {"C_vbnmf_cluster_id", (DL_FUNC)&C_vbnmf_cluster_id, 1},
     {"C_mlnmf_run", (DL_FUNC)&C_mlnmf_run, 5},
+    {"C_vbnmf_set_precision", (DL_FUNC)&C_vbnmf_set_precision, 2},
+    {"C_vbnmf_set_host_threads", (DL_FUNC)&C_vbnmf_set_host_threads, 1},
+    {"C_vbnmf_nccl_unique_id", (DL_FUNC)&C_vbnmf_nccl_unique_id, 0},
+    {"C_vbnmf_comm_create", (DL_FUNC)&C_vbnmf_comm_create, 4},
+    {"C_vbnmf_comm_destroy", (DL_FUNC)&C_vbnmf_comm_destroy, 1},
+    {"C_vbnmf_attach_comm", (DL_FUNC)&C_vbnmf_attach_comm, 2},
     {NULL, NULL, 0}};
 
 /* mirrors R_init_ccfindR, src/RcppExports.cpp:29-32 */

@@ -83,6 +83,22 @@ def main():
         assert np.array_equal(par.measure[key], ser.measure[key]), key
     for k in range(len(ser.ranks)):
         assert np.array_equal(par.basis[k], ser.basis[k]) and np.array_equal(par.coeff[k], ser.coeff[k])
+    # one factorization at a time with the cells sharded over the GPUs, through the front end:
+    # same measure / basis / coeff as the single-GPU front end (1e-9: the all-reduce changes the
+    # order of the sums over cells), same cluster labels
+    for extra in (dict(), dict(device_init=True)):
+        shd = api.vb_factorize(api.scNMFSet(Xc), shard_cells=True, **kw, **extra)
+        one = api.vb_factorize(api.scNMFSet(Xc), **kw, **extra)
+        assert list(shd.ranks) == list(one.ranks)
+        for key in one.measure:
+            assert relerr(shd.measure[key], one.measure[key]) < 1e-9, key
+        for k in range(len(one.ranks)):
+            assert shd.coeff[k].shape == one.coeff[k].shape
+            e = max(e, relerr(shd.basis[k], one.basis[k]), relerr(shd.coeff[k], one.coeff[k]),
+                    relerr(shd.dcoeff[k], one.dcoeff[k]))
+            assert np.array_equal(api.cluster_id(shd, rank=one.ranks[k]),
+                                  api.cluster_id(one, rank=one.ranks[k]))
+        assert e < 1e-9, ("shard_cells", extra, e)
     t = torch.tensor([max(worst, e)], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
