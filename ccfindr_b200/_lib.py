@@ -51,11 +51,14 @@ SIGNATURES = {
     "vbnmf_uniform_columns": (C.c_int, [C.c_void_p, C.c_double, c_i32p]),
     "mlnmf_run": (C.c_int, [C.c_void_p, C.c_int, c_dp, c_dp, C.c_int, C.c_double, c_dp, c_dp, c_dp,
                             c_ip]),
+    "mlnmf_run2": (C.c_int, [C.c_void_p, C.c_int, c_dp, c_dp, C.c_int, C.c_double, C.c_int, C.c_int,
+                             c_dp, c_dp, c_dp, c_dp, c_ip]),
     "vbnmf_bench_iterations": (C.c_int, [C.c_void_p, c_dp, C.c_double, C.c_int, C.c_int, c_dp,
                                          c_i64p, c_dp]),
     "vbnmf_set_host_threads": (C.c_int, [C.c_int]),
     "vbnmf_trim_pool": (C.c_int, [C.c_int]),
     "vbnmf_init_random": (C.c_int, [C.c_void_p, C.c_int, c_dp, C.c_uint64, C.c_int64]),
+    "vbnmf_init_svd2": (C.c_int, [C.c_void_p, C.c_int, c_dp, C.c_uint64, C.c_int64]),
     "vbnmf_info": (C.c_int, [C.c_void_p, c_i64p]),
     "vbnmf_layout_info": (C.c_int, [C.c_void_p, c_i64p]),
 }

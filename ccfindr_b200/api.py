@@ -155,15 +155,22 @@ def vb_init(nrow, ncol, mat, rank, hyper, initializer, seed):
 def dispersion_from_labels(label_runs):
     """dispersion(conav/irun, ncol) of R/factorize.R:51-67 without the m(m-1)/2 connectivity vector:
     cells are grouped by their tuple of cluster labels over the runs; two cells are co-clustered in
-    t runs iff their tuples agree in t positions."""
+    t runs iff their tuples agree in t positions.  Cost: (distinct tuples)^2, not cells^2."""
     L = np.stack([np.asarray(v) for v in label_runs], axis=1)
     nc, nrun = L.shape
     tup, cnt = np.unique(L, axis=0, return_counts=True)
-    con = 0.0
-    for a in range(len(tup)):
-        con += cnt[a] * (cnt[a] - 1) / 2 * (1.0 - 0.5) ** 2
-        same = (tup[a + 1:] == tup[a]).sum(axis=1) / nrun
-        con += float((cnt[a] * cnt[a + 1:] * (same - 0.5) ** 2).sum())
+    cnt = cnt.astype(np.float64)
+    con = float(np.sum(cnt * (cnt - 1.0) / 2.0)) * 0.25        # same tuple: (1 - 0.5)^2
+    G = len(tup)
+    step = max(1, int(4e6 // max(G, 1)))
+    for a0 in range(0, G, step):                                # blocks of rows of the G x G table
+        blk = tup[a0:a0 + step]
+        same = np.zeros((len(blk), G))
+        for t in range(nrun):
+            same += blk[:, t][:, None] == tup[:, t][None, :]
+        wgt = cnt[a0:a0 + step][:, None] * cnt[None, :]
+        mask = np.arange(a0, a0 + len(blk))[:, None] < np.arange(G)[None, :]   # pairs a < b once
+        con += float(np.sum(np.where(mask, wgt * (same / nrun - 0.5) ** 2, 0.0)))
     return 1.0 / nc + 8.0 * con / nc ** 2
 
 
@@ -193,7 +200,9 @@ def vb_factorize(object, ranks=2, nrun=1, verbose=2, progress_bar=True, initiali
     `ncores` and `useC` are accepted and ignored: the update always runs on the GPU.
     `precision`: 0 = fp64 (reference arithmetic), 1 = fp32-storage / fp64-accumulate.
     `device_init=True`: the 'random' initializer is drawn on the GPU (Engine.init_random, a counter
-    RNG keyed by seed and matrix position) instead of on the host and uploaded.
+    RNG keyed by seed and matrix position) and the 'svd2' initializer is computed on the GPU
+    (Engine.init_svd2, randomized truncated SVD of the resident matrix) instead of on the host and
+    uploaded.
     `parallel=True` (inside an initialised torch.distributed job, one process per GPU): the
     nrun x len(ranks) independent factorizations are spread over the ranks (the role of
     Rmpi::mpi.applyLB, R/bayesian.R:263), every rank holds a full copy of the matrix, results are
@@ -216,10 +225,10 @@ def vb_factorize(object, ranks=2, nrun=1, verbose=2, progress_bar=True, initiali
     ga = np.atleast_1d(np.asarray(gamma_a, dtype=np.float64))
     gb = np.atleast_1d(np.asarray(gamma_b, dtype=np.float64))
 
-    if device_init and initializer != "random":
-        raise ValueError("device_init applies to the 'random' initializer")
+    if device_init and initializer not in ("random", "svd2"):
+        raise ValueError("device_init applies to the 'random' and 'svd2' initializers")
     if device_init:
-        initializer = "random_device"
+        initializer += "_device"
     common = (ga, gb, initializer, Itmax, hyper_update, Tol, hyper_update_n0, hyper_update_dn,
               connectivity, fudge)
     vb = []
@@ -378,6 +387,8 @@ def _vb_iterate(eng, irun, mat, ranks, ga, gb, initializer, Itmax, hyper_update,
             eng.set_state(w0, h0[:, c0:c1])                     # lw = ew = w, lh = eh = h (:170)
         elif initializer == "random_device":
             eng.init_random(rank, hyper, seed * 100003 + 1000 * rank + irun, cell_offset=c0)
+        elif initializer == "svd2_device":                      # :150-159 where the matrix lives
+            eng.init_svd2(rank, hyper, seed * 100003 + 1000 * rank + irun, cell_offset=c0)
         else:
             w0, h0 = vb_init(nrow, ncol, mat, rank, hyper, initializer,
                              seed * 100003 + 1000 * rank + irun)
@@ -399,7 +410,7 @@ def _vb_iterate(eng, irun, mat, ranks, ga, gb, initializer, Itmax, hyper_update,
         if connectivity:                                        # :353-357 (only printed)
             out["labels"][irank] = eng.cluster_id()
             runs = [p["labels"][irank] for p in previous if p["labels"][irank] is not None]
-            disp = dispersion_from_labels(runs + [out["labels"][irank]]) if ncol <= 200000 else np.nan
+            disp = dispersion_from_labels(runs + [out["labels"][irank]])
         if verbose >= 2:
             msg = "Rank = %d: Nsteps = %d, log(evidence) = %s, hyper = (%s,%s,%s,%s)" % (
                 rank, it, lk0, hyper["aw"], hyper["bw"], hyper["ah"], hyper["bh"])
@@ -427,12 +438,11 @@ def factorize(object, ranks=2, nrun=20, randomize=False, nsmpl=1, verbose=2, pro
               Itmax=10000, ncnn_step=40, criterion="likelihood", linkage="average", Tol=1e-5,
               store_connectivity=False, seed=1, device=0):
     """Maximum likelihood factorization (R/factorize.R:139-276); the it-loop (:189-212) runs on the
-    GPU.  criterion='connectivity' (:194-206) needs the cluster labels of every iteration and is not
-    offered by the device loop."""
-    if criterion != "likelihood":
-        if criterion == "connectivity":
-            raise NotImplementedError("criterion='connectivity' is not available on the GPU path")
-        raise ValueError("Unknown stopping criterion.")
+    GPU with either stopping criterion.  The consensus measures never form the m(m-1)/2
+    connectivity vector of the reference (:51-78): dispersion and the cophenetic correlation are
+    computed from the groups of cells that share their labels over the runs."""
+    if criterion not in ("likelihood", "connectivity"):
+        raise ValueError("Unknown stopping criterion.")        # :212
     mat0 = object.counts
     _check_no_empty(mat0)
     nrow, ncol = mat0.shape
@@ -462,7 +472,8 @@ def factorize(object, ranks=2, nrun=20, randomize=False, nsmpl=1, verbose=2, pro
                 for irun in range(1, nrun + 1):
                     w0, h0 = synth.uniform_init(nrow, ncol, rank,
                                                 seed * 100003 + 1000 * rank + 37 * ismpl + irun)
-                    res = eng.ml_run(w0, h0, Itmax=Itmax, Tol=Tol)
+                    res = eng.ml_run(w0, h0, Itmax=Itmax, Tol=Tol, criterion=criterion,
+                                     ncnn_step=ncnn_step)
                     lk0 = res["lik"]
                     labels.append(np.argmax(res["h"], axis=0) + 1)  # connectivity(), :51-60
                     disp = dispersion_from_labels(labels)
@@ -505,22 +516,99 @@ def factorize(object, ranks=2, nrun=20, randomize=False, nsmpl=1, verbose=2, pro
     return object
 
 
+def label_groups(label_runs):
+    """Cells grouped by their tuple of labels over the runs: (tuples G x nrun, sizes G).  Two cells
+    of the same group are co-clustered in every run; cells of groups a, b in as many runs as their
+    tuples agree in."""
+    L = np.stack([np.asarray(v) for v in label_runs], axis=1)
+    tup, cnt = np.unique(L, axis=0, return_counts=True)
+    return tup, cnt.astype(np.float64)
+
+
+def _linkage_weighted(D, sizes, method):
+    """Agglomerative clustering of G groups of identical points (sizes = points per group) by the
+    Lance-Williams recurrence, the same trees as stats::hclust / scipy on the expanded point set:
+    identical points merge first at height 0, which leaves exactly the groups with their sizes.
+    Returns the G x G matrix of cophenetic distances between groups.  O(G^3) worst case, G = number
+    of distinct label tuples (hundreds to a few thousand), independent of the number of cells."""
+    G = len(sizes)
+    D = np.array(D, dtype=np.float64)
+    np.fill_diagonal(D, np.inf)
+    n = np.array(sizes, dtype=np.float64)
+    active = np.ones(G, dtype=bool)
+    members = [[g] for g in range(G)]
+    coph = np.zeros((G, G))
+    if method in ("centroid", "median", "ward.D2"):
+        raise ValueError("linkage %r needs Euclidean squared distances" % method)
+    for _ in range(G - 1):
+        idx = np.flatnonzero(active)
+        sub = D[np.ix_(idx, idx)]
+        k = int(np.argmin(sub))
+        i, j = idx[k // len(idx)], idx[k % len(idx)]
+        if i > j:
+            i, j = j, i
+        dij = D[i, j]
+        for a in members[i]:
+            coph[a, members[j]] = dij
+        for a in members[j]:
+            coph[a, members[i]] = dij
+        rest = idx[(idx != i) & (idx != j)]
+        if method == "average":
+            new = (n[i] * D[i, rest] + n[j] * D[j, rest]) / (n[i] + n[j])
+        elif method == "single":
+            new = np.minimum(D[i, rest], D[j, rest])
+        elif method == "complete":
+            new = np.maximum(D[i, rest], D[j, rest])
+        elif method == "mcquitty":
+            new = 0.5 * (D[i, rest] + D[j, rest])
+        elif method in ("ward", "ward.D"):
+            t = n[i] + n[j] + n[rest]
+            new = ((n[i] + n[rest]) * D[i, rest] + (n[j] + n[rest]) * D[j, rest] - n[rest] * dij) / t
+        else:
+            raise ValueError("unknown linkage %r" % method)
+        D[i, rest] = new
+        D[rest, i] = new
+        active[j] = False
+        D[j, :] = np.inf
+        D[:, j] = np.inf
+        n[i] += n[j]
+        members[i] += members[j]
+    return coph
+
+
+def cophenet_from_labels(label_runs, method="average", max_groups=6000):
+    """cophenet(conav/nrun, ncol) of R/factorize.R:69-78 -- cor(d, cophenetic(hclust(d))) with
+    d = 1 - average connectivity -- without the nc x nc matrix: hclust on the groups of cells with
+    identical label tuples (weighted by their sizes) and the Pearson correlation accumulated over
+    group pairs with multiplicity size_a * size_b (same-group pairs contribute (0, 0)).
+    The cost depends on the number of distinct label tuples, not on the number of cells."""
+    tup, sz = label_groups(label_runs)
+    G, nrun = tup.shape
+    if sz.sum() < 3:
+        return np.nan
+    if G > max_groups:
+        return np.nan
+    agree = np.zeros((G, G))
+    for t in range(nrun):
+        agree += tup[:, t][:, None] == tup[:, t][None, :]
+    D = 1.0 - agree / nrun
+    C = _linkage_weighted(D, sz, method)
+    iu = np.triu_indices(G, 1)
+    wgt = (sz[:, None] * sz[None, :])[iu]
+    d, c = D[iu], C[iu]
+    same = float(np.sum(sz * (sz - 1.0) / 2.0))              # pairs inside a group: d = coph = 0
+    N = same + wgt.sum()
+    md, mc = (wgt * d).sum() / N, (wgt * c).sum() / N
+    vd = (wgt * (d - md) ** 2).sum() + same * md ** 2
+    vc = (wgt * (c - mc) ** 2).sum() + same * mc ** 2
+    cov = (wgt * (d - md) * (c - mc)).sum() + same * md * mc
+    if vd <= 0 or vc <= 0:
+        return np.nan
+    return float(cov / np.sqrt(vd * vc))
+
+
 def _cophenet(labels, nc, method="average"):
-    """cophenet(conav/nrun, ncol) of R/factorize.R:69-78.  Needs the nc x nc distance matrix, so it
-    is only evaluated for nc <= 5000 (the reference itself cannot go further)."""
-    if nc > 5000 or nc < 3:
-        return np.nan
-    from scipy.cluster.hierarchy import cophenet, linkage
-    from scipy.spatial.distance import squareform
-    L = np.stack(labels, axis=1)
-    con = np.zeros((nc, nc))
-    for t in range(L.shape[1]):
-        con += (L[:, t][:, None] == L[:, t][None, :])
-    d = squareform(1.0 - con / L.shape[1], checks=False)
-    if np.all(d == d[0]):
-        return np.nan
-    z = linkage(d, method=method)
-    return float(np.corrcoef(d, cophenet(z))[0, 1])
+    return cophenet_from_labels(labels, method)
 
 
 def cluster_id(object, rank=2):

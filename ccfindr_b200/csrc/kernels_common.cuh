@@ -695,6 +695,43 @@ xchg_reduce_kernel(const XchgArgs a, double2 *__restrict__ out) {
     }
 }
 
+// ---- criterion = 'connectivity' of factorize() (R/factorize.R:194-206) ---------------------------
+// lab[row] = index of the first maximum of the row of an l panel (h of the ML path), -1 for the
+// padding rows: which.max(h[,j]) of connectivity() (R/factorize.R:51-60)
+__global__ void __launch_bounds__(kBlock)
+ml_labels_kernel(int64_t rows, int T, int S, int64_t nvalid, int rs, int r, int tsplit,
+                 const double *__restrict__ v, int32_t *__restrict__ lab) {
+    const int64_t row = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (row >= rows) return;
+    const int64_t slab = row / T, local = row - slab * T;
+    if (local * S + slab >= nvalid) { lab[row] = -1; return; }
+    int best = 0;
+    double bv = v[panel_ofs(row, 0, rs, tsplit)];
+    for (int k = 1; k < r; k++) {
+        const double x = v[panel_ofs(row, k, rs, tsplit)];
+        if (x > bv) { bv = x; best = k; }
+    }
+    lab[row] = best;
+}
+// C[a * r + b] += number of cells with old label a and new label b (r x r doubles, zeroed before).
+// The connectivity matrices of two labelings are equal iff every row and column of C has at most
+// one non-zero; the number of changed pairs is sum_a C(n_a.,2) + sum_b C(n_.b,2) - 2 sum C(C_ab,2).
+__global__ void __launch_bounds__(kBlock)
+contingency_kernel(int64_t rows, int r, const int32_t *__restrict__ a, const int32_t *__restrict__ b,
+                   double *__restrict__ Cm) {
+    extern __shared__ unsigned int hist[];
+    for (int i = threadIdx.x; i < r * r; i += kBlock) hist[i] = 0u;
+    __syncthreads();
+    for (int64_t row = (int64_t)blockIdx.x * kBlock + threadIdx.x; row < rows;
+         row += (int64_t)gridDim.x * kBlock) {
+        const int la = a[row], lb = b[row];
+        if (la >= 0 && lb >= 0) atomicAdd(&hist[la * r + lb], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < r * r; i += kBlock)
+        if (hist[i]) atomicAdd(&Cm[i], (double)hist[i]);
+}
+
 // cid[d] = 1 + index of the first maximum over k of alh[d][k] / beh[k]   (R/utils.R:906)
 __global__ void __launch_bounds__(kBlock)
 cluster_id_kernel(int64_t rows, int RS, int r, const double *__restrict__ alh,

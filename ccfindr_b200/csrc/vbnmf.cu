@@ -37,6 +37,7 @@
 
 #include "../../include/vbnmf.h"
 #include "kernels_common.cuh"
+#include "svd_init.cuh"
 #include "rp_ranks.h"
 #include "rp_table.h"
 
@@ -1124,6 +1125,143 @@ int init_common(H *h, int device) {
 
 }  // namespace
 
+// ---- vb_init(initializer = 'svd2') on the device (svd_init.cuh) ------------------------------------
+namespace {
+
+template <typename VT>
+struct SvdCtx {
+    H *h;
+    int k;
+    double *d_part = nullptr, *d_G = nullptr, *d_M = nullptr, *d_tmp = nullptr;
+    int gblocks;
+    // G (k x k, host) = A^T A summed over the rows of all shards
+    int gram(const double *A, int64_t rows, std::vector<double> &G) {
+        const int kk = k * k;
+        vb::gram_part_kernel<<<gblocks, vb::kBlock, (size_t)vb::kGramRows * k * 8, h->stream>>>(
+            rows, k, A, d_part);
+        vb::gram_sum_kernel<<<cdiv(kk, vb::kBlock), vb::kBlock, 0, h->stream>>>(gblocks, kk, d_part, d_G);
+        h->launches += 2;
+        int rc = allreduce(h, d_G, kk);
+        if (rc) return rc;
+        G.resize((size_t)kk);
+        CK(cudaMemcpyAsync(G.data(), d_G, (size_t)kk * 8, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        return 0;
+    }
+    // A <- A M (M k x kout on the host); d_tmp must hold rows x kout
+    int right_mult(double *A, int64_t rows, const std::vector<double> &M, int kout, double *out) {
+        CK(cudaMemcpyAsync(d_M, M.data(), (size_t)k * kout * 8, cudaMemcpyHostToDevice, h->stream));
+        vb::right_mult_kernel<<<cdiv(rows * kout, vb::kBlock), vb::kBlock, 0, h->stream>>>(
+            rows, k, kout, A, d_M, out);
+        h->launches += 1;
+        return 0;
+    }
+    // orthonormalise the columns of A (sum over all shards' rows): Cholesky-QR, twice
+    int orth(double *A, int64_t rows, bool *ok) {
+        std::vector<double> G, R, Ri;
+        *ok = true;
+        for (int pass = 0; pass < 2; pass++) {
+            int rc = gram(A, rows, G);
+            if (rc) return rc;
+            if (!svdhost::cholesky_upper(k, G, R)) { *ok = false; return 0; }
+            svdhost::invert_upper(k, R, Ri);
+            if ((rc = right_mult(A, rows, Ri, k, d_tmp))) return rc;
+            CK(cudaMemcpyAsync(A, d_tmp, (size_t)rows * k * 8, cudaMemcpyDeviceToDevice, h->stream));
+        }
+        return 0;
+    }
+    int xt(const double *Q, double *out) {  // out (m x k) = X^T Q
+        vb::spmm_xt_kernel<VT><<<h->num_sms * 8, vb::kBlock, 0, h->stream>>>(
+            h->m, k, h->d_colptr, h->d_rowidx, (const VT *)h->d_val, Q, out);
+        h->launches += 1;
+        return 0;
+    }
+    int x(const double *Z, double *Y) {     // Y (n x k) = X Z, summed over the shards
+        CK(cudaMemsetAsync(Y, 0, (size_t)h->n * k * 8, h->stream));
+        vb::spmm_x_kernel<VT><<<h->num_sms * 8, vb::kBlock, 0, h->stream>>>(
+            h->m, k, h->d_colptr, h->d_rowidx, (const VT *)h->d_val, Z, Y);
+        h->launches += 1;
+        return allreduce(h, Y, h->n * (int64_t)k);
+    }
+};
+
+template <typename VT>
+int init_svd2_t(H *h, int r, const double hyper[4], uint64_t seed, int64_t cell_offset, int k,
+                int power_iters, bool *ok) {
+    const Layout *L = h->L;
+    const int64_t n = h->n, m = h->m, big = std::max(n, m);
+    SvdCtx<VT> c;
+    c.h = h; c.k = k;
+    c.gblocks = h->num_sms * 2;
+    double *d_Y = nullptr, *d_Z = nullptr, *d_sum = nullptr, *d_spart = nullptr;
+    CK(vmalloc(h, &d_Y, (size_t)n * k * 8));
+    CK(vmalloc(h, &d_Z, (size_t)m * k * 8));
+    CK(vmalloc(h, &c.d_tmp, (size_t)big * k * 8));
+    CK(vmalloc(h, &c.d_part, (size_t)c.gblocks * k * k * 8));
+    CK(vmalloc(h, &c.d_G, (size_t)k * k * 8));
+    CK(vmalloc(h, &c.d_M, (size_t)k * k * 8));
+    CK(vmalloc(h, &d_sum, 8));
+    CK(vmalloc(h, &d_spart, (size_t)h->num_sms * 4 * 8));
+    struct Free {
+        cudaStream_t s; double *p[8];
+        ~Free() { for (double *q : p) vfree(s, q); }
+    } fr{h->stream, {d_Y, d_Z, c.d_tmp, c.d_part, c.d_G, c.d_M, d_sum, d_spart}};
+    int rc;
+    vb::gauss_fill_kernel<<<cdiv(m * k, vb::kBlock), vb::kBlock, 0, h->stream>>>(
+        m, k, (unsigned long long)seed, cell_offset, d_Z);
+    h->launches += 1;
+    if ((rc = c.x(d_Z, d_Y))) return rc;                 // Y = X Omega
+    if ((rc = c.orth(d_Y, n, ok)) || !*ok) return rc;
+    for (int q = 0; q < power_iters; q++) {              // Y <- X X^T Y, re-orthonormalised
+        if ((rc = c.xt(d_Y, d_Z))) return rc;
+        if ((rc = c.orth(d_Z, m, ok)) || !*ok) return rc;
+        if ((rc = c.x(d_Z, d_Y))) return rc;
+        if ((rc = c.orth(d_Y, n, ok)) || !*ok) return rc;
+    }
+    if ((rc = c.xt(d_Y, d_Z))) return rc;                // B^T = X^T Q  (m x k)
+    std::vector<double> G, ev, V;
+    if ((rc = c.gram(d_Z, m, G))) return rc;             // B B^T
+    svdhost::jacobi_eigen(k, G, ev, V);                  // = U_B diag(d^2) U_B^T
+    std::vector<double> M1((size_t)k * r);               // first r eigenvectors
+    for (int a = 0; a < k; a++)
+        for (int q = 0; q < r; q++) M1[(size_t)a * r + q] = V[(size_t)a * k + q];
+    // U = Q U_B (n x r), T = B^T U_B = (diag(d) V^T)^T (m x r)
+    double *d_U = c.d_tmp;
+    if ((rc = c.right_mult(d_Y, n, M1, r, d_U))) return rc;
+    double *d_T = d_Y;                                    // reuse: n*k >= ... not guaranteed, so:
+    double *d_T2 = nullptr;
+    CK(vmalloc(h, &d_T2, (size_t)m * r * 8));
+    d_T = d_T2;
+    struct Free2 { cudaStream_t s; double *p; ~Free2() { vfree(s, p); } } fr2{h->stream, d_T2};
+    if ((rc = c.right_mult(d_Z, m, M1, r, d_T))) return rc;
+    // scale <- bh / mean(h), h = |T|^T over all cells
+    vb::abs_sum_kernel<<<h->num_sms * 4, vb::kBlock, 0, h->stream>>>(m * r, d_T, d_spart, d_sum,
+                                                                   h->d_counters + 5);
+    h->launches += 1;
+    if ((rc = allreduce(h, d_sum, 1))) return rc;
+    double sum = 0.0;
+    CK(cudaMemcpyAsync(&sum, d_sum, 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    const double mean_h = sum / ((double)r * (double)h->m_global);
+    if (!(mean_h > 0.0) || !std::isfinite(mean_h)) { *ok = false; return 0; }
+    const double scale = hyper[3] / mean_h;              // :156
+    const int rs = h->rs;
+    const size_t gr = (size_t)L->NG * rs * 8, cr = (size_t)L->NC * rs * 8;
+    CK(cudaMemsetAsync(h->d_lw, 0, gr, h->stream));
+    CK(cudaMemsetAsync(h->d_alw, 0, gr, h->stream));
+    CK(cudaMemsetAsync(h->d_lh, 0, cr, h->stream));
+    CK(cudaMemsetAsync(h->d_alh, 0, cr, h->stream));
+    vb::svd_store_kernel<<<cdiv(n * r, vb::kBlock), vb::kBlock, 0, h->stream>>>(
+        n, r, rs, L->d_gene_dev, d_U, 1.0 / scale, h->d_lw, h->d_alw, h->tsplit);   // w / scale
+    vb::svd_store_kernel<<<cdiv(m * r, vb::kBlock), vb::kBlock, 0, h->stream>>>(
+        m, r, rs, L->d_cell_dev, d_T, scale, h->d_lh, h->d_alh, h->tsplit);         // h * scale
+    h->launches += 2;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
 extern "C" {
 
 const char *vbnmf_last_error(const vbnmf_handle *h) {
@@ -1458,6 +1596,32 @@ int vbnmf_init_random(vbnmf_handle *h, int r, const double hyper[4], uint64_t se
     h->launches += 2;
     if ((rc = refresh_mirrors(h))) return rc;
     return initial_ehsum(h);
+}
+
+int vbnmf_init_svd2(vbnmf_handle *h, int r, const double hyper[4], uint64_t seed,
+                    int64_t cell_offset) {
+    if (!h || !hyper) return VBNMF_ERR_ARG;
+    if (r < 1 || r > kMaxRank) return fail(h, VBNMF_ERR_ARG, "rank must be in 1..64");
+    if (!(hyper[3] > 0) || cell_offset < 0) return fail(h, VBNMF_ERR_ARG, "bh must be positive");
+    if (r > std::min(h->n, h->m_global)) return fail(h, VBNMF_ERR_ARG, "rank exceeds min(n, m)");
+    CK(cudaSetDevice(h->device));
+    StageTimer tm("vbnmf_init_svd2(total)");
+    int rc;
+    if ((rc = alloc_panels(h, r))) return rc;
+    const int kmax = (int)std::min<int64_t>(std::min(h->n, h->m_global), vb::kSvdMaxK);
+    // oversampling 10 and 4 power iterations; a rank-deficient sketch (Cholesky fails) falls back
+    // to no oversampling
+    for (int k : {std::min(r + 10, kmax), r}) {
+        bool ok = true;
+        rc = h->val_float ? init_svd2_t<float>(h, r, hyper, seed, cell_offset, k, 4, &ok)
+                          : init_svd2_t<double>(h, r, hyper, seed, cell_offset, k, 4, &ok);
+        if (rc) return rc;
+        if (ok) {
+            if ((rc = refresh_mirrors(h))) return rc;
+            return initial_ehsum(h);
+        }
+    }
+    return fail(h, VBNMF_ERR_ARG, "svd2 initializer: the matrix has numerical rank below `rank`");
 }
 
 int vbnmf_step(vbnmf_handle *h, const double hyper[4], double fudge, double *lkh) {
@@ -1812,8 +1976,19 @@ int vbnmf_layout_info(const vbnmf_handle *h, int64_t info[8]) {
 
 int mlnmf_run(vbnmf_handle *h, int r, const double *w0, const double *h0, int itmax, double tol,
               double *w, double *h_out, double *lik_trace, int *niter) {
+    return mlnmf_run2(h, r, w0, h0, itmax, tol, VBNMF_ML_LIKELIHOOD, 0, w, h_out, lik_trace, nullptr,
+                      niter);
+}
+
+int mlnmf_run2(vbnmf_handle *h, int r, const double *w0, const double *h0, int itmax, double tol,
+               int criterion, int ncnn_step, double *w, double *h_out, double *lik_trace,
+               double *nchange_trace, int *niter) {
     if (!h || !w0 || !h0 || !niter || itmax < 1) return VBNMF_ERR_ARG;
     if (r < 1 || r > kMaxRank) return fail(h, VBNMF_ERR_ARG, "rank must be in 1..64");
+    if (criterion != VBNMF_ML_LIKELIHOOD && criterion != VBNMF_ML_CONNECTIVITY)
+        return fail(h, VBNMF_ERR_ARG, "Unknown stopping criterion.");   // R/factorize.R:212
+    if (criterion == VBNMF_ML_CONNECTIVITY && ncnn_step < 1)
+        return fail(h, VBNMF_ERR_ARG, "ncnn_step must be >= 1");
     CK(cudaSetDevice(h->device));
     int rc;
     if ((rc = alloc_panels(h, r))) return rc;
@@ -1828,6 +2003,20 @@ int mlnmf_run(vbnmf_handle *h, int r, const double *w0, const double *h0, int it
     const double eps = 2.220446049250313e-16;  // .Machine$double.eps, R/factorize.R:15,24
     const int rs = h->rs, wd = rs + 8;
     double *tail = h->d_red + tail_off(h);
+    // connectivity criterion: labels of the previous and the current h, their contingency table
+    int32_t *d_lab[2] = {nullptr, nullptr};
+    double *d_cont = nullptr;
+    std::vector<double> cont;
+    struct Guard {
+        cudaStream_t s; int32_t **l; double **c;
+        ~Guard() { vfree(s, l[0]); vfree(s, l[1]); vfree(s, *c); }
+    } guard{h->stream, d_lab, &d_cont};
+    if (criterion == VBNMF_ML_CONNECTIVITY) {
+        CK(vmalloc(h, &d_lab[0], (size_t)L->NC * 4));
+        CK(vmalloc(h, &d_lab[1], (size_t)L->NC * 4));
+        CK(vmalloc(h, &d_cont, (size_t)r * r * 8));
+        cont.resize((size_t)r * r);
+    }
     auto colsum = [&](bool wside) -> int {
         vb::ColsumArgs a{wside ? L->NG : L->NC, wside ? h->d_lw : h->d_lh,
                          wside ? h->d_partW : h->d_partH, wside ? h->d_scal : tail,
@@ -1856,21 +2045,61 @@ int mlnmf_run(vbnmf_handle *h, int r, const double *w0, const double *h0, int it
         *lik = (h->h_scal[wd + rs + 4] - swh + h->mlconst) / (double)h->n / (double)h->m_global;
         return 0;
     };
+    // number of cell pairs whose co-clustering changed between labelings `prev` and `cur`
+    // (sum(cnn != cnn0), R/factorize.R:197) from their contingency table
+    auto nchange_of = [&](int prev, int cur, double *nchange) -> int {
+        CK(cudaMemsetAsync(d_cont, 0, (size_t)r * r * 8, h->stream));
+        vb::contingency_kernel<<<h->num_sms * 2, vb::kBlock, (size_t)r * r * 4, h->stream>>>(
+            L->NC, r, d_lab[prev], d_lab[cur], d_cont);
+        h->launches += 1;
+        if ((rc = allreduce(h, d_cont, (int64_t)r * r))) return rc;
+        CK(cudaMemcpyAsync(cont.data(), d_cont, (size_t)r * r * 8, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        auto c2 = [](double x) { return x * (x - 1.0) * 0.5; };
+        double both = 0.0, rows2 = 0.0, cols2 = 0.0;
+        for (int a = 0; a < r; a++) {
+            double ra = 0.0, ca = 0.0;
+            for (int b2 = 0; b2 < r; b2++) {
+                ra += cont[(size_t)a * r + b2];
+                ca += cont[(size_t)b2 * r + a];
+                both += c2(cont[(size_t)a * r + b2]);
+            }
+            rows2 += c2(ra);
+            cols2 += c2(ca);
+        }
+        *nchange = rows2 + cols2 - 2.0 * both;
+        return 0;
+    };
     if ((rc = colsum(true))) return rc;   // colSums(w0)
     if ((rc = colsum(false))) return rc;  // rowSums(h0) (local)
     if ((rc = allreduce(h, tail, rs))) return rc;
     double lkold = -INFINITY, lk0 = NAN;
-    int it, done = 0;
+    int it, done = 0, zstep = 0;
+    bool stop_after = false;
     for (it = 1; it <= itmax; it++) {                                      // R/factorize.R:191
         if ((rc = launch_sweep_cols(h))) return rc;  // ShRaw and xlogp at (w, h) of iteration it-1
         if ((rc = allreduce(h, tail + rs + 3, 2))) return rc;
         if (it > 1) {
             if ((rc = lik_now(&lk0))) return rc;                           // :193
             if (lik_trace) lik_trace[it - 2] = lk0;
-            if (fabs(lkold - lk0) < tol * fabs(lkold)) { done = it - 1; break; }  // :207
-            lkold = lk0;
+            if (stop_after) { done = it - 1; break; }                      // :203 (zstep == ncnn.step)
+            if (criterion == VBNMF_ML_LIKELIHOOD) {
+                if (fabs(lkold - lk0) < tol * fabs(lkold)) { done = it - 1; break; }  // :207
+                lkold = lk0;
+            }
         }
         if ((rc = mlupd(false))) return rc;          // h update, :8-15 -> rowSums(h_new) in tail
+        if (criterion == VBNMF_ML_CONNECTIVITY) {                          // :194-204 on h of iteration it
+            const int cur = it & 1, prev = cur ^ 1;
+            vb::ml_labels_kernel<<<cdiv(L->NC, vb::kBlock), vb::kBlock, 0, h->stream>>>(
+                L->NC, L->T, L->Sc, h->m, rs, r, h->tsplit, h->d_lh, d_lab[cur]);
+            h->launches += 1;
+            double nchange = (double)h->m_global * ((double)h->m_global - 1.0) * 0.5;  // it == 1: npair
+            if (it > 1 && (rc = nchange_of(prev, cur, &nchange))) return rc;
+            if (nchange_trace) nchange_trace[it - 1] = nchange;
+            zstep = nchange == 0.0 ? zstep + 1 : 0;
+            if (zstep == ncnn_step) stop_after = true;
+        }
         if ((rc = launch_sweep_rows(h))) return rc;  // SwRaw at (w, h_new), :17
         if ((rc = allreduce(h, h->d_red, tail_off(h) + rs))) return rc;
         if ((rc = mlupd(true))) return rc;           // w update, :17-24 -> colSums(w_new) in d_scal

@@ -153,6 +153,14 @@ class Engine:
                                             int(cell_offset)))
         self.r = int(rank)
 
+    def init_svd2(self, rank, hyper, seed=1, cell_offset=0):
+        """vb_init(initializer='svd2') (R/bayesian.R:150-159) computed on the device from the
+        resident count matrix (randomized truncated SVD): no host SVD, no upload."""
+        hy = hyper_vec(hyper)
+        self._ck(self.lib.vbnmf_init_svd2(self.handle, int(rank), _dp(hy), int(seed),
+                                          int(cell_offset)))
+        self.r = int(rank)
+
     def get_state(self, which=("lw", "lh", "ew", "eh", "dw", "dh")):
         r = self.r
         out = {}
@@ -205,20 +213,27 @@ class Engine:
         return fl.astype(bool)
 
     # -- ML path -------------------------------------------------------------------------------
-    def ml_run(self, w0, h0, Itmax=10000, Tol=1e-5):
-        """it-loop of factorize(), criterion='likelihood' (R/factorize.R:189-212)."""
+    def ml_run(self, w0, h0, Itmax=10000, Tol=1e-5, criterion="likelihood", ncnn_step=40):
+        """it-loop of factorize() (R/factorize.R:189-212) with either stopping criterion:
+        'likelihood' (:207) or 'connectivity' (:194-204, unchanged cell co-clustering for
+        ncnn_step iterations)."""
+        if criterion not in ("likelihood", "connectivity"):
+            raise ValueError("Unknown stopping criterion.")
         w0 = np.asfortranarray(w0, dtype=np.float64)
         h0 = np.asfortranarray(h0, dtype=np.float64)
         r = w0.shape[1]
         w = np.zeros((self.n, r), order="F")
         h = np.zeros((r, self.m), order="F")
         trace = np.full(int(Itmax), np.nan)
+        nch = np.full(int(Itmax), np.nan)
         niter = C.c_int(0)
-        self._ck(self.lib.mlnmf_run(self.handle, r, _dp(w0), _dp(h0), int(Itmax), float(Tol),
-                                    _dp(w), _dp(h), _dp(trace), C.byref(niter)))
+        self._ck(self.lib.mlnmf_run2(self.handle, r, _dp(w0), _dp(h0), int(Itmax), float(Tol),
+                                     int(criterion == "connectivity"), int(ncnn_step), _dp(w),
+                                     _dp(h), _dp(trace), _dp(nch), C.byref(niter)))
         self.r = r
         it = niter.value
-        return dict(w=w, h=h, niter=it, lik_trace=trace[:it].copy(), lik=float(trace[it - 1]))
+        return dict(w=w, h=h, niter=it, lik_trace=trace[:it].copy(), lik=float(trace[it - 1]),
+                    nchange_trace=nch[:it].copy())
 
     # -- measurement ---------------------------------------------------------------------------
     def bench_iterations(self, hyper, iters, fudge=EPS, hyper_on=False):

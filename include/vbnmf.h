@@ -121,6 +121,16 @@ VBNMF_API int vbnmf_set_state(vbnmf_handle *h, int r, const double *lw, const do
 VBNMF_API int vbnmf_init_random(vbnmf_handle *h, int r, const double hyper[4], uint64_t seed,
                                 int64_t cell_offset);
 
+/* vb_init(initializer = 'svd2') (R/bayesian.R:150-159) on the device: w = |u| / scale,
+ * h = |diag(d) v^T| * scale, scale = bh / mean(h), from a rank-r truncated SVD of the count matrix
+ * computed where it lives (randomized range finder with oversampling 10 and 4 power iterations in
+ * place of irlba; k x k factorizations on the host).  Singular vectors are defined up to sign, which
+ * abs() removes; accuracy against an exact truncated SVD is ~1e-8 for separated singular values.
+ * seed keys the Gaussian test matrix by GLOBAL cell index (cell_offset + j): the result does not
+ * depend on the sharding.  hyper = {aw, bw, ah, bh} (only bh is used, as in the reference). */
+VBNMF_API int vbnmf_init_svd2(vbnmf_handle *h, int r, const double hyper[4], uint64_t seed,
+                              int64_t cell_offset);
+
 /* One call of vbnmf_update (src/vbnmf_update.cpp:16-102): state <- update(state); *lkh = bound. */
 VBNMF_API int vbnmf_step(vbnmf_handle *h, const double hyper[4], double fudge, double *lkh);
 
@@ -149,6 +159,18 @@ VBNMF_API int vbnmf_uniform_columns(vbnmf_handle *h, double tol, int32_t *flags)
  * (R/factorize.R:189-212) from initial w0 (n x r), h0 (r x m).  lik_trace may be NULL. */
 VBNMF_API int mlnmf_run(vbnmf_handle *h, int r, const double *w0, const double *h0, int itmax, double tol,
               double *w, double *h_out, double *lik_trace, int *niter);
+
+/* Same loop with the stopping rule of factorize() selectable (R/factorize.R:194-212):
+ * criterion = VBNMF_ML_LIKELIHOOD: |lkold - lk0| < tol |lkold| (:207, what mlnmf_run does);
+ * criterion = VBNMF_ML_CONNECTIVITY: stop when the connectivity matrix of the cells
+ * (outer(cid, cid, '=='), cid = which.max of each column of h, :51-60) has not changed for
+ * ncnn_step consecutive iterations (:195-203).  The m(m-1)/2 connectivity vector is never formed:
+ * sum(cnn != cnn0) is taken from the r x r contingency table of consecutive labelings.
+ * nchange_trace (itmax doubles, may be NULL): that count per iteration (npair at iteration 1). */
+enum { VBNMF_ML_LIKELIHOOD = 0, VBNMF_ML_CONNECTIVITY = 1 };
+VBNMF_API int mlnmf_run2(vbnmf_handle *h, int r, const double *w0, const double *h0, int itmax,
+               double tol, int criterion, int ncnn_step, double *w, double *h_out,
+               double *lik_trace, double *nchange_trace, int *niter);
 
 /* Measurement hooks (bench.py).  Runs `iters` steady-state VB iterations (posterior update +
  * nonzero sweep [+ all-reduce]) with fixed hypers and reports CUDA-event times in ms:

@@ -281,20 +281,61 @@ def likelihood(mat, w, h):
     return float(x / mat.shape[0] / mat.shape[1])               # :47
 
 
-def ml_iterate(mat, w0, h0, *, Itmax=10000, Tol=1e-5):
-    """R/factorize.R:187-212, criterion='likelihood'.  Returns (w, h, lk0, it, trace)."""
+def connectivity(h):
+    """R/factorize.R:51-60, literally: the m(m-1)/2 vector of outer(cid, cid, '==') below the
+    diagonal (small m only)."""
+    cid = np.argmax(np.asarray(h), axis=0)
+    cnn = cid[:, None] == cid[None, :]
+    return cnn.T[np.tril_indices(len(cid), -1)[::-1]].astype(float)
+
+
+def dispersion(cnn, nc):
+    """R/factorize.R:62-67."""
+    return 1.0 / nc + 8.0 * float(np.sum((cnn - 0.5) ** 2)) / nc ** 2
+
+
+def cophenet(conav, nc, method="average"):
+    """R/factorize.R:69-78 with scipy standing in for stats::hclust / cophenetic / cor."""
+    from scipy.cluster.hierarchy import cophenet as sc_cophenet, linkage
+    tmp = np.zeros((nc, nc))
+    tmp[np.tril_indices(nc, -1)[::-1]] = 1.0 - conav
+    d = (tmp + tmp.T)[np.triu_indices(nc, 1)]
+    z = linkage(d, method=method)
+    return float(np.corrcoef(d, sc_cophenet(z))[0, 1])
+
+
+def ml_iterate(mat, w0, h0, *, Itmax=10000, Tol=1e-5, criterion="likelihood", ncnn_step=40):
+    """R/factorize.R:187-212, both stopping criteria.  Returns (w, h, lk0, it, trace) and, for
+    criterion='connectivity', the per-iteration nchange as a sixth element."""
     wh = dict(ew=np.array(w0, float), eh=np.array(h0, float))
     lkold = -np.inf                                             # :190
-    trace = []
+    zstep = 0                                                   # :189
+    trace, nch = [], []
     it = 0
     lk0 = np.nan
+    ncol = np.asarray(mat).shape[1]
+    npair = ncol * (ncol - 1) / 2
+    cnn0 = None
     for it in range(1, int(Itmax) + 1):                         # :191
         wh = nmf_updateR(mat, wh["ew"], wh["eh"])               # :192
         lk0 = likelihood(mat, wh["ew"], wh["eh"])               # :193
         trace.append(lk0)
-        if abs(lkold - lk0) < Tol * abs(lkold):                 # :207
-            break
-        lkold = lk0                                             # :209
+        if criterion == "connectivity":                         # :194-204
+            cnn = connectivity(wh["eh"])
+            nchange = npair if it == 1 else float(np.sum(cnn != cnn0))
+            nch.append(nchange)
+            zstep = zstep + 1 if nchange == 0 else 0
+            if zstep == ncnn_step:
+                break
+            cnn0 = cnn
+        elif criterion == "likelihood":
+            if abs(lkold - lk0) < Tol * abs(lkold):             # :207
+                break
+            lkold = lk0                                         # :209
+        else:
+            raise ValueError("Unknown stopping criterion.")     # :212
+    if criterion == "connectivity":
+        return wh["ew"], wh["eh"], lk0, it, np.array(trace), np.array(nch)
     return wh["ew"], wh["eh"], lk0, it, np.array(trace)
 
 

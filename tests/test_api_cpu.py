@@ -120,3 +120,72 @@ def test_device_random_init_reference_is_a_gamma_sampler():
     # mean b, variance b^2 / a (1200 and 160 draws: loose bounds)
     assert abs(w.mean() - 2.0) < 0.35 and abs(w.var() - 8.0) < 3.0
     assert abs(h.mean() - 0.7) < 0.12
+
+
+def _label_runs(rng, m, nrun, rank, noise):
+    """labelings that mostly agree with a planted partition (like converged NMF runs)"""
+    truth = rng.integers(0, rank, size=m)
+    runs = []
+    for _ in range(nrun):
+        lab = truth.copy()
+        flip = rng.random(m) < noise
+        lab[flip] = rng.integers(0, rank, size=int(flip.sum()))
+        runs.append(rng.permutation(rank)[lab] + 1)            # labels are arbitrary per run
+    return runs
+
+
+@pytest.mark.parametrize("m,nrun,rank,noise", [(40, 4, 3, 0.2), (150, 6, 4, 0.1), (300, 10, 5, 0.3)])
+def test_consensus_measures_from_label_groups_match_the_literal_ones(m, nrun, rank, noise):
+    """dispersion and the cophenetic correlation computed from groups of cells with identical
+    label tuples equal the reference's definitions on the full m(m-1)/2 connectivity vector
+    (R/factorize.R:51-78, restated literally in oracle/oracle_dense.py)."""
+    from oracle import oracle_dense as od
+    rng = np.random.default_rng(m + nrun)
+    runs = _label_runs(rng, m, nrun, rank, noise)
+    conav = np.zeros(m * (m - 1) // 2)
+    for lab in runs:
+        h = np.zeros((rank, m)); h[lab - 1, np.arange(m)] = 1.0
+        conav += od.connectivity(h)
+    conav /= nrun
+    assert abs(api.dispersion_from_labels(runs) - od.dispersion(conav, m)) < 1e-12
+    for method in ("average", "single"):
+        got = api.cophenet_from_labels(runs, method)
+        ref = od.cophenet(conav, m, method)
+        # connectivity distances are multiples of 1/nrun, so equal distances abound and the two
+        # agglomerations break them in a different order: 'single' does not depend on that order,
+        # 'average' (the reference's default) barely; 'complete' trees are not unique under ties
+        # (checked tie-free in the next test)
+        assert abs(got - ref) < (1e-9 if method == "single" else 5e-3), (method, got, ref)
+
+
+def test_cophenetic_scales_with_the_number_of_label_tuples_not_cells():
+    rng = np.random.default_rng(5)
+    runs = _label_runs(rng, 200000, 8, 4, 0.02)
+    c = api.cophenet_from_labels(runs)
+    d = api.dispersion_from_labels(runs)
+    assert 0.9 < c <= 1.0 and 0.5 < d <= 1.0
+
+
+@pytest.mark.parametrize("method", ["average", "single", "complete", "mcquitty", "ward.D"])
+def test_weighted_linkage_equals_linkage_of_the_expanded_point_set(method):
+    """Tie-free check of the agglomeration on groups of identical points: random distances between
+    G groups of random sizes against scipy on the expanded set (zero distance inside a group)."""
+    from scipy.cluster.hierarchy import cophenet, linkage
+    from scipy.spatial.distance import squareform
+    rng = np.random.default_rng(3)
+    G = 9
+    sizes = rng.integers(1, 5, size=G)
+    D = rng.random((G, G)) + 0.5
+    D = (D + D.T) / 2
+    np.fill_diagonal(D, 0.0)
+    owner = np.repeat(np.arange(G), sizes)
+    full = D[np.ix_(owner, owner)]
+    z = linkage(squareform(full, checks=False),
+                method={"mcquitty": "weighted", "ward.D": "ward"}.get(method, method))
+    if method == "ward.D":
+        pytest.skip("scipy's ward works on Euclidean distances (ward.D2); no tie-free twin here")
+    cf = squareform(cophenet(z))
+    got = api._linkage_weighted(D, sizes.astype(float), method)
+    first = np.array([np.flatnonzero(owner == g)[0] for g in range(G)])
+    ref = cf[np.ix_(first, first)]
+    assert np.allclose(got + np.diag(np.diag(ref)), ref, atol=1e-12)

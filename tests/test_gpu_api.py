@@ -122,3 +122,33 @@ def test_graph_replay_and_plain_launches_give_the_same_run(monkeypatch):
     assert out[0]["niter"] == out[1]["niter"] and out[0]["stop_reason"] == out[1]["stop_reason"]
     assert np.array_equal(out[0]["lkh_trace"], out[1]["lkh_trace"])
     assert np.array_equal(out[0]["hyper_trace"], out[1]["hyper_trace"])
+
+
+@pytest.mark.parametrize("counts,rank", [("pbmc", 5), ("c1s1", 3), ("pbmc", 2)])
+def test_device_svd2_initializer_matches_the_host_one(counts, rank):
+    """vb_init(initializer='svd2') (R/bayesian.R:150-159) computed on the GPU (randomized truncated
+    SVD of the resident CSC matrix) against the host restatement on scipy's ARPACK SVD: the
+    singular subspaces agree, abs() removes the sign freedom."""
+    from ccfindr_b200 import api
+    from ccfindr_b200.engine import Engine
+    X = load_counts(counts)
+    n, m = X.shape
+    hyper = dict(aw=1.0, bw=1.0, ah=1.0, bh=0.7)
+    w_ref, h_ref = api.vb_init(n, m, X, rank, hyper, "svd2", seed=1)
+    with Engine(X) as eng:
+        eng.init_svd2(rank, hyper, seed=5)
+        st = eng.get_state(("lw", "lh", "ew", "eh", "dw"))
+    for got, ref in ((st["lw"], w_ref), (st["lh"], h_ref), (st["ew"], w_ref), (st["eh"], h_ref)):
+        assert np.max(np.abs(got - ref)) / np.max(np.abs(ref)) < 1e-6
+    assert abs(st["lh"].mean() - hyper["bh"]) < 1e-12 * hyper["bh"] * 10   # scale = bh / mean(h)
+    assert not st["dw"].any()                                   # dw = dh = 0 at initialisation (:161-162)
+
+
+def test_vb_factorize_with_device_svd2_equals_host_svd2():
+    from ccfindr_b200 import api
+    X = load_counts("pbmc")
+    kw = dict(ranks=[3, 4], nrun=1, verbose=0, Itmax=30, initializer="svd2")
+    a = api.vb_factorize(api.scNMFSet(X), **kw)
+    b = api.vb_factorize(api.scNMFSet(X), device_init=True, **kw)
+    assert list(a.ranks) == list(b.ranks)
+    assert np.max(np.abs(a.measure["lml"] - b.measure["lml"]) / np.abs(a.measure["lml"])) < 1e-6

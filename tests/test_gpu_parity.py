@@ -172,6 +172,26 @@ def test_ml_path_matches_oracle(Engine, counts, r):
     assert relerr(res["w"], ref["w"]) < TOL and relerr(res["h"], ref["h"]) < TOL
 
 
+@pytest.mark.parametrize("counts,r,ncnn", [("tiny", 2, 3), ("pbmc", 4, 5), ("c1s1", 3, 4)])
+def test_ml_connectivity_criterion_matches_literal_reference_loop(Engine, counts, r, ncnn):
+    """criterion='connectivity' (R/factorize.R:194-204): stop after ncnn.step iterations without a
+    change of the cell co-clustering matrix.  The device loop takes sum(cnn != cnn0) from the r x r
+    contingency table of consecutive labelings; the oracle forms the m(m-1)/2 vectors literally."""
+    from ccfindr_b200 import synth
+    from oracle import oracle_dense as od
+    X = load_counts(counts)
+    n, m = X.shape
+    w0, h0 = synth.uniform_init(n, m, r, 11)
+    w, h, lk0, it, trace, nch = od.ml_iterate(np.asarray(X.todense()), w0, h0, Itmax=60,
+                                              criterion="connectivity", ncnn_step=ncnn)
+    with Engine(X) as eng:
+        res = eng.ml_run(w0, h0, Itmax=60, criterion="connectivity", ncnn_step=ncnn)
+    assert res["niter"] == it
+    assert np.array_equal(res["nchange_trace"], nch)            # exact pair counts
+    assert relerr(res["lik_trace"], trace) < TOL
+    assert relerr(res["w"], w) < TOL and relerr(res["h"], h) < TOL
+
+
 def test_errors_are_reported_not_thrown(Engine):
     from ccfindr_b200 import _lib
     X, w0, h0 = _random_problem(40, 30, 4, 0.3, seed=3)
