@@ -34,6 +34,8 @@ SIGNATURES = {
                                c_i64p, c_i32p, c_dp, C.c_int]),
     "vbnmf_create_from_device": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64, C.c_int64, C.c_int64,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "vbnmf_create_from_mtx": (C.c_int, [C.POINTER(C.c_void_p), C.c_char_p, C.c_int, c_i64p]),
+    "vbnmf_get_csc": (C.c_int, [C.c_void_p, c_i64p, c_i32p, c_dp]),
     "vbnmf_destroy": (None, [C.c_void_p]),
     "vbnmf_last_error": (C.c_char_p, [C.c_void_p]),
     "vbnmf_set_precision": (C.c_int, [C.c_void_p, C.c_int]),

@@ -64,9 +64,11 @@ def remove_zeros(object):
 
 
 def read_10x(dir, count="matrix.mtx", genes="genes.tsv", barcodes="barcodes.tsv",
-             remove_zeros_=True):
+             remove_zeros_=True, device=None):
     """R/utils.R:28-54: MatrixMarket counts + gene / barcode tables -> scNMFSet whose counts are
-    CSC (the dgCMatrix of :34), ready for the device upload without densification."""
+    CSC (the dgCMatrix of :34), ready for the device upload without densification.
+    device=<CUDA ordinal>: the text of matrix.mtx is parsed and sorted into CSC on the GPU
+    (Engine.from_mtx) instead of by scipy on the host."""
     import os
     import scipy.io
     if not os.path.isdir(dir):
@@ -74,7 +76,12 @@ def read_10x(dir, count="matrix.mtx", genes="genes.tsv", barcodes="barcodes.tsv"
     for f in (count, genes, barcodes):
         if not os.path.exists(os.path.join(dir, f)):
             raise FileNotFoundError("Count file %s does not exist" % os.path.join(dir, f))
-    mat = sp.csc_matrix(scipy.io.mmread(os.path.join(dir, count)), dtype=np.float64)
+    if device is not None:
+        os.environ.setdefault("VBNMF_ALLOW_EMPTY", "1")        # empties are dropped just below
+        with Engine.from_mtx(os.path.join(dir, count), device=device) as eng:
+            mat = eng.csc()
+    else:
+        mat = sp.csc_matrix(scipy.io.mmread(os.path.join(dir, count)), dtype=np.float64)
     glist = [ln.split() for ln in open(os.path.join(dir, genes)) if ln.strip()]
     clist = [ln.split() for ln in open(os.path.join(dir, barcodes)) if ln.strip()]
     if len(glist) != mat.shape[0] or len(clist) != mat.shape[1]:

@@ -38,6 +38,7 @@
 #include "../../include/vbnmf.h"
 #include "kernels_common.cuh"
 #include "svd_init.cuh"
+#include "mtx_ingest.cuh"
 #include "rp_ranks.h"
 #include "rp_table.h"
 
@@ -1212,8 +1213,19 @@ int init_svd2_t(H *h, int r, const double hyper[4], uint64_t seed, int64_t cell_
     h->launches += 1;
     if ((rc = c.x(d_Z, d_Y))) return rc;                 // Y = X Omega
     if ((rc = c.orth(d_Y, n, ok)) || !*ok) return rc;
-    for (int q = 0; q < power_iters; q++) {              // Y <- X X^T Y, re-orthonormalised
+    // subspace iteration Y <- X X^T Y, re-orthonormalised, until the r leading Ritz values
+    // (eigenvalues of Y^T X X^T Y = gram(X^T Y)) stop moving: their error is the square of the
+    // error of the vectors, so 1e-13 relative leaves the singular vectors good to ~1e-7
+    std::vector<double> Gz, evz, Vz, prev;
+    for (int q = 0; q < power_iters; q++) {
         if ((rc = c.xt(d_Y, d_Z))) return rc;
+        if ((rc = c.gram(d_Z, m, Gz))) return rc;
+        svdhost::jacobi_eigen(k, Gz, evz, Vz);
+        bool conv = q >= 2 && !prev.empty();
+        for (int a = 0; a < r && conv; a++)
+            conv = std::fabs(evz[(size_t)a] - prev[(size_t)a]) <= 1e-13 * std::fabs(evz[(size_t)a]);
+        prev = evz;
+        if (conv) break;
         if ((rc = c.orth(d_Z, m, ok)) || !*ok) return rc;
         if ((rc = c.x(d_Z, d_Y))) return rc;
         if ((rc = c.orth(d_Y, n, ok)) || !*ok) return rc;
@@ -1417,6 +1429,177 @@ int vbnmf_create_from_device(vbnmf_handle **out, int64_t n, int64_t m, int64_t n
     return 0;
 }
 
+int vbnmf_create_from_mtx(vbnmf_handle **out, const char *path, int device, int64_t dims[3]) {
+    if (!out || !path) return VBNMF_ERR_ARG;
+    *out = nullptr;
+    H *h = new H();
+    FILE *fp = nullptr;
+    auto bail = [&](int rc) {
+        if (fp) fclose(fp);
+        g_create_error = h->err;
+        vbnmf_destroy(h);
+        return rc;
+    };
+    StageTimer tm("vbnmf_create_from_mtx(total)");
+    fp = fopen(path, "rb");
+    if (!fp) return bail(fail(h, VBNMF_ERR_ARG, std::string("cannot open ") + path));
+    // header (host): banner, comments, the size line
+    char line[1024];
+    if (!fgets(line, sizeof(line), fp) || strncmp(line, "%%MatrixMarket", 14) != 0)
+        return bail(fail(h, VBNMF_ERR_ARG, "not a MatrixMarket file"));
+    std::string banner(line);
+    for (auto &ch : banner) ch = (char)tolower((unsigned char)ch);
+    if (banner.find("matrix") == std::string::npos || banner.find("coordinate") == std::string::npos ||
+        banner.find("general") == std::string::npos ||
+        (banner.find("real") == std::string::npos && banner.find("integer") == std::string::npos))
+        return bail(fail(h, VBNMF_ERR_ARG,
+                         "MatrixMarket: only 'matrix coordinate real|integer general' is supported"));
+    long long n = 0, m = 0, nnz = 0;
+    for (;;) {
+        if (!fgets(line, sizeof(line), fp))
+            return bail(fail(h, VBNMF_ERR_ARG, "MatrixMarket: missing size line"));
+        if (line[0] == '%' || line[0] == '\n' || line[0] == '\r') continue;
+        if (sscanf(line, "%lld %lld %lld", &n, &m, &nnz) != 3)
+            return bail(fail(h, VBNMF_ERR_ARG, "MatrixMarket: malformed size line"));
+        break;
+    }
+    if (n <= 0 || m <= 0 || nnz <= 0 || n > INT32_MAX || m > INT32_MAX || nnz >= (long long)UINT32_MAX)
+        return bail(fail(h, VBNMF_ERR_ARG, "MatrixMarket: dimensions out of range"));
+    const long off = ftell(fp);
+    fseek(fp, 0, SEEK_END);
+    const int64_t nbytes = (int64_t)ftell(fp) - off;
+    fseek(fp, off, SEEK_SET);
+    if (nbytes <= 0) return bail(fail(h, VBNMF_ERR_ARG, "MatrixMarket: no entries"));
+    h->n = n; h->m = m; h->nnz = nnz;
+    int rc = init_common(h, device);
+    if (rc) return bail(rc);
+    bool as_float = true;
+    auto body = [&]() -> int {
+        char *d_buf = nullptr;
+        uint8_t *d_flag = nullptr;
+        int64_t *d_start = nullptr, *d_num = nullptr;
+        unsigned long long *d_key = nullptr, *d_key2 = nullptr;
+        double *d_v = nullptr, *d_v2 = nullptr;
+        unsigned *d_bad = nullptr;
+        void *d_tmp = nullptr;
+        struct Free {
+            cudaStream_t s; void **p[10];
+            ~Free() { for (void **q : p) if (q) vfree(s, *q); }
+        } fr{h->stream, {(void **)&d_buf, (void **)&d_flag, (void **)&d_start, (void **)&d_num,
+                         (void **)&d_key, (void **)&d_key2, (void **)&d_v, (void **)&d_v2,
+                         (void **)&d_bad, &d_tmp}};
+        CK(vmalloc(h, &d_buf, (size_t)nbytes));
+        {   // file bytes -> device through the pinned staging buffers
+            std::lock_guard<std::mutex> lock(g_staging_mu);
+            if (!g_staging.init()) return fail(h, VBNMF_ERR_CUDA, "cannot allocate pinned staging buffers");
+            int slot = 0;
+            for (int64_t lo = 0; lo < nbytes; lo += (int64_t)Staging::kBytes, slot = (slot + 1) % Staging::kSlots) {
+                const size_t len = (size_t)std::min<int64_t>((int64_t)Staging::kBytes, nbytes - lo);
+                CK(cudaEventSynchronize(g_staging.ev[slot]));
+                if (fread(g_staging.buf[slot], 1, len, fp) != len)
+                    return fail(h, VBNMF_ERR_ARG, "MatrixMarket: short read");
+                CK(cudaMemcpyAsync(d_buf + lo, g_staging.buf[slot], len, cudaMemcpyHostToDevice, h->stream));
+                CK(cudaEventRecord(g_staging.ev[slot], h->stream));
+            }
+            CK(cudaStreamSynchronize(h->stream));
+        }
+        // line starts
+        CK(vmalloc(h, &d_flag, (size_t)nbytes));
+        CK(vmalloc(h, &d_start, (size_t)(nnz + 1) * 8));
+        CK(vmalloc(h, &d_num, 8));
+        CK(vmalloc(h, &d_bad, 4 * sizeof(unsigned)));
+        CK(cudaMemsetAsync(d_bad, 0, 4 * sizeof(unsigned), h->stream));
+        vb::mtx_line_flags_kernel<<<h->num_sms * 8, vb::kBlock, 0, h->stream>>>(nbytes, d_buf, d_flag);
+        // count first (the output must not overflow when the file has more lines than declared)
+        size_t tb = 0;
+        cub::CountingInputIterator<int64_t> iota(0);
+        int64_t *d_cnt = d_num;
+        CK(cub::DeviceReduce::Sum(nullptr, tb, d_flag, d_cnt, nbytes, h->stream));
+        CK(vmalloc(h, &d_tmp, tb));
+        CK(cub::DeviceReduce::Sum(d_tmp, tb, d_flag, d_cnt, nbytes, h->stream));
+        int64_t nlines = 0;
+        CK(cudaMemcpyAsync(&nlines, d_cnt, 8, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        vfree(h->stream, d_tmp); d_tmp = nullptr;
+        if (nlines != nnz)
+            return fail(h, VBNMF_ERR_ARG, "MatrixMarket: number of entry lines differs from the size line");
+        CK(cub::DeviceSelect::Flagged(nullptr, tb, iota, d_flag, d_start, d_num, nbytes, h->stream));
+        CK(vmalloc(h, &d_tmp, tb));
+        CK(cub::DeviceSelect::Flagged(d_tmp, tb, iota, d_flag, d_start, d_num, nbytes, h->stream));
+        vfree(h->stream, d_tmp); d_tmp = nullptr;
+        // parse, sort by (column, row)
+        CK(vmalloc(h, &d_key, (size_t)nnz * 8));
+        CK(vmalloc(h, &d_key2, (size_t)nnz * 8));
+        CK(vmalloc(h, &d_v, (size_t)nnz * 8));
+        CK(vmalloc(h, &d_v2, (size_t)nnz * 8));
+        vb::mtx_parse_kernel<<<cdiv(nnz, vb::kBlock), vb::kBlock, 0, h->stream>>>(
+            nnz, nbytes, d_buf, d_start, n, m, d_key, d_v, d_bad);
+        int cbits = 1;
+        while ((1ll << cbits) < m) cbits++;
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, d_key, d_key2, d_v, d_v2, nnz, 0, 32 + cbits, h->stream));
+        CK(vmalloc(h, &d_tmp, tb));
+        CK(cub::DeviceRadixSort::SortPairs(d_tmp, tb, d_key, d_key2, d_v, d_v2, nnz, 0, 32 + cbits, h->stream));
+        // CSC arrays owned by the handle
+        CK(vmalloc(h, &h->d_arena, (size_t)std::max<int64_t>(nnz * 5, 4 * std::max(n, m)) * 4));
+        CK(vmalloc(h, &h->d_colptr, (size_t)(m + 1) * 8));
+        CK(vmalloc(h, &h->d_rowidx, (size_t)nnz * 4));
+        float *dv = nullptr;
+        CK(vmalloc(h, &dv, (size_t)nnz * 4));
+        vb::mtx_unpack_kernel<float><<<cdiv(nnz, vb::kBlock), vb::kBlock, 0, h->stream>>>(
+            nnz, d_key2, d_v2, h->d_rowidx, dv, d_bad);
+        vb::mtx_colptr_kernel<<<cdiv(m + 1, vb::kBlock), vb::kBlock, 0, h->stream>>>(m, nnz, d_key2,
+                                                                                   h->d_colptr);
+        unsigned bad[4];
+        CK(cudaMemcpyAsync(bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        CK(cudaGetLastError());
+        if (bad[0]) { vfree(h->stream, dv); return fail(h, VBNMF_ERR_ARG, "MatrixMarket: malformed entry line or index out of range"); }
+        if (bad[1]) { vfree(h->stream, dv); return fail(h, VBNMF_ERR_ARG, "MatrixMarket: duplicate entries"); }
+        if (bad[2]) {  // counts not exact in fp32: keep them in fp64
+            vfree(h->stream, dv);
+            double *dd = nullptr;
+            CK(vmalloc(h, &dd, (size_t)nnz * 8));
+            vb::mtx_unpack_kernel<double><<<cdiv(nnz, vb::kBlock), vb::kBlock, 0, h->stream>>>(
+                nnz, d_key2, d_v2, h->d_rowidx, dd, d_bad + 3);
+            h->d_val = dd;
+            as_float = false;
+        } else {
+            h->d_val = dv;
+        }
+        CK(cudaStreamSynchronize(h->stream));
+        return 0;
+    };
+    if ((rc = body())) return bail(rc);
+    fclose(fp);
+    fp = nullptr;
+    h->val_float = as_float;
+    rc = as_float ? scan_matrix_t<float>(h) : scan_matrix_t<double>(h);
+    if (rc) return bail(rc);
+    if (dims) { dims[0] = n; dims[1] = m; dims[2] = nnz; }
+    *out = h;
+    return 0;
+}
+
+/* the CSC arrays a handle holds, back on the host (colptr m+1 int64, rowidx nnz int32, values nnz
+ * doubles; any may be NULL) */
+int vbnmf_get_csc(vbnmf_handle *h, int64_t *colptr, int32_t *rowidx, double *values) {
+    if (!h) return VBNMF_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    if (colptr) CK(cudaMemcpyAsync(colptr, h->d_colptr, (size_t)(h->m + 1) * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (rowidx) CK(cudaMemcpyAsync(rowidx, h->d_rowidx, (size_t)h->nnz * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (values) {
+        if (h->val_float) {
+            std::vector<float> tmp((size_t)h->nnz);
+            CK(copy_sync(h, tmp.data(), h->d_val, (size_t)h->nnz * 4, cudaMemcpyDeviceToHost));
+            for (int64_t t = 0; t < h->nnz; t++) values[t] = (double)tmp[(size_t)t];
+        } else {
+            CK(copy_sync(h, values, h->d_val, (size_t)h->nnz * 8, cudaMemcpyDeviceToHost));
+        }
+    }
+    return 0;
+}
+
 int vbnmf_set_precision(vbnmf_handle *h, int precision) {
     if (!h) return VBNMF_ERR_ARG;
     if (precision != VBNMF_FP64 && precision != VBNMF_FP32_STORAGE)
@@ -1609,12 +1792,12 @@ int vbnmf_init_svd2(vbnmf_handle *h, int r, const double hyper[4], uint64_t seed
     int rc;
     if ((rc = alloc_panels(h, r))) return rc;
     const int kmax = (int)std::min<int64_t>(std::min(h->n, h->m_global), vb::kSvdMaxK);
-    // oversampling 10 and 4 power iterations; a rank-deficient sketch (Cholesky fails) falls back
-    // to no oversampling
-    for (int k : {std::min(r + 10, kmax), r}) {
+    // oversampling 20, at most 60 subspace iterations; a rank-deficient sketch (Cholesky fails)
+    // falls back to no oversampling
+    for (int k : {std::min(r + 20, kmax), r}) {
         bool ok = true;
-        rc = h->val_float ? init_svd2_t<float>(h, r, hyper, seed, cell_offset, k, 4, &ok)
-                          : init_svd2_t<double>(h, r, hyper, seed, cell_offset, k, 4, &ok);
+        rc = h->val_float ? init_svd2_t<float>(h, r, hyper, seed, cell_offset, k, 60, &ok)
+                          : init_svd2_t<double>(h, r, hyper, seed, cell_offset, k, 60, &ok);
         if (rc) return rc;
         if (ok) {
             if ((rc = refresh_mirrors(h))) return rc;

@@ -74,6 +74,34 @@ class Engine:
         return cls(device=device, _device_csc=(int(n), int(m), int(nnz), colptr_i64.data_ptr(),
                                                rowidx_i32.data_ptr(), values_f32.data_ptr(), keep))
 
+    @classmethod
+    def from_mtx(cls, path, device=0):
+        """MatrixMarket coordinate file (10x `matrix.mtx`) parsed and sorted into CSC on the GPU
+        (readMM + as(., 'dgCMatrix') of read_10x, R/utils.R:34)."""
+        self = cls.__new__(cls)
+        self.lib = _lib.load()
+        self.handle = C.c_void_p()
+        self._keep = None
+        dims = (C.c_int64 * 3)()
+        rc = self.lib.vbnmf_create_from_mtx(C.byref(self.handle), str(path).encode(), int(device), dims)
+        if rc != 0:
+            msg = self.lib.vbnmf_last_error(None)
+            self.handle = C.c_void_p()
+            raise _lib.VbnmfError(rc, msg.decode() if msg else "unknown")
+        self.n, self.m, self.nnz = int(dims[0]), int(dims[1]), int(dims[2])
+        self.r = 0
+        return self
+
+    def csc(self):
+        """The count matrix the handle holds, as a scipy CSC matrix."""
+        import scipy.sparse as sp
+        colptr = np.zeros(self.m + 1, dtype=np.int64)
+        rowidx = np.zeros(self.nnz, dtype=np.int32)
+        values = np.zeros(self.nnz, dtype=np.float64)
+        self._ck(self.lib.vbnmf_get_csc(self.handle, colptr.ctypes.data_as(_lib.c_i64p),
+                                        rowidx.ctypes.data_as(_lib.c_i32p), _dp(values)))
+        return sp.csc_matrix((values, rowidx, colptr), shape=(self.n, self.m))
+
     # -- lifetime ------------------------------------------------------------------------------
     def close(self):
         if getattr(self, "handle", None) and self.handle.value:

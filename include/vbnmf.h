@@ -87,6 +87,16 @@ VBNMF_API int vbnmf_set_host_threads(int nthreads);
 /* Return the device memory the engine's stream-ordered pool keeps cached to the driver. */
 VBNMF_API int vbnmf_trim_pool(int device);
 
+/* Read a MatrixMarket coordinate file (the `matrix.mtx` of a 10x directory, R/utils.R:28-54:
+ * Matrix::readMM + as(., 'dgCMatrix')) straight into a device-resident handle: the host reads the
+ * bytes and the header, the text is parsed, sorted into CSC and validated on the GPU.  Supports
+ * `matrix coordinate real|integer general`.  dims (may be NULL) receives n, m, nnz. */
+VBNMF_API int vbnmf_create_from_mtx(vbnmf_handle **out, const char *path, int device, int64_t dims[3]);
+
+/* The CSC arrays of a handle copied to the host: colptr (m+1), rowidx (nnz), values (nnz); any may
+ * be NULL.  (After vbnmf_create_from_mtx the front end needs them for the row/column filters.) */
+VBNMF_API int vbnmf_get_csc(vbnmf_handle *h, int64_t *colptr, int32_t *rowidx, double *values);
+
 VBNMF_API void vbnmf_destroy(vbnmf_handle *h);
 VBNMF_API const char *vbnmf_last_error(const vbnmf_handle *h); /* h may be NULL: error of the last create */
 
@@ -123,9 +133,9 @@ VBNMF_API int vbnmf_init_random(vbnmf_handle *h, int r, const double hyper[4], u
 
 /* vb_init(initializer = 'svd2') (R/bayesian.R:150-159) on the device: w = |u| / scale,
  * h = |diag(d) v^T| * scale, scale = bh / mean(h), from a rank-r truncated SVD of the count matrix
- * computed where it lives (randomized range finder with oversampling 10 and 4 power iterations in
- * place of irlba; k x k factorizations on the host).  Singular vectors are defined up to sign, which
- * abs() removes; accuracy against an exact truncated SVD is ~1e-8 for separated singular values.
+ * computed where it lives (randomized subspace iteration with oversampling 20, run until the r
+ * leading Ritz values stop moving, in place of irlba; k x k factorizations on the host).  Singular
+ * vectors are defined up to sign, which abs() removes; they match an exact truncated SVD to ~1e-7.
  * seed keys the Gaussian test matrix by GLOBAL cell index (cell_offset + j): the result does not
  * depend on the sharding.  hyper = {aw, bw, ah, bh} (only bh is used, as in the reference). */
 VBNMF_API int vbnmf_init_svd2(vbnmf_handle *h, int r, const double hyper[4], uint64_t seed,

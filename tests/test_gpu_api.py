@@ -152,3 +152,64 @@ def test_vb_factorize_with_device_svd2_equals_host_svd2():
     b = api.vb_factorize(api.scNMFSet(X), device_init=True, **kw)
     assert list(a.ranks) == list(b.ranks)
     assert np.max(np.abs(a.measure["lml"] - b.measure["lml"]) / np.abs(a.measure["lml"])) < 1e-6
+
+
+def test_matrix_market_parsed_on_the_device_equals_host_reader(tmp_path):
+    """read_10x's Matrix::readMM + as(., 'dgCMatrix') (R/utils.R:34) done on the GPU: the bundled
+    PBMC matrix.mtx (integer field), a real-valued file with exponents and unsorted entries, and
+    the error paths."""
+    import scipy.io
+    import scipy.sparse as sp
+    from ccfindr_b200 import _lib
+    from ccfindr_b200.engine import Engine
+    rng = np.random.default_rng(0)
+    # integer counts, as 10x writes them
+    X = load_counts("pbmc")
+    p = tmp_path / "matrix.mtx"
+    scipy.io.mmwrite(str(p), sp.coo_matrix(X), field="integer")
+    with Engine.from_mtx(str(p)) as eng:
+        got = eng.csc()
+    assert got.shape == X.shape and (got != X).nnz == 0
+    assert np.array_equal(got.indptr, X.indptr) and np.array_equal(got.indices, X.indices)
+    # real values (normalized counts), shuffled order, exponents
+    Y = sp.random(300, 200, density=0.05, random_state=rng, format="coo")
+    Y.data = np.round(Y.data * 10 ** rng.integers(-3, 6, size=Y.nnz), 6) + 1e-3
+    perm = rng.permutation(Y.nnz)
+    p2 = tmp_path / "real.mtx"
+    with open(p2, "w") as f:
+        f.write("%%MatrixMarket matrix coordinate real general\n% a comment\n")
+        f.write("%d %d %d\n" % (300, 200, Y.nnz))
+        for t in perm:
+            f.write("%d %d %.10e\n" % (Y.row[t] + 1, Y.col[t] + 1, Y.data[t]))
+    ref = sp.csc_matrix(scipy.io.mmread(str(p2)))
+    ref.sort_indices()
+    import os
+    os.environ["VBNMF_ALLOW_EMPTY"] = "1"
+    try:
+        with Engine.from_mtx(str(p2)) as eng:
+            got = eng.csc()
+    finally:
+        del os.environ["VBNMF_ALLOW_EMPTY"]
+    assert np.array_equal(got.indptr, ref.indptr) and np.array_equal(got.indices, ref.indices)
+    assert np.max(np.abs(got.data - ref.data) / ref.data) < 4e-16
+    # errors: wrong entry count, index out of range, unsupported banner
+    bad = tmp_path / "bad.mtx"
+    bad.write_text("%%MatrixMarket matrix coordinate integer general\n3 3 3\n1 1 1\n2 2 2\n")
+    with pytest.raises(_lib.VbnmfError, match="number of entry lines"):
+        Engine.from_mtx(str(bad))
+    bad.write_text("%%MatrixMarket matrix coordinate integer general\n3 3 2\n1 1 1\n4 2 2\n")
+    with pytest.raises(_lib.VbnmfError, match="out of range"):
+        Engine.from_mtx(str(bad))
+    bad.write_text("%%MatrixMarket matrix array real general\n3 3\n")
+    with pytest.raises(_lib.VbnmfError, match="supported"):
+        Engine.from_mtx(str(bad))
+
+
+def test_read_10x_on_the_device_then_factorize(tmp_path):
+    from ccfindr_b200 import api
+    X = load_counts("pbmc")
+    s = api.scNMFSet(X)
+    api.write_10x(s, str(tmp_path))
+    a = api.read_10x(str(tmp_path))
+    b = api.read_10x(str(tmp_path), device=0)
+    assert (a.counts != b.counts).nnz == 0 and a.rowData == b.rowData and a.colData == b.colData
