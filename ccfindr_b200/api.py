@@ -77,7 +77,6 @@ def read_10x(dir, count="matrix.mtx", genes="genes.tsv", barcodes="barcodes.tsv"
         if not os.path.exists(os.path.join(dir, f)):
             raise FileNotFoundError("Count file %s does not exist" % os.path.join(dir, f))
     if device is not None:
-        os.environ.setdefault("VBNMF_ALLOW_EMPTY", "1")        # empties are dropped just below
         with Engine.from_mtx(os.path.join(dir, count), device=device) as eng:
             mat = eng.csc()
     else:

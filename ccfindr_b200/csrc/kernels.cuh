@@ -1127,12 +1127,14 @@ __global__ void __launch_bounds__(post_threads(row_stride(RP)))
 ml_update_kernel(int64_t rows, int T, int S, int64_t nvalid, int r, double eps,
                  const double *__restrict__ osum, const double *__restrict__ SRaw,
                  double *__restrict__ v, double *__restrict__ part, double *__restrict__ out,
-                 unsigned *counter, float *__restrict__ l32, int tsplit) {
+                 unsigned *counter, float *__restrict__ l32, int tsplit,
+                 const double *__restrict__ ctl) {
     constexpr int RS = row_stride(RP);
     constexpr int kPostLanes = post_lanes(RS);
     constexpr int NT = post_threads(RS);
     __shared__ double sm[NT / 32];
     __shared__ double colbuf[NT];
+    if (ctl && ctl[kCtlDone] != 0.0) return;  // device-controlled loop: the run has ended
     const int k = threadIdx.x % RS, lane_row = threadIdx.x / RS;
     const bool kact = k < r;
     const double os = kact ? osum[k] : 1.0;

@@ -565,6 +565,37 @@ __global__ void control_kernel(const ControlArgs a) {
     }
 }
 
+// One thread: the host half of an ML iteration on the device (R/factorize.R:193,207-209).  Called
+// once per loop turn t = 1 .. itmax + 1, after the cell-owner sweep at the current (w, h):
+//   lik = (sum x log(wh) - sum_k colSums(w)_k rowSums(h)_k + sum(-x log x + x)) / (n m)   :40-49
+// is the likelihood of the state left by iteration t - 1; |lkold - lk0| < tol |lkold| (:207) or
+// t - 1 == itmax ends the run (the update kernels of this and later turns are then no-ops).
+struct MlControlArgs {
+    double *ctl;
+    const double *scal;   // [colSums(w) rs | ...]
+    const double *tail;   // [rowSums(h) rs | . . . | . , xlogp at rs + 4]
+    double *trace;
+    double n, m_global, mlconst, tol;
+    int r, rs, itmax;
+};
+__global__ void ml_control_kernel(const MlControlArgs a) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double *c = a.ctl;
+    if (c[kCtlDone] != 0.0) return;
+    const int t = (int)c[kCtlIt] + 1;   // loop turn
+    c[kCtlIt] = t;
+    if (t == 1) return;                  // nothing to evaluate before the first update
+    double swh = 0.0;
+    for (int k = 0; k < a.r; k++) swh += a.scal[k] * a.tail[k];
+    const double lk0 = (a.tail[a.rs + 4] - swh + a.mlconst) / a.n / a.m_global;
+    const double lkold = c[kCtlLk0];
+    a.trace[t - 2] = lk0;
+    c[kCtlLkh] = lk0;
+    if (fabs(lkold - lk0) < a.tol * fabs(lkold)) { c[kCtlReason] = 1.0; c[kCtlDone] = 1.0; return; }
+    c[kCtlLk0] = lk0;
+    if (t - 1 >= a.itmax) { c[kCtlReason] = 0.0; c[kCtlDone] = 1.0; }
+}
+
 // ---- on-device 'random' initialiser (vb_init(initializer = 'random'), R/bayesian.R:111-115) ----
 // w_ik ~ Gamma(shape aw, scale bw/aw), h_kj ~ Gamma(shape ah, scale bh/ah).  R's RNG stream cannot be
 // reproduced, so the draw is DEFINED here by a counter RNG keyed by (seed, side, global row, k):

@@ -84,7 +84,7 @@ void posterior(const PosteriorArgs &a, cudaStream_t s) {
 void ml_update(const MlUpdateArgs &a, cudaStream_t s) {
     ml_update_kernel<RP><<<cdiv(a.rows, kPostRows), post_threads(RS), 0, s>>>(
         a.rows, a.T, a.S, a.nvalid, a.r, a.eps, a.osum, a.SRaw, a.v, a.part, a.out, a.counter,
-        a.l32, a.tsplit);
+        a.l32, a.tsplit, a.ctl);
 }
 void mirror(int64_t rows, const double *v, float *v32, cudaStream_t s) {
     mirror_kernel<RP><<<cdiv(rows, kBlock), kBlock, 0, s>>>(rows, v, v32);

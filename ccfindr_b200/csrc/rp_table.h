@@ -48,6 +48,7 @@ struct MlUpdateArgs {
     unsigned *counter;
     float *l32;
     int tsplit;  // layout of v (panel_ofs)
+    const double *ctl;  // device loop control block or nullptr
 };
 
 struct ColsumArgs {

@@ -172,7 +172,7 @@ struct vbnmf_handle {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     int num_sms = 148;
-    int64_t n = 0, m = 0, nnz = 0, m_global = 0;
+    int64_t n = 0, m = 0, nnz = 0, m_global = 0, nnz_global = 0;
     int r = 0, rp = 0, rs = 0;
     int precision = VBNMF_FP64;
     bool val_float = true;
@@ -298,12 +298,15 @@ int choose_tile_rows(const H *h, int row_bytes) {
     // pass has about four segments per group, but keep ~40 nonzeros per segment (below that the
     // per-segment overhead wins).  Measured: 1,000 x 200 r=3 0.072 -> 0.059 ms per iteration,
     // 5,000 x 3,000 r=8 0.091 -> 0.075; C2 and larger keep the largest tile.
-    if (h->nranks == 1 && h->nnz > 0) {
-        const double density = (double)h->nnz / ((double)h->n * (double)h->m);
+    // (sharded: the same formula on the global matrix divided evenly over the ranks)
+    const int64_t nnz_all = h->nranks > 1 ? h->nnz_global : h->nnz;
+    if (nnz_all > 0) {
+        const double density = (double)nnz_all / ((double)h->n * (double)h->m_global);
         const int tmin = std::max(64, (int)((40.0 / density + 31.0) / 32.0) * 32);
         const int64_t want = 4 * (int64_t)h->num_sms * 64;
+        const int64_t m_eff = (h->m_global + h->nranks - 1) / h->nranks;
         auto segments = [&](int t) {
-            return std::min((int64_t)cdiv(h->n, t) * h->m, (int64_t)cdiv(h->m, t) * h->n);
+            return std::min((int64_t)cdiv(h->n, t) * m_eff, (int64_t)cdiv(m_eff, t) * h->n);
         };
         while (T - kTileRowsStep >= tmin && segments(T) < want) T -= kTileRowsStep;
     }
@@ -666,10 +669,10 @@ int scan_matrix_t(H *h) {
         return fail(h, VBNMF_ERR_ARG, "counts must be finite and non-negative");
     h->empty_rows = flags[1];
     h->empty_cols = flags[2];
-    // R/bayesian.R:244-247.  Empty genes of ONE shard are legal (the test is on the whole matrix:
-    // vbnmf_attach_comm repeats it on the all-reduced gene counts), empty cells never are.
-    if (h->empty_cols && !getenv("VBNMF_ALLOW_EMPTY"))
-        return fail(h, VBNMF_ERR_EMPTY, "Input matrix contains empty columns");
+    // R/bayesian.R:244-247: refused when a factorization is set up (alloc_panels), not here -- a
+    // handle made by vbnmf_create_from_mtx may hold a matrix the front end has yet to filter
+    // (read_10x drops empty genes / cells, R/utils.R:52), and the empty genes of ONE shard are
+    // legal (vbnmf_attach_comm repeats the test on the all-reduced gene counts).
     h->lgx = consts[0];
     h->mlconst = consts[1];
     // VBNMF_NO_P16=1 keeps the 8-byte entries (A/B measurements, tests of that path)
@@ -701,8 +704,10 @@ int alloc_panels(H *h, int r) {
     const bool f32 = h->precision == VBNMF_FP32_STORAGE;
     const int row_bytes = f32 ? tab->rsf * 4 : rs * 8;
     // R/bayesian.R:244-245 (for a sharded matrix the test was made on the global gene counts)
-    if (h->empty_rows && !getenv("VBNMF_ALLOW_EMPTY"))
-        return fail(h, VBNMF_ERR_EMPTY, "Input matrix contains empty rows");
+    if (!getenv("VBNMF_ALLOW_EMPTY")) {
+        if (h->empty_rows) return fail(h, VBNMF_ERR_EMPTY, "Input matrix contains empty rows");
+        if (h->empty_cols) return fail(h, VBNMF_ERR_EMPTY, "Input matrix contains empty columns");
+    }
     const int T = choose_tile_rows(h, row_bytes);
     // split layout + conflict-free rotated gathers: fp64 panels, packed-16 entries, 8..10 units
     const bool split = !f32 && h->p16 && tab->split64 && !getenv("VBNMF_NO_SPLIT");
@@ -1121,6 +1126,7 @@ int init_common(H *h, int device) {
     CK(cudaMallocHost(&h->h_ctl, vb::kCtlLen * sizeof(double)));
     CK(cudaStreamSynchronize(h->stream));
     h->m_global = h->m;
+    h->nnz_global = h->nnz;
     return 0;
 }
 
@@ -1672,28 +1678,29 @@ int vbnmf_attach_comm(vbnmf_handle *h, vbnmf_comm *c) {
     h->rank = c->rank;
     // global quantities: total cells, the sums over nonzeros, and the per-gene nonzero counts
     // (every rank must derive the same gene renumbering)
-    double hv[3] = {(double)h->m, h->lgx, h->mlconst};
+    double hv[4] = {(double)h->m, h->lgx, h->mlconst, (double)h->nnz};
     double *dv = nullptr;
     unsigned *d_flag = nullptr;
     uint32_t *d_scr = nullptr;
-    CK(vmalloc(h, &dv, 3 * 8));
+    CK(vmalloc(h, &dv, 4 * 8));
     CK(vmalloc(h, &d_flag, 4));
     CK(vmalloc(h, &d_scr, (size_t)2 * h->n * 4));
     CK(cudaMemsetAsync(d_flag, 0, 4, h->stream));
-    CK(cudaMemcpyAsync(dv, hv, 3 * 8, cudaMemcpyHostToDevice, h->stream));
-    int rc = allreduce(h, dv, 3);
+    CK(cudaMemcpyAsync(dv, hv, 4 * 8, cudaMemcpyHostToDevice, h->stream));
+    int rc = allreduce(h, dv, 4);
     if (rc) return rc;
     CKN(g_nccl.AllReduce(h->d_cnt, h->d_cnt, (size_t)h->n, ncclUint64, ncclSum, h->comm, h->stream));
     vb::order_keys_kernel<<<cdiv(h->n, vb::kBlock), vb::kBlock, 0, h->stream>>>(
         h->n, h->d_cnt, d_scr, d_scr + h->n, d_flag);
     unsigned nzero = 0;
-    CK(cudaMemcpyAsync(hv, dv, 3 * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(hv, dv, 4 * 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(&nzero, d_flag, 4, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     vfree(h->stream, dv); vfree(h->stream, d_flag); vfree(h->stream, d_scr);
     h->m_global = (int64_t)llround(hv[0]);
     h->lgx = hv[1];
     h->mlconst = hv[2];
+    h->nnz_global = (int64_t)llround(hv[3]);
     h->empty_rows = nzero;  // of the whole matrix now (R/bayesian.R:244); tested at set_state
     free_panels(h);
     drop_layouts(h);
@@ -2214,7 +2221,7 @@ int mlnmf_run2(vbnmf_handle *h, int r, const double *w0, const double *h0, int i
                            wside ? h->d_red : h->d_ShRaw, wside ? h->d_lw : h->d_lh,
                            wside ? h->d_partW : h->d_partH, wside ? h->d_scal : tail,
                            h->d_counters + (wside ? 0 : 1), wside ? h->d_lw32 : h->d_lh32,
-                           h->tsplit};
+                           h->tsplit, h->ctl};
         h->tab->ml_update(a, h->stream);
         h->launches += 1;
         return 0;
@@ -2256,6 +2263,55 @@ int mlnmf_run2(vbnmf_handle *h, int r, const double *w0, const double *h0, int i
     if ((rc = colsum(true))) return rc;   // colSums(w0)
     if ((rc = colsum(false))) return rc;  // rowSums(h0) (local)
     if ((rc = allreduce(h, tail, rs))) return rc;
+    if (criterion == VBNMF_ML_LIKELIHOOD && !getenv("VBNMF_HOST_LOOP")) {
+        // Device-controlled loop: the likelihood, the stopping rule (:207) and the iteration count
+        // live in the control block; turns are enqueued in batches of 8 without a host round trip
+        // and become no-ops once the run has ended (as in run_device_loop for the VB path).
+        double *c = h->h_ctl;
+        for (int i = 0; i < vb::kCtlLen; i++) c[i] = 0.0;
+        c[vb::kCtlLk0] = -INFINITY;                                        // lkold, :190
+        CK(cudaMemcpyAsync(h->d_ctl, c, vb::kCtlLen * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        double *d_trace = nullptr;
+        CK(vmalloc(h, &d_trace, (size_t)itmax * 8));
+        struct CtlGuard {
+            H *h; double *t;
+            ~CtlGuard() { h->ctl = nullptr; vfree(h->stream, t); }
+        } cg{h, d_trace};
+        h->ctl = h->d_ctl;
+        vb::MlControlArgs ca{h->d_ctl, h->d_scal, tail, d_trace, (double)h->n, (double)h->m_global,
+                             h->mlconst, tol, r, rs, itmax};
+        int turns = 0;
+        bool fin = false;
+        while (!fin && turns < itmax + 1) {
+            const int nb = std::min(8, itmax + 1 - turns);
+            for (int b = 0; b < nb; b++) {
+                if ((rc = launch_sweep_cols(h))) return rc;      // ShRaw, xlogp at (w, h) of turn - 1
+                if ((rc = allreduce(h, tail + rs + 3, 2))) return rc;
+                vb::ml_control_kernel<<<1, 32, 0, h->stream>>>(ca);
+                h->launches += 1;
+                if (turns + b + 1 <= itmax) {
+                    if ((rc = mlupd(false))) return rc;          // h update, :8-15
+                    if ((rc = launch_sweep_rows(h))) return rc;  // SwRaw at (w, h_new), :17
+                    if ((rc = allreduce(h, h->d_red, tail_off(h) + rs))) return rc;
+                    if ((rc = mlupd(true))) return rc;           // w update, :17-24
+                }
+            }
+            turns += nb;
+            CK(cudaMemcpyAsync(c, h->d_ctl, vb::kCtlLen * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            CK(cudaGetLastError());
+            fin = c[vb::kCtlDone] != 0.0;
+        }
+        const int done_it = (int)c[vb::kCtlIt] - 1;              // likelihoods evaluated = iterations
+        if (lik_trace && done_it > 0)
+            CK(copy_sync(h, lik_trace, d_trace, (size_t)done_it * 8, cudaMemcpyDeviceToHost));
+        *niter = done_it;
+        h->ctl = nullptr;
+        if (w || h_out) {
+            if ((rc = vbnmf_get_state(h, w, h_out, nullptr, nullptr, nullptr, nullptr))) return rc;
+        }
+        return 0;
+    }
     double lkold = -INFINITY, lk0 = NAN;
     int it, done = 0, zstep = 0;
     bool stop_after = false;

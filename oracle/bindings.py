@@ -194,8 +194,10 @@ def sparse_vb_run(csc, w0, h0, hyper, *, Itmax=10000, hyper_update_flags=(True,)
 
 
 def sparse_ml_run(csc, w0, h0, *, Itmax=10000, Tol=1e-5):
+    """oracle_sparse.c osp_ml_run (R/factorize.R:189-212, criterion='likelihood').  csc: a scipy
+    matrix or the tuple (n, m, colptr int64, rowidx int32, val float64)."""
     lib = sparse_lib()
-    n, m, colptr, rowidx, val = _csc_args(csc)
+    n, m, colptr, rowidx, val = csc if isinstance(csc, tuple) else _csc_args(csc)
     w = np.array(w0, dtype=np.float64, order="F")
     h = np.array(h0, dtype=np.float64, order="F")
     r = w.shape[1]

@@ -173,7 +173,7 @@ def test_matrix_market_parsed_on_the_device_equals_host_reader(tmp_path):
     assert np.array_equal(got.indptr, X.indptr) and np.array_equal(got.indices, X.indices)
     # real values (normalized counts), shuffled order, exponents
     Y = sp.random(300, 200, density=0.05, random_state=rng, format="coo")
-    Y.data = np.round(Y.data * 10 ** rng.integers(-3, 6, size=Y.nnz), 6) + 1e-3
+    Y.data = np.round(Y.data * 10.0 ** rng.integers(-3, 6, size=Y.nnz), 6) + 1e-3
     perm = rng.permutation(Y.nnz)
     p2 = tmp_path / "real.mtx"
     with open(p2, "w") as f:
@@ -183,13 +183,8 @@ def test_matrix_market_parsed_on_the_device_equals_host_reader(tmp_path):
             f.write("%d %d %.10e\n" % (Y.row[t] + 1, Y.col[t] + 1, Y.data[t]))
     ref = sp.csc_matrix(scipy.io.mmread(str(p2)))
     ref.sort_indices()
-    import os
-    os.environ["VBNMF_ALLOW_EMPTY"] = "1"
-    try:
-        with Engine.from_mtx(str(p2)) as eng:
-            got = eng.csc()
-    finally:
-        del os.environ["VBNMF_ALLOW_EMPTY"]
+    with Engine.from_mtx(str(p2)) as eng:                      # (empty rows/cells are refused at
+        got = eng.csc()                                        # set_state, not at creation)
     assert np.array_equal(got.indptr, ref.indptr) and np.array_equal(got.indices, ref.indices)
     assert np.max(np.abs(got.data - ref.data) / ref.data) < 4e-16
     # errors: wrong entry count, index out of range, unsupported banner

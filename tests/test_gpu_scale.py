@@ -40,3 +40,30 @@ def test_bench_size_matrix_matches_oracle(name, cells):
     assert max(f32["lkh_rel_err"]) < 1e-4
     assert f32["ew_max_rel_err"] < 1e-4 and f32["eh_max_rel_err"] < 1e-4
     assert f32["cid_mismatches"] <= cells // 1000                   # near-ties only
+
+
+def test_ml_path_at_bench_size_matches_oracle():
+    """BASELINE config 5: factorize() maximum-likelihood updates on the 20,000 x 100,000 matrix,
+    rank 15 -- three iterations of the device loop against oracle_sparse.c (1e-9)."""
+    import torch
+    import bench
+    from ccfindr_b200 import synth
+    from ccfindr_b200.engine import Engine
+    from oracle import bindings as ob
+    wl = bench.WORKLOADS["c2"]
+    n, cells, r = wl["n"], 100000, 15
+    dev = torch.device("cuda", 0)
+    colptr, rowidx, values, _ = synth.tenx_like_device(n, cells, wl["r_true"], wl["density"],
+                                                       wl["seed"], dev, 0, cells)
+    w0, h0 = synth.uniform_init(n, cells, r, 5)
+    bench.restore_omp_threads()
+    ref = ob.sparse_ml_run((n, cells, colptr.cpu().numpy(), rowidx.cpu().numpy(),
+                            values.double().cpu().numpy()), w0, h0, Itmax=3, Tol=0.0)
+    with Engine.from_device_csc(n, cells, int(rowidx.numel()), colptr, rowidx, values) as eng:
+        res = eng.ml_run(w0, h0, Itmax=3, Tol=0.0)
+        lay = eng.layout_info()
+    assert lay["tile_rows"] >= 1280 and res["niter"] == ref["niter"] == 3
+    err = lambda a, b: float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)))
+    print("ml c5", err(res["lik_trace"], ref["lik_trace"]), err(res["w"], ref["w"]), err(res["h"], ref["h"]))
+    assert err(res["lik_trace"], ref["lik_trace"]) < 1e-9
+    assert err(res["w"], ref["w"]) < 1e-9 and err(res["h"], ref["h"]) < 1e-9
