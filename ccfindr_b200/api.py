@@ -270,6 +270,9 @@ def vb_factorize(object, ranks=2, nrun=1, verbose=2, progress_bar=True, initiali
         for key in ("aw", "bw", "ah", "bh"):
             cols[key].append(vb[imax]["hyperp"][k][key])
         cols["nunif"].append(vb[imax]["nunif"][k])
+    # (extra, not in the reference: iterations each run took, for throughput accounting)
+    object.metadata["niter"] = {(i + 1, ranks[k]): int(vb[i]["niter"][k]) for i in range(nrun)
+                                for k in range(nrank) if vb[i]["hyperp"][k] is not None}
     object.ranks = cols["rank"]                                 # :293-299
     object.basis, object.dbasis = basis, dbasis
     object.coeff, object.dcoeff = coeff, dcoeff
@@ -349,7 +352,7 @@ def _vb_parallel(mat, ranks, nrun, common, unif_stop, verbose, seed, inits, devi
     for irun in range(1, nrun + 1):
         out = dict(rdat=[-np.inf] * len(ranks), wdat=[None] * len(ranks), hdat=[None] * len(ranks),
                    dwdat=[None] * len(ranks), dhdat=[None] * len(ranks),
-                   hyperp=[None] * len(ranks), nunif=[0] * len(ranks))
+                   hyperp=[None] * len(ranks), nunif=[0] * len(ranks), niter=[0] * len(ranks))
         for k in range(len(ranks)):
             res = allres[(irun, k)]
             if res["unif"]:                                     # R/bayesian.R:370-378, post hoc
@@ -359,7 +362,7 @@ def _vb_parallel(mat, ranks, nrun, common, unif_stop, verbose, seed, inits, devi
                     if k == 0:
                         raise RuntimeError("Rerun with lower ranks")
                     break
-            for key in ("rdat", "wdat", "hdat", "dwdat", "dhdat", "hyperp", "nunif"):
+            for key in ("rdat", "wdat", "hdat", "dwdat", "dhdat", "hyperp", "nunif", "niter"):
                 out[key][k] = res[key]
         if verbose >= 2:
             for k in range(len(ranks)):

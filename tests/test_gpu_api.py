@@ -208,3 +208,27 @@ def test_read_10x_on_the_device_then_factorize(tmp_path):
     a = api.read_10x(str(tmp_path))
     b = api.read_10x(str(tmp_path), device=0)
     assert (a.counts != b.counts).nnz == 0 and a.rowData == b.rowData and a.colData == b.colData
+
+
+def test_job_farm_front_end_in_a_single_process_group():
+    """vb_factorize(parallel=True) -- the (run, rank) job farm that replaces Rmpi::mpi.applyLB
+    (R/bayesian.R:263) -- inside a one-rank process group equals the serial front end bit for bit
+    (the multi-rank version of this check lives in tests/mgpu_check.py and needs 2 GPUs)."""
+    import os
+    import torch.distributed as dist
+    from ccfindr_b200 import api
+    X = load_counts("c1s2")
+    kw = dict(ranks=[2, 3], nrun=2, verbose=0, Itmax=30, seed=4)
+    ser = api.vb_factorize(api.scNMFSet(X), **kw)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29741")
+    dist.init_process_group("gloo", rank=0, world_size=1)
+    try:
+        par = api.vb_factorize(api.scNMFSet(X), parallel=True, **kw)
+    finally:
+        dist.destroy_process_group()
+    assert list(par.ranks) == list(ser.ranks) and par.metadata["niter"] == ser.metadata["niter"]
+    for key in ser.measure:
+        assert np.array_equal(par.measure[key], ser.measure[key]), key
+    for k in range(len(ser.ranks)):
+        assert np.array_equal(par.basis[k], ser.basis[k]) and np.array_equal(par.coeff[k], ser.coeff[k])
