@@ -30,6 +30,8 @@ if os.environ.get("VBNMF_SWEEP_THREADS_F32"):
     NVCC_FLAGS.append("-DVB_SWEEP_THREADS_F32=" + os.environ["VBNMF_SWEEP_THREADS_F32"])
 if os.environ.get("VBNMF_MID_THREADS"):
     NVCC_FLAGS.append("-DVB_MID_THREADS=" + os.environ["VBNMF_MID_THREADS"])
+if os.environ.get("VBNMF_MID_THREADS_COLS"):
+    NVCC_FLAGS.append("-DVB_MID_THREADS_COLS=" + os.environ["VBNMF_MID_THREADS_COLS"])
 if os.environ.get("VBNMF_WIDE_THREADS"):
     NVCC_FLAGS.append("-DVB_WIDE_THREADS=" + os.environ["VBNMF_WIDE_THREADS"])
 if os.environ.get("VBNMF_UNROLL"):
@@ -38,6 +40,8 @@ if os.environ.get("VBNMF_SPLIT_PRED"):
     NVCC_FLAGS.append("-DVB_SPLIT_PRED=" + os.environ["VBNMF_SPLIT_PRED"])
 if os.environ.get("VBNMF_SKIP_DEAD"):
     NVCC_FLAGS.append("-DVB_SKIP_DEAD=" + os.environ["VBNMF_SKIP_DEAD"])
+if os.environ.get("VBNMF_LP_IMMEDIATE"):
+    NVCC_FLAGS.append("-DVB_LP_IMMEDIATE=" + os.environ["VBNMF_LP_IMMEDIATE"])
 if os.environ.get("VBNMF_DOT_CHAINS"):
     NVCC_FLAGS.append("-DVB_DOT_CHAINS=" + os.environ["VBNMF_DOT_CHAINS"])
 if os.environ.get("VBNMF_LP_BITS"):   # count bits of the log-product bound term (kernels.cuh)

@@ -16,6 +16,12 @@
 #define VB_SKIP_DEAD 1    // split kernels: skip the all-hole steps at the end of a segment (their
                           // number rides in the low 2 bits of the segment's quad pointer)
 #endif
+#ifndef VB_LP_IMMEDIATE
+#define VB_LP_IMMEDIATE 0 // 1: large counts of the log-product bound term take their log at once
+                          // (group vote per nonzero) instead of per chunk from kept p values.
+                          // Measured SLOWER at r = 20 (cell-owner pass 3.06 -> 4.15 ms): the vote
+                          // serialises the four nonzeros of a chunk, and the spills stay
+#endif
 #ifndef VB_DOT_CHAINS
 #define VB_DOT_CHAINS 2   // independent FMA chains of the rank-r dot product (fp64)
 #endif
@@ -207,6 +213,9 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
 #ifndef VB_MID_THREADS
 #define VB_MID_THREADS 384   // threads per sweep CTA when a lane holds 97..160 bytes of a row
 #endif
+#ifndef VB_MID_THREADS_COLS
+#define VB_MID_THREADS_COLS VB_MID_THREADS
+#endif
 #ifndef VB_WIDE_THREADS
 #define VB_WIDE_THREADS 256  // ... more than 160 bytes
 #endif
@@ -232,6 +241,12 @@ struct SweepCfg {
         return VB_UNROLL ? VB_UNROLL : ((kLPN == 1 && (sizeof(PT) == 8 || !cols)) ? 6 : 4);
     }
     static constexpr int kGroups = kThreads / kGroup;
+    // threads of the packed-16 kernel per pass: the fp64 cell-owner pass of the 97..160-byte rows
+    // also carries the log-product state and spills at kThreads
+    __host__ __device__ static constexpr int p16_threads(bool cols) {
+        return (cols && sizeof(PT) == 8 && kRowShare > 96 && kRowShare <= 160) ? VB_MID_THREADS_COLS
+                                                                               : kThreads;
+    }
 };
 
 
@@ -705,7 +720,7 @@ struct LogProd {
 // c in its register c ^ b).  Entries with count 0 (schedule holes) skip their gathers: the lane
 // keeps the previous row, and x = 0 adds nothing.
 template <int RP, bool COLS, typename PT, bool SPLIT = false>
-__global__ void __launch_bounds__(SweepCfg<RP, PT>::kThreads, 1)
+__global__ void __launch_bounds__(SweepCfg<RP, PT>::p16_threads(COLS), 1)
 sweep_p16_kernel(const SweepTiledArgs a) {
     using Cfg = SweepCfg<RP, PT>;
     constexpr int RS = row_stride(RP);
@@ -714,10 +729,10 @@ sweep_p16_kernel(const SweepTiledArgs a) {
                   "split layout: fp64 panels, one lane per nonzero, 8..15 units per row");
     constexpr int NUB = SPLIT ? Cfg::kNU - 8 : 0;            // units of block B
     constexpr int BSB = SPLIT ? (RS - 16) * 8 : 0;           // bytes per row of block B
-    constexpr int NT = Cfg::kThreads;
+    constexpr int NT = Cfg::p16_threads(COLS);
     constexpr int UE = Cfg::kUE, NU = Cfg::kNU, LPN = Cfg::kLPN, NUL = Cfg::kNUL, KL = Cfg::kKL;
     constexpr int NPG = Cfg::kNPG;
-    constexpr int kGroups = Cfg::kGroups;
+    constexpr int kGroups = NT / kGroup;
     // the next owner row is requested one segment ahead where the register budget allows it
     // (checked with -Xptxas -v: wider row shares, and the fp64 cell-owner pass with its log, spill)
     constexpr int kRowShare = KL * (int)sizeof(PT);  // bytes of a row held per lane
@@ -875,8 +890,15 @@ sweep_p16_kernel(const SweepTiledArgs a) {
                     axpy_row<KL>(acc, tr, q);
                     if (kLogProd) {
                         // LPN == 2: both lanes of a pair hold p, each takes every other nonzero
-                        if (LPN == 1 || (u & 1) == hf) {
-                            lp.add((int)(v >> 16), (double)p);
+                        const bool mine = LPN == 1 || (u & 1) == hf;
+                        if (mine) lp.add((int)(v >> 16), (double)p);
+                        if (VB_LP_IMMEDIATE) {
+                            // counts >= 2^kLpBits: the log right here, inside a branch the whole
+                            // group takes together (no p kept for a per-chunk slow path)
+                            if (__any_sync(gmask, mine && (v >> (16 + kLpBits)) != 0u)) {
+                                if (mine) lp.add_slow((int)(v >> 16), (double)p);
+                            }
+                        } else if (mine) {
                             big |= v;
                             pu[u] = p;
                         }
@@ -885,7 +907,7 @@ sweep_p16_kernel(const SweepTiledArgs a) {
                         else { pu[u] = p; xu[u] = x; }
                     }
                 }
-                if (kLogProd && big >= (1u << (16 + kLpBits))) {
+                if (kLogProd && !VB_LP_IMMEDIATE && big >= (1u << (16 + kLpBits))) {
                     const uint32_t cv[4] = {cur.x, cur.y, cur.z, cur.w};
 #pragma unroll 1
                     for (int u = 0; u < 4; u++)

@@ -44,16 +44,17 @@ void sweep_pt(const SweepTiledArgs &a, bool cols, int fmt, bool split, int grid,
               cudaStream_t s) {
     constexpr int NT = SweepCfg<RP, PT>::kThreads;
     const bool vf = fmt == kEntF32;
+    constexpr int NTC = SweepCfg<RP, PT>::p16_threads(true), NTR = SweepCfg<RP, PT>::p16_threads(false);
     if constexpr (split_rank(RP) && sizeof(PT) == 8) {
         if (fmt == kEntP16 && split) {
-            if (cols) sweep_p16_kernel<RP, true, PT, true><<<grid, NT, smem, s>>>(a);
-            else sweep_p16_kernel<RP, false, PT, true><<<grid, NT, smem, s>>>(a);
+            if (cols) sweep_p16_kernel<RP, true, PT, true><<<grid, NTC, smem, s>>>(a);
+            else sweep_p16_kernel<RP, false, PT, true><<<grid, NTR, smem, s>>>(a);
             return;
         }
     }
     if (fmt == kEntP16) {
-        if (cols) sweep_p16_kernel<RP, true, PT><<<grid, NT, smem, s>>>(a);
-        else sweep_p16_kernel<RP, false, PT><<<grid, NT, smem, s>>>(a);
+        if (cols) sweep_p16_kernel<RP, true, PT><<<grid, NTC, smem, s>>>(a);
+        else sweep_p16_kernel<RP, false, PT><<<grid, NTR, smem, s>>>(a);
     } else if (cols) {
         if (vf) sweep_tiled_kernel<RP, float, true, PT><<<grid, NT, smem, s>>>(a);
         else sweep_tiled_kernel<RP, double, true, PT><<<grid, NT, smem, s>>>(a);
