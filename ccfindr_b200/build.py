@@ -73,14 +73,14 @@ def _source_hash():
 
 
 def kernel_hash():
-    """Hash of the CUDA sources alone (profiles/traffic.json is stamped with it: an ncu capture
-    describes the kernels it was taken from)."""
+    """Hash of the sweep / update kernel sources (profiles/traffic.json is stamped with it: an ncu
+    capture describes the kernels it was taken from; the host side, vbnmf.cu, does not enter)."""
     hsh = hashlib.sha256()
-    for f in sorted(os.listdir(CSRC)):
-        p = os.path.join(CSRC, f)
-        if os.path.isfile(p) and p.endswith((".cu", ".cuh", ".h")):
-            hsh.update(f.encode())
-            hsh.update(open(p, "rb").read())
+    for f in ("kernels.cuh", "kernels_common.cuh", "special.cuh", "rp_inst.cu", "rp_table.h",
+              "rp_ranks.h"):
+        hsh.update(f.encode())
+        hsh.update(open(os.path.join(CSRC, f), "rb").read())
+    hsh.update(" ".join(a for a in NVCC_FLAGS if a.startswith("-DVB_")).encode())
     return hsh.hexdigest()[:16]
 
 

@@ -3,9 +3,10 @@
 set -x
 O=gpurun_out
 # 1. launch list of one bench run (gpu__time_duration per launch, cold caches, serialised)
-python bench.py --steps 2 --warmup 3 --no-e2e --no-parity --no-cpu --secondary none --workload c2 > $O/r02_ll_plain.json 2> $O/r02_ll_plain.err &&
-ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/r02_launch_list_c2.csv \
-    python bench.py --steps 2 --warmup 3 --no-e2e --no-parity --no-cpu --secondary none --workload c2 > $O/r02_ll_ncu.log 2>&1
+python bench.py --steps 2 --warmup 3 --no-e2e --parity-iters 0 --no-cpu --secondary none --workload c2 > $O/r02_ll_plain.json 2> $O/r02_ll_plain.err &&
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/r02_launch_list_c2.csv \
+    -k regex:'sweep_|combine_kernel|posterior_kernel|control_kernel|make_keys|segment_ptr|plan_p16|build_segments|split_|tag_dead|expand_cols|count_constants|order_keys|deal_kernel|scatter_panel|gather_panel|panel_colsum|mirror_kernel|cluster_id|DeviceRadixSort|DeviceScan' \
+    python bench.py --steps 2 --warmup 3 --no-e2e --parity-iters 0 --no-cpu --secondary none --workload c2 > $O/r02_ll_ncu.log 2>&1
 # 2. DRAM traffic of the two sweep launches at the bench sizes (one pass, two metrics)
 for w in c2 c3; do
   python profiles/prof_run.py --workload $w --iters 2 > $O/r02_prof_$w.log 2>&1 &&
