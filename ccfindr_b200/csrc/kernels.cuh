@@ -53,20 +53,28 @@ __host__ __device__ constexpr int panel_stride(int rp) {
 }
 
 // ---- split layout of the gathered fp64 panels (lw, lh) -----------------------------------------
-// Rows of at least 8 sixteen-byte units (RP >= 16) gathered by one lane per nonzero are stored per
-// slab of T rows as two blocks, A = T x 16 doubles (units 0..7, row stride exactly 128 bytes) then
-// B = T x (RS - 16) doubles (the remaining units; stride an odd number of units or a single unit).
-// In block A every row presents the 8 bank groups of shared memory identically, so the 8 lanes of
-// a group, reading unit (c XOR lane) of THEIR row in step c, hit 8 different bank groups whatever
-// the rows are: conflict free with no scheduling at all.  Only block B (2 of the 10 units at
-// r = 20) still depends on the residue schedule of the segment.  tsplit = T selects this layout
-// (0: plain row-major rows of RS doubles).
-__host__ __device__ constexpr bool split_rank(int rp) { return rp >= 16 && rp * 8 <= VB_LPN_BYTES; }
+// Rows gathered by one lane per nonzero are stored per slab of T rows as two blocks: A = the first
+// SA sixteen-byte units of every row with row stride exactly SA units (SA = 8 for ranks 16..20,
+// 4 for ranks 8..14), then B = T x (RS - 2 SA) doubles (the remaining units; stride an odd number
+// of units or a single unit).
+//   SA = 8: a row of block A presents the 8 bank groups of shared memory identically, so the 8
+//     lanes of a group, reading unit (c XOR lane) of THEIR row in step c, hit 8 different bank
+//     groups whatever the rows are: conflict free with no scheduling at all.
+//   SA = 4: a row of block A covers bank groups 0..3 (even row) or 4..7 (odd row); lanes l and
+//     l + 4 read the same unit (c XOR (l & 3)), so a step is conflict free when lanes 0..3 hold
+//     even rows and lanes 4..7 odd rows -- two parity classes instead of eight residue classes.
+// Only block B still depends on the residue schedule of the segment.  tsplit = T selects this
+// layout (0: plain row-major rows of RS doubles).
+__host__ __device__ constexpr int split_units(int rp) {
+    return rp * 8 > VB_LPN_BYTES ? 0 : (rp >= 16 ? 8 : (rp >= 8 ? 4 : 0));
+}
+__host__ __device__ constexpr bool split_rank(int rp) { return split_units(rp) != 0; }
 __host__ __device__ __forceinline__ int64_t panel_ofs(int64_t row, int k, int rs, int tsplit) {
     if (tsplit == 0) return row * rs + k;
+    const int aw = rs >= 18 ? 16 : 8;  // doubles of block A (rs 10, 14: ranks 8..14; 18, 22: 16..20)
     const int64_t slab = row / tsplit, local = row - slab * tsplit;
     return slab * tsplit * rs +
-           (k < 16 ? local * 16 + k : (int64_t)tsplit * 16 + local * (rs - 16) + (k - 16));
+           (k < aw ? local * aw + k : (int64_t)tsplit * aw + local * (rs - aw) + (k - aw));
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -725,10 +733,11 @@ sweep_p16_kernel(const SweepTiledArgs a) {
     using Cfg = SweepCfg<RP, PT>;
     constexpr int RS = row_stride(RP);
     constexpr int PS = panel_stride<PT>(RP);
-    static_assert(!SPLIT || (sizeof(PT) == 8 && Cfg::kLPN == 1 && Cfg::kNU >= 8 && Cfg::kNU <= 15),
-                  "split layout: fp64 panels, one lane per nonzero, 8..15 units per row");
-    constexpr int NUB = SPLIT ? Cfg::kNU - 8 : 0;            // units of block B
-    constexpr int BSB = SPLIT ? (RS - 16) * 8 : 0;           // bytes per row of block B
+    static_assert(!SPLIT || (sizeof(PT) == 8 && Cfg::kLPN == 1 && split_units(RP) != 0),
+                  "split layout: fp64 panels, one lane per nonzero, 4..10 units per row");
+    constexpr int SA = SPLIT ? split_units(RP) : 8;          // units of block A (8 or 4)
+    constexpr int NUB = SPLIT ? Cfg::kNU - SA : 0;           // units of block B
+    constexpr int BSB = SPLIT ? (RS - 2 * SA) * 8 : 0;       // bytes per row of block B
     constexpr int NT = Cfg::p16_threads(COLS);
     constexpr int UE = Cfg::kUE, NU = Cfg::kNU, LPN = Cfg::kLPN, NUL = Cfg::kNUL, KL = Cfg::kKL;
     constexpr int NPG = Cfg::kNPG;
@@ -758,20 +767,21 @@ sweep_p16_kernel(const SweepTiledArgs a) {
     LogProd lp;
     if (kLogProd) lp.init();
 
-    const uint32_t tileB_s = tile_s + (uint32_t)a.T * 128u;
-    const uint32_t rot = (uint32_t)gl << 4;
-    if (SPLIT && (tile_s & 127u)) __trap();  // block A rows must start on 128-byte boundaries
+    const uint32_t tileB_s = tile_s + (uint32_t)a.T * (uint32_t)(SA * 16);
+    const uint32_t rot = (uint32_t)(gl & (SA - 1)) << 4;
+    if (SPLIT && (tile_s & 127u)) __trap();  // block A rows must start on SA * 16-byte boundaries
 
     // this lane's share of an owner row: units hf, hf + LPN, ...
     auto load_owner = [&](int64_t o, PT(&dst)[KL]) {
         if constexpr (SPLIT) {
             const uint32_t so = (uint32_t)o / (uint32_t)a.T, lo = (uint32_t)o - so * (uint32_t)a.T;
             const PT *blk = reinterpret_cast<const PT *>(a.owner) + (int64_t)so * a.T * PS;
-            const PT *ra = blk + (int64_t)lo * 16, *rb = blk + (int64_t)a.T * 16 + (int64_t)lo * (RS - 16);
+            const PT *ra = blk + (int64_t)lo * (2 * SA);
+            const PT *rb = blk + (int64_t)a.T * (2 * SA) + (int64_t)lo * (RS - 2 * SA);
 #pragma unroll
-            for (int c = 0; c < 8; c++) ldg_unit(ra, c ^ gl, dst + c * UE);
+            for (int c = 0; c < SA; c++) ldg_unit(ra, c ^ (gl & (SA - 1)), dst + c * UE);
 #pragma unroll
-            for (int c = 0; c < NUB; c++) ldg_unit(rb, c, dst + (8 + c) * UE);
+            for (int c = 0; c < NUB; c++) ldg_unit(rb, c, dst + (SA + c) * UE);
         } else {
             const PT *orow = reinterpret_cast<const PT *>(a.owner) + o * PS;
 #pragma unroll
@@ -864,12 +874,12 @@ sweep_p16_kernel(const SweepTiledArgs a) {
                     if constexpr (SPLIT) {
                         if (!VB_SPLIT_PRED || (v >> 16)) {  // a hole keeps the previous row: no shared-memory traffic
                             const uint32_t row = v & 0xffffu;
-                            const uint32_t ra = (tile_s + row * 128u) ^ rot;
+                            const uint32_t ra = (tile_s + row * (uint32_t)(SA * 16)) ^ rot;
                             const uint32_t rb = tileB_s + row * (uint32_t)BSB;
 #pragma unroll
-                            for (int c = 0; c < 8; c++) lds_unit(ra ^ (uint32_t)(c << 4), tr + c * UE);
+                            for (int c = 0; c < SA; c++) lds_unit(ra ^ (uint32_t)(c << 4), tr + c * UE);
 #pragma unroll
-                            for (int c = 0; c < NUB; c++) lds_unit(rb + c * 16, tr + (8 + c) * UE);
+                            for (int c = 0; c < NUB; c++) lds_unit(rb + c * 16, tr + (SA + c) * UE);
                         }
                     } else {
                         const uint32_t raddr = tile_s + (v & 0xffffu) * (uint32_t)(PS * sizeof(PT));
@@ -932,21 +942,34 @@ sweep_p16_kernel(const SweepTiledArgs a) {
 #pragma unroll
             for (int k = 0; k < KL; k++) v0[k] = (double)acc[k];
             if constexpr (SPLIT) {
-                // block A: register unit c of lane gl is rank unit c ^ gl; the partner gl ^ b
-                // holds the same rank unit in its register unit c ^ b
-                double a1[8], a2[4], a3[2];
+                // block A: register unit c of lane gl is rank unit c ^ (gl & (SA - 1)); the partner
+                // gl ^ b holds the same rank unit in its register unit c ^ b
+                if constexpr (SA == 8) {
+                    double a1[8], a2[4], a3[2];
 #pragma unroll
-                for (int k = 0; k < 8; k++) a1[k] = v0[k] + __shfl_xor_sync(gmask, v0[k + 8], 4);
+                    for (int k = 0; k < 8; k++) a1[k] = v0[k] + __shfl_xor_sync(gmask, v0[k + 8], 4);
 #pragma unroll
-                for (int k = 0; k < 4; k++) a2[k] = a1[k] + __shfl_xor_sync(gmask, a1[k + 4], 2);
+                    for (int k = 0; k < 4; k++) a2[k] = a1[k] + __shfl_xor_sync(gmask, a1[k + 4], 2);
 #pragma unroll
-                for (int k = 0; k < 2; k++) a3[k] = a2[k] + __shfl_xor_sync(gmask, a2[k + 2], 1);
-                *reinterpret_cast<double2 *>(out + 2 * gl) = make_double2(a3[0], a3[1]);
+                    for (int k = 0; k < 2; k++) a3[k] = a2[k] + __shfl_xor_sync(gmask, a2[k + 2], 1);
+                    *reinterpret_cast<double2 *>(out + 2 * gl) = make_double2(a3[0], a3[1]);
+                } else {
+                    // SA == 4: halve over the four rotations, then add the two parity halves
+                    double a1[4], a2[2];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) a1[k] = v0[k] + __shfl_xor_sync(gmask, v0[k + 4], 2);
+#pragma unroll
+                    for (int k = 0; k < 2; k++) a2[k] = a1[k] + __shfl_xor_sync(gmask, a1[k + 2], 1);
+#pragma unroll
+                    for (int k = 0; k < 2; k++) a2[k] += __shfl_xor_sync(gmask, a2[k], 4);
+                    if (gl < 4 && 2 * gl < RP)
+                        *reinterpret_cast<double2 *>(out + 2 * gl) = make_double2(a2[0], a2[1]);
+                }
                 if constexpr (NUB > 0) {
                     double vb[2 * NUB];
 #pragma unroll
-                    for (int k = 0; k < 2 * NUB; k++) vb[k] = v0[16 + k];
-                    halve_reduce_store<2 * NUB>(vb, gl, gmask, out + 16, RP - 16);
+                    for (int k = 0; k < 2 * NUB; k++) vb[k] = v0[2 * SA + k];
+                    halve_reduce_store<2 * NUB>(vb, gl, gmask, out + 2 * SA, RP - 2 * SA);
                 }
             } else {
             constexpr int H1 = (KL + 1) / 2, H2 = (H1 + 1) / 2, H3 = (H2 + 1) / 2;

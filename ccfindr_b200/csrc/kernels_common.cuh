@@ -304,8 +304,12 @@ struct SegSchedule {
 // of 4 steps is all holes, which kernels that skip the gathers of hole entries get for free).
 // NL = 4: two classes of K multiples of 2 (an odd number of step pairs gets one more pair of hole
 // steps in class 1).
-__device__ __forceinline__ void make_schedule(const int (&cnt8)[8], int NL, int kmult,
+// sbs ("side by side", the 4-unit split layout, NL = 8 lanes): the two parity classes are scheduled
+// like the NL = 4 classes but run in the SAME steps, even rows in lanes 0..3 and odd rows in lanes
+// 4..7, K = the larger of the two step counts (a multiple of kmult).
+__device__ __forceinline__ void make_schedule(const int (&cnt8)[8], int NLp, int kmult, bool sbs,
                                               SegSchedule &sc) {
+    const int NL = sbs ? 4 : NLp;
     const int ncls = NL == 8 ? 1 : 2, NB = NL;
     for (int cl = 0; cl < 2; cl++) {
         sc.K[cl] = 0; sc.pl[cl].R = 0; sc.pl[cl].P = 0;
@@ -315,9 +319,10 @@ __device__ __forceinline__ void make_schedule(const int (&cnt8)[8], int NL, int 
     for (int cl = 0; cl < ncls; cl++) {
         int n = 0, L = 0;
         for (int b = 0; b < NB; b++) { n += sc.cnt[cl][b]; L = max(L, sc.cnt[cl][b]); }
-        sc.K[cl] = class_steps(n, L, NL, NL == 8 ? kmult : 2);
+        sc.K[cl] = class_steps(n, L, NL, (NL == 8 || sbs) ? kmult : 2);
     }
-    if (ncls == 2 && ((sc.K[0] + sc.K[1]) & 3)) sc.K[1] += 2;
+    if (sbs) sc.K[0] = sc.K[1] = max(sc.K[0], sc.K[1]);
+    else if (ncls == 2 && ((sc.K[0] + sc.K[1]) & 3)) sc.K[1] += 2;
     for (int cl = 0; cl < ncls; cl++) {
         if (sc.K[cl] == 0) continue;
         if (NL == 8) {
@@ -339,7 +344,9 @@ __device__ __forceinline__ void make_schedule(const int (&cnt8)[8], int NL, int 
 
 // item index (step * NL + lane, steps of class 1 after those of class 0) of the k-th nonzero of
 // residue rr
-__device__ __forceinline__ int schedule_item(const SegSchedule &sc, int NL, int rr, int k) {
+__device__ __forceinline__ int schedule_item(const SegSchedule &sc, int NLp, bool sbs, int rr,
+                                             int k) {
+    const int NL = sbs ? 4 : NLp;
     const int cl = res_class(rr, NL), b = res_bucket(rr, NL);
     const int R = sc.pl[cl].R, P = sc.pl[cl].P;
     int step, lane;
@@ -351,6 +358,7 @@ __device__ __forceinline__ int schedule_item(const SegSchedule &sc, int NL, int 
         step = R + row % P;
         lane = (row >= P) ? NL - 1 - level : level;
     }
+    if (sbs) return step * 8 + cl * 4 + lane;
     return ((cl ? sc.K[0] : 0) + step) * NL + lane;
 }
 
@@ -372,7 +380,8 @@ __device__ __forceinline__ void warp_residue_counts(const uint32_t *__restrict__
 // One warp per segment.
 __global__ void __launch_bounds__(kBlock)
 plan_p16_kernel(int64_t E, const int64_t *__restrict__ ptr, const uint32_t *__restrict__ words,
-                int NL, int kmult, uint32_t *__restrict__ len4, uint8_t *__restrict__ dead) {
+                int NL, int kmult, bool sbs, uint32_t *__restrict__ len4,
+                uint8_t *__restrict__ dead) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * kBlock + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * kBlock) >> 5;
@@ -383,13 +392,15 @@ plan_p16_kernel(int64_t E, const int64_t *__restrict__ ptr, const uint32_t *__re
         int cnt[8];
         warp_residue_counts(words, beg, end, lane, cnt);
         int n0 = 0, n1 = 0, L0 = 0, L1 = 0;
+        const int NLs = sbs ? 4 : NL;
 #pragma unroll
         for (int rr = 0; rr < 8; rr++) {
-            if (res_class(rr, NL)) { n1 += cnt[rr]; L1 = max(L1, cnt[rr]); }
+            if (res_class(rr, NLs)) { n1 += cnt[rr]; L1 = max(L1, cnt[rr]); }
             else { n0 += cnt[rr]; L0 = max(L0, cnt[rr]); }
         }
-        int K = class_steps(n0, L0, NL, NL == 8 ? kmult : 2);
-        if (NL != 8) K += class_steps(n1, L1, NL, 2);
+        int K = class_steps(n0, L0, NLs, (NLs == 8 || sbs) ? kmult : 2);
+        if (sbs) K = max(K, class_steps(n1, L1, 4, kmult));
+        else if (NL != 8) K += class_steps(n1, L1, NL, 2);
         const int Kst = (K + 3) & ~3;  // stored steps: whole chunks of 4
         if (lane == 0) {
             len4[e] = (uint32_t)(Kst * NL / 4);
@@ -415,7 +426,7 @@ __device__ __forceinline__ int64_t p16_position(int64_t p, int NL) {
 __global__ void __launch_bounds__(kBlock)
 build_segments_p16_kernel(int64_t E, int64_t NO, const int64_t *__restrict__ ptr,
                           const uint32_t *__restrict__ ptr4, const uint32_t *__restrict__ words,
-                          int NL, int kmult, int64_t nvalid, int S,
+                          int NL, int kmult, bool sbs, int64_t nvalid, int S,
                           uint32_t *__restrict__ ent_out) {
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
@@ -430,12 +441,12 @@ build_segments_p16_kernel(int64_t E, int64_t NO, const int64_t *__restrict__ ptr
         int cnt[8];
         warp_residue_counts(words, beg, end, lane, cnt);
         SegSchedule sc;
-        make_schedule(cnt, NL, kmult, sc);
+        make_schedule(cnt, NL, kmult, sbs, sc);
         // holes: lane <-> bucket in the single steps, so the residue of the lane's bucket is free
         for (int p = lane; p < nitems; p += 32) {
             const int step = p / NL, ln = p - step * NL;
-            const int cl = (NL != 8 && step >= sc.K[0]) ? 1 : 0;
-            int rr = bucket_res(cl, ln, NL);
+            const int cl = sbs ? (ln >> 2) : ((NL != 8 && step >= sc.K[0]) ? 1 : 0);
+            int rr = sbs ? 2 * (ln & 3) + cl : bucket_res(cl, ln, NL);
             if ((int64_t)rr * S + slab >= nvalid) rr = 0;
             dst[p16_position(p, NL)] = (uint32_t)rr;
         }
@@ -455,7 +466,7 @@ build_segments_p16_kernel(int64_t E, int64_t NO, const int64_t *__restrict__ ptr
                 if (rr == b) k = seen[b] + __popc(mk & lt);
                 seen[b] += __popc(mk);
             }
-            if (valid) dst[p16_position(schedule_item(sc, NL, rr, k), NL)] = w;
+            if (valid) dst[p16_position(schedule_item(sc, NL, sbs, rr, k), NL)] = w;
         }
         __syncwarp();
     }

@@ -100,7 +100,7 @@ void colsum(const ColsumArgs &a, cudaStream_t s) {
 extern const RpTable VB_CAT(rp_table_, VB_RP);
 const RpTable VB_CAT(rp_table_, VB_RP) = {
     RP,      RS,        row_stride_f32(RP),
-    SweepCfg<RP, double>::kNPG, SweepCfg<RP, float>::kNPG, split_rank(RP) ? 1 : 0, sweep_prepare,
+    SweepCfg<RP, double>::kNPG, SweepCfg<RP, float>::kNPG, split_units(RP), sweep_prepare,
     sweep, mirror,
     combine, posterior, ml_update,          colsum};
 

@@ -148,6 +148,7 @@ struct Layout {
     int T = 0, Sg = 0, Sc = 0;
     int npg = 0;  // packed-16 layout: nonzeros per group step it was ordered for (0: 8-byte layout)
     int kmult = 4;  // packed-16 layout: the schedule's step count is a multiple of this (4 or 1)
+    bool sbs = false;  // packed-16 layout: parity classes side by side (4-unit split layout)
     int64_t NG = 0, NC = 0;
     int32_t *d_gene_dev = nullptr, *d_cell_dev = nullptr;  // original index -> device row
     PassLayout cols, rows;
@@ -497,7 +498,7 @@ int build_pass(H *h, Layout *L, bool cols_pass, const int32_t *d_colof, uint32_t
         const uint32_t *d_words = p_out;  // the sorted payloads are the packed words
         { StageTimer t1("  plan(p16)");
         vb::plan_p16_kernel<<<g, vb::kBlock, 0, h->stream>>>(P.E, P.d_ptr, d_words, L->npg,
-                                                             L->kmult, d_len4, d_dead); }
+                                                             L->kmult, L->sbs, d_len4, d_dead); }
         size_t scan_bytes = 0;
         CK(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, d_len4, P.d_ptr4, P.E + 1, h->stream));
         void *d_scan = nullptr;
@@ -513,7 +514,7 @@ int build_pass(H *h, Layout *L, bool cols_pass, const int32_t *d_colof, uint32_t
         P.nent = (int64_t)quads * 4;
         { StageTimer t1("  build_segments(p16)");
         vb::build_segments_p16_kernel<<<g, vb::kBlock, 0, h->stream>>>(
-            P.E, NO, P.d_ptr, P.d_ptr4, d_words, L->npg, L->kmult, cols_pass ? h->n : h->m,
+            P.E, NO, P.d_ptr, P.d_ptr4, d_words, L->npg, L->kmult, L->sbs, cols_pass ? h->n : h->m,
             cols_pass ? L->Sg : L->Sc, (uint32_t *)P.d_ent); }
         CK(vmalloc(h, &P.d_split, (size_t)(L->grid + 1) * 8));
         // per-segment overhead in quads (VBNMF_SPLIT_KAPPA: tuning)
@@ -557,16 +558,17 @@ void launch_expand_cols(H *h, int32_t *d_colof, unsigned long long *d_cnt, unsig
         d_cnt ? d_cnt + h->n : nullptr, d_bad);
 }
 
-int get_layout(H *h, int T, int npg, int kmult, Layout **out) {
+int get_layout(H *h, int T, int npg, int kmult, bool sbs, Layout **out) {
     if (!h->p16) npg = 0;
-    if (npg != 8) kmult = 4;
+    if (npg != 8) { kmult = 4; sbs = false; }
     for (Layout *l : h->layouts)
-        if (l->T == T && l->npg == npg && l->kmult == kmult) { *out = l; return 0; }
+        if (l->T == T && l->npg == npg && l->kmult == kmult && l->sbs == sbs) { *out = l; return 0; }
     StageTimer tm("get_layout(total)");
     Layout *L = new Layout();
     L->T = T;
     L->npg = npg;
     L->kmult = kmult;
+    L->sbs = sbs;
     L->Sg = cdiv(h->n, T);
     L->Sc = cdiv(h->m, T);
     L->NG = (int64_t)L->Sg * T;
@@ -709,12 +711,18 @@ int alloc_panels(H *h, int r) {
         if (h->empty_cols) return fail(h, VBNMF_ERR_EMPTY, "Input matrix contains empty columns");
     }
     const int T = choose_tile_rows(h, row_bytes);
-    // split layout + conflict-free rotated gathers: fp64 panels, packed-16 entries, 8..10 units
-    const bool split = !f32 && h->p16 && tab->split64 && !getenv("VBNMF_NO_SPLIT");
+    // split layout + rotated gathers: fp64 panels, packed-16 entries, rows of 4..10 units
+    // (tab->split64 = units of block A: 8 for ranks 16..20, 4 for ranks 8..14)
+    // The 4-unit variant is opt-in (VBNMF_SPLIT4=1): measured at C2 (r = 10) it is SLOWER than the
+    // lock-step layout (1.48 vs 1.41 ms per iteration) although it saves ~11 % of the gather
+    // wavefronts -- with rows of 5 units the pass is bound by issue slots and latency as much as by
+    // the LSU pipe, and the rotated addresses add one LOP3 per unit.
+    const bool split = !f32 && h->p16 && tab->split64 && !getenv("VBNMF_NO_SPLIT") &&
+                       (tab->split64 == 8 || getenv("VBNMF_SPLIT4"));
     Layout *L = nullptr;
     int kmult = split ? 1 : 4;
     if (const char *e = getenv("VBNMF_KMULT")) kmult = atoi(e) == 1 ? 1 : 4;  // experiments
-    int rc = get_layout(h, T, f32 ? tab->npg32 : tab->npg64, kmult, &L);
+    int rc = get_layout(h, T, f32 ? tab->npg32 : tab->npg64, kmult, split && tab->split64 == 4, &L);
     if (rc) return rc;
     if (rp == h->rp && L == h->L && h->d_lw && h->panel_precision == h->precision) {
         h->r = r;

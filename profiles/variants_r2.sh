@@ -1,7 +1,6 @@
 #!/bin/bash
-# A/B of build knobs on a C3-shaped matrix (20k genes x 200k cells, r = 20)
-P="python profiles/prof_run.py --workload c3 --cells 200000 --iters 10"
-echo "== default (immediate slow path of the log-product)"; $P
-echo "== b: cell-owner pass with 352 threads"; VBNMF_LIB_NAME=libvbnmf_b.so $P
-echo "== c: per-chunk slow path (round-2 baseline)"; VBNMF_LIB_NAME=libvbnmf_c.so $P
-echo "== d: 352 threads, per-chunk slow path"; VBNMF_LIB_NAME=libvbnmf_d.so $P
+# A/B of the 4-unit split layout (ranks 8..14, fp64) against the lock-step layout
+for w in "c2 --iters 20"; do
+  echo "== $w: split (default)"; python profiles/prof_run.py --workload $w
+  echo "== $w: lock-step (VBNMF_NO_SPLIT4=1)"; VBNMF_NO_SPLIT4=1 python profiles/prof_run.py --workload $w
+done

@@ -29,17 +29,22 @@ def res_bucket(rr, NL):
     return rr if NL == 8 else rr >> 1
 
 
-def make_schedule(cnt8, NL, kmult=4):
+def make_schedule(cnt8, NLp, kmult=4, sbs=False):
     """kmult (NL = 8 only): the step count is a multiple of it -- 4: every stored step is
-    scheduled; 1: fewest steps, the rest of the last stored chunk of 4 steps is all holes."""
+    scheduled; 1: fewest steps, the rest of the last stored chunk of 4 steps is all holes.
+    sbs (8 lanes, the 4-unit split layout): the parity classes are scheduled like the NL = 4
+    classes but share their steps, even rows in lanes 0..3 and odd rows in lanes 4..7."""
+    NL = 4 if sbs else NLp
     ncls, NB = (1, 8) if NL == 8 else (2, 4)
     sc = dict(K=[0, 0], pl=[(0, 0), (0, 0)], offr=[[0] * 8, [0] * 8], cnt=[[0] * 8, [0] * 8])
     for rr in range(8):
         sc["cnt"][res_class(rr, NL)][res_bucket(rr, NL)] = cnt8[rr]
     for cl in range(ncls):
         c = sc["cnt"][cl][:NB]
-        sc["K"][cl] = class_steps(sum(c), max(c), NL, kmult if NL == 8 else 2)
-    if ncls == 2 and ((sc["K"][0] + sc["K"][1]) & 3):
+        sc["K"][cl] = class_steps(sum(c), max(c), NL, kmult if (NL == 8 or sbs) else 2)
+    if sbs:
+        sc["K"][0] = sc["K"][1] = max(sc["K"])
+    elif ncls == 2 and ((sc["K"][0] + sc["K"][1]) & 3):
         sc["K"][1] += 2
     for cl in range(ncls):
         if sc["K"][cl] == 0:
@@ -53,8 +58,9 @@ def make_schedule(cnt8, NL, kmult=4):
     return sc
 
 
-def schedule_item(sc, NL, rr, k):
+def schedule_item(sc, NLp, rr, k, sbs=False):
     """Item index (step * NL + lane) of the k-th nonzero whose tile row has residue rr."""
+    NL = 4 if sbs else NLp
     cl, b = res_class(rr, NL), res_bucket(rr, NL)
     R, P = sc["pl"][cl]
     if k < R:
@@ -64,7 +70,28 @@ def schedule_item(sc, NL, rr, k):
         row, level = t % (2 * P), t // (2 * P)
         step = R + row % P
         lane = NL - 1 - level if row >= P else level
+    if sbs:
+        return step * 8 + cl * 4 + lane
     return ((sc["K"][0] if cl else 0) + step) * NL + lane
+
+
+def wavefronts_sbs(cnt8, kmult=1):
+    """4-unit split layout: (steps K, wavefronts of block A per unit, of block B per unit).
+    Block A is conflict free when lanes 0..3 hold even rows and lanes 4..7 odd rows (asserted);
+    block B costs the largest residue multiplicity of the step."""
+    sc = make_schedule(cnt8, 8, kmult, sbs=True)
+    K = sc["K"][0]
+    mult = np.zeros((K, 8), dtype=int)
+    seen = set()
+    for rr in range(8):
+        for k in range(cnt8[rr]):
+            p = schedule_item(sc, 8, rr, k, sbs=True)
+            assert 0 <= p < K * 8 and p not in seen
+            seen.add(p)
+            step, lane = divmod(p, 8)
+            assert (lane >> 2) == (rr & 1)           # parity class <-> lane half
+            mult[step, rr] += 1
+    return K, K, int(np.maximum(mult.max(axis=1), 1).sum()) if K else 0
 
 
 def wavefronts(cnt8, NL, kmult=4):

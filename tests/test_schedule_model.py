@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 from hypothesis import given, settings, strategies as st
 
-from schedule_model import make_schedule, wavefronts
+from schedule_model import make_schedule, wavefronts, wavefronts_sbs
 
 counts = st.lists(st.integers(min_value=0, max_value=90), min_size=8, max_size=8).filter(lambda c: sum(c) > 0)
 
@@ -85,3 +85,31 @@ def test_split_layout_cost_model():
         new += 8 * K1 + 2 * w1
         ideal += 10 * sum(cnt) / 8
     assert old / ideal > 1.30 and new / ideal < 1.15
+
+
+@settings(max_examples=300, deadline=None)
+@given(counts)
+def test_side_by_side_parity_schedule_of_the_four_unit_split(cnt):
+    """Every nonzero gets its own slot in the lane half of its row parity; the step count is the
+    larger class's max(ceil(n/4), ceil(L/2)); block B never sees more than a 2-way conflict."""
+    K, wa, wb = wavefronts_sbs(cnt)
+    even, odd = cnt[0::2], cnt[1::2]
+    need = max(max((sum(c) + 3) // 4, (max(c) + 1) // 2) for c in (even, odd))
+    assert K == need and wa == K and K <= wb <= 2 * K
+
+
+def test_four_unit_split_cost_model():
+    """Wavefronts per segment at r = 10 (5 units per row, ~230 nonzeros per segment): block A
+    (4 units) costs one wavefront per step under the parity rule, block B (1 unit) follows the
+    residues.  Against the lock-step layout where all 5 units pay max(K, largest bucket)."""
+    rng = np.random.default_rng(2)
+    old = new = ideal = 0.0
+    for _ in range(400):
+        rows = rng.choice(2880, size=rng.binomial(2880, 0.08), replace=False)
+        cnt = np.bincount(rows % 8, minlength=8).tolist()
+        _, w4 = wavefronts(cnt, 8, kmult=4)
+        K, wa, wb = wavefronts_sbs(cnt)
+        old += 5 * w4
+        new += 4 * wa + 1 * wb
+        ideal += 5 * sum(cnt) / 8
+    assert old / ideal > 1.22 and new / ideal < 1.13
