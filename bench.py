@@ -40,7 +40,7 @@ if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
 
 WORKLOADS = {
     # name: genes, cells (per GPU = weak scaling, total = strong), true rank, density, seed, fit rank
-    "c2": dict(n=20000, m_per_gpu=100000, r_true=10, density=0.08, seed=2, rank=10,
+    "c2": dict(n=20000, m_per_gpu=100000, r_true=10, density=0.08, seed=2, rank=10, ml_rank=15,
                label="C2: vb_factorize rank=10, 20k genes x 100k cells per GPU, ~8% nonzero"),
     "c3": dict(n=20000, m_total=1300000, r_true=20, density=0.08, seed=3, rank=20,
                label="C3: vb_factorize rank=20, 20k genes x 1.3M cells, ~8% nonzero, cells "
@@ -298,6 +298,35 @@ def cpu_baseline_port(n, r, colptr, rowidx, values, w0, h0, max_cols=24000, iter
             "seconds_per_iteration": sec}
 
 
+def ml_leg(eng, n, m, nnz, r, peak, k1=5, k2=25, parity_iters=3):
+    """BASELINE config 5: factorize()'s maximum-likelihood loop (R/factorize.R:189-212) on the
+    engine's matrix.  mlnmf_run is called through the C ABI with k1 and k2 > k1 iterations
+    (Tol = 0: the likelihood rule never fires); the per-iteration time is the difference quotient,
+    so the upload of w0/h0 and the download of w/h drop out.  One iteration = cell-owner sweep +
+    h update + gene-owner sweep + w update + the likelihood and stopping rule on the device."""
+    import torch
+    from ccfindr_b200 import synth
+    w0, h0 = synth.uniform_init(n, m, r, seed=5)              # init(): w, h ~ U(0, 1) (:30-38)
+    eng.set_precision(0)
+    g = eng.ml_run(w0, h0, Itmax=parity_iters, Tol=0.0)      # warm-up + the state the oracle checks
+    ts = {}
+    for k in (k1, k2, k1, k2):
+        torch.cuda.synchronize()
+        t0 = time.time()
+        res = eng.ml_run(w0, h0, Itmax=k, Tol=0.0)
+        torch.cuda.synchronize()
+        ts.setdefault(k, []).append(time.time() - t0)
+        assert res["niter"] == k and np.isfinite(res["lik"])
+    t_iter = (min(ts[k2]) - min(ts[k1])) / (k2 - k1)
+    b_alg = 2 * nnz * 8 + 2 * 8 * (m + 1) + 3 * r * m * 8 + 3 * n * r * 8    # SURVEY.md 8(d), ML row
+    return {"workload": "C5: factorize() ML path, rank %d, on the same matrix" % r,
+            "value": nnz * r / t_iter, "unit": UNIT, "ms_per_iteration": t_iter * 1e3,
+            "algorithmic_bytes_per_iteration": b_alg, "roofline_frac": b_alg / t_iter / 1e9 / peak,
+            "timing": "wall-clock difference quotient of mlnmf_run(%d) and mlnmf_run(%d) through the "
+                      "C ABI (host buffers in and out)" % (k1, k2),
+            "_gpu": g}
+
+
 def run_config(args, name, ctx):
     """One workload through every leg.  Returns the record (rank 0) or None."""
     import torch
@@ -378,6 +407,10 @@ def run_config(args, name, ctx):
              "tile_rows": layout32["tile_rows"],
              "what": "panels lw/lh held in fp32, per-nonzero arithmetic fp32, every sum over "
                      "lanes/slabs/ranks and the posterior update in fp64 (tolerance 1e-4)"}
+    # ---- BASELINE config 5 on the same matrix: the ML path of factorize(), rank 15 ----------------
+    ml = None
+    if wl.get("ml_rank") and world == 1:
+        ml = ml_leg(eng, n, m_loc, nnz_loc, wl["ml_rank"], peak)
     eng.close()
 
     # ---- end-to-end arm: HOST buffers through the C ABI, copies inside the timed region ---------
@@ -456,6 +489,20 @@ def run_config(args, name, ctx):
             parity["lkh_rel_err"] = max(parity["lkh_rel_err_vs_single_gpu"])
             parity["cid_mismatches"] = parity["cid_mismatches_vs_single_gpu"]
         barrier()
+    if ml is not None and P and not args.no_parity and h_colptr is not None:
+        from ccfindr_b200 import synth as _synth
+        from oracle import bindings as ob
+        restore_omp_threads()
+        w0m, h0m = _synth.uniform_init(n, m_loc, wl["ml_rank"], seed=5)
+        t0 = time.time()
+        ref = ob.sparse_ml_run((n, m_loc, h_colptr, h_rowidx, h_values), w0m, h0m, Itmax=P, Tol=0.0)
+        g = ml.pop("_gpu")
+        ml["parity"] = {"iterations": P, "oracle": "oracle_sparse.c osp_ml_run on the whole matrix",
+                        "oracle_seconds": round(time.time() - t0, 2),
+                        "lik_rel_err": [abs(a - b) / abs(b) for a, b in zip(g["lik_trace"], ref["lik_trace"])],
+                        "w_max_rel_err": relerr(g["w"], ref["w"]), "h_max_rel_err": relerr(g["h"], ref["h"])}
+    elif ml is not None:
+        ml.pop("_gpu", None)
     if cpu is None and rank == 0 and not args.no_cpu and h_colptr is not None:
         cpu = cpu_baseline_port(n, r, h_colptr, h_rowidx, h_values, w0, h0_loc)
     barrier()
@@ -509,6 +556,7 @@ def run_config(args, name, ctx):
         "cpu_baseline": cpu,
         "parity": parity,
         "fp32_storage_mode": mixed,
+        "ml_path": ml,
         "wall_ms_per_step": t64["wall_ms"],
         "lkh_last": t64["res"]["lkh"],
         "hyper_last": t64["res"]["hyper"],

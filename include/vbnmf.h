@@ -13,7 +13,9 @@
  *   hyper_update(), R/bayesian.R:2-53                                  (inside vbnmf_run)
  *   uniform-column test, R/bayesian.R:368-369                          vbnmf_uniform_columns
  *   cluster_id(): apply(h,2,which.max), R/utils.R:903-909              vbnmf_cluster_id
- *   nmf_updateR() + likelihood() loop, R/factorize.R:189-212           mlnmf_run
+ *   nmf_updateR() + likelihood() loop, R/factorize.R:189-212           mlnmf_run, mlnmf_run2 (both criteria)
+ *   vb_init(): 'random', 'svd2', R/bayesian.R:111-115,150-159          vbnmf_init_random, vbnmf_init_svd2
+ *   read_10x(): readMM + as(., 'dgCMatrix'), R/utils.R:34               vbnmf_create_from_mtx
  *   Rmpi task farm over restarts, R/bayesian.R:263                     one handle per process/GPU;
  *                                                                      cells sharded: vbnmf_attach_comm
  *

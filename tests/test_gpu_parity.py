@@ -192,6 +192,26 @@ def test_ml_connectivity_criterion_matches_literal_reference_loop(Engine, counts
     assert relerr(res["w"], w) < TOL and relerr(res["h"], h) < TOL
 
 
+@pytest.mark.parametrize("r", [7, 10, 13])
+def test_opt_in_four_unit_split_layout_matches_oracle(Engine, monkeypatch, r):
+    """VBNMF_SPLIT4=1: ranks 8..14 through the 4-unit split layout (parity classes side by side,
+    rotated gathers) -- opt-in because it measured slower, but it must stay correct."""
+    from oracle import bindings as ob
+    from oracle import oracle_dense as od
+    monkeypatch.setenv("VBNMF_SPLIT4", "1")
+    X, w0, h0 = _random_problem(700, 900, r, 0.06, seed=50 + r)
+    hyper = dict(aw=0.9, bw=1.1, ah=1.2, bh=0.8)
+    ref = od.vb_init_from(w0, h0)
+    with Engine(X) as eng:
+        eng.set_state(w0, h0)
+        for it in range(3):
+            ref = ob.sparse_vb_step(X, ref, hyper, od.EPS)
+            assert relerr(eng.step(hyper, od.EPS), ref["lkh"]) < TOL, it
+        st = eng.get_state()
+    for k in FACT:
+        assert relerr(st[k], ref[k]) < TOL, k
+
+
 def test_errors_are_reported_not_thrown(Engine):
     from ccfindr_b200 import _lib
     X, w0, h0 = _random_problem(40, 30, 4, 0.3, seed=3)

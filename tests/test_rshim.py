@@ -158,3 +158,53 @@ def test_factorization_through_the_shim_matches_the_reference_golden(shim):
     unif = vec(C.c_void_p(shim.C_vbnmf_uniform_columns(h, real([kw["Tol"]]))), np.int32, r)
     assert not unif.any()
     shim.C_vbnmf_destroy(h)
+
+
+@pytest.mark.gpu
+def test_remaining_shim_entry_points_execute(shim):
+    """C_vbnmf_init_random, C_vbnmf_step, C_vbnmf_set_precision, C_vbnmf_set_host_threads,
+    C_mlnmf_run and C_vbnmf_nccl_unique_id through the stand-in runtime, against the ctypes path."""
+    from ccfindr_b200 import synth
+    from ccfindr_b200.engine import Engine
+    X = load_counts("c1s1")
+    n, m = X.shape
+    r = 3
+    hyper = np.array([1.0, 1.0, 1.0, 1.0])
+
+    def real(a, nrow=0, ncol=0):
+        a = np.asfortranarray(a, dtype=np.float64)
+        return C.c_void_p(shim.rstub_real(a.ctypes.data_as(C.c_void_p), a.size, nrow, ncol))
+
+    def ints(a, logical=0):
+        a = np.ascontiguousarray(a, dtype=np.int32)
+        return C.c_void_p(shim.rstub_int(a.ctypes.data_as(C.c_void_p), a.size, logical))
+
+    def vec(sexp, dtype, count):
+        buf = (C.c_char * (np.dtype(dtype).itemsize * count)).from_address(shim.rstub_data(sexp))
+        return np.frombuffer(buf, dtype=dtype).copy()
+
+    for f in ("C_vbnmf_create", "C_vbnmf_step", "C_vbnmf_get_state", "C_mlnmf_run",
+              "C_vbnmf_nccl_unique_id", "C_vbnmf_init_random", "C_vbnmf_set_precision",
+              "C_vbnmf_set_host_threads", "C_vbnmf_destroy"):
+        getattr(shim, f).restype = C.c_void_p
+    shim.C_vbnmf_set_host_threads(ints([4]))
+    h = C.c_void_p(shim.C_vbnmf_create(ints(X.indptr), ints(X.indices), real(X.data),
+                                       ints([n, m]), ints([0])))
+    shim.C_vbnmf_set_precision(h, ints([0]))
+    shim.C_vbnmf_init_random(h, ints([r]), real(hyper), real([7.0]))
+    lkh = vec(C.c_void_p(shim.C_vbnmf_step(h, real(hyper), real([float(np.finfo(float).eps)]))),
+              np.float64, 1)[0]
+    with Engine(X) as eng:                                      # same calls through ctypes
+        eng.init_random(r, hyper, 7)
+        ref = eng.step(hyper)
+        w0, h0 = synth.uniform_init(n, m, r, 3)
+        mref = eng.ml_run(w0, h0, Itmax=12, Tol=1e-7)
+    assert lkh == ref
+    out = C.c_void_p(shim.C_mlnmf_run(h, real(w0, n, r), real(h0, r, m), ints([12]), real([1e-7])))
+    niter = int(vec(C.c_void_p(shim.VECTOR_ELT(out, 3)), np.int32, 1)[0])
+    assert niter == mref["niter"]
+    wgot = vec(C.c_void_p(shim.VECTOR_ELT(out, 0)), np.float64, n * r).reshape((n, r), order="F")
+    assert np.array_equal(wgot, mref["w"])
+    uid = C.c_void_p(shim.C_vbnmf_nccl_unique_id())
+    assert shim.XLENGTH(uid) == 128 and vec(uid, np.uint8, 128).any()
+    shim.C_vbnmf_destroy(h)
