@@ -1124,11 +1124,13 @@ posterior_kernel(int64_t rows, int T, int S, int64_t nvalid, int r, double a, do
         if (valid && kact) {
             al = a + l[lo] * SRaw[row * RS + k];
             const double e = al / be;
-            const double tmp = exp(vb_digamma(al)) / be;
+            double psi_al, lg_al;
+            vb_psi_lgamma(al, &psi_al, &lg_al);
+            const double tmp = exp(psi_al) / be;
             ln = tmp > fud ? tmp : fud;
             es += e;
             sll += log(ln);
-            prior += -aob * e + al * (1.0 - lbe) + lgamma(al);
+            prior += -aob * e + al * (1.0 - lbe) + lg_al;
         }
         if (valid) {
             l[lo] = ln;

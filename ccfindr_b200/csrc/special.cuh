@@ -28,6 +28,47 @@ VB_HD double vb_digamma(double x) {
     return acc;
 }
 
+// 1/x for the shift terms: hardware seed + two Newton steps on the device (~1 ulp, a quarter of the
+// instructions of an IEEE division), plain division on the host
+VB_HD double vb_rcp(double x) {
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(fma(-x, r, 1.0), r, r);
+    r = fma(fma(-x, r, 1.0), r, r);
+    return r;
+#else
+    return 1.0 / x;
+#endif
+}
+
+// psi(x) and lgamma(x) together, x > 0 (the posterior update needs both of the same argument,
+// src/vbnmf_update.cpp:59,63 and :85,89): ONE upward shift to xs = x + n >= 10 serves both --
+//   psi(x)    = psi(xs) - sum_{j<n} 1/(x+j),   lgamma(x) = lgamma(xs) - log prod_{j<n} (x+j)
+// and both Stirling series run in 1/xs^2 (truncation < 1e-17).  About a third of the instructions
+// of vb_digamma() + the library lgamma(); same accuracy (checked against mpmath on the host twin,
+// tests/test_special_cpu.py).
+VB_HD void vb_psi_lgamma(double x, double *psi, double *lgam) {
+    const int nstep = x < 10.0 ? (int)ceil(10.0 - x) : 0;
+    const double xs = x + (double)nstep;
+    const double xi = vb_rcp(xs), x2 = xi * xi, lx = log(xs);
+    const double sp = x2 * (1.0 / 12.0 - x2 * (1.0 / 120.0 - x2 * (1.0 / 252.0 - x2 * (1.0 / 240.0 -
+                      x2 * (1.0 / 132.0 - x2 * (691.0 / 32760.0 - x2 * (1.0 / 12.0 -
+                      x2 * (3617.0 / 8160.0))))))));
+    const double sl = xi * (1.0 / 12.0 - x2 * (1.0 / 360.0 - x2 * (1.0 / 1260.0 - x2 * (1.0 / 1680.0 -
+                      x2 * (1.0 / 1188.0 - x2 * (691.0 / 360360.0 - x2 * (1.0 / 156.0 -
+                      x2 * (3617.0 / 122400.0))))))));
+    double acc = lx - 0.5 * xi - sp, prod = 1.0;
+    for (int j = nstep - 1; j >= 0; j--) {
+        const double t = x + (double)j;
+        acc -= vb_rcp(t);
+        prod *= t;
+    }
+    *psi = acc;
+    // (xs - 1/2) log xs - xs + log(2 pi)/2 + series, minus the log of the shift product
+    *lgam = (xs - 0.5) * lx - xs + 0.91893853320467274178 + sl - (nstep ? log(prod) : 0.0);
+}
+
 // psi'(x), x > 0 (hyper-parameter Newton step only; host side)
 VB_HD double vb_trigamma(double x) {
     const int nstep = x < 10.0 ? (int)ceil(10.0 - x) : 0;
