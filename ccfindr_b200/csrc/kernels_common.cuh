@@ -667,37 +667,41 @@ init_random_kernel(int64_t rows, int r, int rs, const int32_t *__restrict__ dev,
 }
 
 // ---- all-reduce of the W-side statistics over NVLink peer memory -----------------------------
-// One process per GPU; every rank owns an exchange region [flags (kXchgFlags x u64) | buffer 0 |
-// buffer 1] that its peers map through CUDA IPC.  An all-reduce with sequence number seq is
-//   publish: copy the local vector into buffer seq & 1 of the own region, then (last CTA, after a
-//            system-scope fence) store seq into flags[my rank] of EVERY rank's region;
-//   reduce:  wait until flags[p] >= seq for all p in the own region, then out[i] = sum over
-//            p = 0..nranks-1 (fixed order -> bitwise identical on every rank) of buffer seq & 1
-//            of rank p, read straight from peer memory (NVLink P2P loads).
-// A rank can only publish seq + 2 (the next use of the same buffer) after its reduce of seq + 1,
+// One process per GPU; every rank owns an exchange region (layout below) that its peers map
+// through CUDA IPC.  An all-reduce with sequence number seq is two launches:
+//   publish: copy the local vector into the own `in` buffer seq & 1, then (last CTA, after a
+//            system-scope fence) store seq into arrive[my rank] of EVERY rank's region;
+//   reduce:  reduce-scatter + all-gather (xchg_reduce_kernel): rank r sums slice r of all `in`
+//            buffers in rank order with P2P loads, publishes the reduced slice, and collects the
+//            other ranks' slices.
+// A rank can only publish seq + 2 (the next use of the same buffers) after its reduce of seq + 1,
 // which waits for every peer's publish of seq + 1, which follows that peer's reduce of seq in
-// stream order: double buffering is enough, no second barrier.  The payload is 1.6 MB at C2 (3.3 MB
-// at C3) per iteration.  Measured (profiles/r01_peer_allreduce_ab.txt): equal to NCCL on 2 GPUs,
-// 20 us per iteration slower on 8 (NCCL reduces in the switch), so it is opt-in
-// (VBNMF_PEER_ALLREDUCE=1) and the default stays one ncclAllReduce per iteration.
-constexpr int kXchgFlags = 16;   // u64 flags per region (>= ranks of one NVLink domain we use)
+// stream order: double buffering is enough, no extra barrier.  The payload is 1.6 MB at C2 (3.6 MB
+// at C3) per iteration.  Round 1 had every rank read ALL peers' vectors (7 vectors over NVLink on 8
+// GPUs) and measured 20 us per iteration slower than NCCL there (profiles/r01_peer_allreduce_ab.txt);
+// the reduce-scatter form moves 1.75 vectors.  Opt-in (VBNMF_PEER_ALLREDUCE=1).
+constexpr int kXchgFlags = 16;   // u64 flags per set (>= ranks of one NVLink domain we use)
+// Region of a rank: [arrive flags (kXchgFlags) | slice flags (kXchgFlags) | in 0 | in 1 | res 0 | res 1]
 struct XchgArgs {
     unsigned long long *peer[kXchgFlags];  // base of every rank's region (own region at [rank])
     int nranks, rank;
     unsigned long long seq;
     int64_t n2;                 // payload in double2 units
-    int64_t buf_stride;         // bytes between buffer 0 and buffer 1
+    int64_t buf_stride;         // bytes between consecutive buffers
     const double *ctl;
 };
-__device__ __forceinline__ double2 *xchg_buf(unsigned long long *base, const XchgArgs &a) {
-    char *p = reinterpret_cast<char *>(base) + kXchgFlags * 8 + (a.seq & 1ull) * a.buf_stride;
+__device__ __forceinline__ double2 *xchg_buf(unsigned long long *base, const XchgArgs &a, int which) {
+    char *p = reinterpret_cast<char *>(base) + 2 * kXchgFlags * 8 +
+              ((int64_t)which * 2 + (int64_t)(a.seq & 1ull)) * a.buf_stride;
     return reinterpret_cast<double2 *>(p);
 }
 
+// publish: copy the local vector into the own `in` buffer of this sequence number, then (last CTA,
+// after a system-scope fence) raise arrive[my rank] = seq in EVERY rank's region
 __global__ void __launch_bounds__(kBlock)
 xchg_publish_kernel(const XchgArgs a, const double2 *__restrict__ src, unsigned *counter) {
     if (a.ctl && a.ctl[kCtlDone] != 0.0) return;
-    double2 *dst = xchg_buf(a.peer[a.rank], a);
+    double2 *dst = xchg_buf(a.peer[a.rank], a, 0);
     for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < a.n2;
          i += (int64_t)gridDim.x * kBlock)
         dst[i] = src[i];
@@ -714,26 +718,67 @@ xchg_publish_kernel(const XchgArgs a, const double2 *__restrict__ src, unsigned 
     }
 }
 
+// bounded spin on a flag of the own region: a peer that never arrives traps this rank instead of
+// hanging the GPU
+__device__ __forceinline__ void xchg_wait(volatile unsigned long long *f, unsigned long long seq) {
+    for (unsigned long long spin = 0; *f < seq; spin++)
+        if (spin > (1ull << 31)) __trap();
+}
+
+// reduce-scatter + all-gather over peer memory in one launch.  Rank r owns slice r of the vector:
+//   phase 1: wait for every rank's publish, sum slice r of all `in` buffers in rank order (P2P
+//            loads) into the own `res` buffer and into `out`; last CTA raises slice[r] = seq in
+//            every rank's region;
+//   phase 2: for every other rank p, wait for slice[p] and copy ITS reduced slice into `out`.
+// Every element is summed by exactly one rank in a fixed order and copied: bitwise identical on
+// all ranks.  NVLink traffic per rank: 2 (nranks - 1)/nranks of the vector, against (nranks - 1)
+// vectors for the all-to-all read this replaces.  All CTAs of the launch are resident together
+// (grid <= SMs), so the CTAs spinning in phase 2 cannot keep phase 1 from finishing.
 __global__ void __launch_bounds__(kBlock)
-xchg_reduce_kernel(const XchgArgs a, double2 *__restrict__ out) {
+xchg_reduce_kernel(const XchgArgs a, double2 *__restrict__ out, unsigned *counter) {
     if (a.ctl && a.ctl[kCtlDone] != 0.0) return;
-    if (threadIdx.x < a.nranks) {
-        volatile unsigned long long *f = a.peer[a.rank] + threadIdx.x;
-        // bounded spin: a peer that never arrives traps this rank instead of hanging the GPU
-        for (unsigned long long spin = 0; *f < a.seq; spin++)
-            if (spin > (1ull << 31)) __trap();
-    }
+    const int64_t L = (a.n2 + a.nranks - 1) / a.nranks;       // slice length in double2
+    unsigned long long *mine = a.peer[a.rank];
+    if (threadIdx.x < a.nranks) xchg_wait(mine + threadIdx.x, a.seq);
     __threadfence_system();
     __syncthreads();
-    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < a.n2;
-         i += (int64_t)gridDim.x * kBlock) {
-        double2 s = make_double2(0.0, 0.0);
-        for (int p = 0; p < a.nranks; p++) {
-            const double2 v = __ldcv(xchg_buf(a.peer[p], a) + i);
-            s.x += v.x;
-            s.y += v.y;
+    {
+        const int64_t lo = (int64_t)a.rank * L, hi = min(a.n2, lo + L);
+        double2 *res = xchg_buf(mine, a, 1);
+        for (int64_t i = lo + (int64_t)blockIdx.x * kBlock + threadIdx.x; i < hi;
+             i += (int64_t)gridDim.x * kBlock) {
+            double2 s = make_double2(0.0, 0.0);
+            for (int p = 0; p < a.nranks; p++) {
+                const double2 v = __ldcv(xchg_buf(a.peer[p], a, 0) + i);
+                s.x += v.x;
+                s.y += v.y;
+            }
+            res[i] = s;
+            out[i] = s;
         }
-        out[i] = s;
+    }
+    __shared__ bool is_last;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicInc(counter, gridDim.x - 1) == gridDim.x - 1;
+    __syncthreads();
+    if (is_last) {
+        __threadfence_system();
+        if (threadIdx.x < a.nranks) {
+            volatile unsigned long long *f = a.peer[threadIdx.x] + kXchgFlags + a.rank;
+            *f = a.seq;
+        }
+    }
+    for (int q = 1; q < a.nranks; q++) {
+        const int p = (a.rank + q) % a.nranks;                 // staggered: not everyone on rank 0 first
+        if (threadIdx.x == 0) xchg_wait(mine + kXchgFlags + p, a.seq);
+        __syncthreads();
+        __threadfence_system();
+        const int64_t lo = (int64_t)p * L, hi = min(a.n2, lo + L);
+        const double2 *src = xchg_buf(a.peer[p], a, 1);
+        for (int64_t i = lo + (int64_t)blockIdx.x * kBlock + threadIdx.x; i < hi;
+             i += (int64_t)gridDim.x * kBlock)
+            out[i] = __ldcv(src + i);
     }
 }
 

@@ -352,7 +352,7 @@ int setup_xchg(H *h) {
     cudaIpcMemHandle_t mine;
     memset(&mine, 0, sizeof(mine));
     h->xchg_stride = (((int64_t)red_len(h) * 8 + 255) / 256) * 256;
-    const size_t bytes = (size_t)vb::kXchgFlags * 8 + 2 * (size_t)h->xchg_stride;
+    const size_t bytes = (size_t)2 * vb::kXchgFlags * 8 + 4 * (size_t)h->xchg_stride;
     if (!bad) {
         if (cudaMalloc((void **)&h->d_xchg, bytes) != cudaSuccess) { h->d_xchg = nullptr; bad = 1; }
         else if (cudaMemset(h->d_xchg, 0, bytes) != cudaSuccess) bad = 1;
@@ -416,8 +416,8 @@ int allreduce_red(H *h) {
     a.ctl = h->ctl;
     vb::xchg_publish_kernel<<<64, vb::kBlock, 0, h->stream>>>(
         a, reinterpret_cast<const double2 *>(h->d_red), h->d_counters + 8);
-    vb::xchg_reduce_kernel<<<128, vb::kBlock, 0, h->stream>>>(a,
-                                                              reinterpret_cast<double2 *>(h->d_red));
+    vb::xchg_reduce_kernel<<<std::min(128, h->num_sms), vb::kBlock, 0, h->stream>>>(
+        a, reinterpret_cast<double2 *>(h->d_red), h->d_counters + 9);
     h->launches += 2;
     return 0;
 }
@@ -1111,9 +1111,8 @@ int init_common(H *h, int device) {
     if (device < 0 || device >= ndev) return fail(h, VBNMF_ERR_ARG, "bad device ordinal");
     h->device = device;
     CK(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, device));
-    h->num_sms = prop.multiProcessorCount;
+    // (cudaGetDeviceProperties fills ~100 fields and takes milliseconds; one attribute is enough)
+    CK(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     h->own_stream = true;
     {   // Keep freed blocks in the device's default pool.  With a finite threshold a large
