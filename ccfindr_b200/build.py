@@ -44,6 +44,9 @@ if os.environ.get("VBNMF_LP_IMMEDIATE"):
     NVCC_FLAGS.append("-DVB_LP_IMMEDIATE=" + os.environ["VBNMF_LP_IMMEDIATE"])
 if os.environ.get("VBNMF_DOT_CHAINS"):
     NVCC_FLAGS.append("-DVB_DOT_CHAINS=" + os.environ["VBNMF_DOT_CHAINS"])
+for _d in os.environ.get("VBNMF_DEFS", "").split():   # experiments: "VB_X=1 VB_Y=0" -> -DVB_X=1 ...
+    if _d.startswith("VB_"):
+        NVCC_FLAGS.append("-D" + _d)
 if os.environ.get("VBNMF_LP_BITS"):   # count bits of the log-product bound term (kernels.cuh)
     NVCC_FLAGS.append("-DVB_LP_BITS=" + os.environ["VBNMF_LP_BITS"])
 

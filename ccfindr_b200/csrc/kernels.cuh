@@ -720,6 +720,25 @@ struct LogProd {
 #ifndef VB_OWN_AHEAD
 #define VB_OWN_AHEAD(dflt) (dflt)
 #endif
+#ifndef VB_OWN_EARLY
+#define VB_OWN_EARLY 1    // owner rows that cannot be requested a whole segment ahead (register budget)
+                          // are requested before the cross-lane sum of the previous segment, when
+                          // the registers of the old owner row are free, instead of at segment start
+                          // (measured at C2: cell-owner pass 0.744 -> 0.708 ms)
+#endif
+#ifndef VB_OWN_RUNNING
+#define VB_OWN_RUNNING 1  // split layout: (slab, row) of the owner kept as a running pair instead of
+                          // a division per segment
+#endif
+#ifndef VB_PTR_RAW
+#define VB_PTR_RAW 0      // 1: segment pointers stay tagged until their segment starts (measured: no
+                          // gain, C3-shaped 5.61 -> 5.69 ms per iteration)
+#endif
+#ifndef VB_OWN_PF
+#define VB_OWN_PF 0       // L2 prefetch of the owner row two segments ahead: 1 = cell-owner pass (its
+                          // owner panel streams from HBM once per gene slab), 2 = both passes.
+                          // Measured SLOWER (C3-shaped cell-owner pass 3.18 -> 3.33 ms): off
+#endif
 
 // SPLIT (fp64 panels, one lane per nonzero, rows of >= 8 units; see split_rank / panel_ofs): the
 // tile is stored as block A (T x 128 bytes) + block B; lane gl gathers unit c ^ gl of block A in
@@ -747,6 +766,9 @@ sweep_p16_kernel(const SweepTiledArgs a) {
     constexpr int kRowShare = KL * (int)sizeof(PT);  // bytes of a row held per lane
     constexpr bool kOwnAhead = VB_OWN_AHEAD(
         kRowShare <= 48 || (kRowShare <= 80 && sizeof(PT) == 8 && !COLS && LPN == 1));
+    // 1: a whole segment ahead; 2: before the cross-lane sum of the previous segment (the old owner
+    // row's registers are free by then); 0: at the start of its segment
+    constexpr int kOwnMode = kOwnAhead ? 1 : (VB_OWN_EARLY ? 2 : 0);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     PT *tile = reinterpret_cast<PT *>(smem_raw);
     const uint32_t tile_s = smem_u32(tile);
@@ -771,23 +793,71 @@ sweep_p16_kernel(const SweepTiledArgs a) {
     const uint32_t rot = (uint32_t)(gl & (SA - 1)) << 4;
     if (SPLIT && (tile_s & 127u)) __trap();  // block A rows must start on SA * 16-byte boundaries
 
-    // this lane's share of an owner row: units hf, hf + LPN, ...
-    auto load_owner = [&](int64_t o, PT(&dst)[KL]) {
+    // this lane's share of an owner row: units hf, hf + LPN, ...  SPLIT: the owner panel is stored
+    // in slabs of T rows (block A, block B); (oso, olo) = slab and row in the slab of the next owner
+    // to be loaded, advanced by kGroups per segment (no division in the loop)
+    constexpr bool kOwnPf = VB_OWN_PF == 2 || (VB_OWN_PF == 1 && COLS);
+    uint32_t oso = 0, olo = 0;     // next owner to load
+    uint32_t pso = 0, plo = 0;     // owner to prefetch into L2 (two segments further)
+    auto own_seek = [&](int64_t o) {
         if constexpr (SPLIT) {
-            const uint32_t so = (uint32_t)o / (uint32_t)a.T, lo = (uint32_t)o - so * (uint32_t)a.T;
-            const PT *blk = reinterpret_cast<const PT *>(a.owner) + (int64_t)so * a.T * PS;
-            const PT *ra = blk + (int64_t)lo * (2 * SA);
-            const PT *rb = blk + (int64_t)a.T * (2 * SA) + (int64_t)lo * (RS - 2 * SA);
+            oso = (uint32_t)o / (uint32_t)a.T; olo = (uint32_t)o - oso * (uint32_t)a.T;
+            const uint32_t o2 = (uint32_t)o + 2u * kGroups;
+            pso = o2 / (uint32_t)a.T; plo = o2 - pso * (uint32_t)a.T;
+        }
+    };
+    auto own_advance = [&]() {
+        if constexpr (SPLIT && (VB_OWN_RUNNING || kOwnPf)) {
+            olo += kGroups;
+            while (olo >= (uint32_t)a.T) { olo -= (uint32_t)a.T; oso++; }
+            plo += kGroups;
+            while (plo >= (uint32_t)a.T) { plo -= (uint32_t)a.T; pso++; }
+        }
+    };
+    // o = owner index (used by the plain layout; the split layout follows (oso, olo) and advances)
+    auto load_owner = [&](int64_t o, bool doit, PT(&dst)[KL]) {
+        if constexpr (SPLIT) {
+            if (doit) {
+                if (!VB_OWN_RUNNING) {
+                    oso = (uint32_t)o / (uint32_t)a.T; olo = (uint32_t)o - oso * (uint32_t)a.T;
+                }
+                const PT *blk = reinterpret_cast<const PT *>(a.owner) + (int64_t)oso * a.T * PS;
+                const PT *ra = blk + (int64_t)olo * (2 * SA);
+                const PT *rb = blk + (int64_t)a.T * (2 * SA) + (int64_t)olo * (RS - 2 * SA);
 #pragma unroll
-            for (int c = 0; c < SA; c++) ldg_unit(ra, c ^ (gl & (SA - 1)), dst + c * UE);
+                for (int c = 0; c < SA; c++) ldg_unit(ra, c ^ (gl & (SA - 1)), dst + c * UE);
 #pragma unroll
-            for (int c = 0; c < NUB; c++) ldg_unit(rb, c, dst + (SA + c) * UE);
+                for (int c = 0; c < NUB; c++) ldg_unit(rb, c, dst + (SA + c) * UE);
+            }
+            own_advance();
         } else {
-            const PT *orow = reinterpret_cast<const PT *>(a.owner) + o * PS;
+            if (doit) {
+                const PT *orow = reinterpret_cast<const PT *>(a.owner) + o * PS;
 #pragma unroll
-            for (int c = 0; c < NUL; c++) {
-                const int u = LPN * c + hf;
-                if (LPN == 1 || u < NU) ldg_unit(orow, u, dst + c * UE);
+                for (int c = 0; c < NUL; c++) {
+                    const int u = LPN * c + hf;
+                    if (LPN == 1 || u < NU) ldg_unit(orow, u, dst + c * UE);
+                }
+            }
+        }
+    };
+    // L2 prefetch of the owner row two segments ahead (one lane per group; rows past the end of the
+    // panel are not requested)
+    auto prefetch_owner = [&](int64_t o2) {
+        if constexpr (kOwnPf) {
+            if constexpr (SPLIT) {
+                if (gl == 0 && (int64_t)pso * a.T + plo < a.NO) {
+                    const PT *blk = reinterpret_cast<const PT *>(a.owner) + (int64_t)pso * a.T * PS;
+                    prefetch_l2(blk + (int64_t)plo * (2 * SA));
+                    if (NUB > 0)
+                        prefetch_l2(blk + (int64_t)a.T * (2 * SA) + (int64_t)plo * (RS - 2 * SA));
+                }
+            } else {
+                if (gl == 0 && o2 < a.NO) {
+                    const PT *orow = reinterpret_cast<const PT *>(a.owner) + o2 * PS;
+                    prefetch_l2(orow);
+                    if (PS * sizeof(PT) > 128) prefetch_l2(reinterpret_cast<const char *>(orow) + 128);
+                }
             }
         }
     };
@@ -805,26 +875,29 @@ sweep_p16_kernel(const SweepTiledArgs a) {
                      tile_bytes, &mbar);
         }
         // prime the group's pipeline while the tile lands: pointers of its first two segments,
-        // first quad and owner row of the first
+        // first quad and owner row of the first.  Pointers stay as loaded ("raw", with the tag of
+        // the split layout) until the segment they belong to starts: nothing waits on a load it
+        // has just issued.
         int64_t e = ebase + gid;
-        uint32_t beg = 0, end = 0, nb = 0, ne = 0;
-        uint32_t dead = 0, ndead = 0, nndead = 0;  // all-hole steps at the end of the segment (SPLIT)
+        uint32_t beg = 0, end = 0, nbr = 0, ner = 0;
+        uint32_t dead = 0;  // all-hole steps at the end of the segment (SPLIT)
+        uint32_t ndead_ = 0, nndead_ = 0;  // (!VB_PTR_RAW: tags split off at load time)
         constexpr uint32_t kTag = SPLIT ? 3u : 0u;
         uint4 f0 = make_uint4(0u, 0u, 0u, 0u);
         PT ownn[KL];
 #pragma unroll
         for (int k = 0; k < KL; k++) ownn[k] = 0;
         if (e < eend) {
-            beg = __ldg(a.ptr4 + e);
-            end = __ldg(a.ptr4 + e + 1) & ~kTag;
-            dead = beg & kTag; beg &= ~kTag;
+            const uint32_t b0 = __ldg(a.ptr4 + e), e0r = __ldg(a.ptr4 + e + 1);
             if (e + kGroups < eend) {
-                nb = __ldg(a.ptr4 + e + kGroups);
-                ne = __ldg(a.ptr4 + e + kGroups + 1) & ~kTag;
-                ndead = nb & kTag; nb &= ~kTag;
+                nbr = __ldg(a.ptr4 + e + kGroups);
+                ner = __ldg(a.ptr4 + e + kGroups + 1);
+                if (!VB_PTR_RAW) { ndead_ = nbr & kTag; nbr &= ~kTag; ner &= ~kTag; }
             }
+            own_seek(e - slab * a.NO);
+            beg = b0 & ~kTag; end = e0r & ~kTag; dead = b0 & kTag;
             if (beg + slot < end) f0 = ldcs_quad(ent4 + beg + slot);
-            if (kOwnAhead && beg < end) load_owner(e - slab * a.NO, ownn);
+            if (kOwnMode != 0) load_owner(e - slab * a.NO, beg < end, ownn);
         }
         mbar_wait(&mbar, parity);
         parity ^= 1;
@@ -836,21 +909,25 @@ sweep_p16_kernel(const SweepTiledArgs a) {
             PT own[KL];
 #pragma unroll
             for (int k = 0; k < KL; k++) own[k] = ownn[k];
-            if (!kOwnAhead && nq > 0) load_owner(e - slab * a.NO, own);
+            if constexpr (SPLIT) prefetch_owner(0);
+            else prefetch_owner(e - slab * a.NO + 2 * kGroups);
+            if (kOwnMode == 0) load_owner(e - slab * a.NO, nq > 0, own);
             uint4 n1 = make_uint4(0u, 0u, 0u, 0u);
             if (NPG + slot < nq) n1 = ldcs_quad(eb + NPG + slot);
             // requests for the NEXT segment (pointers arrived during the previous one) and the
             // pointers of the one after it
-            uint32_t nnb = 0, nne = 0;
+            if (!VB_PTR_RAW) { ner &= ~kTag; }
+            const uint32_t nb = nbr & ~kTag, ne = ner & ~kTag;
+            uint32_t nnbr = 0, nner = 0;
             f0 = make_uint4(0u, 0u, 0u, 0u);
             if (en < eend) {
                 if (en + kGroups < eend) {
-                    nnb = __ldg(a.ptr4 + en + kGroups);
-                    nne = __ldg(a.ptr4 + en + kGroups + 1) & ~kTag;
-                    nndead = nnb & kTag; nnb &= ~kTag;
+                    nnbr = __ldg(a.ptr4 + en + kGroups);
+                    nner = __ldg(a.ptr4 + en + kGroups + 1);
+                    if (!VB_PTR_RAW) { nndead_ = nnbr & kTag; nnbr &= ~kTag; nner &= ~kTag; }
                 }
                 if (nb + slot < ne) f0 = ldcs_quad(ent4 + nb + slot);
-                if (kOwnAhead && nb < ne) load_owner(en - slab * a.NO, ownn);
+                if (kOwnMode == 1) load_owner(en - slab * a.NO, nb < ne, ownn);
                 if (gl == 0 && nb + NPG < ne)
                     bulk_prefetch_l2(ent4 + nb + NPG, (ne - nb - NPG) * 16u);
             }
@@ -936,6 +1013,7 @@ sweep_p16_kernel(const SweepTiledArgs a) {
             }
             if (kLogProd) lp.end_segment();
             else if (COLS) xl += (double)xls;
+            if (kOwnMode == 2 && en < eend) load_owner(en - slab * a.NO, nb < ne, ownn);
             // sum over the lanes that hold the same rank entries (fp64), recursive halving
             double *out = a.Part + e * RS;
             double v0[KL];
@@ -996,8 +1074,8 @@ sweep_p16_kernel(const SweepTiledArgs a) {
             }
             }
             e = en;
-            beg = nb; end = ne; dead = ndead;
-            nb = nnb; ne = nne; ndead = nndead;
+            beg = nb; end = ne; dead = VB_PTR_RAW ? (nbr & kTag) : ndead_;
+            nbr = nnbr; ner = nner; ndead_ = nndead_;
         }
         ebase = eend;
     }
