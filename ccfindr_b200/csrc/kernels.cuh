@@ -55,8 +55,14 @@ __host__ __device__ constexpr int panel_stride(int rp) {
 // ---- split layout of the gathered fp64 panels (lw, lh) -----------------------------------------
 // Rows gathered by one lane per nonzero are stored per slab of T rows as two blocks: A = the first
 // SA sixteen-byte units of every row with row stride exactly SA units (SA = 8 for ranks 16..20,
-// 4 for ranks 8..14), then B = T x (RS - 2 SA) doubles (the remaining units; stride an odd number
-// of units or a single unit).
+// 4 for ranks 8..14), then B = T x split_bs(rp) doubles (the remaining units).
+//   SA = 8: block B is dense, RP - 16 doubles per row (0, 1 or 2 units), so a slab is T x RP
+//     doubles.  With 2 units (ranks 19, 20) a row of block B covers bank groups 2 (i mod 4) and
+//     2 (i mod 4) + 1: four residue classes of TWO lanes each -- lanes l and l + 4 hold rows of
+//     class l mod 4, lane l reads unit 8 first and unit 9 second, lane l + 4 the other way round
+//     (the registers of block B are rotated by bit 2 of the lane like those of block A by the
+//     whole lane index), so a step with at most two rows per class is conflict free.
+//   SA = 4: RS - 8 doubles per row (stride an odd number of units or a single unit).
 //   SA = 8: a row of block A presents the 8 bank groups of shared memory identically, so the 8
 //     lanes of a group, reading unit (c XOR lane) of THEIR row in step c, hit 8 different bank
 //     groups whatever the rows are: conflict free with no scheduling at all.
@@ -69,12 +75,22 @@ __host__ __device__ constexpr int split_units(int rp) {
     return rp * 8 > VB_LPN_BYTES ? 0 : (rp >= 16 ? 8 : (rp >= 8 ? 4 : 0));
 }
 __host__ __device__ constexpr bool split_rank(int rp) { return split_units(rp) != 0; }
+// doubles per row of block B, and of a whole row of the split layout
+__host__ __device__ constexpr int split_bs(int rp) {
+    return split_units(rp) == 8 ? rp - 16 : (split_units(rp) == 4 ? row_stride(rp) - 8 : 0);
+}
+__host__ __device__ constexpr int split_ps(int rp) {
+    return split_units(rp) ? 2 * split_units(rp) + split_bs(rp) : row_stride(rp);
+}
+// tsplit = 0: plain rows of rs doubles; else T | (doubles per row of block B) << 16
+__host__ __device__ constexpr int make_tsplit(int T, int rp) { return T | (split_bs(rp) << 16); }
 __host__ __device__ __forceinline__ int64_t panel_ofs(int64_t row, int k, int rs, int tsplit) {
     if (tsplit == 0) return row * rs + k;
     const int aw = rs >= 18 ? 16 : 8;  // doubles of block A (rs 10, 14: ranks 8..14; 18, 22: 16..20)
-    const int64_t slab = row / tsplit, local = row - slab * tsplit;
-    return slab * tsplit * rs +
-           (k < aw ? local * aw + k : (int64_t)tsplit * aw + local * (rs - aw) + (k - aw));
+    const int T = tsplit & 0xffff, bs = tsplit >> 16;
+    const int64_t slab = row / T, local = row - slab * T;
+    return slab * T * (aw + bs) +
+           (k < aw ? local * aw + k : (int64_t)T * aw + local * bs + (k - aw));
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -756,7 +772,11 @@ sweep_p16_kernel(const SweepTiledArgs a) {
                   "split layout: fp64 panels, one lane per nonzero, 4..10 units per row");
     constexpr int SA = SPLIT ? split_units(RP) : 8;          // units of block A (8 or 4)
     constexpr int NUB = SPLIT ? Cfg::kNU - SA : 0;           // units of block B
-    constexpr int BSB = SPLIT ? (RS - 2 * SA) * 8 : 0;       // bytes per row of block B
+    constexpr int BSD = SPLIT ? split_bs(RP) : 0;            // doubles per row of block B
+    constexpr int BSB = BSD * 8;                             // ... bytes
+    constexpr int PSS = SPLIT ? split_ps(RP) : PS;           // doubles per row of a slab
+    // block B of two dense units: registers rotated by bit 2 of the lane (see split layout above)
+    constexpr bool kRotB = SPLIT && SA == 8 && NUB == 2 && BSD == 4;
     constexpr int NT = Cfg::p16_threads(COLS);
     constexpr int UE = Cfg::kUE, NU = Cfg::kNU, LPN = Cfg::kLPN, NUL = Cfg::kNUL, KL = Cfg::kKL;
     constexpr int NPG = Cfg::kNPG;
@@ -778,7 +798,7 @@ sweep_p16_kernel(const SweepTiledArgs a) {
     const int slot = gl / LPN, hf = gl % LPN;
     const unsigned gmask = 0xffu << ((threadIdx.x & 31) & ~(kGroup - 1));
     const int64_t e0 = a.split[blockIdx.x], e1 = a.split[blockIdx.x + 1];
-    const unsigned tile_bytes = (unsigned)a.T * PS * (unsigned)sizeof(PT);
+    const unsigned tile_bytes = (unsigned)a.T * PSS * (unsigned)sizeof(PT);
     const uint4 *ent4 = reinterpret_cast<const uint4 *>(a.ent);
     if (a.ctl && a.ctl[kCtlDone] != 0.0) return;
     if (threadIdx.x == 0) mbar_init(&mbar, 1);
@@ -791,6 +811,7 @@ sweep_p16_kernel(const SweepTiledArgs a) {
 
     const uint32_t tileB_s = tile_s + (uint32_t)a.T * (uint32_t)(SA * 16);
     const uint32_t rot = (uint32_t)(gl & (SA - 1)) << 4;
+    const uint32_t rotb = kRotB ? (uint32_t)((gl >> 2) & 1) << 4 : 0u;
     if (SPLIT && (tile_s & 127u)) __trap();  // block A rows must start on SA * 16-byte boundaries
 
     // this lane's share of an owner row: units hf, hf + LPN, ...  SPLIT: the owner panel is stored
@@ -821,13 +842,14 @@ sweep_p16_kernel(const SweepTiledArgs a) {
                 if (!VB_OWN_RUNNING) {
                     oso = (uint32_t)o / (uint32_t)a.T; olo = (uint32_t)o - oso * (uint32_t)a.T;
                 }
-                const PT *blk = reinterpret_cast<const PT *>(a.owner) + (int64_t)oso * a.T * PS;
+                const PT *blk = reinterpret_cast<const PT *>(a.owner) + (int64_t)oso * a.T * PSS;
                 const PT *ra = blk + (int64_t)olo * (2 * SA);
-                const PT *rb = blk + (int64_t)a.T * (2 * SA) + (int64_t)olo * (RS - 2 * SA);
+                const PT *rb = blk + (int64_t)a.T * (2 * SA) + (int64_t)olo * BSD;
 #pragma unroll
                 for (int c = 0; c < SA; c++) ldg_unit(ra, c ^ (gl & (SA - 1)), dst + c * UE);
 #pragma unroll
-                for (int c = 0; c < NUB; c++) ldg_unit(rb, c, dst + (SA + c) * UE);
+                for (int c = 0; c < NUB; c++)
+                    ldg_unit(rb, kRotB ? (c ^ ((gl >> 2) & 1)) : c, dst + (SA + c) * UE);
             }
             own_advance();
         } else {
@@ -847,10 +869,9 @@ sweep_p16_kernel(const SweepTiledArgs a) {
         if constexpr (kOwnPf) {
             if constexpr (SPLIT) {
                 if (gl == 0 && (int64_t)pso * a.T + plo < a.NO) {
-                    const PT *blk = reinterpret_cast<const PT *>(a.owner) + (int64_t)pso * a.T * PS;
+                    const PT *blk = reinterpret_cast<const PT *>(a.owner) + (int64_t)pso * a.T * PSS;
                     prefetch_l2(blk + (int64_t)plo * (2 * SA));
-                    if (NUB > 0)
-                        prefetch_l2(blk + (int64_t)a.T * (2 * SA) + (int64_t)plo * (RS - 2 * SA));
+                    if (NUB > 0) prefetch_l2(blk + (int64_t)a.T * (2 * SA) + (int64_t)plo * BSD);
                 }
             } else {
                 if (gl == 0 && o2 < a.NO) {
@@ -871,7 +892,7 @@ sweep_p16_kernel(const SweepTiledArgs a) {
         __syncthreads();
         if (threadIdx.x == 0) {
             mbar_expect_tx(&mbar, tile_bytes);
-            bulk_g2s(tile, reinterpret_cast<const PT *>(a.tiles) + slab * (int64_t)a.T * PS,
+            bulk_g2s(tile, reinterpret_cast<const PT *>(a.tiles) + slab * (int64_t)a.T * PSS,
                      tile_bytes, &mbar);
         }
         // prime the group's pipeline while the tile lands: pointers of its first two segments,
@@ -952,11 +973,13 @@ sweep_p16_kernel(const SweepTiledArgs a) {
                         if (!VB_SPLIT_PRED || (v >> 16)) {  // a hole keeps the previous row: no shared-memory traffic
                             const uint32_t row = v & 0xffffu;
                             const uint32_t ra = (tile_s + row * (uint32_t)(SA * 16)) ^ rot;
-                            const uint32_t rb = tileB_s + row * (uint32_t)BSB;
+                            const uint32_t rb = (tileB_s + row * (uint32_t)BSB) ^ rotb;
 #pragma unroll
                             for (int c = 0; c < SA; c++) lds_unit(ra ^ (uint32_t)(c << 4), tr + c * UE);
 #pragma unroll
-                            for (int c = 0; c < NUB; c++) lds_unit(rb + c * 16, tr + (SA + c) * UE);
+                            for (int c = 0; c < NUB; c++)
+                                lds_unit(kRotB ? (rb ^ (uint32_t)(c << 4)) : (rb + c * 16),
+                                         tr + (SA + c) * UE);
                         }
                     } else {
                         const uint32_t raddr = tile_s + (v & 0xffffu) * (uint32_t)(PS * sizeof(PT));
@@ -1043,7 +1066,21 @@ sweep_p16_kernel(const SweepTiledArgs a) {
                     if (gl < 4 && 2 * gl < RP)
                         *reinterpret_cast<double2 *>(out + 2 * gl) = make_double2(a2[0], a2[1]);
                 }
-                if constexpr (NUB > 0) {
+                if constexpr (kRotB) {
+                    // register unit c of lane gl is rank unit 8 + (c ^ h), h = bit 2 of gl: the
+                    // partner gl ^ 4 holds my unit of register 0 in its register 1; then the four
+                    // lanes of equal h hold the same unit and halve its two doubles
+                    double b1[2];
+#pragma unroll
+                    for (int k = 0; k < 2; k++)
+                        b1[k] = v0[2 * SA + k] + __shfl_xor_sync(gmask, v0[2 * SA + 2 + k], 4);
+                    const bool hi2 = (gl & 2) != 0;
+                    double b2 = (hi2 ? b1[1] : b1[0]) + __shfl_xor_sync(gmask, hi2 ? b1[0] : b1[1], 2);
+                    b2 += __shfl_xor_sync(gmask, b2, 1);
+                    // lane gl: rank entry 16 + 2 * h + (bit 1 of gl)
+                    const int kk = 2 * SA + 2 * ((gl >> 2) & 1) + ((gl >> 1) & 1);
+                    if ((gl & 1) == 0 && kk < RP) out[kk] = b2;
+                } else if constexpr (NUB > 0) {
                     double vb[2 * NUB];
 #pragma unroll
                     for (int k = 0; k < 2 * NUB; k++) vb[k] = v0[2 * SA + k];
@@ -1115,7 +1152,9 @@ combine_kernel(int64_t NO, int nslabs, int r, const double *__restrict__ Part,
         }
         if (k2 >= RP) s = make_double2(0.0, 0.0);
         *reinterpret_cast<double2 *>(SRaw + o * RS + k2) = s;
-        const double2 lv = *reinterpret_cast<const double2 *>(l + panel_ofs(o, k2, RS, tsplit));
+        // (a row of the split layout ends at RP: the padding columns of SRaw have no l)
+        const double2 lv = k2 < RP ? *reinterpret_cast<const double2 *>(l + panel_ofs(o, k2, RS, tsplit))
+                                   : make_double2(0.0, 0.0);
         if (k2 < r && lv.x > 0.0) ent += log(lv.x) * lv.x * s.x;
         if (k2 + 1 < r && lv.y > 0.0) ent += log(lv.y) * lv.y * s.y;
     }
@@ -1211,7 +1250,7 @@ posterior_kernel(int64_t rows, int T, int S, int64_t nvalid, int r, double a, do
             prior += -aob * e + al * (1.0 - lbe) + lg_al;
         }
         if (valid) {
-            l[lo] = ln;
+            if (k < RP || tsplit == 0) l[lo] = ln;  // a row of the split layout ends at RP
             al_out[row * RS + k] = al;
             if (l32 && k < row_stride_f32(RP)) l32[row * row_stride_f32(RP) + k] = (float)ln;
         }
@@ -1278,7 +1317,7 @@ ml_update_kernel(int64_t rows, int T, int S, int64_t nvalid, int r, double eps,
             if (x < eps) x = eps;
             es += x;
         }
-        v[lo] = x;
+        if (k < RP || tsplit == 0) v[lo] = x;  // a row of the split layout ends at RP
         if (l32 && k < row_stride_f32(RP)) l32[row * row_stride_f32(RP) + k] = (float)x;
     }
     colbuf[threadIdx.x] = es;

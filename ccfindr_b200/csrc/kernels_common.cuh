@@ -378,10 +378,29 @@ __device__ __forceinline__ void warp_residue_counts(const uint32_t *__restrict__
 
 // quads (4 entries = 16 bytes) of every segment under the schedule above; len4[E] = 0.
 // One warp per segment.
+// Schedule modes of the 8-lane layouts.  kSchedPlain: eight residue classes (row mod 8), one lane
+// each.  kSchedSbs: two parity classes side by side (4-unit split layout).  kSchedCls4: four
+// classes (row mod 4) of TWO lanes each (split layout with two dense units in block B, ranks 19
+// and 20): the nonzeros of class c are dealt alternately to the "virtual residues" c and c + 4,
+// which are then scheduled like eight residue classes -- lane l of a single step holds a row of
+// class l mod 4, and lanes l, l + 4 read the two units of their rows in opposite order.
+enum { kSchedPlain = 0, kSchedSbs = 1, kSchedCls4 = 2 };
+
+// counts per real residue -> counts per virtual residue (kSchedCls4)
+__device__ __forceinline__ void virtual_counts(int (&cnt)[8]) {
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+        const int c4 = cnt[b] + cnt[b + 4];
+        cnt[b] = (c4 + 1) >> 1;
+        cnt[b + 4] = c4 >> 1;
+    }
+}
+
 __global__ void __launch_bounds__(kBlock)
 plan_p16_kernel(int64_t E, const int64_t *__restrict__ ptr, const uint32_t *__restrict__ words,
-                int NL, int kmult, bool sbs, uint32_t *__restrict__ len4,
+                int NL, int kmult, int mode, uint32_t *__restrict__ len4,
                 uint8_t *__restrict__ dead) {
+    const bool sbs = mode == kSchedSbs;
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * kBlock + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * kBlock) >> 5;
@@ -391,6 +410,7 @@ plan_p16_kernel(int64_t E, const int64_t *__restrict__ ptr, const uint32_t *__re
         if (beg == end) { if (lane == 0) { len4[e] = 0u; if (dead) dead[e] = 0; } continue; }
         int cnt[8];
         warp_residue_counts(words, beg, end, lane, cnt);
+        if (mode == kSchedCls4) virtual_counts(cnt);
         int n0 = 0, n1 = 0, L0 = 0, L1 = 0;
         const int NLs = sbs ? 4 : NL;
 #pragma unroll
@@ -426,8 +446,9 @@ __device__ __forceinline__ int64_t p16_position(int64_t p, int NL) {
 __global__ void __launch_bounds__(kBlock)
 build_segments_p16_kernel(int64_t E, int64_t NO, const int64_t *__restrict__ ptr,
                           const uint32_t *__restrict__ ptr4, const uint32_t *__restrict__ words,
-                          int NL, int kmult, bool sbs, int64_t nvalid, int S,
+                          int NL, int kmult, int mode, int64_t nvalid, int S,
                           uint32_t *__restrict__ ent_out) {
+    const bool sbs = mode == kSchedSbs, cls4 = mode == kSchedCls4;
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
     const int64_t warp = ((int64_t)blockIdx.x * kBlock + threadIdx.x) >> 5;
@@ -438,15 +459,18 @@ build_segments_p16_kernel(int64_t E, int64_t NO, const int64_t *__restrict__ ptr
         uint32_t *dst = ent_out + (int64_t)ptr4[e] * 4;
         const int nitems = (int)(ptr4[e + 1] - ptr4[e]) * 4;
         const int64_t slab = e / NO;
-        int cnt[8];
+        int cnt[8], cntv[8];
         warp_residue_counts(words, beg, end, lane, cnt);
+#pragma unroll
+        for (int b = 0; b < 8; b++) cntv[b] = cnt[b];
+        if (cls4) virtual_counts(cntv);
         SegSchedule sc;
-        make_schedule(cnt, NL, kmult, sbs, sc);
+        make_schedule(cntv, NL, kmult, sbs, sc);
         // holes: lane <-> bucket in the single steps, so the residue of the lane's bucket is free
         for (int p = lane; p < nitems; p += 32) {
             const int step = p / NL, ln = p - step * NL;
             const int cl = sbs ? (ln >> 2) : ((NL != 8 && step >= sc.K[0]) ? 1 : 0);
-            int rr = sbs ? 2 * (ln & 3) + cl : bucket_res(cl, ln, NL);
+            int rr = sbs ? 2 * (ln & 3) + cl : (cls4 ? (ln & 3) : bucket_res(cl, ln, NL));
             if ((int64_t)rr * S + slab >= nvalid) rr = 0;
             dst[p16_position(p, NL)] = (uint32_t)rr;
         }
@@ -466,7 +490,14 @@ build_segments_p16_kernel(int64_t E, int64_t NO, const int64_t *__restrict__ ptr
                 if (rr == b) k = seen[b] + __popc(mk & lt);
                 seen[b] += __popc(mk);
             }
-            if (valid) dst[p16_position(schedule_item(sc, NL, sbs, rr, k), NL)] = w;
+            int vr = rr, vk = k;
+            if (cls4 && valid) {
+                // rank in the class (rows = c mod 4: residues c, then c + 4), dealt alternately
+                const int kc = rr < 4 ? k : cnt[rr - 4] + k;
+                vr = (rr & 3) + 4 * (kc & 1);
+                vk = kc >> 1;
+            }
+            if (valid) dst[p16_position(schedule_item(sc, NL, sbs, vr, vk), NL)] = w;
         }
         __syncwarp();
     }

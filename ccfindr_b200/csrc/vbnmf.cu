@@ -148,7 +148,7 @@ struct Layout {
     int T = 0, Sg = 0, Sc = 0;
     int npg = 0;  // packed-16 layout: nonzeros per group step it was ordered for (0: 8-byte layout)
     int kmult = 4;  // packed-16 layout: the schedule's step count is a multiple of this (4 or 1)
-    bool sbs = false;  // packed-16 layout: parity classes side by side (4-unit split layout)
+    int mode = 0;  // packed-16 layout: schedule mode (vb::kSchedPlain / kSchedSbs / kSchedCls4)
     int64_t NG = 0, NC = 0;
     int32_t *d_gene_dev = nullptr, *d_cell_dev = nullptr;  // original index -> device row
     PassLayout cols, rows;
@@ -498,7 +498,7 @@ int build_pass(H *h, Layout *L, bool cols_pass, const int32_t *d_colof, uint32_t
         const uint32_t *d_words = p_out;  // the sorted payloads are the packed words
         { StageTimer t1("  plan(p16)");
         vb::plan_p16_kernel<<<g, vb::kBlock, 0, h->stream>>>(P.E, P.d_ptr, d_words, L->npg,
-                                                             L->kmult, L->sbs, d_len4, d_dead); }
+                                                             L->kmult, L->mode, d_len4, d_dead); }
         size_t scan_bytes = 0;
         CK(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, d_len4, P.d_ptr4, P.E + 1, h->stream));
         void *d_scan = nullptr;
@@ -514,7 +514,7 @@ int build_pass(H *h, Layout *L, bool cols_pass, const int32_t *d_colof, uint32_t
         P.nent = (int64_t)quads * 4;
         { StageTimer t1("  build_segments(p16)");
         vb::build_segments_p16_kernel<<<g, vb::kBlock, 0, h->stream>>>(
-            P.E, NO, P.d_ptr, P.d_ptr4, d_words, L->npg, L->kmult, L->sbs, cols_pass ? h->n : h->m,
+            P.E, NO, P.d_ptr, P.d_ptr4, d_words, L->npg, L->kmult, L->mode, cols_pass ? h->n : h->m,
             cols_pass ? L->Sg : L->Sc, (uint32_t *)P.d_ent); }
         CK(vmalloc(h, &P.d_split, (size_t)(L->grid + 1) * 8));
         // per-segment overhead in quads (VBNMF_SPLIT_KAPPA: tuning)
@@ -558,17 +558,17 @@ void launch_expand_cols(H *h, int32_t *d_colof, unsigned long long *d_cnt, unsig
         d_cnt ? d_cnt + h->n : nullptr, d_bad);
 }
 
-int get_layout(H *h, int T, int npg, int kmult, bool sbs, Layout **out) {
+int get_layout(H *h, int T, int npg, int kmult, int mode, Layout **out) {
     if (!h->p16) npg = 0;
-    if (npg != 8) { kmult = 4; sbs = false; }
+    if (npg != 8) { kmult = 4; mode = vb::kSchedPlain; }
     for (Layout *l : h->layouts)
-        if (l->T == T && l->npg == npg && l->kmult == kmult && l->sbs == sbs) { *out = l; return 0; }
+        if (l->T == T && l->npg == npg && l->kmult == kmult && l->mode == mode) { *out = l; return 0; }
     StageTimer tm("get_layout(total)");
     Layout *L = new Layout();
     L->T = T;
     L->npg = npg;
     L->kmult = kmult;
-    L->sbs = sbs;
+    L->mode = mode;
     L->Sg = cdiv(h->n, T);
     L->Sc = cdiv(h->m, T);
     L->NG = (int64_t)L->Sg * T;
@@ -704,13 +704,11 @@ int alloc_panels(H *h, int r) {
     if (!tab) return fail(h, VBNMF_ERR_ARG, "no kernels compiled for this rank");
     const int rs = tab->rs;
     const bool f32 = h->precision == VBNMF_FP32_STORAGE;
-    const int row_bytes = f32 ? tab->rsf * 4 : rs * 8;
     // R/bayesian.R:244-245 (for a sharded matrix the test was made on the global gene counts)
     if (!getenv("VBNMF_ALLOW_EMPTY")) {
         if (h->empty_rows) return fail(h, VBNMF_ERR_EMPTY, "Input matrix contains empty rows");
         if (h->empty_cols) return fail(h, VBNMF_ERR_EMPTY, "Input matrix contains empty columns");
     }
-    const int T = choose_tile_rows(h, row_bytes);
     // split layout + rotated gathers: fp64 panels, packed-16 entries, rows of 4..10 units
     // (tab->split64 = units of block A: 8 for ranks 16..20, 4 for ranks 8..14)
     // The 4-unit variant is opt-in (VBNMF_SPLIT4=1): measured at C2 (r = 10) it is SLOWER than the
@@ -719,10 +717,18 @@ int alloc_panels(H *h, int r) {
     // the LSU pipe, and the rotated addresses add one LOP3 per unit.
     const bool split = !f32 && h->p16 && tab->split64 && !getenv("VBNMF_NO_SPLIT") &&
                        (tab->split64 == 8 || getenv("VBNMF_SPLIT4"));
+    // a slab row of the split layout is block A + a dense block B (kernels.cuh split_ps)
+    const int row_bytes = f32 ? tab->rsf * 4 : (split ? vb::split_ps(rp) * 8 : rs * 8);
+    const int T = choose_tile_rows(h, row_bytes);
     Layout *L = nullptr;
     int kmult = split ? 1 : 4;
     if (const char *e = getenv("VBNMF_KMULT")) kmult = atoi(e) == 1 ? 1 : 4;  // experiments
-    int rc = get_layout(h, T, f32 ? tab->npg32 : tab->npg64, kmult, split && tab->split64 == 4, &L);
+    // schedule of block B: parity classes side by side (4-unit block A), four classes of two
+    // lanes (8-unit block A + two dense units: ranks 19, 20), else eight residue classes
+    int mode = vb::kSchedPlain;
+    if (split && tab->split64 == 4) mode = vb::kSchedSbs;
+    else if (split && vb::split_bs(rp) == 4 && !getenv("VBNMF_NO_CLS4")) mode = vb::kSchedCls4;
+    int rc = get_layout(h, T, f32 ? tab->npg32 : tab->npg64, kmult, mode, &L);
     if (rc) return rc;
     if (rp == h->rp && L == h->L && h->d_lw && h->panel_precision == h->precision) {
         h->r = r;
@@ -731,7 +737,7 @@ int alloc_panels(H *h, int r) {
     free_panels(h);
     h->tab = tab;
     h->L = L;
-    h->tsplit = split ? T : 0;
+    h->tsplit = split ? vb::make_tsplit(T, rp) : 0;
     h->r = r; h->rp = rp; h->rs = rs; h->rsf = tab->rsf;
     h->panel_precision = h->precision;
     h->smem_bytes = T * row_bytes;

@@ -111,3 +111,41 @@ def wavefronts(cnt8, NL, kmult=4):
         for s in range(K):
             assert not (mult[s, 0::2].any() and mult[s, 1::2].any())
     return K, int(np.maximum(mult.max(axis=1), 1).sum())
+
+
+def virtual_counts(cnt8):
+    """kSchedCls4 (split layout with two dense units in block B, ranks 19 and 20): four classes
+    (row mod 4) of two lanes each; the nonzeros of class c are dealt alternately to the virtual
+    residues c and c + 4, which are scheduled like eight residue classes."""
+    v = [0] * 8
+    for b in range(4):
+        c4 = cnt8[b] + cnt8[b + 4]
+        v[b], v[b + 4] = (c4 + 1) // 2, c4 // 2
+    return v
+
+
+def wavefronts_cls4(rows, kmult=1):
+    """(steps K, wavefronts of the two block-B gathers) for the tile rows of one segment.  Lane l of
+    a step reads unit (c XOR (l >> 2)) of block B in gather c; a row of block B (32 bytes) covers
+    the bank groups 2 (row mod 4) and 2 (row mod 4) + 1."""
+    rows = list(rows)
+    cnt8 = np.bincount(np.asarray(rows, dtype=int) % 8, minlength=8).tolist()
+    sc = make_schedule(virtual_counts(cnt8), 8, kmult)
+    K = sc["K"][0]
+    bg = np.zeros((2, K, 8), dtype=int)
+    seen = set()
+    rank = {}
+    # rank in the class: residues c first, then c + 4 (the device code's order)
+    for rr in list(range(4)) + list(range(4, 8)):
+        for row in [x for x in rows if x % 8 == rr]:
+            c = row % 4
+            kc = rank.get(c, 0)
+            rank[c] = kc + 1
+            p = schedule_item(sc, 8, c + 4 * (kc & 1), kc >> 1)
+            assert 0 <= p < K * 8 and p not in seen
+            seen.add(p)
+            step, lane = divmod(p, 8)
+            for g in range(2):
+                bg[g, step, (2 * c + (g ^ (lane >> 2))) % 8] += 1
+    w = int(np.maximum(bg.max(axis=2), 1).sum()) if K else 0
+    return K, w

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 from hypothesis import given, settings, strategies as st
 
-from schedule_model import make_schedule, wavefronts, wavefronts_sbs
+from schedule_model import make_schedule, wavefronts, wavefronts_sbs, wavefronts_cls4
 
 counts = st.lists(st.integers(min_value=0, max_value=90), min_size=8, max_size=8).filter(lambda c: sum(c) > 0)
 
@@ -113,3 +113,30 @@ def test_four_unit_split_cost_model():
         new += 4 * wa + 1 * wb
         ideal += 5 * sum(cnt) / 8
     assert old / ideal > 1.22 and new / ideal < 1.13
+
+
+def test_four_classes_of_two_lanes_cost_model():
+    """r = 20 with a dense block B (rows of exactly 160 bytes, T = 1440 instead of 1312): block A
+    costs one wavefront per step, block B is scheduled in four classes of two lanes.  Against the
+    eight residue classes of the padded block B (stride 3 units)."""
+    rng = np.random.default_rng(3)
+    old = new = ideal_old = ideal_new = 0.0
+    for _ in range(400):
+        rows = rng.choice(1312, size=rng.binomial(1312, 0.08), replace=False)
+        cnt = np.bincount(rows % 8, minlength=8).tolist()
+        K1, w1 = wavefronts(cnt, 8, kmult=1)
+        old += 8 * K1 + 2 * w1
+        ideal_old += 10 * len(rows) / 8
+        rows = rng.choice(1440, size=rng.binomial(1440, 0.08), replace=False)
+        K, wb = wavefronts_cls4(rows)
+        assert K == max((len(rows) + 7) // 8, 1) or K > (len(rows) + 7) // 8
+        new += 8 * K + wb
+        ideal_new += 10 * len(rows) / 8
+    assert old / ideal_old > 1.09 and new / ideal_new < 1.08
+
+
+@settings(max_examples=200, deadline=None)
+@given(st.lists(st.integers(min_value=0, max_value=1439), min_size=1, max_size=300, unique=True))
+def test_four_class_schedule_places_every_nonzero_once(rows):
+    K, wb = wavefronts_cls4(rows)
+    assert K * 8 >= len(rows) and 2 * K <= wb <= 8 * K
