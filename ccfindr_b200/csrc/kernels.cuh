@@ -243,6 +243,23 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
 #ifndef VB_WIDE_THREADS
 #define VB_WIDE_THREADS 256  // ... more than 160 bytes
 #endif
+#ifndef VB_OWN_AHEAD
+#define VB_OWN_AHEAD(dflt) (dflt)
+#endif
+#ifndef VB_OWN_EARLY
+#define VB_OWN_EARLY 1    // owner rows that cannot be requested a whole segment ahead (register budget)
+                          // are requested before the cross-lane sum of the previous segment, when
+                          // the registers of the old owner row are free, instead of at segment start
+                          // (measured at C2: cell-owner pass 0.744 -> 0.708 ms)
+#endif
+#ifndef VB_OWN_STAGE
+#define VB_OWN_STAGE 1    // owner rows that cannot be requested a whole segment ahead in registers are
+                          // staged through shared memory instead: cp.async into an 8-lane group's own
+                          // slot behind the tile during the previous segment, read back with LDS at
+                          // segment start (the global-load latency of the owner row was the largest
+                          // part of the per-segment overhead)
+#endif
+
 template <int RP, typename PT>
 struct SweepCfg {
     // Register budget per lane: own + acc + tile row = 3 * KL values of PT plus the prefetched
@@ -270,6 +287,23 @@ struct SweepCfg {
     __host__ __device__ static constexpr int p16_threads(bool cols) {
         return (cols && sizeof(PT) == 8 && kRowShare > 96 && kRowShare <= 160) ? VB_MID_THREADS_COLS
                                                                                : kThreads;
+    }
+    // packed-16 kernels: the next owner row is requested a whole segment ahead, into registers,
+    // where the register budget allows it (checked with -Xptxas -v: wider row shares, and the fp64
+    // cell-owner pass with its log, spill) ...
+    __host__ __device__ static constexpr bool own_ahead(bool cols) {
+        return VB_OWN_AHEAD(kRowShare <= 48 ||
+                            (kRowShare <= 80 && sizeof(PT) == 8 && !cols && kLPN == 1));
+    }
+    // ... and staged through shared memory otherwise: bytes of one group's slot (all kNU units of
+    // a row), and of the slots of the larger of the two passes' CTAs (what the host leaves free
+    // behind the tile)
+    __host__ __device__ static constexpr int stage_bytes(bool, bool) { return kNU * 16; }
+    __host__ __device__ static constexpr int stage_pass(bool cols) {
+        return (VB_OWN_STAGE && !own_ahead(cols)) ? p16_threads(cols) / 8 * kNU * 16 : 0;
+    }
+    __host__ __device__ static constexpr int stage_total() {
+        return stage_pass(true) > stage_pass(false) ? stage_pass(true) : stage_pass(false);
     }
 };
 
@@ -733,29 +767,6 @@ struct LogProd {
     }
 };
 
-#ifndef VB_OWN_AHEAD
-#define VB_OWN_AHEAD(dflt) (dflt)
-#endif
-#ifndef VB_OWN_EARLY
-#define VB_OWN_EARLY 1    // owner rows that cannot be requested a whole segment ahead (register budget)
-                          // are requested before the cross-lane sum of the previous segment, when
-                          // the registers of the old owner row are free, instead of at segment start
-                          // (measured at C2: cell-owner pass 0.744 -> 0.708 ms)
-#endif
-#ifndef VB_OWN_RUNNING
-#define VB_OWN_RUNNING 1  // split layout: (slab, row) of the owner kept as a running pair instead of
-                          // a division per segment
-#endif
-#ifndef VB_PTR_RAW
-#define VB_PTR_RAW 0      // 1: segment pointers stay tagged until their segment starts (measured: no
-                          // gain, C3-shaped 5.61 -> 5.69 ms per iteration)
-#endif
-#ifndef VB_OWN_PF
-#define VB_OWN_PF 0       // L2 prefetch of the owner row two segments ahead: 1 = cell-owner pass (its
-                          // owner panel streams from HBM once per gene slab), 2 = both passes.
-                          // Measured SLOWER (C3-shaped cell-owner pass 3.18 -> 3.33 ms): off
-#endif
-
 // SPLIT (fp64 panels, one lane per nonzero, rows of >= 8 units; see split_rank / panel_ofs): the
 // tile is stored as block A (T x 128 bytes) + block B; lane gl gathers unit c ^ gl of block A in
 // step c -- conflict free for ANY 8 rows -- and holds its owner row and accumulators in the same
@@ -784,11 +795,12 @@ sweep_p16_kernel(const SweepTiledArgs a) {
     // the next owner row is requested one segment ahead where the register budget allows it
     // (checked with -Xptxas -v: wider row shares, and the fp64 cell-owner pass with its log, spill)
     constexpr int kRowShare = KL * (int)sizeof(PT);  // bytes of a row held per lane
-    constexpr bool kOwnAhead = VB_OWN_AHEAD(
-        kRowShare <= 48 || (kRowShare <= 80 && sizeof(PT) == 8 && !COLS && LPN == 1));
+    constexpr bool kOwnAhead = Cfg::own_ahead(COLS);
     // 1: a whole segment ahead; 2: before the cross-lane sum of the previous segment (the old owner
     // row's registers are free by then); 0: at the start of its segment
-    constexpr int kOwnMode = kOwnAhead ? 1 : (VB_OWN_EARLY ? 2 : 0);
+    // 3: staged through shared memory a segment ahead (sweep_stage_bytes() behind the tile)
+    constexpr int kOwnMode = kOwnAhead ? 1 : (VB_OWN_STAGE ? 3 : (VB_OWN_EARLY ? 2 : 0));
+    static_assert(kOwnMode != 3 || Cfg::stage_bytes(COLS, SPLIT) > 0, "staging slot size");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     PT *tile = reinterpret_cast<PT *>(smem_raw);
     const uint32_t tile_s = smem_u32(tile);
@@ -814,73 +826,78 @@ sweep_p16_kernel(const SweepTiledArgs a) {
     const uint32_t rotb = kRotB ? (uint32_t)((gl >> 2) & 1) << 4 : 0u;
     if (SPLIT && (tile_s & 127u)) __trap();  // block A rows must start on SA * 16-byte boundaries
 
-    // this lane's share of an owner row: units hf, hf + LPN, ...  SPLIT: the owner panel is stored
-    // in slabs of T rows (block A, block B); (oso, olo) = slab and row in the slab of the next owner
-    // to be loaded, advanced by kGroups per segment (no division in the loop)
-    constexpr bool kOwnPf = VB_OWN_PF == 2 || (VB_OWN_PF == 1 && COLS);
-    uint32_t oso = 0, olo = 0;     // next owner to load
-    uint32_t pso = 0, plo = 0;     // owner to prefetch into L2 (two segments further)
+    // Owner rows.  A lane holds units hf, hf + LPN, ... of the row (SPLIT: in the rotated order of
+    // its tile gathers).  SPLIT: the owner panel is stored in slabs of T rows (block A, block B);
+    // (oso, olo) = slab and row in the slab of the next owner to be requested, advanced by kGroups
+    // per segment (no division in the loop).
+    uint32_t oso = 0, olo = 0;
     auto own_seek = [&](int64_t o) {
         if constexpr (SPLIT) {
             oso = (uint32_t)o / (uint32_t)a.T; olo = (uint32_t)o - oso * (uint32_t)a.T;
-            const uint32_t o2 = (uint32_t)o + 2u * kGroups;
-            pso = o2 / (uint32_t)a.T; plo = o2 - pso * (uint32_t)a.T;
         }
     };
     auto own_advance = [&]() {
-        if constexpr (SPLIT && (VB_OWN_RUNNING || kOwnPf)) {
+        if constexpr (SPLIT) {
             olo += kGroups;
             while (olo >= (uint32_t)a.T) { olo -= (uint32_t)a.T; oso++; }
-            plo += kGroups;
-            while (plo >= (uint32_t)a.T) { plo -= (uint32_t)a.T; pso++; }
         }
     };
-    // o = owner index (used by the plain layout; the split layout follows (oso, olo) and advances)
-    auto load_owner = [&](int64_t o, bool doit, PT(&dst)[KL]) {
+    // storage unit (16 bytes) held by register unit c of this lane
+    auto own_unit = [&](int c) -> int {
         if constexpr (SPLIT) {
-            if (doit) {
-                if (!VB_OWN_RUNNING) {
-                    oso = (uint32_t)o / (uint32_t)a.T; olo = (uint32_t)o - oso * (uint32_t)a.T;
-                }
-                const PT *blk = reinterpret_cast<const PT *>(a.owner) + (int64_t)oso * a.T * PSS;
-                const PT *ra = blk + (int64_t)olo * (2 * SA);
-                const PT *rb = blk + (int64_t)a.T * (2 * SA) + (int64_t)olo * BSD;
-#pragma unroll
-                for (int c = 0; c < SA; c++) ldg_unit(ra, c ^ (gl & (SA - 1)), dst + c * UE);
-#pragma unroll
-                for (int c = 0; c < NUB; c++)
-                    ldg_unit(rb, kRotB ? (c ^ ((gl >> 2) & 1)) : c, dst + (SA + c) * UE);
-            }
-            own_advance();
+            return c < SA ? (c ^ (gl & (SA - 1))) : SA + (kRotB ? ((c - SA) ^ ((gl >> 2) & 1)) : (c - SA));
         } else {
-            if (doit) {
-                const PT *orow = reinterpret_cast<const PT *>(a.owner) + o * PS;
-#pragma unroll
-                for (int c = 0; c < NUL; c++) {
-                    const int u = LPN * c + hf;
-                    if (LPN == 1 || u < NU) ldg_unit(orow, u, dst + c * UE);
-                }
-            }
+            return LPN * c + hf;
         }
     };
-    // L2 prefetch of the owner row two segments ahead (one lane per group; rows past the end of the
-    // panel are not requested)
-    auto prefetch_owner = [&](int64_t o2) {
-        if constexpr (kOwnPf) {
-            if constexpr (SPLIT) {
-                if (gl == 0 && (int64_t)pso * a.T + plo < a.NO) {
-                    const PT *blk = reinterpret_cast<const PT *>(a.owner) + (int64_t)pso * a.T * PSS;
-                    prefetch_l2(blk + (int64_t)plo * (2 * SA));
-                    if (NUB > 0) prefetch_l2(blk + (int64_t)a.T * (2 * SA) + (int64_t)plo * BSD);
-                }
-            } else {
-                if (gl == 0 && o2 < a.NO) {
-                    const PT *orow = reinterpret_cast<const PT *>(a.owner) + o2 * PS;
-                    prefetch_l2(orow);
-                    if (PS * sizeof(PT) > 128) prefetch_l2(reinterpret_cast<const char *>(orow) + 128);
-                }
+    // global address of storage unit u of owner o (SPLIT: of owner (oso, olo))
+    auto own_src = [&](int64_t o, int u) -> const PT * {
+        if constexpr (SPLIT) {
+            const PT *blk = reinterpret_cast<const PT *>(a.owner) + (int64_t)oso * a.T * PSS;
+            return u < SA ? blk + (int64_t)olo * (2 * SA) + u * UE
+                          : blk + (int64_t)a.T * (2 * SA) + (int64_t)olo * BSD + (u - SA) * UE;
+        } else {
+            return reinterpret_cast<const PT *>(a.owner) + o * PS + u * UE;
+        }
+    };
+    // request owner o into registers (modes 0, 1, 2); advances the running index
+    auto load_owner = [&](int64_t o, bool doit, PT(&dst)[KL]) {
+        if (doit) {
+#pragma unroll
+            for (int c = 0; c < NUL; c++) {
+                const int u = own_unit(c);
+                if (LPN == 1 || u < NU) ldg_unit(own_src(o, u), 0, dst + c * UE);
             }
         }
+        own_advance();
+    };
+    // mode 3: this group's staging slot behind the tile; stage_owner() copies the row into it with
+    // cp.async (lane gl: units gl, gl + 8, ...), take_owner() waits for the copy and reads the
+    // lane's units.  One slot is enough: the next copy is issued after every lane has read.
+    constexpr int kStage = Cfg::stage_bytes(COLS, SPLIT);
+    const uint32_t stage_s = tile_s + tile_bytes + (uint32_t)gid * (uint32_t)kStage;
+    auto stage_owner = [&](int64_t o, bool doit) {
+        if (doit) {
+#pragma unroll
+            for (int u0 = 0; u0 < NU; u0 += kGroup) {
+                const int u = u0 + gl;
+                if (u < NU)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(stage_s + u * 16),
+                                 "l"(own_src(o, u)) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        own_advance();
+    };
+    auto take_owner = [&](PT(&dst)[KL]) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp(gmask);
+#pragma unroll
+        for (int c = 0; c < NUL; c++) {
+            const int u = own_unit(c);
+            if (LPN == 1 || u < NU) lds_unit(stage_s + u * 16, dst + c * UE);
+        }
+        __syncwarp(gmask);
     };
     PT tr[KL];  // the gathered row; SPLIT: kept by hole entries (overwritten in full otherwise)
 #pragma unroll
@@ -896,29 +913,28 @@ sweep_p16_kernel(const SweepTiledArgs a) {
                      tile_bytes, &mbar);
         }
         // prime the group's pipeline while the tile lands: pointers of its first two segments,
-        // first quad and owner row of the first.  Pointers stay as loaded ("raw", with the tag of
-        // the split layout) until the segment they belong to starts: nothing waits on a load it
-        // has just issued.
+        // first quad and owner row of the first
         int64_t e = ebase + gid;
-        uint32_t beg = 0, end = 0, nbr = 0, ner = 0;
-        uint32_t dead = 0;  // all-hole steps at the end of the segment (SPLIT)
-        uint32_t ndead_ = 0, nndead_ = 0;  // (!VB_PTR_RAW: tags split off at load time)
+        uint32_t beg = 0, end = 0, nb = 0, ne = 0;
+        uint32_t dead = 0, ndead = 0, nndead = 0;  // all-hole steps at the end of the segment (SPLIT)
         constexpr uint32_t kTag = SPLIT ? 3u : 0u;
         uint4 f0 = make_uint4(0u, 0u, 0u, 0u);
         PT ownn[KL];
 #pragma unroll
         for (int k = 0; k < KL; k++) ownn[k] = 0;
         if (e < eend) {
-            const uint32_t b0 = __ldg(a.ptr4 + e), e0r = __ldg(a.ptr4 + e + 1);
+            beg = __ldg(a.ptr4 + e);
+            end = __ldg(a.ptr4 + e + 1) & ~kTag;
+            dead = beg & kTag; beg &= ~kTag;
             if (e + kGroups < eend) {
-                nbr = __ldg(a.ptr4 + e + kGroups);
-                ner = __ldg(a.ptr4 + e + kGroups + 1);
-                if (!VB_PTR_RAW) { ndead_ = nbr & kTag; nbr &= ~kTag; ner &= ~kTag; }
+                nb = __ldg(a.ptr4 + e + kGroups);
+                ne = __ldg(a.ptr4 + e + kGroups + 1) & ~kTag;
+                ndead = nb & kTag; nb &= ~kTag;
             }
             own_seek(e - slab * a.NO);
-            beg = b0 & ~kTag; end = e0r & ~kTag; dead = b0 & kTag;
             if (beg + slot < end) f0 = ldcs_quad(ent4 + beg + slot);
-            if (kOwnMode != 0) load_owner(e - slab * a.NO, beg < end, ownn);
+            if (kOwnMode == 1 || kOwnMode == 2) load_owner(e - slab * a.NO, beg < end, ownn);
+            if (kOwnMode == 3) stage_owner(e - slab * a.NO, beg < end);
         }
         mbar_wait(&mbar, parity);
         parity ^= 1;
@@ -930,22 +946,22 @@ sweep_p16_kernel(const SweepTiledArgs a) {
             PT own[KL];
 #pragma unroll
             for (int k = 0; k < KL; k++) own[k] = ownn[k];
-            if constexpr (SPLIT) prefetch_owner(0);
-            else prefetch_owner(e - slab * a.NO + 2 * kGroups);
             if (kOwnMode == 0) load_owner(e - slab * a.NO, nq > 0, own);
+            if (kOwnMode == 3) {
+                take_owner(own);   // (a segment without entries reads the previous row: unused)
+                stage_owner(en - slab * a.NO, en < eend && nb < ne);
+            }
             uint4 n1 = make_uint4(0u, 0u, 0u, 0u);
             if (NPG + slot < nq) n1 = ldcs_quad(eb + NPG + slot);
             // requests for the NEXT segment (pointers arrived during the previous one) and the
             // pointers of the one after it
-            if (!VB_PTR_RAW) { ner &= ~kTag; }
-            const uint32_t nb = nbr & ~kTag, ne = ner & ~kTag;
-            uint32_t nnbr = 0, nner = 0;
+            uint32_t nnb = 0, nne = 0;
             f0 = make_uint4(0u, 0u, 0u, 0u);
             if (en < eend) {
                 if (en + kGroups < eend) {
-                    nnbr = __ldg(a.ptr4 + en + kGroups);
-                    nner = __ldg(a.ptr4 + en + kGroups + 1);
-                    if (!VB_PTR_RAW) { nndead_ = nnbr & kTag; nnbr &= ~kTag; nner &= ~kTag; }
+                    nnb = __ldg(a.ptr4 + en + kGroups);
+                    nne = __ldg(a.ptr4 + en + kGroups + 1) & ~kTag;
+                    nndead = nnb & kTag; nnb &= ~kTag;
                 }
                 if (nb + slot < ne) f0 = ldcs_quad(ent4 + nb + slot);
                 if (kOwnMode == 1) load_owner(en - slab * a.NO, nb < ne, ownn);
@@ -1111,8 +1127,8 @@ sweep_p16_kernel(const SweepTiledArgs a) {
             }
             }
             e = en;
-            beg = nb; end = ne; dead = VB_PTR_RAW ? (nbr & kTag) : ndead_;
-            nbr = nnbr; ner = nner; ndead_ = nndead_;
+            beg = nb; end = ne; dead = ndead;
+            nb = nnb; ne = nne; ndead = nndead;
         }
         ebase = eend;
     }

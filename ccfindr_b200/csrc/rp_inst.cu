@@ -100,7 +100,8 @@ void colsum(const ColsumArgs &a, cudaStream_t s) {
 extern const RpTable VB_CAT(rp_table_, VB_RP);
 const RpTable VB_CAT(rp_table_, VB_RP) = {
     RP,      RS,        row_stride_f32(RP),
-    SweepCfg<RP, double>::kNPG, SweepCfg<RP, float>::kNPG, split_units(RP), sweep_prepare,
+    SweepCfg<RP, double>::kNPG, SweepCfg<RP, float>::kNPG, split_units(RP),
+    SweepCfg<RP, double>::stage_total(), SweepCfg<RP, float>::stage_total(), sweep_prepare,
     sweep, mirror,
     combine, posterior, ml_update,          colsum};
 

@@ -64,6 +64,7 @@ struct RpTable {
     int npg64, npg32;  // nonzeros per 8-lane group step of the sweep (fp64 / fp32 panels)
     int split64;       // units of block A of the split layout the fp64 packed-16 sweep reads lw/lh in
                        // (panel_ofs): 8 (ranks 16..20), 4 (ranks 8..14) or 0 (plain rows)
+    int stage64, stage32;  // bytes behind the tile the packed-16 sweeps use as owner staging slots
     // cols: cell-owner pass; fmt = storage format of the nonzeros (kEnt*); grid = CTAs (one per
     // SM, persistent)
     int (*sweep_prepare)(int smem_bytes);  // opt in to the dynamic shared memory size; 0 = ok

@@ -285,9 +285,10 @@ inline int pad_rank(int r) {
 inline int64_t tail_off(const H *h) { return h->L->NG * h->rs; }
 inline int64_t red_len(const H *h) { return h->L->NG * h->rs + h->rs + 8; }
 
-int choose_tile_rows(const H *h, int row_bytes) {
-    // largest multiple of 32 rows that fits (ranks with the same row stride share a layout)
-    int T = (kTileBytes / row_bytes / kTileRowsStep) * kTileRowsStep;
+int choose_tile_rows(const H *h, int row_bytes, int stage_bytes) {
+    // largest multiple of 32 rows that fits beside the owner staging slots of the packed-16 sweeps
+    // (ranks with the same row stride share a layout)
+    int T = ((kTileBytes - stage_bytes) / row_bytes / kTileRowsStep) * kTileRowsStep;
     T = std::max(kTileRowsStep, std::min(T, kTileRowsMax));
     // every rank of a sharded factorization must arrive at the same T (the gene panels are
     // all-reduced in device order): only global quantities enter
@@ -719,7 +720,8 @@ int alloc_panels(H *h, int r) {
                        (tab->split64 == 8 || getenv("VBNMF_SPLIT4"));
     // a slab row of the split layout is block A + a dense block B (kernels.cuh split_ps)
     const int row_bytes = f32 ? tab->rsf * 4 : (split ? vb::split_ps(rp) * 8 : rs * 8);
-    const int T = choose_tile_rows(h, row_bytes);
+    const int stage_bytes = h->p16 ? (f32 ? tab->stage32 : tab->stage64) : 0;
+    const int T = choose_tile_rows(h, row_bytes, stage_bytes);
     Layout *L = nullptr;
     int kmult = split ? 1 : 4;
     if (const char *e = getenv("VBNMF_KMULT")) kmult = atoi(e) == 1 ? 1 : 4;  // experiments
@@ -740,7 +742,7 @@ int alloc_panels(H *h, int r) {
     h->tsplit = split ? vb::make_tsplit(T, rp) : 0;
     h->r = r; h->rp = rp; h->rs = rs; h->rsf = tab->rsf;
     h->panel_precision = h->precision;
-    h->smem_bytes = T * row_bytes;
+    h->smem_bytes = T * row_bytes + stage_bytes;
     // The opt-in is per kernel and device, i.e. shared by every handle of the process: always ask
     // for the largest tile so that a second handle with a smaller tile cannot lower the limit
     // under this one.
