@@ -376,6 +376,8 @@ struct SweepTiledArgs {
     double *xl_part;         // COLS: gridDim.x partial sums of x log p
     const double *ctl;       // device loop control block (see control_kernel) or nullptr
     const uint32_t *ptr4;    // packed-16 layout: segment pointers in units of 4 entries (16 bytes)
+    const uint32_t *seg;     // packed-16 layout: owner row of each segment position (inside windows
+                             // of consecutive owners the segments are stored by decreasing length)
 };
 
 // Device loop control block (doubles).  When a kernel is given it and ctl[kCtlDone] != 0 the run
@@ -828,18 +830,11 @@ sweep_p16_kernel(const SweepTiledArgs a) {
 
     // Owner rows.  A lane holds units hf, hf + LPN, ... of the row (SPLIT: in the rotated order of
     // its tile gathers).  SPLIT: the owner panel is stored in slabs of T rows (block A, block B);
-    // (oso, olo) = slab and row in the slab of the next owner to be requested, advanced by kGroups
-    // per segment (no division in the loop).
+    // (oso, olo) = slab and row in the slab of the owner being requested.
     uint32_t oso = 0, olo = 0;
-    auto own_seek = [&](int64_t o) {
+    auto own_seek = [&](uint32_t o) {
         if constexpr (SPLIT) {
-            oso = (uint32_t)o / (uint32_t)a.T; olo = (uint32_t)o - oso * (uint32_t)a.T;
-        }
-    };
-    auto own_advance = [&]() {
-        if constexpr (SPLIT) {
-            olo += kGroups;
-            while (olo >= (uint32_t)a.T) { olo -= (uint32_t)a.T; oso++; }
+            oso = o / (uint32_t)a.T; olo = o - oso * (uint32_t)a.T;
         }
     };
     // storage unit (16 bytes) held by register unit c of this lane
@@ -861,23 +856,24 @@ sweep_p16_kernel(const SweepTiledArgs a) {
         }
     };
     // request owner o into registers (modes 0, 1, 2); advances the running index
-    auto load_owner = [&](int64_t o, bool doit, PT(&dst)[KL]) {
+    auto load_owner = [&](uint32_t o, bool doit, PT(&dst)[KL]) {
         if (doit) {
+            own_seek(o);
 #pragma unroll
             for (int c = 0; c < NUL; c++) {
                 const int u = own_unit(c);
                 if (LPN == 1 || u < NU) ldg_unit(own_src(o, u), 0, dst + c * UE);
             }
         }
-        own_advance();
     };
     // mode 3: this group's staging slot behind the tile; stage_owner() copies the row into it with
     // cp.async (lane gl: units gl, gl + 8, ...), take_owner() waits for the copy and reads the
     // lane's units.  One slot is enough: the next copy is issued after every lane has read.
     constexpr int kStage = Cfg::stage_bytes(COLS, SPLIT);
     const uint32_t stage_s = tile_s + tile_bytes + (uint32_t)gid * (uint32_t)kStage;
-    auto stage_owner = [&](int64_t o, bool doit) {
+    auto stage_owner = [&](uint32_t o, bool doit) {
         if (doit) {
+            own_seek(o);
 #pragma unroll
             for (int u0 = 0; u0 < NU; u0 += kGroup) {
                 const int u = u0 + gl;
@@ -887,7 +883,6 @@ sweep_p16_kernel(const SweepTiledArgs a) {
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
-        own_advance();
     };
     auto take_owner = [&](PT(&dst)[KL]) {
         asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -912,10 +907,15 @@ sweep_p16_kernel(const SweepTiledArgs a) {
             bulk_g2s(tile, reinterpret_cast<const PT *>(a.tiles) + slab * (int64_t)a.T * PSS,
                      tile_bytes, &mbar);
         }
-        // prime the group's pipeline while the tile lands: pointers of its first two segments,
-        // first quad and owner row of the first
+        // prime the group's pipeline while the tile lands: pointers and owners of its first two
+        // segments, first quad and owner row of the first.  e runs over the POSITIONS of the
+        // slab's segments in the stored order (a.seg[e] = owner row of position e): inside windows
+        // of consecutive owners the segments are ordered by decreasing length, so that the four
+        // groups of a warp, which run their chunk loops in lock step, get segments of (nearly
+        // always) the same number of steps.
         int64_t e = ebase + gid;
         uint32_t beg = 0, end = 0, nb = 0, ne = 0;
+        uint32_t og = 0, nog = 0;   // owner rows of the current and the next segment
         uint32_t dead = 0, ndead = 0, nndead = 0;  // all-hole steps at the end of the segment (SPLIT)
         constexpr uint32_t kTag = SPLIT ? 3u : 0u;
         uint4 f0 = make_uint4(0u, 0u, 0u, 0u);
@@ -925,16 +925,17 @@ sweep_p16_kernel(const SweepTiledArgs a) {
         if (e < eend) {
             beg = __ldg(a.ptr4 + e);
             end = __ldg(a.ptr4 + e + 1) & ~kTag;
+            og = __ldg(a.seg + e);
             dead = beg & kTag; beg &= ~kTag;
             if (e + kGroups < eend) {
                 nb = __ldg(a.ptr4 + e + kGroups);
                 ne = __ldg(a.ptr4 + e + kGroups + 1) & ~kTag;
+                nog = __ldg(a.seg + e + kGroups);
                 ndead = nb & kTag; nb &= ~kTag;
             }
-            own_seek(e - slab * a.NO);
             if (beg + slot < end) f0 = ldcs_quad(ent4 + beg + slot);
-            if (kOwnMode == 1 || kOwnMode == 2) load_owner(e - slab * a.NO, beg < end, ownn);
-            if (kOwnMode == 3) stage_owner(e - slab * a.NO, beg < end);
+            if (kOwnMode == 1 || kOwnMode == 2) load_owner(og, beg < end, ownn);
+            if (kOwnMode == 3) stage_owner(og, beg < end);
         }
         mbar_wait(&mbar, parity);
         parity ^= 1;
@@ -946,25 +947,26 @@ sweep_p16_kernel(const SweepTiledArgs a) {
             PT own[KL];
 #pragma unroll
             for (int k = 0; k < KL; k++) own[k] = ownn[k];
-            if (kOwnMode == 0) load_owner(e - slab * a.NO, nq > 0, own);
+            if (kOwnMode == 0) load_owner(og, nq > 0, own);
             if (kOwnMode == 3) {
                 take_owner(own);   // (a segment without entries reads the previous row: unused)
-                stage_owner(en - slab * a.NO, en < eend && nb < ne);
+                stage_owner(nog, en < eend && nb < ne);
             }
             uint4 n1 = make_uint4(0u, 0u, 0u, 0u);
             if (NPG + slot < nq) n1 = ldcs_quad(eb + NPG + slot);
             // requests for the NEXT segment (pointers arrived during the previous one) and the
             // pointers of the one after it
-            uint32_t nnb = 0, nne = 0;
+            uint32_t nnb = 0, nne = 0, nnog = 0;
             f0 = make_uint4(0u, 0u, 0u, 0u);
             if (en < eend) {
                 if (en + kGroups < eend) {
                     nnb = __ldg(a.ptr4 + en + kGroups);
                     nne = __ldg(a.ptr4 + en + kGroups + 1) & ~kTag;
+                    nnog = __ldg(a.seg + en + kGroups);
                     nndead = nnb & kTag; nnb &= ~kTag;
                 }
                 if (nb + slot < ne) f0 = ldcs_quad(ent4 + nb + slot);
-                if (kOwnMode == 1) load_owner(en - slab * a.NO, nb < ne, ownn);
+                if (kOwnMode == 1) load_owner(nog, nb < ne, ownn);
                 if (gl == 0 && nb + NPG < ne)
                     bulk_prefetch_l2(ent4 + nb + NPG, (ne - nb - NPG) * 16u);
             }
@@ -1052,9 +1054,9 @@ sweep_p16_kernel(const SweepTiledArgs a) {
             }
             if (kLogProd) lp.end_segment();
             else if (COLS) xl += (double)xls;
-            if (kOwnMode == 2 && en < eend) load_owner(en - slab * a.NO, nb < ne, ownn);
+            if (kOwnMode == 2 && en < eend) load_owner(nog, nb < ne, ownn);
             // sum over the lanes that hold the same rank entries (fp64), recursive halving
-            double *out = a.Part + e * RS;
+            double *out = a.Part + (slab * a.NO + (int64_t)og) * RS;
             double v0[KL];
 #pragma unroll
             for (int k = 0; k < KL; k++) v0[k] = (double)acc[k];
@@ -1127,8 +1129,8 @@ sweep_p16_kernel(const SweepTiledArgs a) {
             }
             }
             e = en;
-            beg = nb; end = ne; dead = ndead;
-            nb = nnb; ne = nne; ndead = nndead;
+            beg = nb; end = ne; dead = ndead; og = nog;
+            nb = nnb; ne = nne; ndead = nndead; nog = nnog;
         }
         ebase = eend;
     }

@@ -429,6 +429,43 @@ plan_p16_kernel(int64_t E, const int64_t *__restrict__ ptr, const uint32_t *__re
     }
 }
 
+// ---- segments in the order of decreasing length inside windows of W owners ------------------------
+// The four 8-lane groups of a warp run their chunk loops in lock step, so a warp takes as long as
+// its longest segment: with ~115 nonzeros per segment (r = 20) the longest of four is ~9 % above
+// the mean.  Inside every window of W consecutive owners of a slab the segments are therefore
+// stored in the order of decreasing step count: neighbouring segments -- the ones a warp processes
+// together -- have the same number of steps, while the owner rows and partial statistics a CTA
+// touches stay within a window (sorting a whole slab scatters them over the panel: measured 25 %
+// SLOWER in the cell-owner pass).  sort key of segment e: window, then 1023 - min(steps, 1023);
+// value e (stable sort: equal lengths stay in owner order).
+__global__ void __launch_bounds__(kBlock)
+seg_order_keys_kernel(int64_t E, int64_t NO, int W, const uint32_t *__restrict__ len4,
+                      const uint8_t *__restrict__ dead, int NL, uint32_t *__restrict__ key,
+                      uint32_t *__restrict__ val) {
+    const int64_t e = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (e >= E) return;
+    int steps = (int)(len4[e] * 4u / (uint32_t)NL) - (dead ? (int)dead[e] : 0);
+    steps = steps > 1023 ? 1023 : steps;
+    const int64_t slab = e / NO, o = e - slab * NO, nwin = (NO + W - 1) / W;
+    key[e] = (uint32_t)(slab * nwin + o / W) * 1024u + (uint32_t)(1023 - steps);
+    val[e] = (uint32_t)e;
+}
+// order[pos] = segment at position pos -> seg[pos] = its owner row, len4p / deadp = its quads and
+// dead steps (len4p[E] = 0)
+__global__ void __launch_bounds__(kBlock)
+seg_permute_kernel(int64_t E, int64_t NO, const uint32_t *__restrict__ order,
+                   const uint32_t *__restrict__ len4, const uint8_t *__restrict__ dead,
+                   uint32_t *__restrict__ len4p, uint8_t *__restrict__ deadp,
+                   uint32_t *__restrict__ seg) {
+    const int64_t pos = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (pos > E) return;
+    if (pos == E) { len4p[E] = 0u; return; }
+    const uint32_t e = order ? order[pos] : (uint32_t)pos;
+    len4p[pos] = len4[e];
+    if (dead) deadp[pos] = dead[e];
+    seg[pos] = (uint32_t)(e - (pos / NO) * NO);
+}
+
 // position of item p of a segment stored in blocks of B = 4*NL entries (4 steps): item p of a
 // block -> quad p mod NL, word p div NL, so that word u of the quads the NL lanes load in one
 // 128-bit access is step u of the block
@@ -445,7 +482,8 @@ __device__ __forceinline__ int64_t p16_position(int64_t p, int NL) {
 // at a real row: local * S + slab < nvalid; row 0 of a slab always is).
 __global__ void __launch_bounds__(kBlock)
 build_segments_p16_kernel(int64_t E, int64_t NO, const int64_t *__restrict__ ptr,
-                          const uint32_t *__restrict__ ptr4, const uint32_t *__restrict__ words,
+                          const uint32_t *__restrict__ ptr4, const uint32_t *__restrict__ seg,
+                          const uint32_t *__restrict__ words,
                           int NL, int kmult, int mode, int64_t nvalid, int S,
                           uint32_t *__restrict__ ent_out) {
     const bool sbs = mode == kSchedSbs, cls4 = mode == kSchedCls4;
@@ -453,12 +491,14 @@ build_segments_p16_kernel(int64_t E, int64_t NO, const int64_t *__restrict__ ptr
     const unsigned lt = (1u << lane) - 1u;
     const int64_t warp = ((int64_t)blockIdx.x * kBlock + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * kBlock) >> 5;
-    for (int64_t e = warp; e < E; e += nwarps) {
+    // pos: position in the stored order (ptr4, seg); e: segment in (slab, owner) order (ptr, words)
+    for (int64_t pos = warp; pos < E; pos += nwarps) {
+        const int64_t slab = pos / NO;
+        const int64_t e = slab * NO + seg[pos];
         const int64_t beg = ptr[e], end = ptr[e + 1];
         if (beg == end) continue;
-        uint32_t *dst = ent_out + (int64_t)ptr4[e] * 4;
-        const int nitems = (int)(ptr4[e + 1] - ptr4[e]) * 4;
-        const int64_t slab = e / NO;
+        uint32_t *dst = ent_out + (int64_t)ptr4[pos] * 4;
+        const int nitems = (int)(ptr4[pos + 1] - ptr4[pos]) * 4;
         int cnt[8], cntv[8];
         warp_residue_counts(words, beg, end, lane, cnt);
 #pragma unroll

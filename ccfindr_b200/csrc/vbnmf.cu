@@ -65,6 +65,7 @@ constexpr int64_t kGraphMaxNnz = 20000000;  // below this the iteration loop is 
 // shared-memory budget of one staged slab: the 227 KB a CTA can opt in to minus the static part
 constexpr int kTileBytes = 231424;
 constexpr int kTileRowsMax = 4096, kTileRowsStep = 32;
+constexpr int kSegWindow = 2048;  // owners per window of the length-sorted segment order (build_pass)
 constexpr double kSplitKappa = 0.0;  // cost of a segment beyond its entries, in quads (split_p16_kernel)
 
 thread_local std::string g_create_error;  // error text of the last failed create on this thread
@@ -132,14 +133,17 @@ struct PassLayout {
     void *d_val = nullptr;      // nnz (double counts only)
     void *d_ent = nullptr;      // nnz packed {int32 tile row, float count} (float counts), or
                                 // the padded {count << 16 | tile row} words of the packed-16 layout
-    uint32_t *d_ptr4 = nullptr; // packed-16 layout: E + 1 segment pointers in quads (16 bytes)
+    uint32_t *d_ptr4 = nullptr; // packed-16 layout: E + 1 segment pointers in quads (16 bytes),
+                                // indexed by the POSITION of a segment in the stored order
+    uint32_t *d_seg = nullptr;  // packed-16 layout: owner row of position pos (inside windows of
+                                // kSegWindow owners the segments are stored by decreasing length)
     int64_t *d_split = nullptr; // grid + 1
     void release(cudaStream_t s) {
-        void *ps[] = {d_ptr, d_idx, d_val, d_ent, d_ptr4, d_split};
+        void *ps[] = {d_ptr, d_idx, d_val, d_ent, d_ptr4, d_seg, d_split};
         for (void *q : ps)
             if (q) cudaFreeAsync(q, s);
         d_ptr = nullptr; d_idx = nullptr; d_val = nullptr; d_ent = nullptr; d_ptr4 = nullptr;
-        d_split = nullptr;
+        d_seg = nullptr; d_split = nullptr;
     }
 };
 
@@ -500,35 +504,68 @@ int build_pass(H *h, Layout *L, bool cols_pass, const int32_t *d_colof, uint32_t
         { StageTimer t1("  plan(p16)");
         vb::plan_p16_kernel<<<g, vb::kBlock, 0, h->stream>>>(P.E, P.d_ptr, d_words, L->npg,
                                                              L->kmult, L->mode, d_len4, d_dead); }
+        // order the segments by decreasing number of steps inside windows of W owners
+        // (seg_order_keys_kernel; VBNMF_SEG_WINDOW: experiments, 0 = owner order)
+        int W = kSegWindow;
+        if (const char *wenv = getenv("VBNMF_SEG_WINDOW")) W = atoi(wenv);
+        uint32_t *d_len4p = nullptr, *d_okey = nullptr, *d_oval = nullptr;
+        uint8_t *d_deadp = nullptr;
+        CK(vmalloc(h, &d_len4p, (size_t)(P.E + 1) * 4));
+        if (d_dead) CK(vmalloc(h, &d_deadp, (size_t)P.E));
+        CK(vmalloc(h, &P.d_seg, (size_t)P.E * 4));
+        { StageTimer t1("  order segments");
+        const int ge = cdiv(P.E + 1, vb::kBlock);
+        void *d_otmp = nullptr;
+        if (W > 0) {
+            CK(vmalloc(h, &d_okey, (size_t)P.E * 4 * 4));  // keys in/out, values in/out
+            d_oval = d_okey + 2 * P.E;
+            vb::seg_order_keys_kernel<<<ge, vb::kBlock, 0, h->stream>>>(P.E, NO, W, d_len4, d_dead,
+                                                                        L->npg, d_okey, d_oval);
+            const int64_t nwin_all = (int64_t)nslabs * ((NO + W - 1) / W);
+            if (nwin_all >= ((int64_t)1 << 22))
+                return fail(h, VBNMF_ERR_ARG, "too many segment windows for 32-bit sort keys");
+            int obits = 10;
+            while (((int64_t)1 << obits) < nwin_all * 1024) obits++;
+            size_t ob = 0;
+            CK(cub::DeviceRadixSort::SortPairs(nullptr, ob, d_okey, d_okey + P.E, d_oval,
+                                               d_oval + P.E, P.E, 0, obits, h->stream));
+            CK(vmalloc(h, &d_otmp, ob));
+            CK(cub::DeviceRadixSort::SortPairs(d_otmp, ob, d_okey, d_okey + P.E, d_oval,
+                                               d_oval + P.E, P.E, 0, obits, h->stream));
+        }
+        vb::seg_permute_kernel<<<ge, vb::kBlock, 0, h->stream>>>(
+            P.E, NO, W > 0 ? d_oval + P.E : nullptr, d_len4, d_dead, d_len4p, d_deadp, P.d_seg);
+        vfree(h->stream, d_otmp); }
         size_t scan_bytes = 0;
-        CK(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, d_len4, P.d_ptr4, P.E + 1, h->stream));
+        CK(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, d_len4p, P.d_ptr4, P.E + 1, h->stream));
         void *d_scan = nullptr;
         CK(vmalloc(h, &d_scan, scan_bytes));
-        CK(cub::DeviceScan::ExclusiveSum(d_scan, scan_bytes, d_len4, P.d_ptr4, P.E + 1, h->stream));
+        CK(cub::DeviceScan::ExclusiveSum(d_scan, scan_bytes, d_len4p, P.d_ptr4, P.E + 1, h->stream));
         if (2 * nnz + 32 * P.E >= ((int64_t)1 << 34))
             return fail(h, VBNMF_ERR_ARG, "matrix too large for 32-bit quad pointers on one GPU");
         uint32_t quads = 0;
         CK(cudaMemcpyAsync(&quads, P.d_ptr4 + P.E, 4, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
         vfree(h->stream, d_len4); vfree(h->stream, d_scan);
+        vfree(h->stream, d_len4p); vfree(h->stream, d_okey);
         CK(vmalloc(h, &P.d_ent, (size_t)quads * 16));
         P.nent = (int64_t)quads * 4;
         { StageTimer t1("  build_segments(p16)");
         vb::build_segments_p16_kernel<<<g, vb::kBlock, 0, h->stream>>>(
-            P.E, NO, P.d_ptr, P.d_ptr4, d_words, L->npg, L->kmult, L->mode, cols_pass ? h->n : h->m,
-            cols_pass ? L->Sg : L->Sc, (uint32_t *)P.d_ent); }
+            P.E, NO, P.d_ptr, P.d_ptr4, P.d_seg, d_words, L->npg, L->kmult, L->mode,
+            cols_pass ? h->n : h->m, cols_pass ? L->Sg : L->Sc, (uint32_t *)P.d_ent); }
         CK(vmalloc(h, &P.d_split, (size_t)(L->grid + 1) * 8));
         // per-segment overhead in quads (VBNMF_SPLIT_KAPPA: tuning)
         const char *kenv = getenv("VBNMF_SPLIT_KAPPA");
         const double kappa = kenv ? atof(kenv) : kSplitKappa;
         vb::split_p16_kernel<<<cdiv(L->grid + 1, 128), 128, 0, h->stream>>>(L->grid, P.E, P.d_ptr4,
                                                                            kappa, P.d_split);
-        if (d_dead)
-            vb::tag_dead_kernel<<<cdiv(P.E, vb::kBlock), vb::kBlock, 0, h->stream>>>(P.E, d_dead,
+        if (d_deadp)
+            vb::tag_dead_kernel<<<cdiv(P.E, vb::kBlock), vb::kBlock, 0, h->stream>>>(P.E, d_deadp,
                                                                                     P.d_ptr4);
         CK(cudaStreamSynchronize(h->stream));
         CK(cudaGetLastError());
-        vfree(h->stream, d_dead);
+        vfree(h->stream, d_dead); vfree(h->stream, d_deadp);
         vfree(h->stream, P.d_ptr);
         P.d_ptr = nullptr;
         return 0;
@@ -836,7 +873,7 @@ int launch_sweep_cols(H *h) {
                          L->cols.d_idx, (const double *)L->cols.d_val,
                          f32 ? (const void *)h->d_lh32 : (const void *)h->d_lh,
                          f32 ? (const void *)h->d_lw32 : (const void *)h->d_lw, h->d_Part1, h->d_xl,
-                         h->ctl, L->cols.d_ptr4};
+                         h->ctl, L->cols.d_ptr4, L->cols.d_seg};
     h->tab->sweep(a, true, entry_format(h), f32, h->tsplit != 0, L->grid, h->smem_bytes, h->stream);
     vb::CombineArgs c{L->NC, L->Sg, h->r, h->d_Part1, h->d_lh, h->d_ShRaw, h->d_partC,
                       tail + h->rs + 3, h->d_counters + 2, h->d_xl, L->grid, h->gridC, h->ctl,
@@ -856,7 +893,7 @@ int launch_sweep_rows(H *h) {
                          L->rows.d_idx, (const double *)L->rows.d_val,
                          f32 ? (const void *)h->d_lw32 : (const void *)h->d_lw,
                          f32 ? (const void *)h->d_lh32 : (const void *)h->d_lh, h->d_Part2, nullptr,
-                         h->ctl, L->rows.d_ptr4};
+                         h->ctl, L->rows.d_ptr4, L->rows.d_seg};
     h->tab->sweep(a, false, entry_format(h), f32, h->tsplit != 0, L->grid, h->smem_bytes, h->stream);
     vb::CombineArgs c{L->NG, L->Sc, h->r, h->d_Part2, h->d_lw, h->d_red, h->d_partC,
                       tail + h->rs + 5, h->d_counters + 3, nullptr, 0, h->gridC, h->ctl,
