@@ -299,11 +299,16 @@ struct SweepCfg {
     // a row), and of the slots of the larger of the two passes' CTAs (what the host leaves free
     // behind the tile)
     __host__ __device__ static constexpr int stage_bytes(bool, bool) { return kNU * 16; }
-    __host__ __device__ static constexpr int stage_pass(bool cols) {
-        return (VB_OWN_STAGE && !own_ahead(cols)) ? p16_threads(cols) / 8 * kNU * 16 : 0;
+    __host__ __device__ static constexpr int stage_pass(bool cols, int g) {
+        return (VB_OWN_STAGE && !own_ahead(cols)) ? p16_threads(cols) / g * kNU * 16 : 0;
     }
-    __host__ __device__ static constexpr int stage_total() {
-        return stage_pass(true) > stage_pass(false) ? stage_pass(true) : stage_pass(false);
+    __host__ __device__ static constexpr int stage_total(int g = 8) {
+        return stage_pass(true, g) > stage_pass(false, g) ? stage_pass(true, g) : stage_pass(false, g);
+    }
+    // 4-lane groups (sweep_p16_kernel, G = 4): split layout with an 8-unit block A and no
+    // single-unit block B
+    __host__ __device__ static constexpr bool g4() {
+        return sizeof(PT) == 8 && kLPN == 1 && split_units(RP) == 8 && kNU != 9;
     }
 };
 
@@ -775,7 +780,14 @@ struct LogProd {
 // rotated order; the cross-lane sum un-rotates for free (partner gl ^ b holds my unit of register
 // c in its register c ^ b).  Entries with count 0 (schedule holes) skip their gathers: the lane
 // keeps the previous row, and x = 0 adds nothing.
-template <int RP, bool COLS, typename PT, bool SPLIT = false>
+// G = lanes per segment: 8, or 4 for the split layout with an 8-unit block A.  The rotation of
+// block A only needs the 8 lanes of a quarter-warp to read 8 different units, whatever segments
+// their rows belong to, so two 4-lane groups can share a bank phase; each lane then walks twice as
+// many steps per segment and the per-segment work (owner row, pointers, cross-lane sum, pipeline
+// drain and fill) is paid half as often per nonzero.  Block B (two dense units): the groups of a
+// quarter-warp read its units in opposite order (even / odd bank groups), and inside a group the
+// four rows of a step must differ mod 4 (kSchedOne4).
+template <int RP, bool COLS, typename PT, bool SPLIT = false, int G = 8>
 __global__ void __launch_bounds__(SweepCfg<RP, PT>::p16_threads(COLS), 1)
 sweep_p16_kernel(const SweepTiledArgs a) {
     using Cfg = SweepCfg<RP, PT>;
@@ -792,8 +804,10 @@ sweep_p16_kernel(const SweepTiledArgs a) {
     constexpr bool kRotB = SPLIT && SA == 8 && NUB == 2 && BSD == 4;
     constexpr int NT = Cfg::p16_threads(COLS);
     constexpr int UE = Cfg::kUE, NU = Cfg::kNU, LPN = Cfg::kLPN, NUL = Cfg::kNUL, KL = Cfg::kKL;
-    constexpr int NPG = Cfg::kNPG;
-    constexpr int kGroups = NT / kGroup;
+    static_assert(G == 8 || (G == 4 && SPLIT && split_units(RP) == 8 && Cfg::kNU != 9),
+                  "4-lane groups: split layout, 8-unit block A, block B empty or two dense units");
+    constexpr int NPG = G / LPN;
+    constexpr int kGroups = NT / G;
     // the next owner row is requested one segment ahead where the register budget allows it
     // (checked with -Xptxas -v: wider row shares, and the fp64 cell-owner pass with its log, spill)
     constexpr int kRowShare = KL * (int)sizeof(PT);  // bytes of a row held per lane
@@ -808,9 +822,10 @@ sweep_p16_kernel(const SweepTiledArgs a) {
     const uint32_t tile_s = smem_u32(tile);
     __shared__ __align__(8) uint64_t mbar;
     __shared__ double red[NT / 32];
-    const int gid = threadIdx.x / kGroup, gl = threadIdx.x % kGroup;
+    const int gid = threadIdx.x / G, gl = threadIdx.x % G;
+    const int l8 = threadIdx.x & 7;  // lane in the quarter-warp (bank phase): rotation of the gathers
     const int slot = gl / LPN, hf = gl % LPN;
-    const unsigned gmask = 0xffu << ((threadIdx.x & 31) & ~(kGroup - 1));
+    const unsigned gmask = ((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1));
     const int64_t e0 = a.split[blockIdx.x], e1 = a.split[blockIdx.x + 1];
     const unsigned tile_bytes = (unsigned)a.T * PSS * (unsigned)sizeof(PT);
     const uint4 *ent4 = reinterpret_cast<const uint4 *>(a.ent);
@@ -824,8 +839,8 @@ sweep_p16_kernel(const SweepTiledArgs a) {
     if (kLogProd) lp.init();
 
     const uint32_t tileB_s = tile_s + (uint32_t)a.T * (uint32_t)(SA * 16);
-    const uint32_t rot = (uint32_t)(gl & (SA - 1)) << 4;
-    const uint32_t rotb = kRotB ? (uint32_t)((gl >> 2) & 1) << 4 : 0u;
+    const uint32_t rot = (uint32_t)(l8 & (SA - 1)) << 4;
+    const uint32_t rotb = kRotB ? (uint32_t)((l8 >> 2) & 1) << 4 : 0u;
     if (SPLIT && (tile_s & 127u)) __trap();  // block A rows must start on SA * 16-byte boundaries
 
     // Owner rows.  A lane holds units hf, hf + LPN, ... of the row (SPLIT: in the rotated order of
@@ -840,7 +855,7 @@ sweep_p16_kernel(const SweepTiledArgs a) {
     // storage unit (16 bytes) held by register unit c of this lane
     auto own_unit = [&](int c) -> int {
         if constexpr (SPLIT) {
-            return c < SA ? (c ^ (gl & (SA - 1))) : SA + (kRotB ? ((c - SA) ^ ((gl >> 2) & 1)) : (c - SA));
+            return c < SA ? (c ^ (l8 & (SA - 1))) : SA + (kRotB ? ((c - SA) ^ ((l8 >> 2) & 1)) : (c - SA));
         } else {
             return LPN * c + hf;
         }
@@ -869,13 +884,13 @@ sweep_p16_kernel(const SweepTiledArgs a) {
     // mode 3: this group's staging slot behind the tile; stage_owner() copies the row into it with
     // cp.async (lane gl: units gl, gl + 8, ...), take_owner() waits for the copy and reads the
     // lane's units.  One slot is enough: the next copy is issued after every lane has read.
-    constexpr int kStage = Cfg::stage_bytes(COLS, SPLIT);
+    constexpr int kStage = Cfg::stage_bytes(COLS, SPLIT);  // (per group, whatever G)
     const uint32_t stage_s = tile_s + tile_bytes + (uint32_t)gid * (uint32_t)kStage;
     auto stage_owner = [&](uint32_t o, bool doit) {
         if (doit) {
             own_seek(o);
 #pragma unroll
-            for (int u0 = 0; u0 < NU; u0 += kGroup) {
+            for (int u0 = 0; u0 < NU; u0 += G) {
                 const int u = u0 + gl;
                 if (u < NU)
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(stage_s + u * 16),
@@ -1063,7 +1078,26 @@ sweep_p16_kernel(const SweepTiledArgs a) {
             if constexpr (SPLIT) {
                 // block A: register unit c of lane gl is rank unit c ^ (gl & (SA - 1)); the partner
                 // gl ^ b holds the same rank unit in its register unit c ^ b
-                if constexpr (SA == 8) {
+                if constexpr (SA == 8 && G == 4) {
+                    // four lanes: register unit c of lane l8 is rank unit c ^ l8; halve over bits 1
+                    // and 0 of the lane; the lane ends with rank units l8 and l8 ^ 4
+                    double a1[8], a2[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {       // keep register units 0, 1, 4, 5
+                        const int c = (u & 1) | ((u & 2) << 1);
+#pragma unroll
+                        for (int j = 0; j < 2; j++)
+                            a1[2 * u + j] = v0[2 * c + j] + __shfl_xor_sync(gmask, v0[2 * (c ^ 2) + j], 2);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 2; u++) {       // keep register units 0, 4 (a1 units 0, 2)
+#pragma unroll
+                        for (int j = 0; j < 2; j++)
+                            a2[2 * u + j] = a1[4 * u + j] + __shfl_xor_sync(gmask, a1[4 * u + 2 + j], 1);
+                    }
+                    *reinterpret_cast<double2 *>(out + 2 * l8) = make_double2(a2[0], a2[1]);
+                    *reinterpret_cast<double2 *>(out + 2 * (l8 ^ 4)) = make_double2(a2[2], a2[3]);
+                } else if constexpr (SA == 8) {
                     double a1[8], a2[4], a3[2];
 #pragma unroll
                     for (int k = 0; k < 8; k++) a1[k] = v0[k] + __shfl_xor_sync(gmask, v0[k + 8], 4);
@@ -1084,7 +1118,23 @@ sweep_p16_kernel(const SweepTiledArgs a) {
                     if (gl < 4 && 2 * gl < RP)
                         *reinterpret_cast<double2 *>(out + 2 * gl) = make_double2(a2[0], a2[1]);
                 }
-                if constexpr (kRotB) {
+                if constexpr (kRotB && G == 4) {
+                    // all four lanes hold rank unit 8 + (c ^ h) in register unit c (h = bit 2 of
+                    // l8 is the same for the group): plain halving of the four doubles
+                    const int h = (l8 >> 2) & 1;
+                    const bool hi1 = (gl & 2) != 0, hi0 = (gl & 1) != 0;
+                    double b1[2];
+#pragma unroll
+                    for (int j = 0; j < 2; j++) {
+                        const double keep = hi1 ? v0[2 * SA + 2 + j] : v0[2 * SA + j];
+                        const double send = hi1 ? v0[2 * SA + j] : v0[2 * SA + 2 + j];
+                        b1[j] = keep + __shfl_xor_sync(gmask, send, 2);
+                    }
+                    const double b2 = (hi0 ? b1[1] : b1[0]) + __shfl_xor_sync(gmask, hi0 ? b1[0] : b1[1], 1);
+                    // register unit (bit 1 of gl) -> rank unit 8 + (that ^ h), double (bit 0 of gl)
+                    const int kk = 2 * SA + 2 * ((hi1 ? 1 : 0) ^ h) + (hi0 ? 1 : 0);
+                    if (kk < RP) out[kk] = b2;
+                } else if constexpr (kRotB) {
                     // register unit c of lane gl is rank unit 8 + (c ^ h), h = bit 2 of gl: the
                     // partner gl ^ 4 holds my unit of register 0 in its register 1; then the four
                     // lanes of equal h hold the same unit and halve its two doubles

@@ -308,7 +308,21 @@ struct SegSchedule {
 // like the NL = 4 classes but run in the SAME steps, even rows in lanes 0..3 and odd rows in lanes
 // 4..7, K = the larger of the two step counts (a multiple of kmult).
 __device__ __forceinline__ void make_schedule(const int (&cnt8)[8], int NLp, int kmult, bool sbs,
-                                              SegSchedule &sc) {
+                                              SegSchedule &sc, bool one4 = false) {
+    if (one4) {  // one class of four buckets (cnt8[0..3]), four lanes, K a multiple of kmult
+        for (int cl = 0; cl < 2; cl++) {
+            sc.K[cl] = 0; sc.pl[cl].R = 0; sc.pl[cl].P = 0;
+            for (int b = 0; b < 8; b++) { sc.cnt[cl][b] = 0; sc.offr[cl][b] = 0; }
+        }
+        int n = 0, L = 0, c[4];
+        for (int b = 0; b < 4; b++) { c[b] = sc.cnt[0][b] = cnt8[b]; n += c[b]; L = max(L, c[b]); }
+        sc.K[0] = class_steps(n, L, 4, kmult);
+        if (sc.K[0] == 0) return;
+        sc.pl[0] = plan_class<4>(c, 4, sc.K[0]);
+        int acc = 0;
+        for (int b = 0; b < 4; b++) { sc.offr[0][b] = acc; acc += max(0, c[b] - sc.pl[0].R); }
+        return;
+    }
     const int NL = sbs ? 4 : NLp;
     const int ncls = NL == 8 ? 1 : 2, NB = NL;
     for (int cl = 0; cl < 2; cl++) {
@@ -345,9 +359,9 @@ __device__ __forceinline__ void make_schedule(const int (&cnt8)[8], int NLp, int
 // item index (step * NL + lane, steps of class 1 after those of class 0) of the k-th nonzero of
 // residue rr
 __device__ __forceinline__ int schedule_item(const SegSchedule &sc, int NLp, bool sbs, int rr,
-                                             int k) {
+                                             int k, bool one4 = false) {
     const int NL = sbs ? 4 : NLp;
-    const int cl = res_class(rr, NL), b = res_bucket(rr, NL);
+    const int cl = one4 ? 0 : res_class(rr, NL), b = one4 ? rr : res_bucket(rr, NL);
     const int R = sc.pl[cl].R, P = sc.pl[cl].P;
     int step, lane;
     if (k < R) {
@@ -384,7 +398,8 @@ __device__ __forceinline__ void warp_residue_counts(const uint32_t *__restrict__
 // and 20): the nonzeros of class c are dealt alternately to the "virtual residues" c and c + 4,
 // which are then scheduled like eight residue classes -- lane l of a single step holds a row of
 // class l mod 4, and lanes l, l + 4 read the two units of their rows in opposite order.
-enum { kSchedPlain = 0, kSchedSbs = 1, kSchedCls4 = 2 };
+// kSchedOne4 (4-lane groups, NL = 4): ONE set of four classes (row mod 4), one lane each.
+enum { kSchedPlain = 0, kSchedSbs = 1, kSchedCls4 = 2, kSchedOne4 = 3 };
 
 // counts per real residue -> counts per virtual residue (kSchedCls4)
 __device__ __forceinline__ void virtual_counts(int (&cnt)[8]) {
@@ -411,6 +426,17 @@ plan_p16_kernel(int64_t E, const int64_t *__restrict__ ptr, const uint32_t *__re
         int cnt[8];
         warp_residue_counts(words, beg, end, lane, cnt);
         if (mode == kSchedCls4) virtual_counts(cnt);
+        if (mode == kSchedOne4) {
+            int n = 0, L = 0;
+#pragma unroll
+            for (int b = 0; b < 4; b++) { const int c4 = cnt[b] + cnt[b + 4]; n += c4; L = max(L, c4); }
+            const int K = class_steps(n, L, 4, kmult), Kst = (K + 3) & ~3;
+            if (lane == 0) {
+                len4[e] = (uint32_t)Kst;  // Kst steps x 4 entries / 4
+                if (dead) dead[e] = (uint8_t)(Kst - K);
+            }
+            continue;
+        }
         int n0 = 0, n1 = 0, L0 = 0, L1 = 0;
         const int NLs = sbs ? 4 : NL;
 #pragma unroll
@@ -486,7 +512,7 @@ build_segments_p16_kernel(int64_t E, int64_t NO, const int64_t *__restrict__ ptr
                           const uint32_t *__restrict__ words,
                           int NL, int kmult, int mode, int64_t nvalid, int S,
                           uint32_t *__restrict__ ent_out) {
-    const bool sbs = mode == kSchedSbs, cls4 = mode == kSchedCls4;
+    const bool sbs = mode == kSchedSbs, cls4 = mode == kSchedCls4, one4 = mode == kSchedOne4;
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
     const int64_t warp = ((int64_t)blockIdx.x * kBlock + threadIdx.x) >> 5;
@@ -504,13 +530,17 @@ build_segments_p16_kernel(int64_t E, int64_t NO, const int64_t *__restrict__ ptr
 #pragma unroll
         for (int b = 0; b < 8; b++) cntv[b] = cnt[b];
         if (cls4) virtual_counts(cntv);
+        if (one4) {
+#pragma unroll
+            for (int b = 0; b < 4; b++) { cntv[b] = cnt[b] + cnt[b + 4]; cntv[b + 4] = 0; }
+        }
         SegSchedule sc;
-        make_schedule(cntv, NL, kmult, sbs, sc);
+        make_schedule(cntv, NL, kmult, sbs, sc, one4);
         // holes: lane <-> bucket in the single steps, so the residue of the lane's bucket is free
         for (int p = lane; p < nitems; p += 32) {
             const int step = p / NL, ln = p - step * NL;
-            const int cl = sbs ? (ln >> 2) : ((NL != 8 && step >= sc.K[0]) ? 1 : 0);
-            int rr = sbs ? 2 * (ln & 3) + cl : (cls4 ? (ln & 3) : bucket_res(cl, ln, NL));
+            const int cl = sbs ? (ln >> 2) : ((NL != 8 && !one4 && step >= sc.K[0]) ? 1 : 0);
+            int rr = sbs ? 2 * (ln & 3) + cl : ((cls4 || one4) ? (ln & 3) : bucket_res(cl, ln, NL));
             if ((int64_t)rr * S + slab >= nvalid) rr = 0;
             dst[p16_position(p, NL)] = (uint32_t)rr;
         }
@@ -537,7 +567,11 @@ build_segments_p16_kernel(int64_t E, int64_t NO, const int64_t *__restrict__ ptr
                 vr = (rr & 3) + 4 * (kc & 1);
                 vk = kc >> 1;
             }
-            if (valid) dst[p16_position(schedule_item(sc, NL, sbs, vr, vk), NL)] = w;
+            if (one4 && valid) {  // rank in the class: residues c, then c + 4
+                vr = rr & 3;
+                vk = rr < 4 ? k : cnt[rr - 4] + k;
+            }
+            if (valid) dst[p16_position(schedule_item(sc, NL, sbs, vr, vk, one4), NL)] = w;
         }
         __syncwarp();
     }

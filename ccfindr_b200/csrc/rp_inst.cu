@@ -35,16 +35,28 @@ int sweep_prepare(int smem_bytes) {
         VB_OPT((sweep_p16_kernel<RP, true, double, true>))
         VB_OPT((sweep_p16_kernel<RP, false, double, true>))
     }
+    if constexpr (SweepCfg<RP, double>::g4()) {
+        VB_OPT((sweep_p16_kernel<RP, true, double, true, 4>))
+        VB_OPT((sweep_p16_kernel<RP, false, double, true, 4>))
+    }
 #undef VB_OPT
     return e == cudaSuccess ? 0 : 1;
 }
 
+// split: 0 plain rows, 1 split layout (8-lane groups), 2 split layout with 4-lane groups
 template <typename PT>
-void sweep_pt(const SweepTiledArgs &a, bool cols, int fmt, bool split, int grid, int smem,
+void sweep_pt(const SweepTiledArgs &a, bool cols, int fmt, int split, int grid, int smem,
               cudaStream_t s) {
     constexpr int NT = SweepCfg<RP, PT>::kThreads;
     const bool vf = fmt == kEntF32;
     constexpr int NTC = SweepCfg<RP, PT>::p16_threads(true), NTR = SweepCfg<RP, PT>::p16_threads(false);
+    if constexpr (SweepCfg<RP, PT>::g4()) {
+        if (fmt == kEntP16 && split == 2) {
+            if (cols) sweep_p16_kernel<RP, true, PT, true, 4><<<grid, NTC, smem, s>>>(a);
+            else sweep_p16_kernel<RP, false, PT, true, 4><<<grid, NTR, smem, s>>>(a);
+            return;
+        }
+    }
     if constexpr (split_rank(RP) && sizeof(PT) == 8) {
         if (fmt == kEntP16 && split) {
             if (cols) sweep_p16_kernel<RP, true, PT, true><<<grid, NTC, smem, s>>>(a);
@@ -64,9 +76,9 @@ void sweep_pt(const SweepTiledArgs &a, bool cols, int fmt, bool split, int grid,
     }
 }
 
-void sweep(const SweepTiledArgs &a, bool cols, int fmt, bool pf32, bool split, int grid, int smem,
+void sweep(const SweepTiledArgs &a, bool cols, int fmt, bool pf32, int split, int grid, int smem,
            cudaStream_t s) {
-    if (pf32) sweep_pt<float>(a, cols, fmt, false, grid, smem, s);
+    if (pf32) sweep_pt<float>(a, cols, fmt, 0, grid, smem, s);
     else sweep_pt<double>(a, cols, fmt, split, grid, smem, s);
 }
 
@@ -101,7 +113,8 @@ extern const RpTable VB_CAT(rp_table_, VB_RP);
 const RpTable VB_CAT(rp_table_, VB_RP) = {
     RP,      RS,        row_stride_f32(RP),
     SweepCfg<RP, double>::kNPG, SweepCfg<RP, float>::kNPG, split_units(RP),
-    SweepCfg<RP, double>::stage_total(), SweepCfg<RP, float>::stage_total(), sweep_prepare,
+    SweepCfg<RP, double>::stage_total(), SweepCfg<RP, float>::stage_total(),
+    SweepCfg<RP, double>::g4() ? SweepCfg<RP, double>::stage_total(4) : -1, sweep_prepare,
     sweep, mirror,
     combine, posterior, ml_update,          colsum};
 

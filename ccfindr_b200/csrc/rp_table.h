@@ -65,10 +65,12 @@ struct RpTable {
     int split64;       // units of block A of the split layout the fp64 packed-16 sweep reads lw/lh in
                        // (panel_ofs): 8 (ranks 16..20), 4 (ranks 8..14) or 0 (plain rows)
     int stage64, stage32;  // bytes behind the tile the packed-16 sweeps use as owner staging slots
+    int stage64_g4;        // ... of the fp64 split kernels with 4-lane groups; -1: no such kernels
     // cols: cell-owner pass; fmt = storage format of the nonzeros (kEnt*); grid = CTAs (one per
     // SM, persistent)
     int (*sweep_prepare)(int smem_bytes);  // opt in to the dynamic shared memory size; 0 = ok
-    void (*sweep)(const SweepTiledArgs &, bool cols, int fmt, bool panels_f32, bool split, int grid,
+    // split: 0 plain rows, 1 split layout, 2 split layout with 4-lane groups
+    void (*sweep)(const SweepTiledArgs &, bool cols, int fmt, bool panels_f32, int split, int grid,
                   int smem_bytes, cudaStream_t);
     void (*mirror)(int64_t rows, const double *v, float *v32, cudaStream_t);
     void (*combine)(const CombineArgs &, cudaStream_t);

@@ -205,6 +205,7 @@ struct vbnmf_handle {
     double *d_lw = nullptr, *d_lh = nullptr, *d_alw = nullptr, *d_alh = nullptr;
     float *d_lw32 = nullptr, *d_lh32 = nullptr;  // fp32 mirrors read by the sweep (fp32-storage mode)
     int rsf = 0, panel_precision = -1;
+    int split_kind = 0;  // 0 plain rows, 1 split layout, 2 split layout + 4-lane groups (rp_table.h)
     int tsplit = 0;  // layout of d_lw / d_lh: 0 row-major, else the tile height T of the split
                      // layout (kernels.cuh panel_ofs) read by the split variant of the p16 sweep
     // d_red = [SwRaw NG*rs | ehsum rs | hprior, sumloglh, sumeh | enth, xlogp | entw, - | pad]
@@ -598,7 +599,7 @@ void launch_expand_cols(H *h, int32_t *d_colof, unsigned long long *d_cnt, unsig
 
 int get_layout(H *h, int T, int npg, int kmult, int mode, Layout **out) {
     if (!h->p16) npg = 0;
-    if (npg != 8) { kmult = 4; mode = vb::kSchedPlain; }
+    if (npg != 8 && mode != vb::kSchedOne4) { kmult = 4; mode = vb::kSchedPlain; }
     for (Layout *l : h->layouts)
         if (l->T == T && l->npg == npg && l->kmult == kmult && l->mode == mode) { *out = l; return 0; }
     StageTimer tm("get_layout(total)");
@@ -757,7 +758,10 @@ int alloc_panels(H *h, int r) {
                        (tab->split64 == 8 || getenv("VBNMF_SPLIT4"));
     // a slab row of the split layout is block A + a dense block B (kernels.cuh split_ps)
     const int row_bytes = f32 ? tab->rsf * 4 : (split ? vb::split_ps(rp) * 8 : rs * 8);
-    const int stage_bytes = h->p16 ? (f32 ? tab->stage32 : tab->stage64) : 0;
+    // 4-lane groups: split layout with an 8-unit block A and no single-unit block B (ranks 15, 16,
+    // 19, 20); VBNMF_NO_G4=1 keeps the 8-lane groups (A/B measurements)
+    const bool g4 = split && tab->stage64_g4 >= 0 && !getenv("VBNMF_NO_G4");
+    const int stage_bytes = h->p16 ? (f32 ? tab->stage32 : (g4 ? tab->stage64_g4 : tab->stage64)) : 0;
     const int T = choose_tile_rows(h, row_bytes, stage_bytes);
     Layout *L = nullptr;
     int kmult = split ? 1 : 4;
@@ -767,9 +771,11 @@ int alloc_panels(H *h, int r) {
     int mode = vb::kSchedPlain;
     if (split && tab->split64 == 4) mode = vb::kSchedSbs;
     else if (split && vb::split_bs(rp) == 4 && !getenv("VBNMF_NO_CLS4")) mode = vb::kSchedCls4;
-    int rc = get_layout(h, T, f32 ? tab->npg32 : tab->npg64, kmult, mode, &L);
+    if (g4) mode = vb::kSchedOne4;
+    int rc = get_layout(h, T, f32 ? tab->npg32 : (g4 ? 4 : tab->npg64), kmult, mode, &L);
     if (rc) return rc;
-    if (rp == h->rp && L == h->L && h->d_lw && h->panel_precision == h->precision) {
+    if (rp == h->rp && L == h->L && h->d_lw && h->panel_precision == h->precision &&
+        h->split_kind == (split ? (g4 ? 2 : 1) : 0)) {
         h->r = r;
         return 0;
     }
@@ -777,6 +783,7 @@ int alloc_panels(H *h, int r) {
     h->tab = tab;
     h->L = L;
     h->tsplit = split ? vb::make_tsplit(T, rp) : 0;
+    h->split_kind = split ? (g4 ? 2 : 1) : 0;
     h->r = r; h->rp = rp; h->rs = rs; h->rsf = tab->rsf;
     h->panel_precision = h->precision;
     h->smem_bytes = T * row_bytes + stage_bytes;
@@ -874,7 +881,7 @@ int launch_sweep_cols(H *h) {
                          f32 ? (const void *)h->d_lh32 : (const void *)h->d_lh,
                          f32 ? (const void *)h->d_lw32 : (const void *)h->d_lw, h->d_Part1, h->d_xl,
                          h->ctl, L->cols.d_ptr4, L->cols.d_seg};
-    h->tab->sweep(a, true, entry_format(h), f32, h->tsplit != 0, L->grid, h->smem_bytes, h->stream);
+    h->tab->sweep(a, true, entry_format(h), f32, h->split_kind, L->grid, h->smem_bytes, h->stream);
     vb::CombineArgs c{L->NC, L->Sg, h->r, h->d_Part1, h->d_lh, h->d_ShRaw, h->d_partC,
                       tail + h->rs + 3, h->d_counters + 2, h->d_xl, L->grid, h->gridC, h->ctl,
                       h->tsplit};
@@ -894,7 +901,7 @@ int launch_sweep_rows(H *h) {
                          f32 ? (const void *)h->d_lw32 : (const void *)h->d_lw,
                          f32 ? (const void *)h->d_lh32 : (const void *)h->d_lh, h->d_Part2, nullptr,
                          h->ctl, L->rows.d_ptr4, L->rows.d_seg};
-    h->tab->sweep(a, false, entry_format(h), f32, h->tsplit != 0, L->grid, h->smem_bytes, h->stream);
+    h->tab->sweep(a, false, entry_format(h), f32, h->split_kind, L->grid, h->smem_bytes, h->stream);
     vb::CombineArgs c{L->NG, L->Sc, h->r, h->d_Part2, h->d_lw, h->d_red, h->d_partC,
                       tail + h->rs + 5, h->d_counters + 3, nullptr, 0, h->gridC, h->ctl,
                       h->tsplit};
