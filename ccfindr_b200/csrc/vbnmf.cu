@@ -65,7 +65,7 @@ constexpr int64_t kGraphMaxNnz = 20000000;  // below this the iteration loop is 
 // shared-memory budget of one staged slab: the 227 KB a CTA can opt in to minus the static part
 constexpr int kTileBytes = 231424;
 constexpr int kTileRowsMax = 4096, kTileRowsStep = 32;
-constexpr int kSegWindow = 2048;  // owners per window of the length-sorted segment order (build_pass)
+constexpr int kSegWindow = 4096;  // owners per window of the length-sorted segment order (build_pass)
 constexpr double kSplitKappa = 0.0;  // cost of a segment beyond its entries, in quads (split_p16_kernel)
 
 thread_local std::string g_create_error;  // error text of the last failed create on this thread
