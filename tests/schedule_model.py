@@ -149,3 +149,77 @@ def wavefronts_cls4(rows, kmult=1):
                 bg[g, step, (2 * c + (g ^ (lane >> 2))) % 8] += 1
     w = int(np.maximum(bg.max(axis=2), 1).sum()) if K else 0
     return K, w
+
+
+def make_schedule_one4(c4, kmult=1):
+    """kSchedOne4 (4-lane groups): ONE set of four classes (row mod 4), one lane each; K =
+    max(ceil(n / 4), ceil(L / 2)) steps, R single + P pair steps (make_schedule(..., one4))."""
+    n, L = sum(c4), max(c4)
+    K = class_steps(n, L, 4, kmult)
+    sc = dict(K=[K, 0], pl=[(0, 0), (0, 0)], offr=[[0] * 8, [0] * 8], cnt=[list(c4) + [0] * 4, [0] * 8])
+    if K:
+        sc["pl"][0] = plan_class(list(c4), 4, K)
+        acc = 0
+        for b in range(4):
+            sc["offr"][0][b] = acc
+            acc += max(0, c4[b] - sc["pl"][0][0])
+    return sc
+
+
+def schedule_item_one4(sc, c, k):
+    """Item index (step * 4 + lane) of the k-th nonzero of class c."""
+    R, P = sc["pl"][0]
+    if k < R:
+        return k * 4 + c
+    t = sc["offr"][0][c] + (k - R)
+    row, level = t % (2 * P), t // (2 * P)
+    return (R + row % P) * 4 + (3 - level if row >= P else level)
+
+
+def wavefronts_one4_pair(rows0, rows1):
+    """Two 4-lane groups share a bank phase (quarter-warp): group 0 (lanes 0..3) reads unit c of
+    block B in gather c, group 1 (lanes 4..7) unit c XOR 1, so they use the even and the odd bank
+    groups and never collide with each other.  Returns (steps K of the longer segment, wavefronts
+    of the two block-B gathers); block A costs one wavefront per step and gather whatever the
+    rows are."""
+    plans = []
+    for rows in (rows0, rows1):
+        rows = list(rows)
+        c4 = np.bincount(np.asarray(rows, dtype=int) % 4, minlength=4).tolist()
+        sc = make_schedule_one4(c4)
+        seen, place, rank = set(), {}, [0] * 4
+        # rank in the class: residues c first, then c + 4 (the device code's order)
+        for rr in range(8):
+            for row in [x for x in rows if x % 8 == rr]:
+                c = row % 4
+                p = schedule_item_one4(sc, c, rank[c])
+                rank[c] += 1
+                assert 0 <= p < sc["K"][0] * 4 and p not in seen
+                seen.add(p)
+                place[p] = c
+        plans.append((sc["K"][0], place))
+    K = max(plans[0][0], plans[1][0])
+    w = 0
+    for g in range(2):                     # gather g reads unit g ^ h of block B
+        for step in range(K):
+            bg = np.zeros(8, dtype=int)
+            for h, (Kh, place) in enumerate(plans):
+                for lane in range(4):
+                    c = place.get(step * 4 + lane)
+                    if c is not None:
+                        bg[(2 * c + (g ^ h)) % 8] += 1
+            w += max(int(bg.max()), 1)
+    return K, w
+
+
+def window_order(steps, NO, W):
+    """Stored order of the segments of one pass (seg_order_keys_kernel): inside every window of W
+    consecutive owners of a slab, by decreasing number of steps; stable.  steps[e], e = slab * NO
+    + owner.  Returns order[pos] = e."""
+    steps = np.asarray(steps)
+    E = len(steps)
+    e = np.arange(E)
+    slab, o = e // NO, e % NO
+    nwin = (NO + W - 1) // W
+    key = (slab * nwin + o // W) * 1024 + (1023 - np.minimum(steps, 1023))
+    return np.argsort(key, kind="stable")

@@ -212,6 +212,38 @@ def test_opt_in_four_unit_split_layout_matches_oracle(Engine, monkeypatch, r):
         assert relerr(st[k], ref[k]) < TOL, k
 
 
+@pytest.mark.parametrize("r", [15, 16, 17, 18, 19, 20])
+@pytest.mark.parametrize("variant", ["default", "eight_lane_groups", "owner_order"])
+def test_split_layout_variants_match_oracle(Engine, monkeypatch, r, variant):
+    """Ranks 15..20 through the split layout with several slabs per side (small tile forced) and
+    small windows of the length-sorted segment order: 4-lane groups with the four-class schedule
+    (ranks 15, 16, 19, 20; default), 8-lane groups (VBNMF_NO_G4: the four classes of two lanes at
+    ranks 19, 20), and the segments left in owner order (VBNMF_SEG_WINDOW=0)."""
+    from oracle import bindings as ob
+    from oracle import oracle_dense as od
+    monkeypatch.setenv("VBNMF_TILE_ROWS", "160")
+    monkeypatch.setenv("VBNMF_SEG_WINDOW", "0" if variant == "owner_order" else "64")
+    if variant == "eight_lane_groups":
+        monkeypatch.setenv("VBNMF_NO_G4", "1")
+    X, w0, h0 = _random_problem(700, 900, r, 0.08, seed=80 + r)
+    hyper = dict(aw=0.9, bw=1.1, ah=1.2, bh=0.8)
+    ref = od.vb_init_from(w0, h0)
+    with Engine(X) as eng:
+        eng.set_state(w0, h0)
+        info = eng.layout_info()
+        assert info["tile_rows"] == 160 and info["gene_slabs"] == 5 and info["cell_slabs"] == 6
+        if r in (15, 16, 19, 20):
+            assert info["nonzeros_per_group_step"] == (8 if variant == "eight_lane_groups" else 4)
+        for it in range(3):
+            ref = ob.sparse_vb_step(X, ref, hyper, od.EPS)
+            assert relerr(eng.step(hyper, od.EPS), ref["lkh"]) < TOL, it
+        st = eng.get_state()
+        cid = eng.cluster_id()
+    for k in FACT:
+        assert relerr(st[k], ref[k]) < TOL, k
+    assert np.array_equal(cid, od.cluster_id(ref["eh"]))
+
+
 def test_errors_are_reported_not_thrown(Engine):
     from ccfindr_b200 import _lib
     X, w0, h0 = _random_problem(40, 30, 4, 0.3, seed=3)

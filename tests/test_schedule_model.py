@@ -5,7 +5,8 @@ import numpy as np
 import pytest
 from hypothesis import given, settings, strategies as st
 
-from schedule_model import make_schedule, wavefronts, wavefronts_sbs, wavefronts_cls4
+from schedule_model import (make_schedule, wavefronts, wavefronts_sbs, wavefronts_cls4,
+                            wavefronts_one4_pair, window_order)
 
 counts = st.lists(st.integers(min_value=0, max_value=90), min_size=8, max_size=8).filter(lambda c: sum(c) > 0)
 
@@ -140,3 +141,49 @@ def test_four_classes_of_two_lanes_cost_model():
 def test_four_class_schedule_places_every_nonzero_once(rows):
     K, wb = wavefronts_cls4(rows)
     assert K * 8 >= len(rows) and 2 * K <= wb <= 8 * K
+
+
+@settings(max_examples=150, deadline=None)
+@given(st.lists(st.integers(min_value=0, max_value=1439), min_size=1, max_size=200, unique=True),
+       st.lists(st.integers(min_value=0, max_value=1439), min_size=1, max_size=200, unique=True))
+def test_four_lane_groups_share_a_bank_phase_without_colliding(rows0, rows1):
+    """Every nonzero of both segments has its own slot, and a step costs at most a 2-way conflict
+    (the pair steps of ONE group): the two groups use disjoint bank groups."""
+    K, w = wavefronts_one4_pair(rows0, rows1)
+    assert K >= max((len(rows0) + 3) // 4, (len(rows1) + 3) // 4)
+    assert 2 * K <= w <= 4 * K
+
+
+def test_four_lane_groups_cost_model():
+    """r = 20, T = 1440, ~115 nonzeros per segment: 4-lane groups store ceil(n / 4) steps (fewer
+    hole slots than ceil(n / 8) * 8) and block B stays nearly conflict free."""
+    rng = np.random.default_rng(4)
+    tot = ideal = slots = nnz = 0.0
+    for _ in range(300):
+        r0 = rng.choice(1440, size=rng.binomial(1440, 0.08), replace=False)
+        r1 = rng.choice(1440, size=rng.binomial(1440, 0.08), replace=False)
+        K, wb = wavefronts_one4_pair(r0, r1)
+        tot += 8 * K + wb                  # 8 conflict-free gathers of block A + 2 of block B
+        ideal += 10 * max(len(r0), len(r1)) / 4
+        slots += 8 * K
+        nnz += len(r0) + len(r1)
+    assert tot / ideal < 1.09
+    assert slots / nnz < 1.12              # (unequal partners included)
+
+
+def test_window_order_keeps_locality_and_groups_equal_lengths():
+    rng = np.random.default_rng(5)
+    NO, S, W = 1000, 3, 128
+    steps = rng.integers(20, 40, size=NO * S)
+    order = window_order(steps, NO, W)
+    assert sorted(order.tolist()) == list(range(NO * S))           # a permutation
+    pos = np.arange(NO * S)
+    slab_of_pos, slab_of_e = pos // NO, order // NO
+    assert (slab_of_pos == slab_of_e).all()                         # slabs keep their ranges
+    o = order % NO
+    assert (np.abs(o - pos % NO) < W).all()                         # owners stay inside their window
+    # inside a window the steps are non-increasing
+    for s0 in range(S):
+        for w0 in range(0, NO, W):
+            seg = steps[order[s0 * NO + w0: s0 * NO + min(w0 + W, NO)]]
+            assert (np.diff(seg) <= 0).all()
