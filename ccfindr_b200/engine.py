@@ -69,7 +69,13 @@ class Engine:
 
     @classmethod
     def from_device_csc(cls, n, m, nnz, colptr_i64, rowidx_i32, values_f32, device=0):
-        """colptr/rowidx/values: torch CUDA tensors (int64, int32, float32) already on `device`."""
+        """colptr/rowidx/values: torch CUDA tensors (int64, int32, float32) already on `device`.
+        The library reads them on its own stream: whatever produced them (the caller's current
+        torch stream) is waited for first -- without this the scan of the counts can overtake a
+        still running torch.cat and miss the tail of the matrix (seen as a constant offset of the
+        bound: the sum of lgamma(x + 1) came out short while the factors were right)."""
+        import torch
+        torch.cuda.current_stream(torch.device("cuda", int(device))).synchronize()
         keep = (colptr_i64, rowidx_i32, values_f32)
         return cls(device=device, _device_csc=(int(n), int(m), int(nnz), colptr_i64.data_ptr(),
                                                rowidx_i32.data_ptr(), values_f32.data_ptr(), keep))

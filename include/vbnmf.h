@@ -76,7 +76,9 @@ VBNMF_API int vbnmf_create(vbnmf_handle **out, int64_t n, int64_t m, int64_t nnz
                  const int64_t *colptr64, const int32_t *rowidx, const double *values, int device);
 
 /* Same, from arrays already resident on `device` (int64 colptr, int32 rowidx, fp32 counts).
- * The arrays are borrowed: they must outlive the handle. */
+ * The arrays are borrowed: they must outlive the handle.  They are read on the handle's own
+ * stream, starting inside this call: the work that produces them must have COMPLETED (synchronise
+ * the producing stream first) -- the library cannot know that stream. */
 VBNMF_API int vbnmf_create_from_device(vbnmf_handle **out, int64_t n, int64_t m, int64_t nnz,
                              const int64_t *d_colptr, const int32_t *d_rowidx, const float *d_values,
                              int device);
