@@ -2219,7 +2219,8 @@ int vbnmf_layout_info(const vbnmf_handle *h, int64_t info[8]) {
     info[0] = fmt; info[1] = L->T; info[2] = L->Sg; info[3] = L->Sc;
     info[4] = L->cols.nent; info[5] = L->rows.nent;
     info[6] = fmt == vb::kEntP16 ? L->npg : 0;
-    info[7] = (L->cols.nent + L->rows.nent) * ebytes + (L->cols.E + L->rows.E + 2) * pbytes;
+    info[7] = (L->cols.nent + L->rows.nent) * ebytes + (L->cols.E + L->rows.E + 2) * pbytes +
+              (fmt == vb::kEntP16 ? (L->cols.E + L->rows.E) * 4 : 0);  // + owner of each position
     return 0;
 }
 
