@@ -1737,22 +1737,25 @@ int vbnmf_attach_comm(vbnmf_handle *h, vbnmf_comm *c) {
     h->rank = c->rank;
     // global quantities: total cells, the sums over nonzeros, and the per-gene nonzero counts
     // (every rank must derive the same gene renumbering)
-    double hv[4] = {(double)h->m, h->lgx, h->mlconst, (double)h->nnz};
+    // ... and whether EVERY shard holds 16-bit integer counts: the packed-16 layout decides the
+    // tile height (split layout, staging slots), which all ranks must share -- the gene panels
+    // are all-reduced in device order
+    double hv[5] = {(double)h->m, h->lgx, h->mlconst, (double)h->nnz, h->p16 ? 0.0 : 1.0};
     double *dv = nullptr;
     unsigned *d_flag = nullptr;
     uint32_t *d_scr = nullptr;
-    CK(vmalloc(h, &dv, 4 * 8));
+    CK(vmalloc(h, &dv, 5 * 8));
     CK(vmalloc(h, &d_flag, 4));
     CK(vmalloc(h, &d_scr, (size_t)2 * h->n * 4));
     CK(cudaMemsetAsync(d_flag, 0, 4, h->stream));
-    CK(cudaMemcpyAsync(dv, hv, 4 * 8, cudaMemcpyHostToDevice, h->stream));
-    int rc = allreduce(h, dv, 4);
+    CK(cudaMemcpyAsync(dv, hv, 5 * 8, cudaMemcpyHostToDevice, h->stream));
+    int rc = allreduce(h, dv, 5);
     if (rc) return rc;
     CKN(g_nccl.AllReduce(h->d_cnt, h->d_cnt, (size_t)h->n, ncclUint64, ncclSum, h->comm, h->stream));
     vb::order_keys_kernel<<<cdiv(h->n, vb::kBlock), vb::kBlock, 0, h->stream>>>(
         h->n, h->d_cnt, d_scr, d_scr + h->n, d_flag);
     unsigned nzero = 0;
-    CK(cudaMemcpyAsync(hv, dv, 4 * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(hv, dv, 5 * 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(&nzero, d_flag, 4, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     vfree(h->stream, dv); vfree(h->stream, d_flag); vfree(h->stream, d_scr);
@@ -1760,6 +1763,7 @@ int vbnmf_attach_comm(vbnmf_handle *h, vbnmf_comm *c) {
     h->lgx = hv[1];
     h->mlconst = hv[2];
     h->nnz_global = (int64_t)llround(hv[3]);
+    if (hv[4] != 0.0) h->p16 = false;
     h->empty_rows = nzero;  // of the whole matrix now (R/bayesian.R:244); tested at set_state
     free_panels(h);
     drop_layouts(h);

@@ -55,9 +55,36 @@ def main():
         assert np.array_equal(cid, g["cid"][c0:c1]), (case, rank)
         worst = max(worst, max(errs))
         eng.close()
-    # ML path, sharded, against the CPU oracle
     from ccfindr_b200 import synth
     from oracle import bindings as ob
+    # mixed storage formats: only the LAST shard holds a non-integer count.  The packed 16-bit
+    # layout decides the tile height at rank 20 (split layout), and the gene panels are all-reduced
+    # in device order: every rank must fall back to the 8-byte entries together.
+    import scipy.sparse as sp
+    rng = np.random.default_rng(11)
+    n, m, r = 300, 480, 20
+    D = rng.poisson(0.25, size=(n, m)).astype(np.float64)
+    D[np.arange(n), rng.integers(0, m, n)] += 1.0        # no empty genes
+    D[rng.integers(0, n, m), np.arange(m)] += 1.0        # no empty cells
+    D[7, m - 1] = 2.5
+    Xm = sp.csc_matrix(D)
+    w0, h0 = rng.random((n, r)) + 0.1, rng.random((r, m)) + 0.1
+    hyp = dict(aw=0.9, bw=1.1, ah=1.2, bh=0.8)
+    ref = ob.sparse_vb_run(Xm, w0, h0, hyp, Itmax=3, Tol=0.0)
+    b = sharding.balanced_bounds(Xm.indptr, world)
+    c0, c1 = b[rank], b[rank + 1]
+    eng = Engine(sharding.shard_csc(Xm, c0, c1), device=local)
+    eng.attach_comm(comm)
+    eng.set_state(w0, h0[:, c0:c1])
+    assert eng.layout_info()["format"] != "p16"
+    out = eng.run(hyp, Itmax=3, Tol=0.0)
+    st = eng.get_state(("ew", "eh"))
+    e = max(relerr(out["lkh_trace"], ref["lkh_trace"]), relerr(st["ew"], ref["ew"]),
+            relerr(st["eh"], ref["eh"][:, c0:c1]))
+    assert e < 1e-9, ("mixed formats", rank, e)
+    worst = max(worst, e)
+    eng.close()
+    # ML path, sharded, against the CPU oracle
     X = load_counts("pbmc")
     n, m = X.shape
     w0, h0 = synth.uniform_init(n, m, 4, 4)
