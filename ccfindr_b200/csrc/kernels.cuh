@@ -778,8 +778,8 @@ struct LogProd {
 // tile is stored as block A (T x 128 bytes) + block B; lane gl gathers unit c ^ gl of block A in
 // step c -- conflict free for ANY 8 rows -- and holds its owner row and accumulators in the same
 // rotated order; the cross-lane sum un-rotates for free (partner gl ^ b holds my unit of register
-// c in its register c ^ b).  Entries with count 0 (schedule holes) skip their gathers: the lane
-// keeps the previous row, and x = 0 adds nothing.
+// c in its register c ^ b).  Schedule holes (count 0) gather a real row and add nothing; with
+// VB_SPLIT_PRED they would skip their gathers (measured slower).
 // G = lanes per segment: 8, or 4 for the split layout with an 8-unit block A.  The rotation of
 // block A only needs the 8 lanes of a quarter-warp to read 8 different units, whatever segments
 // their rows belong to, so two 4-lane groups can share a bank phase; each lane then walks twice as
