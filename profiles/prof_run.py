@@ -11,9 +11,10 @@ from ccfindr_b200.engine import Engine
 ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="c2"); ap.add_argument("--precision", type=int, default=0)
 ap.add_argument("--iters", type=int, default=3); ap.add_argument("--cells", type=int, default=0)
+ap.add_argument("--rank", type=int, default=0)
 a = ap.parse_args()
 wl = bench.WORKLOADS[a.workload]
-n, r = wl["n"], wl["rank"]
+n, r = wl["n"], (a.rank or wl["rank"])
 m = a.cells or wl.get("m_per_gpu") or wl["m_total"]
 dev = torch.device("cuda", 0)
 colptr, rowidx, values, _ = synth.tenx_like_device(n, m, wl["r_true"], wl["density"], wl["seed"], dev)
