@@ -243,6 +243,13 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
 #ifndef VB_WIDE_THREADS
 #define VB_WIDE_THREADS 256  // ... more than 160 bytes
 #endif
+#ifndef VB_G4_NU9
+#define VB_G4_NU9 1       // 4-lane groups also for rows of 9 units (ranks 17, 18).  The single unit of
+                          // block B (bank group = row mod 8) makes lanes l and l + 4 of a bank phase
+                          // collide when their rows agree in bit 2; the builder orders the classes of
+                          // even / odd positions in opposite directions to avoid most of it.  Measured
+                          // (C2 matrix, r = 18): 2.35 -> 2.20 ms per iteration against 8-lane groups
+#endif
 #ifndef VB_OWN_AHEAD
 #define VB_OWN_AHEAD(dflt) (dflt)
 #endif
@@ -308,7 +315,7 @@ struct SweepCfg {
     // 4-lane groups (sweep_p16_kernel, G = 4): split layout with an 8-unit block A and no
     // single-unit block B
     __host__ __device__ static constexpr bool g4() {
-        return sizeof(PT) == 8 && kLPN == 1 && split_units(RP) == 8 && kNU != 9;
+        return sizeof(PT) == 8 && kLPN == 1 && split_units(RP) == 8 && (VB_G4_NU9 || kNU != 9);
     }
 };
 
@@ -804,7 +811,7 @@ sweep_p16_kernel(const SweepTiledArgs a) {
     constexpr bool kRotB = SPLIT && SA == 8 && NUB == 2 && BSD == 4;
     constexpr int NT = Cfg::p16_threads(COLS);
     constexpr int UE = Cfg::kUE, NU = Cfg::kNU, LPN = Cfg::kLPN, NUL = Cfg::kNUL, KL = Cfg::kKL;
-    static_assert(G == 8 || (G == 4 && SPLIT && split_units(RP) == 8 && Cfg::kNU != 9),
+    static_assert(G == 8 || (G == 4 && SPLIT && split_units(RP) == 8 && (VB_G4_NU9 || Cfg::kNU != 9)),
                   "4-lane groups: split layout, 8-unit block A, block B empty or two dense units");
     constexpr int NPG = G / LPN;
     constexpr int kGroups = NT / G;
@@ -1149,6 +1156,15 @@ sweep_p16_kernel(const SweepTiledArgs a) {
                     // lane gl: rank entry 16 + 2 * h + (bit 1 of gl)
                     const int kk = 2 * SA + 2 * ((gl >> 2) & 1) + ((gl >> 1) & 1);
                     if ((gl & 1) == 0 && kk < RP) out[kk] = b2;
+                } else if constexpr (NUB > 0 && G == 4) {
+                    // (VB_G4_NU9) a plain unit of block B over four lanes
+#pragma unroll
+                    for (int k = 0; k < 2 * NUB; k++) {
+                        double sB = v0[2 * SA + k];
+                        sB += __shfl_xor_sync(gmask, sB, 2);
+                        sB += __shfl_xor_sync(gmask, sB, 1);
+                        if (gl == (k & 3) && 2 * SA + k < RP) out[2 * SA + k] = sB;
+                    }
                 } else if constexpr (NUB > 0) {
                     double vb[2 * NUB];
 #pragma unroll

@@ -567,9 +567,16 @@ build_segments_p16_kernel(int64_t E, int64_t NO, const int64_t *__restrict__ ptr
                 vr = (rr & 3) + 4 * (kc & 1);
                 vk = kc >> 1;
             }
-            if (one4 && valid) {  // rank in the class: residues c, then c + 4
+            if (one4 && valid) {
+                // rank in the class: residues c, then c + 4 -- the other way round in segments at
+                // odd positions.  The two 4-lane groups of a bank phase sit at an even and an odd
+                // position (CTA ranges start at even positions, split_p16_kernel): with a single
+                // unit in block B (ranks 17, 18; bank group = row mod 8) lanes l and l + 4 collide
+                // when their rows agree in bit 2, which this order avoids except around the
+                // middle of the segments.
                 vr = rr & 3;
-                vk = rr < 4 ? k : cnt[rr - 4] + k;
+                if ((pos & 1) == 0) vk = rr < 4 ? k : cnt[rr - 4] + k;
+                else vk = rr >= 4 ? k : cnt[rr + 4] + k;
             }
             if (valid) dst[p16_position(schedule_item(sc, NL, sbs, vr, vk, one4), NL)] = w;
         }
@@ -590,6 +597,7 @@ tag_dead_kernel(int64_t E, const uint8_t *__restrict__ dead, uint32_t *__restric
 // per-segment part (pointers, owner row, cross-lane sum, store) is worth a few quads of gathers, so
 // a CTA whose range holds the short segments of a slab (the owners are sorted by count) would be
 // late under an equal-entries split (measured: sm__cycles_elapsed.max 5.7 % above the mean).
+// The boundaries are even positions (see kSchedOne4 in build_segments_p16_kernel).
 __global__ void split_p16_kernel(int nparts, int64_t E, const uint32_t *__restrict__ ptr4,
                                  double kappa, int64_t *__restrict__ split) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -601,7 +609,7 @@ __global__ void split_p16_kernel(int nparts, int64_t E, const uint32_t *__restri
         const int64_t mid = (lo + hi) >> 1;
         if ((double)ptr4[mid] + kappa * (double)mid < target) lo = mid + 1; else hi = mid;
     }
-    split[b] = lo;
+    split[b] = lo & ~(int64_t)1;
 }
 
 // split[b] = first segment whose start offset is >= b * nnz / nparts; split[nparts] = E

@@ -758,8 +758,8 @@ int alloc_panels(H *h, int r) {
                        (tab->split64 == 8 || getenv("VBNMF_SPLIT4"));
     // a slab row of the split layout is block A + a dense block B (kernels.cuh split_ps)
     const int row_bytes = f32 ? tab->rsf * 4 : (split ? vb::split_ps(rp) * 8 : rs * 8);
-    // 4-lane groups: split layout with an 8-unit block A and no single-unit block B (ranks 15, 16,
-    // 19, 20); VBNMF_NO_G4=1 keeps the 8-lane groups (A/B measurements)
+    // 4-lane groups: split layout with an 8-unit block A (ranks 15..20); VBNMF_NO_G4=1 keeps the
+    // 8-lane groups (A/B measurements)
     const bool g4 = split && tab->stage64_g4 >= 0 && !getenv("VBNMF_NO_G4");
     const int stage_bytes = h->p16 ? (f32 ? tab->stage32 : (g4 ? tab->stage64_g4 : tab->stage64)) : 0;
     const int T = choose_tile_rows(h, row_bytes, stage_bytes);

@@ -217,8 +217,8 @@ def test_opt_in_four_unit_split_layout_matches_oracle(Engine, monkeypatch, r):
 def test_split_layout_variants_match_oracle(Engine, monkeypatch, r, variant):
     """Ranks 15..20 through the split layout with several slabs per side (small tile forced) and
     small windows of the length-sorted segment order: 4-lane groups with the four-class schedule
-    (ranks 15, 16, 19, 20; default), 8-lane groups (VBNMF_NO_G4: the four classes of two lanes at
-    ranks 19, 20), and the segments left in owner order (VBNMF_SEG_WINDOW=0)."""
+    (default), 8-lane groups (VBNMF_NO_G4: the four classes of two lanes at ranks 19, 20), and the
+    segments left in owner order (VBNMF_SEG_WINDOW=0)."""
     from oracle import bindings as ob
     from oracle import oracle_dense as od
     monkeypatch.setenv("VBNMF_TILE_ROWS", "160")
@@ -232,8 +232,7 @@ def test_split_layout_variants_match_oracle(Engine, monkeypatch, r, variant):
         eng.set_state(w0, h0)
         info = eng.layout_info()
         assert info["tile_rows"] == 160 and info["gene_slabs"] == 5 and info["cell_slabs"] == 6
-        if r in (15, 16, 19, 20):
-            assert info["nonzeros_per_group_step"] == (8 if variant == "eight_lane_groups" else 4)
+        assert info["nonzeros_per_group_step"] == (8 if variant == "eight_lane_groups" else 4)
         for it in range(3):
             ref = ob.sparse_vb_step(X, ref, hyper, od.EPS)
             assert relerr(eng.step(hyper, od.EPS), ref["lkh"]) < TOL, it
