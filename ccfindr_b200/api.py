@@ -343,11 +343,37 @@ def _vb_parallel(mat, ranks, nrun, common, unif_stop, verbose, seed, inits, devi
             out = _vb_iterate(eng, irun, mat, [ranks[k]], *common, False, nrun, 0, seed, inits, [])
             done[(irun, k)] = {key: out[key][0] for key in out}
             done[(irun, k)]["unif"] = out["unif_flag"][0]
+    # Results back to every rank in two steps: the scalars of all jobs first, then the factor
+    # matrices of the jobs that can still be chosen -- the best run of every rank (strict >, the
+    # first of equals: the rule of the aggregation, R/bayesian.R:271).  Exchanging the matrices of
+    # all 145 jobs of the C4 sweep (4.5 GB, pickled and padded per rank) took longer than the
+    # factorizations on 8 GPUs.  If a job raised the uniform-column flag the run order matters
+    # (R/bayesian.R:370-378 breaks the rank scan of that run), so everything is exchanged.
+    big_keys = ("wdat", "hdat", "dwdat", "dhdat")
+    small = {key: {f: v for f, v in res.items() if f not in big_keys} for key, res in done.items()}
     gathered = [None] * world
-    dist.all_gather_object(gathered, done)
+    dist.all_gather_object(gathered, small)
     allres = {}
     for d in gathered:
         allres.update(d)
+    if any(res["unif"] for res in allres.values()):
+        keep = set(allres)
+    else:
+        keep = set()
+        for k in range(len(ranks)):
+            rmax, imax = -np.inf, None
+            for irun in range(1, nrun + 1):
+                if allres[(irun, k)]["rdat"] > rmax:
+                    imax, rmax = irun, allres[(irun, k)]["rdat"]
+            if imax is not None:
+                keep.add((imax, k))
+    big = {key: {f: done[key][f] for f in big_keys} for key in done if key in keep}
+    dist.all_gather_object(gathered, big)
+    for key in allres:
+        allres[key].update({f: None for f in big_keys})
+    for d in gathered:
+        for key, mats in d.items():
+            allres[key].update(mats)
     vb = []
     for irun in range(1, nrun + 1):
         out = dict(rdat=[-np.inf] * len(ranks), wdat=[None] * len(ranks), hdat=[None] * len(ranks),
