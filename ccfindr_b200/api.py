@@ -326,6 +326,24 @@ def _vb_sharded(mat, ranks, nrun, common, unif_stop, verbose, seed, inits, devic
     return vb
 
 
+def jobs_to_keep(scalars, nrun, nrank):
+    """(irun, k) of the jobs whose factor matrices the aggregation can still ask for: the best run
+    of every rank index k -- strict >, the first of equals (R/bayesian.R:271) -- or every job when
+    one raised the uniform-column flag (the rank scan of that run then breaks, R/bayesian.R:370-378,
+    and what is best depends on the run order).  scalars[(irun, k)] = dict(rdat=..., unif=...)."""
+    if any(res["unif"] for res in scalars.values()):
+        return set(scalars)
+    keep = set()
+    for k in range(nrank):
+        rmax, imax = -np.inf, None
+        for irun in range(1, nrun + 1):
+            if scalars[(irun, k)]["rdat"] > rmax:
+                imax, rmax = irun, scalars[(irun, k)]["rdat"]
+        if imax is not None:
+            keep.add((imax, k))
+    return keep
+
+
 def _vb_parallel(mat, ranks, nrun, common, unif_stop, verbose, seed, inits, device, precision):
     """Independent (run, rank) factorizations spread over the ranks of torch.distributed."""
     import torch.distributed as dist
@@ -359,17 +377,7 @@ def _vb_parallel(mat, ranks, nrun, common, unif_stop, verbose, seed, inits, devi
     allres = {}
     for d in gathered:
         allres.update(d)
-    if any(res["unif"] for res in allres.values()):
-        keep = set(allres)
-    else:
-        keep = set()
-        for k in range(len(ranks)):
-            rmax, imax = -np.inf, None
-            for irun in range(1, nrun + 1):
-                if allres[(irun, k)]["rdat"] > rmax:
-                    imax, rmax = irun, allres[(irun, k)]["rdat"]
-            if imax is not None:
-                keep.add((imax, k))
+    keep = jobs_to_keep(allres, nrun, len(ranks))
     big = {key: {f: done[key][f] for f in big_keys} for key in done if key in keep}
     dist.all_gather_object(gathered, big)
     for key in allres:

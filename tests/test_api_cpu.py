@@ -189,3 +189,18 @@ def test_weighted_linkage_equals_linkage_of_the_expanded_point_set(method):
     first = np.array([np.flatnonzero(owner == g)[0] for g in range(G)])
     ref = cf[np.ix_(first, first)]
     assert np.allclose(got + np.diag(np.diag(ref)), ref, atol=1e-12)
+
+
+def test_job_farm_exchanges_only_the_matrices_that_can_be_chosen():
+    """The best run per rank index by strict > (first of equals, NaN never wins); everything when a
+    job raised the uniform-column flag."""
+    nan = float("nan")
+    sc = {(1, 0): dict(rdat=-2.0, unif=False), (2, 0): dict(rdat=-1.0, unif=False),
+          (3, 0): dict(rdat=-1.0, unif=False),
+          (1, 1): dict(rdat=nan, unif=False), (2, 1): dict(rdat=-5.0, unif=False),
+          (3, 1): dict(rdat=-7.0, unif=False),
+          (1, 2): dict(rdat=nan, unif=False), (2, 2): dict(rdat=nan, unif=False),
+          (3, 2): dict(rdat=nan, unif=False)}
+    assert api.jobs_to_keep(sc, 3, 3) == {(2, 0), (2, 1)}
+    sc[(3, 1)]["unif"] = True
+    assert api.jobs_to_keep(sc, 3, 3) == set(sc)
