@@ -260,11 +260,15 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
                           // (measured at C2: cell-owner pass 0.744 -> 0.708 ms)
 #endif
 #ifndef VB_OWN_STAGE
-#define VB_OWN_STAGE 1    // owner rows that cannot be requested a whole segment ahead in registers are
+#define VB_OWN_STAGE 0    // 1: owner rows that cannot be requested a whole segment ahead in registers are
                           // staged through shared memory instead: cp.async into an 8-lane group's own
                           // slot behind the tile during the previous segment, read back with LDS at
-                          // segment start (the global-load latency of the owner row was the largest
-                          // part of the per-segment overhead)
+                          // segment start.  Built and measured: -0.7 % at r = 20 before the segments
+                          // were length-sorted, but with the final layouts the slots' share of the
+                          // tile costs more than the latency they hide (C2 matrix: r = 10 1.379 vs
+                          // 1.360 ms per iteration without, r = 12 1.70 vs 1.62, r = 30 4.96 vs
+                          // 4.73), so it is off: the row is requested before the cross-lane sum of
+                          // the previous segment (VB_OWN_EARLY)
 #endif
 
 template <int RP, typename PT>
